@@ -1,0 +1,158 @@
+/* irs_mpc_b200 — C ABI of the B200-native iRS-MPC hot path.
+ *
+ * The reference (hjsuh94/irs_mpc) is pure Python and has no FFI of its own; these entry points
+ * are what a ctypes binding placed behind the reference's Python call surface binds (see
+ * INTEGRATION.md).  Each function cites the reference interface it replaces (paths relative to
+ * the reference tree).
+ *
+ * Conventions
+ *   - every pointer named in a signature is a DEVICE pointer unless it says "host";
+ *   - matrices are dense row-major; state/input dims (n, m) are fixed by `system`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls enqueue work on `stream` and return without synchronising;
+ *   - return value 0 = ok, non-zero = error, message via irs_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef IRS_MPC_B200_H
+#define IRS_MPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRS_ABI_VERSION 1
+
+/* system ids — the reference's four analytic DynamicalSystem subclasses
+ * (examples/pendulum/pendulum_dynamics.py:8, examples/bicycle/bicycle_dynamics.py:8,
+ *  examples/quadrotor/quadrotor_dynamics.py:15, examples/three_cart/three_cart_dynamics.py:8).
+ * `params` (host, doubles): pendulum [h]; bicycle [h];
+ *   quadrotor [h, mass, L, g, Ixx, Iyy, Izz, kF, kM]; three_cart [h, d]. */
+enum { IRS_PENDULUM = 0, IRS_BICYCLE = 1, IRS_QUADROTOR = 2, IRS_THREE_CART = 3 };
+
+/* smoothing flags */
+enum {
+  IRS_SAMPLES_BATCH_VARIANT = 1, /* samples use dynamics_batch semantics (irs_lqr_zero_order.py:51);
+                                    only three_cart distinguishes (three_cart_dynamics.py:109-194) */
+  IRS_PROJECT_ABSOLUTE = 2,      /* three_cart_zero_order.py:43: sampling returns projection(...) =
+                                    absolute points (three_cart_dynamics.py:196-264), reproduced literally */
+  IRS_PROJECT_DELTA = 4          /* corrected variant: projected point minus nominal */
+};
+
+int irs_abi_version(void);
+const char* irs_last_error(void);
+
+/* DynamicalSystem.dim_x / dim_u (irs_lqr/dynamical_system.py:8-10); nj = varying Jacobian scalars */
+int irs_system_dims(int system, int* n, int* m, int* nj);
+
+/* Number of fp32 accumulators per (nominal point, chunk): order 0 = zero-order Gram
+ * d(d+1)/2 + d*n, order 1 = first-order nj. */
+int irs_partial_width(int system, int order);
+
+/* Chunking plan for P nominal points x N samples: C chunks of S samples each. */
+int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long* S);
+
+/* IrsLqrZeroOrder.get_TV_matrices sampling + fit, accumulation stage
+ * (irs_lqr/irs_lqr_zero_order.py:49-57): for each nominal point p and sample i
+ *   (dx,du) = noise[p,i,:]                     if noise != NULL   (replay / parity mode)
+ *           = sigma * Philox-normal(seed; i0+i, p0+p, iter, stream)   otherwise
+ *   dF      = f(xbar+dx, ubar+du) - f(xbar, ubar)
+ * and accumulates [dx du]^T [dx du | dF] into partials[P, C, irs_partial_width(system,0)].
+ * x_nom [P,n] f64, u_nom [P,m] f64, sigma [n+m] f32, noise [P,N,n+m] f32 or NULL. */
+int irs_smooth_zero_order_accumulate(int system, const double* params_host, int nparams, int flags,
+                                     const double* x_nom, const double* u_nom, int P, long long N,
+                                     const float* sigma, const float* noise,
+                                     unsigned long long seed, unsigned iter, unsigned stream_id,
+                                     unsigned p0, unsigned long long i0,
+                                     int C, long long S, float* partials, void* stream);
+
+/* IrsLqrFirstOrder.get_TV_matrices sampling + Jacobian averaging, accumulation stage
+ * (irs_lqr/irs_lqr_first_order.py:42-48; Jacobians of pendulum_dynamics.py:110-127,
+ * bicycle_dynamics.py:115-132, quadrotor_dynamics.py:132-148).  partials [P, C, nj]. */
+int irs_smooth_first_order_accumulate(int system, const double* params_host, int nparams, int flags,
+                                      const double* x_nom, const double* u_nom, int P, long long N,
+                                      const float* sigma, const float* noise,
+                                      unsigned long long seed, unsigned iter, unsigned stream_id,
+                                      unsigned p0, unsigned long long i0,
+                                      int C, long long S, float* partials, void* stream);
+
+/* Fit / mean + affine offset (irs_lqr_zero_order.py:27-36,:59-62; irs_lqr_first_order.py:48-53):
+ * sums `nranks` partial buffers (partials + r*rank_stride floats, r = 0..nranks-1; peer-mapped
+ * pointers are fine) in fixed order, solves the normal equations (order 0) or divides by n_total
+ * (order 1), writes At [P,n,n], Bt [P,n,m], ct [P,n] (f64) and status [P] (0 ok, 1 rank deficient). */
+int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
+                        const double* x_nom, const double* u_nom, int P, int C,
+                        const float* partials, int nranks, long long rank_stride, double n_total,
+                        double* At, double* Bt, double* ct, int* status, void* stream);
+
+/* IrsLqrExact.get_TV_matrices (irs_lqr/irs_lqr_exact.py:15-31), all fp64: [A|B] = jacobian_xu at
+ * the nominal points, c = f(xbar,ubar) - A xbar - B ubar.  x_nom [P,n], u_nom [P,m]. */
+int irs_exact_linearize(int system, const double* params_host, int nparams,
+                        const double* x_nom, const double* u_nom, int P,
+                        double* At, double* Bt, double* ct, void* stream);
+
+/* The Philox words / deltas exactly as the fused kernels draw them (bookkeeping tests).
+ * words [P,N,ceil(d/4),4] u32 or NULL; deltas [P,N,d] f32 or NULL. */
+int irs_philox_dump(int P, long long N, int d, const float* sigma, unsigned long long seed,
+                    unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
+                    unsigned* words, float* deltas, void* stream);
+
+/* DynamicalSystem.dynamics_batch (irs_lqr/dynamical_system.py:24-37). batch_variant != 0 selects
+ * the reference's dynamics_batch semantics, 0 the scalar dynamics semantics (three_cart differs).
+ * x [B,n], u [B,m], out [B,n]; *_f32 in float, *_f64 in double. */
+int irs_dynamics_batch_f32(int system, const double* params_host, int nparams, int batch_variant,
+                           const float* x, const float* u, float* out, long long B, void* stream);
+int irs_dynamics_batch_f64(int system, const double* params_host, int nparams, int batch_variant,
+                           const double* x, const double* u, double* out, long long B, void* stream);
+
+/* DynamicalSystem.jacobian_xu_batch (irs_lqr/dynamical_system.py:53-66): J [B,n,n+m]. */
+int irs_jacobian_xu_batch_f32(int system, const double* params_host, int nparams,
+                              const float* x, const float* u, float* J, long long B, void* stream);
+int irs_jacobian_xu_batch_f64(int system, const double* params_host, int nparams,
+                              const double* x, const double* u, double* J, long long B, void* stream);
+
+/* ThreeCartDynamics.projection (examples/three_cart/three_cart_dynamics.py:196-264) applied to
+ * absolute states x [B,n] in place (non-penetration projection, half-depth push-out).
+ * A no-op for systems without a projection. */
+int irs_project_batch_f64(int system, const double* params_host, int nparams, double* x,
+                          long long B, void* stream);
+
+/* solve_tvlqr backward pass (irs_lqr/tv_lqr.py:30-145, inactive bounds): affine Riccati recursion
+ * for I independent instances.  At [I,T,n,n], Bt [I,T,n,m], ct [I,T,n], Q/Qd [n,n], R [m,m]
+ * (full R; the QP's 1/2 u'Ru of tv_lqr.py:110 is applied inside), xd [I,T+1,n] (xd_stride =
+ * (T+1)*n) or one shared trajectory (xd_stride = 0).  Outputs K [I,T,m,n], k [I,T,m],
+ * status [I] (1 = H not SPD / NaN -> the caller raises the reference's ValueError, tv_lqr.py:139). */
+int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const double* ct,
+                      const double* Q, const double* Qd, const double* R,
+                      const double* xd, long long xd_stride, int I, int T,
+                      double* K, double* k, int* status, void* stream);
+
+/* (x*, u*) of solve_tvlqr: rollout of the affine model under u = K x + k (tv_lqr.py:142-145).
+ * x0 [I,n]; xs [I,T+1,n]; us [I,T,m]. */
+int irs_tvlqr_linear_rollout(int n, int m, const double* At, const double* Bt, const double* ct,
+                             const double* K, const double* k, const double* x0, int I, int T,
+                             double* xs, double* us, void* stream);
+
+/* IrsLqr.local_descent forward pass (irs_lqr/irs_lqr.py:169-184): u_t = K_t x_t + k_t on the TRUE
+ * dynamics, plus IrsLqr.evaluate_cost (irs_lqr.py:121-137, terminal term uses Q).
+ * x0 [I,n]; x_trj [I,T+1,n]; u_trj [I,T,m]; cost [I]. */
+int irs_rollout_closed_loop(int system, const double* params_host, int nparams,
+                            const double* K, const double* k, const double* x0,
+                            const double* xd, long long xd_stride, const double* Q, const double* R,
+                            int I, int T, double* x_trj, double* u_trj, double* cost, void* stream);
+
+/* IrsLqr.rollout + evaluate_cost (irs_lqr/irs_lqr.py:105-137) for given inputs u_in [I,T,m]. */
+int irs_rollout_open_loop(int system, const double* params_host, int nparams,
+                          const double* u_in, const double* x0,
+                          const double* xd, long long xd_stride, const double* Q, const double* R,
+                          int I, int T, double* x_trj, double* cost, void* stream);
+
+/* IrsLqr.evaluate_cost (irs_lqr/irs_lqr.py:121-137) for given trajectories x_trj [I,T+1,n],
+ * u_trj [I,T,m]: sum_t e'Qe + u'Ru + terminal e'Qe (Q, not Qd, :135-136).  cost [I]. */
+int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,
+                      const double* xd, long long xd_stride, const double* Q, const double* R,
+                      int I, int T, double* cost, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRS_MPC_B200_H */

@@ -1,0 +1,442 @@
+// extern "C" entry points declared in include/irs_mpc_b200.h: argument validation + launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/irs_mpc_b200.h"
+#include "smooth.cuh"
+#include "tvlqr.cuh"
+
+namespace irs {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+static int load_params(int system, const double* params_host, int nparams, SysParams* out) {
+    static const int expected[kNumSystems] = {1, 1, 9, 2};
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    IRS_REQUIRE(params_host != nullptr && nparams == expected[system],
+                "system %d expects %d parameters, got %d", system, expected[system], nparams);
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < nparams; ++i) out->v[i] = params_host[i];
+    return 0;
+}
+
+// Group size (warps sharing one sample tile) for the zero-order Gram split; quadrotor only.
+static int quadrotor_group() {
+    static int g = -1;
+    if (g < 0) {
+        const char* e = getenv("IRS_QUAD_GROUP");
+        g = e ? atoi(e) : 4;
+        if (g != 1 && g != 2 && g != 4) g = 4;
+    }
+    return g;
+}
+
+template <class Sys, int G>
+static int launch_zero_order(const SmoothArgs& a, cudaStream_t st) {
+    using C = ZeroOrderCfg<Sys, G>;
+    const size_t smem = G == 1 ? sizeof(float) * (C::kThreads / 32) * C::NACC
+                               : sizeof(float) * C::kTile * C::RS;
+    auto kern = smooth_zero_order_kernel<Sys, G>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(smooth_zero_order)");
+    }
+    kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
+    return check_launch("smooth_zero_order_kernel");
+}
+
+static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host, int nparams,
+                            int flags, const double* x_nom, const double* u_nom, int P, long long N,
+                            const float* sigma, const float* noise, unsigned long long seed,
+                            unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
+                            int C, long long S, float* partials) {
+    if (load_params(system, params_host, nparams, &a->prm)) return 1;
+    IRS_REQUIRE(x_nom && u_nom && partials, "null pointer argument");
+    IRS_REQUIRE(P >= 1 && N >= 1, "need at least one nominal point and one sample (P=%d, N=%lld)", P, N);
+    IRS_REQUIRE(C >= 1 && S >= 1 && (long long)C * S >= N, "chunk plan (C=%d, S=%lld) does not cover N=%lld", C, S, N);
+    IRS_REQUIRE((long long)P * C < (1ll << 31), "grid too large");
+    IRS_REQUIRE(noise != nullptr || sigma != nullptr, "need either replayed noise or sigma");
+    IRS_REQUIRE(iter < (1u << 24), "iter out of range");
+    IRS_REQUIRE(!((flags & (IRS_PROJECT_ABSOLUTE | IRS_PROJECT_DELTA)) && system != kThreeCart),
+                "projection flags are only defined for three_cart");
+    IRS_REQUIRE(!((flags & IRS_PROJECT_ABSOLUTE) && (flags & IRS_PROJECT_DELTA)),
+                "IRS_PROJECT_ABSOLUTE and IRS_PROJECT_DELTA are exclusive");
+    a->x_nom = x_nom;  a->u_nom = u_nom;  a->sigma = sigma;  a->noise = noise;
+    a->partials = partials;  a->N = N;  a->S = S;  a->P = P;  a->C = C;
+    a->seed_lo = (uint32_t)(seed & 0xffffffffull);
+    a->seed_hi = (uint32_t)(seed >> 32);
+    a->iter = iter;  a->stream = stream_id;  a->p0 = p0;  a->i0 = i0;  a->flags = flags;
+    return 0;
+}
+
+template <typename R, class Sys>
+__global__ void __launch_bounds__(128) dyn_batch_kernel(SysParams prm, int batch_variant, const R* x,
+                                                        const R* u, R* out, long long B) {
+    constexpr int n = Sys::N, m = Sys::M;
+    const Sys sys(prm);
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B;
+         b += (long long)gridDim.x * blockDim.x) {
+        R xs[n], us[m], o[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) xs[q] = x[b * n + q];
+#pragma unroll
+        for (int q = 0; q < m; ++q) us[q] = u[b * m + q];
+        if (batch_variant) sys.template step<true>(xs, us, o);
+        else sys.template step<false>(xs, us, o);
+#pragma unroll
+        for (int q = 0; q < n; ++q) out[b * n + q] = o[q];
+    }
+}
+
+template <typename R, class Sys>
+__global__ void __launch_bounds__(128) jac_batch_kernel(SysParams prm, const R* x, const R* u, R* J,
+                                                        long long B) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    constexpr int NJ = Sys::NJ > 0 ? Sys::NJ : 1;
+    const Sys sys(prm);
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B;
+         b += (long long)gridDim.x * blockDim.x) {
+        R xs[n], us[m], v[NJ], Jl[n * d];
+#pragma unroll
+        for (int q = 0; q < n; ++q) xs[q] = x[b * n + q];
+#pragma unroll
+        for (int q = 0; q < m; ++q) us[q] = u[b * m + q];
+        sys.jac_var(xs, us, v);
+        sys.jac_assemble(v, Jl);
+#pragma unroll
+        for (int q = 0; q < n * d; ++q) J[b * n * d + q] = Jl[q];
+    }
+}
+
+template <typename R, class Sys>
+__global__ void __launch_bounds__(128) project_batch_kernel(SysParams prm, R* x, long long B) {
+    constexpr int n = Sys::N;
+    const Sys sys(prm);
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B;
+         b += (long long)gridDim.x * blockDim.x) {
+        R xs[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) xs[q] = x[b * n + q];
+        sys.project(xs);
+#pragma unroll
+        for (int q = 0; q < n; ++q) x[b * n + q] = xs[q];
+    }
+}
+
+static unsigned grid_for(long long work, int threads) {
+    long long g = (work + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > 148 * 32) g = 148 * 32;
+    return (unsigned)g;
+}
+
+template <typename R>
+static int dynamics_batch_impl(int system, const double* params_host, int nparams, int batch_variant,
+                               const R* x, const R* u, R* out, long long B, void* stream) {
+    SysParams prm;
+    if (load_params(system, params_host, nparams, &prm)) return 1;
+    IRS_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return 0;
+    IRS_REQUIRE(x && u && out, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_SYSTEM(system, R, Sys,
+                        (dyn_batch_kernel<R, Sys><<<grid_for(B, 128), 128, 0, st>>>(prm, batch_variant, x, u, out, B)));
+    return check_launch("dynamics_batch_kernel");
+}
+
+template <typename R>
+static int jacobian_batch_impl(int system, const double* params_host, int nparams, const R* x,
+                               const R* u, R* J, long long B, void* stream) {
+    SysParams prm;
+    if (load_params(system, params_host, nparams, &prm)) return 1;
+    IRS_REQUIRE(system != kThreeCart,
+                "three_cart is not differentiable and has no Jacobian (three_cart_dynamics.py:20)");
+    IRS_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return 0;
+    IRS_REQUIRE(x && u && J, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_SYSTEM(system, R, Sys,
+                        (jac_batch_kernel<R, Sys><<<grid_for(B, 128), 128, 0, st>>>(prm, x, u, J, B)));
+    return check_launch("jacobian_batch_kernel");
+}
+
+#define IRS_DISPATCH_DIMS(n, m, ...)                                                \
+    if (n == 2 && m == 1) { constexpr int N_ = 2, M_ = 1; __VA_ARGS__; }            \
+    else if (n == 5 && m == 2) { constexpr int N_ = 5, M_ = 2; __VA_ARGS__; }       \
+    else if (n == 12 && m == 4) { constexpr int N_ = 12, M_ = 4; __VA_ARGS__; }     \
+    else if (n == 6 && m == 2) { constexpr int N_ = 6, M_ = 2; __VA_ARGS__; }       \
+    else { irs::set_error("unsupported TVLQR dims n=%d m=%d", n, m); return 1; }
+
+}  // namespace irs
+
+using namespace irs;
+
+extern "C" {
+
+int irs_abi_version(void) { return IRS_ABI_VERSION; }
+
+const char* irs_last_error(void) { return g_error; }
+
+int irs_system_dims(int system, int* n, int* m, int* nj) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    const SystemDims d = system_dims(system);
+    if (n) *n = d.n;
+    if (m) *m = d.m;
+    if (nj) *nj = d.nj;
+    return 0;
+}
+
+int irs_partial_width(int system, int order) {
+    if (system < 0 || system >= kNumSystems) return -1;
+    const SystemDims d = system_dims(system);
+    return order == 0 ? gram_nacc(d.n, d.m) : (d.nj > 0 ? d.nj : 1);
+}
+
+int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long* S) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    IRS_REQUIRE(P >= 1 && N >= 1 && C && S, "bad plan arguments");
+    // samples per chunk: large enough to amortise the end-of-chunk reduction, small enough that
+    // P*C blocks give several waves over 148 SMs
+    const long long tile = 128;
+    long long target = 4096;
+    const char* e = getenv("IRS_CHUNK_SAMPLES");
+    if (e && atoll(e) > 0) target = atoll(e);
+    long long c = (N + target - 1) / target;
+    // keep at least ~4 waves worth of blocks when N allows it
+    const long long want_blocks = 148ll * 12;
+    while (c * P < want_blocks && (N + c) / (c + 1) >= 1024) ++c;
+    long long s = (N + c - 1) / c;
+    s = (s + tile - 1) / tile * tile;
+    c = (N + s - 1) / s;
+    *C = (int)c;
+    *S = s;
+    return 0;
+}
+
+int irs_smooth_zero_order_accumulate(int system, const double* params_host, int nparams, int flags,
+                                     const double* x_nom, const double* u_nom, int P, long long N,
+                                     const float* sigma, const float* noise,
+                                     unsigned long long seed, unsigned iter, unsigned stream_id,
+                                     unsigned p0, unsigned long long i0,
+                                     int C, long long S, float* partials, void* stream) {
+    SmoothArgs a;
+    if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma, noise,
+                         seed, iter, stream_id, p0, i0, C, S, partials))
+        return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (system) {
+        case kPendulum: return launch_zero_order<Pendulum<float>, 1>(a, st);
+        case kBicycle: return launch_zero_order<Bicycle<float>, 1>(a, st);
+        case kThreeCart: return launch_zero_order<ThreeCart<float>, 1>(a, st);
+        case kQuadrotor:
+            IRS_REQUIRE(S % 128 == 0, "quadrotor chunk size must be a multiple of 128");
+            switch (quadrotor_group()) {
+                case 1: return launch_zero_order<Quadrotor<float>, 1>(a, st);
+                case 2: return launch_zero_order<Quadrotor<float>, 2>(a, st);
+                default: return launch_zero_order<Quadrotor<float>, 4>(a, st);
+            }
+    }
+    set_error("unknown system id %d", system);
+    return 1;
+}
+
+int irs_smooth_first_order_accumulate(int system, const double* params_host, int nparams, int flags,
+                                      const double* x_nom, const double* u_nom, int P, long long N,
+                                      const float* sigma, const float* noise,
+                                      unsigned long long seed, unsigned iter, unsigned stream_id,
+                                      unsigned p0, unsigned long long i0,
+                                      int C, long long S, float* partials, void* stream) {
+    SmoothArgs a;
+    IRS_REQUIRE(system != kThreeCart,
+                "three_cart is not differentiable and has no Jacobian (three_cart_dynamics.py:20)");
+    if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma, noise,
+                         seed, iter, stream_id, p0, i0, C, S, partials))
+        return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((long long)P * C);
+    switch (system) {
+        case kPendulum: smooth_first_order_kernel<Pendulum<float>><<<grid, 128, 0, st>>>(a); break;
+        case kBicycle: smooth_first_order_kernel<Bicycle<float>><<<grid, 128, 0, st>>>(a); break;
+        case kQuadrotor: smooth_first_order_kernel<Quadrotor<float>><<<grid, 128, 0, st>>>(a); break;
+        default: set_error("unknown system id %d", system); return 1;
+    }
+    return check_launch("smooth_first_order_kernel");
+}
+
+int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
+                        const double* x_nom, const double* u_nom, int P, int C,
+                        const float* partials, int nranks, long long rank_stride, double n_total,
+                        double* At, double* Bt, double* ct, int* status, void* stream) {
+    FinalizeArgs a;
+    if (load_params(system, params_host, nparams, &a.prm)) return 1;
+    IRS_REQUIRE(order == 0 || order == 1, "order must be 0 or 1");
+    IRS_REQUIRE(x_nom && u_nom && partials && At && Bt && ct && status, "null pointer argument");
+    IRS_REQUIRE(P >= 1 && C >= 1 && nranks >= 1 && n_total >= 1.0, "bad finalize arguments");
+    IRS_REQUIRE(!(order == 1 && system == kThreeCart), "three_cart has no Jacobian");
+    a.x_nom = x_nom;  a.u_nom = u_nom;  a.partials = partials;  a.rank_stride = rank_stride;
+    a.R = nranks;  a.P = P;  a.C = C;  a.n_total = n_total;
+    a.At = At;  a.Bt = Bt;  a.ct = ct;  a.status = status;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((P + 3) / 4);
+    if (order == 0) {
+        IRS_DISPATCH_SYSTEM(system, double, Sys, (finalize_zero_order_kernel<Sys><<<grid, 128, 0, st>>>(a)));
+    } else {
+        switch (system) {
+            case kPendulum: finalize_first_order_kernel<Pendulum<double>><<<grid, 128, 0, st>>>(a); break;
+            case kBicycle: finalize_first_order_kernel<Bicycle<double>><<<grid, 128, 0, st>>>(a); break;
+            case kQuadrotor: finalize_first_order_kernel<Quadrotor<double>><<<grid, 128, 0, st>>>(a); break;
+            default: set_error("unknown system id %d", system); return 1;
+        }
+    }
+    return check_launch("finalize_kernel");
+}
+
+int irs_exact_linearize(int system, const double* params_host, int nparams,
+                        const double* x_nom, const double* u_nom, int P,
+                        double* At, double* Bt, double* ct, void* stream) {
+    SysParams prm;
+    if (load_params(system, params_host, nparams, &prm)) return 1;
+    IRS_REQUIRE(system != kThreeCart,
+                "three_cart is not differentiable and has no Jacobian (three_cart_dynamics.py:20)");
+    IRS_REQUIRE(x_nom && u_nom && At && Bt && ct, "null pointer argument");
+    IRS_REQUIRE(P >= 1, "need at least one nominal point");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (system) {
+        case kPendulum: exact_linearize_kernel<Pendulum<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
+        case kBicycle: exact_linearize_kernel<Bicycle<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
+        case kQuadrotor: exact_linearize_kernel<Quadrotor<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
+        default: set_error("unknown system id %d", system); return 1;
+    }
+    return check_launch("exact_linearize_kernel");
+}
+
+int irs_philox_dump(int P, long long N, int d, const float* sigma, unsigned long long seed,
+                    unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
+                    unsigned* words, float* deltas, void* stream) {
+    IRS_REQUIRE(P >= 1 && N >= 1 && d >= 1, "bad dump arguments");
+    IRS_REQUIRE(deltas == nullptr || sigma != nullptr, "deltas need sigma");
+    const long long total = (long long)P * N * ((d + 3) / 4);
+    philox_dump_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        P, N, d, sigma, (uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32), iter, stream_id, p0, i0,
+        words, deltas);
+    return check_launch("philox_dump_kernel");
+}
+
+int irs_dynamics_batch_f32(int system, const double* params_host, int nparams, int batch_variant,
+                           const float* x, const float* u, float* out, long long B, void* stream) {
+    return dynamics_batch_impl<float>(system, params_host, nparams, batch_variant, x, u, out, B, stream);
+}
+int irs_dynamics_batch_f64(int system, const double* params_host, int nparams, int batch_variant,
+                           const double* x, const double* u, double* out, long long B, void* stream) {
+    return dynamics_batch_impl<double>(system, params_host, nparams, batch_variant, x, u, out, B, stream);
+}
+int irs_jacobian_xu_batch_f32(int system, const double* params_host, int nparams,
+                              const float* x, const float* u, float* J, long long B, void* stream) {
+    return jacobian_batch_impl<float>(system, params_host, nparams, x, u, J, B, stream);
+}
+int irs_jacobian_xu_batch_f64(int system, const double* params_host, int nparams,
+                              const double* x, const double* u, double* J, long long B, void* stream) {
+    return jacobian_batch_impl<double>(system, params_host, nparams, x, u, J, B, stream);
+}
+
+int irs_project_batch_f64(int system, const double* params_host, int nparams, double* x,
+                          long long B, void* stream) {
+    SysParams prm;
+    if (load_params(system, params_host, nparams, &prm)) return 1;
+    IRS_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return 0;
+    IRS_REQUIRE(x != nullptr, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_SYSTEM(system, double, Sys,
+                        (project_batch_kernel<double, Sys><<<grid_for(B, 128), 128, 0, st>>>(prm, x, B)));
+    return check_launch("project_batch_kernel");
+}
+
+int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const double* ct,
+                      const double* Q, const double* Qd, const double* R,
+                      const double* xd, long long xd_stride, int I, int T,
+                      double* K, double* k, int* status, void* stream) {
+    IRS_REQUIRE(At && Bt && ct && Q && Qd && R && xd && K && k && status, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
+    TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T};
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((I + kTvlqrWarps - 1) / kTvlqrWarps);
+    IRS_DISPATCH_DIMS(n, m, {
+        const size_t smem = sizeof(TvlqrSmem<N_, M_>) * kTvlqrWarps;
+        tvlqr_riccati_kernel<N_, M_><<<grid, 32 * kTvlqrWarps, smem, st>>>(a);
+    });
+    return check_launch("tvlqr_riccati_kernel");
+}
+
+int irs_tvlqr_linear_rollout(int n, int m, const double* At, const double* Bt, const double* ct,
+                             const double* K, const double* k, const double* x0, int I, int T,
+                             double* xs, double* us, void* stream) {
+    IRS_REQUIRE(At && Bt && ct && K && k && x0 && xs && us, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
+    TvlqrArgs a{At, Bt, ct, nullptr, nullptr, nullptr, nullptr, 0, const_cast<double*>(K),
+                const_cast<double*>(k), nullptr, I, T};
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_DIMS(n, m, (linear_rollout_kernel<N_, M_><<<(I + 63) / 64, 64, 0, st>>>(a, x0, xs, us)));
+    return check_launch("linear_rollout_kernel");
+}
+
+int irs_rollout_closed_loop(int system, const double* params_host, int nparams,
+                            const double* K, const double* k, const double* x0,
+                            const double* xd, long long xd_stride, const double* Q, const double* R,
+                            int I, int T, double* x_trj, double* u_trj, double* cost, void* stream) {
+    RolloutArgs a;
+    if (load_params(system, params_host, nparams, &a.prm)) return 1;
+    IRS_REQUIRE(K && k && x0 && xd && Q && R && x_trj && u_trj && cost, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
+    a.K = K;  a.k = k;  a.x0 = x0;  a.u_in = nullptr;  a.xd = xd;  a.xd_stride = xd_stride;
+    a.Q = Q;  a.R = R;  a.x_trj = x_trj;  a.u_trj = u_trj;  a.cost = cost;  a.I = I;  a.T = T;
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, true><<<(I + 63) / 64, 64, 0, st>>>(a)));
+    return check_launch("rollout_kernel<closed>");
+}
+
+int irs_rollout_open_loop(int system, const double* params_host, int nparams,
+                          const double* u_in, const double* x0,
+                          const double* xd, long long xd_stride, const double* Q, const double* R,
+                          int I, int T, double* x_trj, double* cost, void* stream) {
+    RolloutArgs a;
+    if (load_params(system, params_host, nparams, &a.prm)) return 1;
+    IRS_REQUIRE(u_in && x0 && xd && Q && R && x_trj && cost, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
+    a.K = nullptr;  a.k = nullptr;  a.x0 = x0;  a.u_in = u_in;  a.xd = xd;  a.xd_stride = xd_stride;
+    a.Q = Q;  a.R = R;  a.x_trj = x_trj;  a.u_trj = nullptr;  a.cost = cost;  a.I = I;  a.T = T;
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, false><<<(I + 63) / 64, 64, 0, st>>>(a)));
+    return check_launch("rollout_kernel<open>");
+}
+
+int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,
+                      const double* xd, long long xd_stride, const double* Q, const double* R,
+                      int I, int T, double* cost, void* stream) {
+    IRS_REQUIRE(x_trj && u_trj && xd && Q && R && cost, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    IRS_DISPATCH_DIMS(n, m, (evaluate_cost_kernel<N_, M_><<<(I + 3) / 4, 128, 0, st>>>(
+                                x_trj, u_trj, xd, xd_stride, Q, R, I, T, cost)));
+    return check_launch("evaluate_cost_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,556 @@
+// Randomized-smoothing linearization kernels.
+//
+//   smooth_zero_order_kernel<Sys,G>  fused: Philox noise (or replayed deltas) -> perturb ->
+//                                    f(xbar+dx, ubar+du) -> delta f -> Gram accumulation of
+//                                    [dx du]^T [dx du | delta f]  (irs_lqr_zero_order.py:49-57)
+//   smooth_first_order_kernel<Sys>   same front end, accumulates the varying Jacobian scalars
+//                                    (irs_lqr_first_order.py:42-48)
+//   finalize_*_kernel                fixed-order fp64 reduction of the per-chunk partials,
+//                                    Cholesky solve of the normal equations (== lstsq for full
+//                                    column rank), c_t from the nominal point (:61-62)
+#pragma once
+#include "systems.cuh"
+
+namespace irs {
+
+enum SmoothFlags {
+    kFlagSamplesBatchVariant = 1,   // samples use dynamics_batch semantics (irs_lqr_zero_order.py:51)
+    kFlagProjectAbsolute = 2,       // three_cart_zero_order.py:43 quirk: sampling returns absolute points
+    kFlagProjectDelta = 4,          // corrected variant: projected point minus nominal
+};
+
+struct SmoothArgs {
+    const double* x_nom;   // [P, n] nominal states
+    const double* u_nom;   // [P, m] nominal inputs
+    const float* sigma;    // [d]     per-column std-dev (Philox mode)
+    const float* noise;    // [P, N, d] replayed deltas (dx | du) or nullptr
+    float* partials;       // [P, C, NACC]
+    long long N;           // samples per nominal point (local to this rank)
+    long long S;           // samples per chunk
+    int P, C;
+    uint32_t seed_lo, seed_hi, iter, stream;
+    uint32_t p0;           // global index of local point 0 (Philox counter word 1)
+    unsigned long long i0; // global index of local sample 0 (Philox counter word 0)
+    int flags;
+    SysParams prm;
+};
+
+__host__ __device__ constexpr int gram_nacc(int n, int m) {
+    return (n + m) * (n + m + 1) / 2 + (n + m) * n;
+}
+// packed upper-row layout: row i holds columns j = i..W-1, W = d + n
+__host__ __device__ constexpr int gram_row_offset(int i, int W) { return i * W - i * (i - 1) / 2; }
+
+// ---------------------------------------------------------------------------------------------
+// One sample: regressors w[0..D) = (dx | du), responses w[D..D+N) = f(xbar+dx, ubar+du) - fbar.
+// ---------------------------------------------------------------------------------------------
+template <class Sys, bool BATCH, int RS>
+__device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a, int p, long long i,
+                                            const float* xbar, const float* ubar,
+                                            const float* fbar, float (&w)[RS], bool want_df = true) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    if (a.noise != nullptr) {
+        const float* src = a.noise + ((long long)p * a.N + i) * d;
+        if constexpr (d % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < d; c += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                w[c] = v.x;  w[c + 1] = v.y;  w[c + 2] = v.z;  w[c + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < d; ++c) w[c] = __ldg(src + c);
+        }
+    } else {
+        constexpr int nblk = (d + 3) / 4;
+        const unsigned long long gi = a.i0 + (unsigned long long)i;
+#pragma unroll
+        for (int j = 0; j < nblk; ++j) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)gi, a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j, a.stream,
+                          a.seed_lo, a.seed_hi, r);
+            float e[4];
+            box_muller(r[0], r[1], e[0], e[1]);
+            box_muller(r[2], r[3], e[2], e[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * j + q < d) w[4 * j + q] = __ldg(a.sigma + 4 * j + q) * e[q];
+        }
+    }
+    float x[n], u[m];
+    if (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) {
+        // three_cart: project the perturbed state onto non-penetration
+        // (three_cart_dynamics.py:196-264 called from three_cart_zero_order.py:38-43)
+        float xp[n];
+#pragma unroll
+        for (int c = 0; c < n; ++c) xp[c] = xbar[c] + w[c];
+        sys.project(xp);
+        if (a.flags & kFlagProjectAbsolute) {
+            // the reference closure returns ABSOLUTE points which the solver adds to the nominal
+            // again and uses as regressors — reproduced literally
+#pragma unroll
+            for (int c = 0; c < n; ++c) w[c] = xp[c];
+#pragma unroll
+            for (int c = 0; c < m; ++c) w[n + c] = ubar[c] + w[n + c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < n; ++c) w[c] = xp[c] - xbar[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < n; ++c) x[c] = xbar[c] + w[c];
+#pragma unroll
+    for (int c = 0; c < m; ++c) u[c] = ubar[c] + w[n + c];
+    if (want_df) {
+        float f[n];
+        sys.template step<BATCH>(x, u, f);
+#pragma unroll
+        for (int c = 0; c < n; ++c) w[d + c] = f[c] - fbar[c];
+    } else {
+        // first-order path: hand the perturbed point back in place of the responses
+#pragma unroll
+        for (int c = 0; c < n; ++c) w[c] = x[c];
+#pragma unroll
+        for (int c = 0; c < m; ++c) w[n + c] = u[c];
+    }
+}
+
+// Row ownership when the Gram rows are split over G warps: rows are paired (i, D-1-i) so that
+// every pair carries the same number of outputs; pair q belongs to warp q % G.
+__host__ __device__ constexpr bool owns_row(int i, int D, int G, int g) {
+    return ((i < D - 1 - i ? i : D - 1 - i) % G) == g;
+}
+__host__ __device__ constexpr int role_pairs(int D, int Wp, int G, int g) {
+    int k = 0;
+    for (int i = 0; i < D; ++i)
+        if (owns_row(i, D, G, g)) k += Wp / 2 - i / 2;
+    return k;
+}
+// smem row stride (floats): multiple of 4 with an odd number of 16-byte units -> the 8 lanes of a
+// quarter warp reading consecutive rows with LDS.128 hit 8 distinct bank groups.
+__host__ __device__ constexpr int smem_row_stride(int Wp) {
+    int rs = (Wp + 3) / 4 * 4;
+    if ((rs / 4) % 2 == 0) rs += 4;
+    return rs;
+}
+
+template <class Sys, int G>
+struct ZeroOrderCfg {
+    static constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    static constexpr int W = d + n;
+    static constexpr int Wp = (W + 1) / 2 * 2;
+    static constexpr int RS = G == 1 ? Wp : smem_row_stride(Wp);
+    static constexpr int NACC = gram_nacc(n, m);
+    static constexpr int kThreads = 32 * (G == 1 ? 4 : G);
+    static constexpr int kTile = 32 * G;             // samples per round when G > 1
+};
+
+// Accumulate role g's share of the Gram update for one sample row w (registers).
+template <class Sys, int G, int g, int NP>
+__device__ __forceinline__ void gram_update(const float* w, float2 (&acc)[NP]) {
+    using C = ZeroOrderCfg<Sys, G>;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < C::d; ++i) {
+        if (owns_row(i, C::d, G, g)) {
+            const float2 zi = make_float2(w[i], w[i]);
+#pragma unroll
+            for (int jj = i / 2; jj < C::Wp / 2; ++jj) {
+                acc[k] = ffma2(zi, make_float2(w[2 * jj], w[2 * jj + 1]), acc[k]);
+                ++k;
+            }
+        }
+    }
+}
+
+// Warp-reduce role g's accumulators and write them into the packed partial block.
+template <class Sys, int G, int g, int NP>
+__device__ __forceinline__ void gram_flush(float2 (&acc)[NP], float* out, int lane) {
+    using C = ZeroOrderCfg<Sys, G>;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < C::d; ++i) {
+        if (owns_row(i, C::d, G, g)) {
+#pragma unroll
+            for (int jj = i / 2; jj < C::Wp / 2; ++jj) {
+                const float sx = warp_sum(acc[k].x);
+                const float sy = warp_sum(acc[k].y);
+                ++k;
+                if (lane == 0) {
+                    const int j0 = 2 * jj, j1 = 2 * jj + 1;
+                    if (j0 >= i && j0 < C::W) out[gram_row_offset(i, C::W) + j0 - i] = sx;
+                    if (j1 >= i && j1 < C::W) out[gram_row_offset(i, C::W) + j1 - i] = sy;
+                }
+            }
+        }
+    }
+}
+
+template <class Sys, int G, int g, bool BATCH>
+__device__ __forceinline__ void zero_order_role(const Sys& sys, const SmoothArgs& a, int p,
+                                                long long s_begin, long long s_end,
+                                                const float* xbar, const float* ubar,
+                                                const float* fbar, float* tile, float* out) {
+    using C = ZeroOrderCfg<Sys, G>;
+    constexpr int NP = role_pairs(C::d, C::Wp, G, g);
+    float2 acc[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
+    const int lane = threadIdx.x & 31;
+
+    if constexpr (G == 1) {
+        for (long long s = s_begin + threadIdx.x; s < s_end; s += C::kThreads) {
+            float w[C::RS];
+#pragma unroll
+            for (int c = 0; c < C::RS; ++c) w[c] = 0.f;
+            make_sample<Sys, BATCH, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
+            gram_update<Sys, G, g, NP>(w, acc);
+        }
+        // cross-warp: each warp flushes into its own smem slab, then the block sums the slabs
+        float* slab = tile + (threadIdx.x >> 5) * C::NACC;
+        gram_flush<Sys, G, g, NP>(acc, slab, lane);
+        __syncthreads();
+        for (int e = threadIdx.x; e < C::NACC; e += C::kThreads) {
+            float s = 0.f;
+#pragma unroll
+            for (int wq = 0; wq < C::kThreads / 32; ++wq) s += tile[wq * C::NACC + e];
+            out[e] = s;
+        }
+    } else {
+        for (long long base = s_begin; base < s_end; base += C::kTile) {
+            {
+                float w[C::RS];
+#pragma unroll
+                for (int c = 0; c < C::RS; ++c) w[c] = 0.f;
+                const long long s = base + threadIdx.x;
+                if (s < s_end) make_sample<Sys, BATCH, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
+                float4* dst = reinterpret_cast<float4*>(tile + threadIdx.x * C::RS);
+#pragma unroll
+                for (int c = 0; c < C::RS / 4; ++c)
+                    dst[c] = make_float4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                float w[C::RS];
+                const float4* src = reinterpret_cast<const float4*>(tile + (q * 32 + lane) * C::RS);
+#pragma unroll
+                for (int c = 0; c < C::RS / 4; ++c) {
+                    const float4 v = src[c];
+                    w[4 * c] = v.x;  w[4 * c + 1] = v.y;  w[4 * c + 2] = v.z;  w[4 * c + 3] = v.w;
+                }
+                gram_update<Sys, G, g, NP>(w, acc);
+            }
+            __syncthreads();
+        }
+        gram_flush<Sys, G, g, NP>(acc, out, lane);
+    }
+}
+
+template <class Sys, int G>
+__global__ void __launch_bounds__(ZeroOrderCfg<Sys, G>::kThreads)
+smooth_zero_order_kernel(const SmoothArgs a) {
+    using C = ZeroOrderCfg<Sys, G>;
+    constexpr int n = Sys::N, m = Sys::M;
+    extern __shared__ __align__(16) float tile[];
+    const Sys sys(a.prm);
+    const int p = blockIdx.x / a.C;
+    const int c = blockIdx.x % a.C;
+    const long long s_begin = (long long)c * a.S;
+    const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+    float xbar[n], ubar[m], fbar[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) xbar[q] = (float)a.x_nom[(long long)p * n + q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) ubar[q] = (float)a.u_nom[(long long)p * m + q];
+    // nominal response: the reference uses the SCALAR dynamics here (irs_lqr_zero_order.py:52)
+    sys.template step<false>(xbar, ubar, fbar);
+    float* out = a.partials + ((long long)p * a.C + c) * C::NACC;
+    const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
+    if constexpr (G == 1) {
+        if (batch) zero_order_role<Sys, 1, 0, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+        else       zero_order_role<Sys, 1, 0, false>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+    } else {
+        // warp-uniform role dispatch: each warp owns a fixed subset of the Gram rows
+        const int role = threadIdx.x >> 5;
+        static_assert(G == 1 || G == 2 || G == 4, "supported group sizes");
+        if (role == 0) zero_order_role<Sys, G, 0, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+        if constexpr (G >= 2)
+            if (role == 1) zero_order_role<Sys, G, 1 % G, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+        if constexpr (G >= 4) {
+            if (role == 2) zero_order_role<Sys, G, 2 % G, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+            if (role == 3) zero_order_role<Sys, G, 3 % G, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// First-order: accumulate the NJ varying Jacobian scalars (irs_lqr_first_order.py:42-48).
+// partials layout [P, C, NJ].
+// ---------------------------------------------------------------------------------------------
+template <class Sys>
+__global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArgs a) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    constexpr int NJ = Sys::NJ > 0 ? Sys::NJ : 1;
+    constexpr int RS = d + n;
+    __shared__ float slab[4][NJ];
+    const Sys sys(a.prm);
+    const int p = blockIdx.x / a.C;
+    const int c = blockIdx.x % a.C;
+    const long long s_begin = (long long)c * a.S;
+    const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+    float xbar[n], ubar[m], fbar[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) xbar[q] = (float)a.x_nom[(long long)p * n + q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) ubar[q] = (float)a.u_nom[(long long)p * m + q];
+#pragma unroll
+    for (int q = 0; q < n; ++q) fbar[q] = 0.f;
+    float acc[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) acc[k] = 0.f;
+    for (long long s = s_begin + threadIdx.x; s < s_end; s += 128) {
+        float w[RS];
+        make_sample<Sys, false, RS>(sys, a, p, s, xbar, ubar, fbar, w, /*want_df=*/false);
+        float v[NJ];
+        sys.jac_var(w, w + n, v);
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) acc[k] += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == 0) slab[warp][k] = s;
+    }
+    __syncthreads();
+    float* out = a.partials + ((long long)p * a.C + c) * NJ;
+    for (int k = threadIdx.x; k < NJ; k += 128) out[k] = (slab[0][k] + slab[1][k]) + (slab[2][k] + slab[3][k]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalize (fp64, one warp per nominal point).
+// ---------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+    const double* x_nom;     // [P, n]
+    const double* u_nom;     // [P, m]
+    const float* partials;   // [R][P, C, NACC or NJ]  (R = number of rank buffers summed in order)
+    long long rank_stride;   // floats between rank buffers
+    int R;
+    int P, C;
+    double n_total;          // total samples per point (first order: divisor of the mean)
+    double* At;              // [P, n, n]
+    double* Bt;              // [P, n, m]
+    double* ct;              // [P, n]
+    int* status;             // [P] 0 ok, 1 rank-deficient Gram
+    SysParams prm;
+};
+
+template <class Sys>
+__device__ __forceinline__ void write_abc(const Sys& sys, const FinalizeArgs& a, int p,
+                                          const double* AB /*[n][d] smem*/, int lane) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    double xb[n], ub[m], fb[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) xb[q] = a.x_nom[(long long)p * n + q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) ub[q] = a.u_nom[(long long)p * m + q];
+    sys.template step<false>(xb, ub, fb);      // scalar dynamics at the nominal (…zero_order.py:61)
+    for (int e = lane; e < n * d; e += 32) {
+        const int r = e / d, cidx = e % d;
+        if (cidx < n) a.At[((long long)p * n + r) * n + cidx] = AB[e];
+        else a.Bt[((long long)p * n + r) * m + (cidx - n)] = AB[e];
+    }
+    for (int r = lane; r < n; r += 32) {
+        double acc = fb[r];
+#pragma unroll
+        for (int q = 0; q < n; ++q) acc -= AB[r * d + q] * xb[q];
+#pragma unroll
+        for (int q = 0; q < m; ++q) acc -= AB[r * d + n + q] * ub[q];
+        a.ct[(long long)p * n + r] = acc;
+    }
+}
+
+template <class Sys>
+__global__ void __launch_bounds__(128) finalize_zero_order_kernel(const FinalizeArgs a) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    constexpr int W = d + n;
+    constexpr int NACC = gram_nacc(n, m);
+    __shared__ double sG[4][d * d];      // Gram (then its Cholesky factor, lower)
+    __shared__ double sB[4][d * n];      // right-hand sides Z^T dF, then the solution
+    __shared__ double sAB[4][n * d];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 4 + warp;
+    if (p >= a.P) return;
+    const Sys sys(a.prm);
+    double* Gm = sG[warp];
+    double* Bm = sB[warp];
+    // 1. fixed-order sum over ranks and chunks (deterministic)
+    for (int e = lane; e < NACC; e += 32) {
+        double s = 0.0;
+        for (int r = 0; r < a.R; ++r) {
+            const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NACC + e;
+            for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NACC];
+        }
+        // unpack (i, j)
+        int i = 0;
+        while (i + 1 < d && gram_row_offset(i + 1, W) <= e) ++i;
+        const int j = i + (e - gram_row_offset(i, W));
+        if (j < d) {
+            Gm[i * d + j] = s;
+            Gm[j * d + i] = s;
+        } else {
+            Bm[i * n + (j - d)] = s;
+        }
+    }
+    __syncwarp();
+    // 2. Cholesky G = L L^T (lanes = rows).  A column whose diagonal is exactly zero (sigma = 0:
+    //    regressor identically zero) gets coefficient 0, which is what the min-norm lstsq of the
+    //    reference returns for it.
+    bool bad = false;
+    double diag0 = 0.0;      // lane k keeps the original diagonal entry G_kk
+    if (lane < d) diag0 = Gm[lane * d + lane];
+    for (int k = 0; k < d; ++k) {
+        double dk = Gm[k * d + k];
+        const double d0 = __shfl_sync(0xffffffffu, diag0, k);
+        __syncwarp();
+        bool zero_col = false;
+        // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones; the
+        // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency
+        if (d0 == 0.0) { zero_col = true; dk = 1.0; }
+        else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
+        const double lkk = sqrt(dk);
+        if (lane == 0) Gm[k * d + k] = lkk;
+        for (int r = k + 1 + lane; r < d; r += 32) Gm[r * d + k] = zero_col ? 0.0 : Gm[r * d + k] / lkk;
+        if (zero_col)
+            for (int q = lane; q < n; q += 32) Bm[k * n + q] = 0.0;
+        __syncwarp();
+        // trailing update, lower triangle
+        for (int e = lane; e < (d - k - 1) * (d - k - 1); e += 32) {
+            const int r = k + 1 + e / (d - k - 1), cc = k + 1 + e % (d - k - 1);
+            if (cc <= r) Gm[r * d + cc] -= Gm[r * d + k] * Gm[cc * d + k];
+        }
+        __syncwarp();
+    }
+    // 3. solve L L^T X = B, one right-hand side per lane
+    for (int q = lane; q < n; q += 32) {
+        for (int r = 0; r < d; ++r) {
+            double s = Bm[r * n + q];
+            for (int k = 0; k < r; ++k) s -= Gm[r * d + k] * Bm[k * n + q];
+            Bm[r * n + q] = s / Gm[r * d + r];
+        }
+        for (int r = d - 1; r >= 0; --r) {
+            double s = Bm[r * n + q];
+            for (int k = r + 1; k < d; ++k) s -= Gm[k * d + r] * Bm[k * n + q];
+            Bm[r * n + q] = s / Gm[r * d + r];
+        }
+        for (int r = 0; r < d; ++r) {
+            const double v = Bm[r * n + q];
+            if (!(v == v) || fabs(v) > 1e300) bad = true;
+            sAB[warp][q * d + r] = v;      // [A|B] = X^T
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    if (lane == 0) a.status[p] = bad ? 1 : 0;
+    write_abc<Sys>(sys, a, p, sAB[warp], lane);
+}
+
+template <class Sys>
+__global__ void __launch_bounds__(128) finalize_first_order_kernel(const FinalizeArgs a) {
+    constexpr int n = Sys::N, d = Sys::D;
+    constexpr int NJ = Sys::NJ > 0 ? Sys::NJ : 1;
+    __shared__ double sV[4][NJ];
+    __shared__ double sAB[4][n * d];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 4 + warp;
+    if (p >= a.P) return;
+    const Sys sys(a.prm);
+    for (int e = lane; e < NJ; e += 32) {
+        double s = 0.0;
+        for (int r = 0; r < a.R; ++r) {
+            const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NJ + e;
+            for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NJ];
+        }
+        sV[warp][e] = s / a.n_total;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double v[NJ], J[n * d];
+        for (int k = 0; k < NJ; ++k) v[k] = sV[warp][k];
+        sys.jac_assemble(v, J);
+        for (int e = 0; e < n * d; ++e) sAB[warp][e] = J[e];
+        a.status[p] = 0;
+    }
+    __syncwarp();
+    write_abc<Sys>(sys, a, p, sAB[warp], lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact linearization at the nominal points, all in fp64 (irs_lqr_exact.py:15-31):
+// [A|B] = jacobian_xu(xbar, ubar), c = f(xbar, ubar) - A xbar - B ubar.  One thread per point.
+// ---------------------------------------------------------------------------------------------
+template <class Sys>
+__global__ void __launch_bounds__(64) exact_linearize_kernel(SysParams prm, const double* x_nom,
+                                                            const double* u_nom, int P, double* At,
+                                                            double* Bt, double* ct) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    constexpr int NJ = Sys::NJ > 0 ? Sys::NJ : 1;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const Sys sys(prm);
+    double xb[n], ub[m], fb[n], v[NJ], J[n * d];
+#pragma unroll
+    for (int q = 0; q < n; ++q) xb[q] = x_nom[(long long)p * n + q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) ub[q] = u_nom[(long long)p * m + q];
+    sys.jac_var(xb, ub, v);
+    sys.jac_assemble(v, J);
+    sys.template step<false>(xb, ub, fb);
+#pragma unroll
+    for (int r = 0; r < n; ++r) {
+        double acc = fb[r];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+            At[((long long)p * n + r) * n + q] = J[r * d + q];
+            acc -= J[r * d + q] * xb[q];
+        }
+#pragma unroll
+        for (int q = 0; q < m; ++q) {
+            Bt[((long long)p * n + r) * m + q] = J[r * d + n + q];
+            acc -= J[r * d + n + q] * ub[q];
+        }
+        ct[(long long)p * n + r] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Debug / bookkeeping kernel: dump the Philox words and the deltas exactly as the fused kernels
+// draw them (same counter function).  Used by the bit-exact index tests.
+// ---------------------------------------------------------------------------------------------
+__global__ void philox_dump_kernel(int P, long long N, int d, const float* sigma, uint32_t seed_lo,
+                                   uint32_t seed_hi, uint32_t iter, uint32_t stream, uint32_t p0,
+                                   unsigned long long i0, uint32_t* words, float* deltas) {
+    const int nblk = (d + 3) / 4;
+    const long long total = (long long)P * N * nblk;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % nblk);
+        const long long i = (idx / nblk) % N;
+        const int p = (int)(idx / nblk / N);
+        uint32_t r[4];
+        philox4x32_10((uint32_t)(i0 + (unsigned long long)i), p0 + (uint32_t)p, (iter << 8) | (uint32_t)j,
+                      stream, seed_lo, seed_hi, r);
+        if (words != nullptr)
+            for (int q = 0; q < 4; ++q) words[idx * 4 + q] = r[q];
+        if (deltas != nullptr) {
+            float e[4];
+            box_muller(r[0], r[1], e[0], e[1]);
+            box_muller(r[2], r[3], e[2], e[3]);
+            for (int q = 0; q < 4; ++q)
+                if (4 * j + q < d) deltas[((long long)p * N + i) * d + 4 * j + q] = sigma[4 * j + q] * e[q];
+        }
+    }
+}
+
+}  // namespace irs

@@ -1,0 +1,279 @@
+// __device__ functors for the four analytic systems of the reference, templated on the scalar
+// type R (float for the T x N sample work, double for the sequential rollouts).
+//
+// Interface (all static-shape, everything stays in registers after unrolling):
+//   N, M, D=N+M          state / input / regressor dimensions
+//   NJ                   number of Jacobian scalars that vary with (x,u)
+//   step<BATCH>(x,u,o)   o = f(x,u).  BATCH selects the reference's `dynamics_batch` semantics
+//                        where it differs from the scalar `dynamics` (three_cart only)
+//   jac_var(x,u,v)       the NJ varying scalars of d f / d(x,u)
+//   jac_assemble(v,J)    J[N*D] (row-major, A|B column order, dynamical_system.py:41-43) from v;
+//                        affine in v, so mean(J) == assemble(mean(v))
+//   project(x)           non-penetration projection of a sample (three_cart); no-op otherwise
+#pragma once
+#include "common.cuh"
+
+namespace irs {
+
+enum SystemId { kPendulum = 0, kBicycle = 1, kQuadrotor = 2, kThreeCart = 3, kNumSystems = 4 };
+
+// ---------------------------------------------------------------------------------------------
+// Pendulum — examples/pendulum/pendulum_dynamics.py:46-81 (dynamics), :110-127 (Jacobian).
+// params: [h]
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+struct Pendulum {
+    static constexpr int N = 2, M = 1, D = 3, NJ = 1;
+    static constexpr bool kHasJacobian = true;
+    R h;
+    __device__ explicit Pendulum(const SysParams& p) : h(R(p.v[0])) {}
+
+    template <bool BATCH>
+    __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
+        R s, c;
+        Math<R>::sincos(x[0], s, c);
+        const R v = x[1] + h * (u[0] - s);      // semi-implicit Euler (:55-57)
+        o[1] = v;
+        o[0] = x[0] + h * v;
+    }
+    __device__ __forceinline__ void jac_var(const R* x, const R* u, R* v) const {
+        R s, c;
+        Math<R>::sincos(x[0], s, c);
+        v[0] = c;
+    }
+    __device__ __forceinline__ void jac_assemble(const R* v, R* J) const {
+        J[0] = R(1) - h * h * v[0];  J[1] = h;     J[2] = h * h;
+        J[3] = -h * v[0];            J[4] = R(1);  J[5] = h;
+    }
+    __device__ __forceinline__ void project(R* x) const {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Bicycle — examples/bicycle/bicycle_dynamics.py:47-86 (dynamics), :115-132 (Jacobian).
+// x = [px, py, heading, speed, steer], u = [accel, steer rate].  params: [h]
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+struct Bicycle {
+    static constexpr int N = 5, M = 2, D = 7, NJ = 6;
+    static constexpr bool kHasJacobian = true;
+    R h;
+    __device__ explicit Bicycle(const SysParams& p) : h(R(p.v[0])) {}
+
+    template <bool BATCH>
+    __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
+        R s, c, sd, cd;
+        Math<R>::sincos(x[2], s, c);
+        Math<R>::sincos(x[4], sd, cd);
+        const R v = x[3];
+        o[0] = x[0] + h * (v * c);
+        o[1] = x[1] + h * (v * s);
+        o[2] = x[2] + h * (v * Math<R>::div(sd, cd));
+        o[3] = x[3] + h * u[0];
+        o[4] = x[4] + h * u[1];
+    }
+    __device__ __forceinline__ void jac_var(const R* x, const R* u, R* v) const {
+        R s, c, sd, cd;
+        Math<R>::sincos(x[2], s, c);
+        Math<R>::sincos(x[4], sd, cd);
+        const R icd = Math<R>::rcp(cd);
+        v[0] = x[3] * s;          // -> J[0][2] = -h v sin(th)
+        v[1] = c;                 // -> J[0][3] =  h cos(th)
+        v[2] = x[3] * c;          // -> J[1][2] =  h v cos(th)
+        v[3] = s;                 // -> J[1][3] =  h sin(th)
+        v[4] = sd * icd;          // -> J[2][3] =  h tan(de)
+        v[5] = x[3] * icd * icd;  // -> J[2][4] =  h v / cos^2(de)
+    }
+    __device__ __forceinline__ void jac_assemble(const R* v, R* J) const {
+#pragma unroll
+        for (int i = 0; i < N * D; ++i) J[i] = R(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) J[i * D + i] = R(1);
+        J[0 * D + 2] = -h * v[0];
+        J[0 * D + 3] = h * v[1];
+        J[1 * D + 2] = h * v[2];
+        J[1 * D + 3] = h * v[3];
+        J[2 * D + 3] = h * v[4];
+        J[2 * D + 4] = h * v[5];
+        J[3 * D + 5] = h;
+        J[4 * D + 6] = h;
+    }
+    __device__ __forceinline__ void project(R* x) const {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Quadrotor — examples/quadrotor/quadrotor_dynamics.py:40-77 with helpers :150-231.
+// x = [xyz, rpy, xyz_dot, rpy_dot], u = 4 rotor commands.
+// params: [h, mass, L, g, Ixx, Iyy, Izz, kF, kM]  (defaults :26-38)
+// ---------------------------------------------------------------------------------------------
+#include "quadrotor_jac.inc"
+
+template <typename R>
+struct Quadrotor {
+    static constexpr int N = 12, M = 4, D = 16, NJ = IRS_QUAD_NJ;
+    static constexpr bool kHasJacobian = true;
+    R h, mass, L, g, I0, I1, I2, kF, kM;
+    __device__ explicit Quadrotor(const SysParams& p)
+        : h(R(p.v[0])), mass(R(p.v[1])), L(R(p.v[2])), g(R(p.v[3])), I0(R(p.v[4])),
+          I1(R(p.v[5])), I2(R(p.v[6])), kF(R(p.v[7])), kM(R(p.v[8])) {}
+
+    template <bool BATCH>
+    __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
+        R sr, cr, sp, cp, sy, cy;
+        Math<R>::sincos(x[3], sr, cr);
+        Math<R>::sincos(x[4], sp, cp);
+        Math<R>::sincos(x[5], sy, cy);
+        const R icp = Math<R>::rcp(cp);
+        const R rd0 = x[9], rd1 = x[10], rd2 = x[11];
+        // thrust and moments (:43-49)
+        const R s03 = u[0] + u[3], s12 = u[1] + u[2];
+        const R Fz = kF * (s03 + s12);
+        const R M0 = (L * kF) * ((u[2] + u[3]) - (u[0] + u[1]));
+        const R M1 = (L * kF) * (s12 - s03);
+        const R M2 = kM * ((u[1] + u[3]) - (u[0] + u[2]));
+        // translational acceleration: third column of Rz Ry Rx times Fz (:51-54, :150-189)
+        const R a = Fz * Math<R>::rcp(mass);
+        const R spcr = sp * cr;
+        o[6] = x[6] + h * (a * (cy * spcr + sy * sr));
+        o[7] = x[7] + h * (a * (sy * spcr - cy * sr));
+        o[8] = x[8] + h * (a * (cp * cr) - g);
+        // body rates pqr = PhiInv rpy_d (:57-58, :191-202)
+        const R cprd2 = cp * rd2;
+        const R p = rd0 - sp * rd2;
+        const R q = cr * rd1 + sr * cprd2;
+        const R r = cr * cprd2 - sr * rd1;
+        // pqr_d = I^-1 (M - pqr x I pqr) (:59)
+        const R pd = (M0 + (I1 - I2) * (q * r)) * Math<R>::rcp(I0);
+        const R qd = (M1 + (I2 - I0) * (r * p)) * Math<R>::rcp(I1);
+        const R rdd = (M2 + (I0 - I1) * (p * q)) * Math<R>::rcp(I2);
+        // rpy_dd = Phi pqr_d + (dPhi/dt) pqr (:61-68, :204-231)
+        const R tp = sp * icp;
+        const R icp2 = icp * icp;
+        const R srq_crr = sr * q + cr * r;       // appears in Phi rows 0 and 2
+        const R crq_srr = cr * q - sr * r;
+        const R srqd_crrd = sr * qd + cr * rdd;
+        o[9] = x[9] + h * (pd + tp * srqd_crrd + rd0 * (tp * crq_srr) + rd1 * (icp2 * srq_crr));
+        o[10] = x[10] + h * ((cr * qd - sr * rdd) - rd0 * srq_crr);
+        o[11] = x[11] + h * (icp * srqd_crrd + rd0 * (icp * crq_srr) + rd1 * (tp * icp * srq_crr));
+        // kinematics (:70)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o[i] = x[i] + h * x[6 + i];
+    }
+    __device__ __forceinline__ void jac_var(const R* x, const R* u, R* v) const {
+        R sr, cr, sp, cp, sy, cy;
+        Math<R>::sincos(x[3], sr, cr);
+        Math<R>::sincos(x[4], sp, cp);
+        Math<R>::sincos(x[5], sy, cy);
+        const R icp = Math<R>::rcp(cp);
+        const R rd0 = x[9], rd1 = x[10], rd2 = x[11];
+        const R u0 = u[0], u1 = u[1], u2 = u[2], u3 = u[3];
+        IRS_QUAD_JAC_BODY(v)
+    }
+    __device__ __forceinline__ void jac_assemble(const R* v, R* J) const {
+        constexpr int rows[NJ] = IRS_QUAD_JAC_ROWS;
+        constexpr int cols[NJ] = IRS_QUAD_JAC_COLS;
+#pragma unroll
+        for (int i = 0; i < N * D; ++i) J[i] = R(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) J[i * D + i] = R(1);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) J[i * D + 6 + i] = h;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) J[rows[k] * D + cols[k]] += h * v[k];
+    }
+    __device__ __forceinline__ void project(R* x) const {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Three carts — examples/three_cart/three_cart_dynamics.py.
+// x = [q1,q2,q3,v1,v2,v3], u = [u1,u3].  params: [h, cart width d]
+//   step<false>: scalar `dynamics` (:22-107): pair collisions push out by HALF the depth
+//   step<true> : `dynamics_batch` (:109-194): pair collisions push out by the FULL depth
+//   project    : `projection` (:196-264), half depth, positions only
+// The gap tests use explicit subtract-then-compare (no contraction) so that the case a sample
+// falls in is a pure function of the rounded free-step state.
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+struct ThreeCart {
+    static constexpr int N = 6, M = 2, D = 8, NJ = 0;
+    static constexpr bool kHasJacobian = false;   // three_cart_dynamics.py:20
+    R h, d;
+    __device__ explicit ThreeCart(const SysParams& p) : h(R(p.v[0])), d(R(p.v[1])) {}
+
+    // case id: 0 none, 1 all three, 2 carts 1-2, 3 carts 2-3  (:146-157)
+    __device__ __forceinline__ int contact_case(R q1, R q2, R q3) const {
+        const bool g12 = (q2 - q1) < d;
+        const bool g23 = (q3 - q2) < d;
+        return g12 ? (g23 ? 1 : 2) : (g23 ? 3 : 0);
+    }
+    template <bool BATCH>
+    __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
+        R v1 = x[3] + h * u[0];
+        R v2 = x[4];
+        R v3 = x[5] + h * u[1];
+        R q1 = x[0] + h * v1;
+        R q2 = x[1] + h * v2;
+        R q3 = x[2] + h * v3;
+        const int cs = contact_case(q1, q2, q3);
+        const R pf = BATCH ? R(1) : R(0.5);
+        if (cs == 1) {
+            const R mid = (q1 + q2 + q3) * R(1.0 / 3.0);
+            const R va = (v1 + v2 + v3) * R(1.0 / 3.0);
+            q1 = mid - d;  q2 = mid;  q3 = mid + d;
+            v1 = va;  v2 = va;  v3 = va;
+        } else if (cs == 2) {
+            const R depth = pf * (d - (q2 - q1));
+            const R va = R(0.5) * (v1 + v2);
+            q2 += depth;  q1 -= depth;
+            v1 = va;  v2 = va;
+        } else if (cs == 3) {
+            const R depth = pf * (d - (q3 - q2));
+            const R va = R(0.5) * (v2 + v3);
+            q3 += depth;  q2 -= depth;
+            v2 = va;  v3 = va;
+        }
+        o[0] = q1;  o[1] = q2;  o[2] = q3;  o[3] = v1;  o[4] = v2;  o[5] = v3;
+    }
+    __device__ __forceinline__ void jac_var(const R*, const R*, R*) const {}
+    __device__ __forceinline__ void jac_assemble(const R*, R*) const {}
+    __device__ __forceinline__ void project(R* x) const {
+        // sequential masks as in :216-261 (each re-evaluated on the partially projected point)
+        if ((x[1] - x[0]) < d && (x[2] - x[1]) < d) {
+            const R mid = (x[0] + x[1] + x[2]) * R(1.0 / 3.0);
+            x[1] = mid;  x[0] = mid - d;  x[2] = mid + d;
+        }
+        if ((x[1] - x[0]) < d && !((x[2] - x[1]) < d)) {
+            const R depth = R(0.5) * (d - (x[1] - x[0]));
+            x[1] += depth;  x[0] -= depth;
+        }
+        if (!((x[1] - x[0]) < d) && (x[2] - x[1]) < d) {
+            const R depth = R(0.5) * (d - (x[2] - x[1]));
+            x[2] += depth;  x[1] -= depth;
+        }
+    }
+};
+
+// Host-side dimension table (kept in sync with the functors by static_asserts in api.cu).
+struct SystemDims {
+    int n, m, nj;
+};
+inline SystemDims system_dims(int id) {
+    switch (id) {
+        case kPendulum: return {2, 1, 1};
+        case kBicycle: return {5, 2, 6};
+        case kQuadrotor: return {12, 4, IRS_QUAD_NJ};
+        case kThreeCart: return {6, 2, 0};
+        default: return {0, 0, 0};
+    }
+}
+
+// Dispatch a generic lambda-like functor over the system id:  IRS_DISPATCH_SYSTEM(id, R, Sys, {...})
+#define IRS_DISPATCH_SYSTEM(id, R, SYS, ...)                                   \
+    switch (id) {                                                              \
+        case irs::kPendulum: { using SYS = irs::Pendulum<R>; __VA_ARGS__; break; }   \
+        case irs::kBicycle: { using SYS = irs::Bicycle<R>; __VA_ARGS__; break; }     \
+        case irs::kQuadrotor: { using SYS = irs::Quadrotor<R>; __VA_ARGS__; break; } \
+        case irs::kThreeCart: { using SYS = irs::ThreeCart<R>; __VA_ARGS__; break; } \
+        default: irs::set_error("unknown system id %d", id); return 1;         \
+    }
+
+}  // namespace irs

@@ -17,3 +17,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Compile (if stale) and dlopen the CUDA library; nvcc cross-compiles without a GPU."""
+    from irs_mpc_b200 import _lib
+    _lib.build()
+    return _lib.lib()

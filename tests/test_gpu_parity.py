@@ -1,0 +1,458 @@
+"""GPU parity tests (run with `-m gpu` on a B200).  Everything here calls the CUDA path through
+the C ABI (ctypes) and compares with (a) vectors produced by the reference's own code
+(tests/golden) and (b) the float64 oracle on identical inputs.
+
+Tolerances: bit-exact for integer bookkeeping (Philox words, contact cases); 1e-4 relative
+(max-abs error over max-abs value per array) for everything that passes through the fp32 sample
+path, as stated in BASELINE.json:north_star; 1e-9 or tighter for the fp64 sequential kernels.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cpu_restatement as cr          # noqa: E402
+from oracle import example_configs as ec          # noqa: E402
+from oracle import philox_ref                     # noqa: E402
+
+SYSTEMS = ["pendulum", "bicycle", "quadrotor", "three_cart"]
+FP32_RTOL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available()
+    import irs_mpc_b200.all as m
+    return m
+
+
+def make_system(api, name):
+    cfg = ec.CONFIGS[name]()
+    return api.__dict__[{"pendulum": "PendulumDynamics", "bicycle": "BicycleDynamics",
+                         "quadrotor": "QuadrotorDynamics", "three_cart": "ThreeCartDynamics"}[name]](cfg["h"])
+
+
+def make_params(api, cfg, T=None, x0=None, u_trj=None):
+    p = api.IrsLqrParameters()
+    T = cfg["T"] if T is None else T
+    p.Q, p.Qd, p.R = cfg["Q"], cfg["Qd"], cfg["R"]
+    p.x0 = cfg["x0"] if x0 is None else x0
+    p.xd_trj = cfg["xd_trj"][:T + 1]
+    p.u_trj_initial = cfg["u_trj_initial"][:T] if u_trj is None else u_trj
+    p.xbound, p.ubound = cfg["xbound"], cfg["ubound"]
+    return p
+
+
+def gold(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ------------------------------------------------------------------------------------------------
+# dynamics / jacobians / projection
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_dynamics_fp64_matches_reference_vectors(api, golden_dir, name):
+    g = gold(golden_dir, "dynamics_%s.npz" % name)
+    s = make_system(api, name)
+    fb = s.dynamics_batch(g["x"], g["u"])
+    np.testing.assert_allclose(fb, g["f_batch"], rtol=0, atol=1e-12)
+    fs = s._run_dynamics(g["x"], g["u"], False)
+    np.testing.assert_allclose(fs, g["f_scalar"], rtol=0, atol=1e-12)
+    one = s.dynamics(g["x"][3], g["u"][3])
+    np.testing.assert_allclose(one, g["f_scalar"][3], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_dynamics_fp32_sample_path(api, golden_dir, name):
+    import torch
+    g = gold(golden_dir, "dynamics_%s.npz" % name)
+    s = make_system(api, name)
+    x32 = g["x"].astype(np.float32)
+    u32 = g["u"].astype(np.float32)
+    f32 = s._run_dynamics(x32, u32, True, dtype=torch.float32)
+    orc = cr.SYSTEMS[name](s.h)
+    ref = orc.dynamics_batch(x32.astype(np.float64), u32.astype(np.float64))
+    if name == "three_cart":
+        # fp32 rounding may flip a contact case for samples within one ulp of the threshold;
+        # compare only rows whose float64 gaps are not marginal
+        sfree = orc._free_step(x32.astype(np.float64), u32.astype(np.float64))
+        margin = np.minimum(np.abs(sfree[:, 1] - sfree[:, 0] - 0.2), np.abs(sfree[:, 2] - sfree[:, 1] - 0.2))
+        keep = margin > 1e-5
+        assert keep.sum() > 0.95 * len(keep)
+        f32, ref = f32[keep], ref[keep]
+    assert rel_err(f32, ref) < 2e-6
+
+
+def test_three_cart_contact_bookkeeping_bit_exact(api, golden_dir):
+    """Which samples fall in which contact case is integer bookkeeping: the fp64 kernel must
+    reproduce the oracle's case ids exactly (deduced from where batch and scalar semantics
+    differ and from the velocity merge pattern)."""
+    g = gold(golden_dir, "dynamics_three_cart.npz")
+    s = make_system(api, "three_cart")
+    orc = cr.ThreeCartOracle(s.h)
+    case = orc.contact_case(g["x"], g["u"])
+    fb = s._run_dynamics(g["x"], g["u"], True)
+    fs = s._run_dynamics(g["x"], g["u"], False)
+    free = orc._free_step(g["x"], g["u"])
+    got = np.zeros_like(case)
+    merged12 = (fb[:, 3] == fb[:, 4]) & (free[:, 3] != free[:, 4])
+    merged23 = (fb[:, 4] == fb[:, 5]) & (free[:, 4] != free[:, 5])
+    got[merged12 & merged23] = 1
+    got[merged12 & ~merged23] = 2
+    got[~merged12 & merged23] = 3
+    np.testing.assert_array_equal(got, case)
+    differs = np.any(fb != fs, axis=1)
+    np.testing.assert_array_equal(differs, (case == 2) | (case == 3))
+
+
+def test_three_cart_projection_matches_reference(api, golden_dir):
+    g = gold(golden_dir, "dynamics_three_cart.npz")
+    s = make_system(api, "three_cart")
+    xp, up = s.projection(g["proj_xbar"], g["proj_dx"], g["proj_ubar"], g["proj_du"])
+    np.testing.assert_allclose(xp, g["proj_x"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(up, g["proj_u"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bicycle", "quadrotor"])
+def test_jacobian_fp64_matches_oracle(api, golden_dir, name):
+    g = gold(golden_dir, "dynamics_%s.npz" % name)
+    s = make_system(api, name)
+    orc = cr.SYSTEMS[name](s.h)
+    J = s.jacobian_xu_batch(g["x"][:64], g["u"][:64])
+    Jo = orc.jacobian_xu_batch(g["x"][:64], g["u"][:64])
+    assert J.shape == Jo.shape
+    assert rel_err(J, Jo) < 1e-11
+    np.testing.assert_allclose(s.jacobian_xu(g["x"][0], g["u"][0]), Jo[0], rtol=0, atol=1e-9)
+
+
+def test_three_cart_has_no_jacobian(api):
+    s = make_system(api, "three_cart")
+    with pytest.raises(NotImplementedError):
+        s.jacobian_xu(np.zeros(6), np.zeros(2))
+
+
+# ------------------------------------------------------------------------------------------------
+# Philox bookkeeping
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [3, 7, 8, 16])
+def test_philox_words_bit_exact_and_normals(api, d):
+    sig = np.linspace(0.5, 2.0, d)
+    s = api.GaussianSampling(sig[:d - 1], sig[d - 1:], 777, power=0.5, seed=0x1234ABCD5678, stream_id=5)
+    T, it, t0, i0 = 3, 4, 11, 1000
+    z, words = s.deltas(T, it, t0=t0, i0=i0, return_words=True)
+    ref_words = philox_ref.words_for(T, 777, d, s.seed, it, instance=5, t0=t0, i0=i0)
+    np.testing.assert_array_equal(words, ref_words)
+    ref_z = philox_ref.deltas(T, 777, s.sigma(it), s.seed, it, instance=5, t0=t0, i0=i0)
+    np.testing.assert_allclose(z, ref_z, rtol=0, atol=2e-5 * float(np.max(s.sigma(it))))
+    # the closure form walks timesteps in call order
+    s.reset_timestep()
+    dx0, du0 = s(None, None, it)
+    dx1, du1 = s(None, None, it)
+    z0 = s.deltas(2, it)
+    np.testing.assert_array_equal(np.hstack((dx0, du0)).astype(np.float32), z0[0])
+    np.testing.assert_array_equal(np.hstack((dx1, du1)).astype(np.float32), z0[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# zero-order smoothing: replay against the REFERENCE's own outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_zero_order_replay_matches_reference(api, golden_dir, name):
+    g = gold(golden_dir, "zero_order_%s.npz" % name)
+    cfg = ec.CONFIGS[name]()
+    s = make_system(api, name)
+    n = s.dim_x
+    T = g["u_trj"].shape[0]
+    deltas = g["deltas"]
+    state = {"t": 0}
+
+    def sampling(xbar, ubar, it):
+        t = state["t"]
+        state["t"] += 1
+        dx = deltas[t][:, :n].astype(np.float64)
+        du = deltas[t][:, n:].astype(np.float64)
+        if cfg["projection"]:
+            return s.projection(xbar, dx, ubar, du)     # as three_cart_zero_order.py:43
+        return dx, du
+
+    solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=T, x0=g["x_trj"][0], u_trj=g["u_trj"]), sampling)
+    np.testing.assert_allclose(solver.x_trj, g["x_trj"], rtol=0, atol=1e-12)
+    assert abs(solver.cost - float(g["initial_cost"])) <= 1e-12 * abs(float(g["initial_cost"]))
+    At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    assert At.shape == g["At"].shape and Bt.shape == g["Bt"].shape and ct.shape == g["ct"].shape
+    assert rel_err(At, g["At"]) < FP32_RTOL
+    assert rel_err(Bt, g["Bt"]) < FP32_RTOL
+    assert rel_err(ct, g["ct"]) < FP32_RTOL
+
+
+def test_zero_order_three_cart_inkernel_projection_matches_reference(api, golden_dir):
+    """Same golden, but the projection runs inside the kernel (IRS_PROJECT_ABSOLUTE) on the raw
+    deltas instead of in the Python closure."""
+    import torch
+    from irs_mpc_b200 import _device, smoothing
+    g = gold(golden_dir, "zero_order_three_cart.npz")
+    s = make_system(api, "three_cart")
+    T = g["u_trj"].shape[0]
+    x_nom = _device.to_device(g["x_trj"][:T])
+    u_nom = _device.to_device(g["u_trj"])
+    noise = _device.to_device(g["deltas"], torch.float32)
+    At, Bt, ct, status, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, x_nom, u_nom, noise.shape[1],
+                                                noise=noise, flags=2)
+    assert int(status.sum().item()) == 0
+    assert rel_err(_device.to_numpy(At), g["At"]) < FP32_RTOL
+    assert rel_err(_device.to_numpy(Bt), g["Bt"]) < FP32_RTOL
+    assert rel_err(_device.to_numpy(ct), g["ct"]) < FP32_RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# Philox fast path vs the oracle fed with the very same deltas
+# ------------------------------------------------------------------------------------------------
+def _nominal(api, name, T):
+    cfg = ec.CONFIGS[name](T=T)
+    s = make_system(api, name)
+    rng = np.random.default_rng(42)
+    u_trj = cfg["u_trj_initial"] + 0.05 * rng.standard_normal(cfg["u_trj_initial"].shape)
+    return cfg, s, u_trj
+
+
+@pytest.mark.parametrize("name,projection", [("pendulum", None), ("bicycle", None), ("quadrotor", None),
+                                             ("three_cart", None), ("three_cart", "absolute"),
+                                             ("three_cart", "delta")])
+def test_zero_order_philox_matches_oracle_on_same_deltas(api, name, projection):
+    T, N = 6, 3000
+    cfg, s, u_trj = _nominal(api, name, T)
+    n = s.dim_x
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=99,
+                                   projection=projection)
+    solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=T, u_trj=u_trj), sampler)
+    solver.iter = 3      # exercise the variance schedule sigma0 / iter**power
+    At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    deltas = sampler.deltas(T, solver.iter).astype(np.float64)
+    orc = cr.SYSTEMS[name](s.h)
+    if projection is not None:
+        for t in range(T):
+            xp, up = orc.projection(solver.x_trj[t], deltas[t][:, :n], solver.u_trj[t], deltas[t][:, n:])
+            if projection == "absolute":
+                deltas[t] = np.hstack((xp, up))
+            else:
+                deltas[t][:, :n] = xp - solver.x_trj[t]
+    At_o, Bt_o, ct_o = cr.zero_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    assert rel_err(At, At_o) < FP32_RTOL
+    assert rel_err(Bt, Bt_o) < FP32_RTOL
+    assert rel_err(ct, ct_o) < FP32_RTOL
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bicycle", "quadrotor"])
+def test_first_order_philox_and_replay_match_oracle(api, name):
+    T, N = 6, 2000
+    cfg, s, u_trj = _nominal(api, name, T)
+    n = s.dim_x
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=5)
+    solver = api.IrsLqrFirstOrder(s, make_params(api, cfg, T=T, u_trj=u_trj), sampler)
+    At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    deltas = sampler.deltas(T, solver.iter).astype(np.float64)
+    orc = cr.SYSTEMS[name](s.h)
+    At_o, Bt_o, ct_o = cr.first_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    assert rel_err(At, At_o) < FP32_RTOL
+    assert rel_err(Bt, Bt_o) < FP32_RTOL
+    assert rel_err(ct, ct_o) < FP32_RTOL
+    # replay path through a plain closure returns the same thing
+    sampler.reset_timestep()
+    solver2 = api.IrsLqrFirstOrder(s, make_params(api, cfg, T=T, u_trj=u_trj),
+                                   lambda xb, ub, it: sampler(xb, ub, it))
+    At2, Bt2, ct2 = solver2.get_TV_matrices(solver2.x_trj, solver2.u_trj)
+    assert rel_err(At2, At_o) < FP32_RTOL and rel_err(Bt2, Bt_o) < FP32_RTOL
+    assert rel_err(ct2, ct_o) < FP32_RTOL
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bicycle", "quadrotor"])
+def test_exact_matches_oracle(api, name):
+    T = 7
+    cfg, s, u_trj = _nominal(api, name, T)
+    solver = api.IrsLqrExact(s, make_params(api, cfg, T=T, u_trj=u_trj))
+    At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    orc = cr.SYSTEMS[name](s.h)
+    At_o, Bt_o, ct_o = cr.exact_tv_matrices(orc, solver.x_trj, solver.u_trj)
+    assert rel_err(At, At_o) < 1e-11 and rel_err(Bt, Bt_o) < 1e-11 and rel_err(ct, ct_o) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# TVLQR
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(2, 1), (5, 2), (6, 2), (12, 4)])
+def test_solve_tvlqr_matches_oracle(api, n, m):
+    rng = np.random.default_rng(n * 10 + m)
+    T = 25
+    At = np.eye(n) + 0.1 * rng.standard_normal((T, n, n))
+    Bt = 0.3 * rng.standard_normal((T, n, m))
+    ct = 0.1 * rng.standard_normal((T, n))
+    Q = np.diag(rng.uniform(0.5, 2.0, n))
+    Qd = 10 * Q
+    R = np.diag(rng.uniform(0.5, 2.0, m))
+    x0 = rng.standard_normal(n)
+    xd = rng.standard_normal((T + 1, n))
+    xs, us = api.solve_tvlqr(At, Bt, ct, Q, Qd, R, x0, xd, api.get_solver("osqp"))
+    xs_o, us_o = cr.solve_tvlqr(At, Bt, ct, Q, Qd, R, x0, xd)
+    assert xs.shape == (T + 1, n) and us.shape == (T, m)
+    assert rel_err(xs, xs_o) < 1e-9 and rel_err(us, us_o) < 1e-9
+
+
+def test_solve_tvlqr_error_conventions(api):
+    n, m, T = 2, 1, 3
+    At = np.tile(np.eye(n), (T, 1, 1))
+    Bt = np.ones((T, n, m))
+    ct = np.zeros((T, n))
+    with pytest.raises(ValueError, match="TV_LQR failed"):
+        api.solve_tvlqr(At, Bt, ct, -np.eye(n), -10 * np.eye(n), 1e-3 * np.eye(m), np.ones(n),
+                        np.zeros((T + 1, n)), None)
+    with pytest.raises(ValueError, match="Do not recognize solver"):
+        api.get_solver("ipopt")
+
+
+def test_constructor_error_conventions(api):
+    cfg = ec.pendulum(T=10)
+    s = make_system(api, "pendulum")
+    p = make_params(api, cfg)
+    p.Q = np.eye(3)
+    with pytest.raises(RuntimeError, match="Q matrix"):
+        api.IrsLqrExact(s, p)
+    p = make_params(api, cfg)
+    p.R = np.eye(2)
+    with pytest.raises(RuntimeError, match="R matrix"):
+        api.IrsLqrExact(s, p)
+    empty = api.DynamicalSystem()
+    with pytest.raises(RuntimeError, match="zero states"):
+        api.IrsLqrExact(empty, make_params(api, cfg))
+
+    class PyOnly(api.DynamicalSystem):
+        def __init__(self):
+            super().__init__()
+            self.dim_x, self.dim_u = 2, 1
+
+    with pytest.raises(RuntimeError, match="Could not evaluate dynamics"):
+        api.IrsLqrExact(PyOnly(), make_params(api, cfg))
+
+
+def test_rank_deficient_fit_raises(api):
+    cfg = ec.quadrotor(T=3)
+    s = make_system(api, "quadrotor")
+    sampler = api.GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], 8, seed=1)   # N < d
+    solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=3), sampler)
+    with pytest.raises(np.linalg.LinAlgError):
+        solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole loop
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,key,rtol", [("pendulum", "pendulum_exact", 1e-10),
+                                           ("quadrotor", "quadrotor_exact", 1e-7)])
+def test_exact_loop_reproduces_stored_cost_curve(api, golden_dir, name, key, rtol):
+    """examples/pendulum/analysis/pendulum_exact.csv and examples/quadrotor/analysis/
+    quadrotor_exact.csv, free-running (no teacher forcing); the whole exact loop is fp64."""
+    with open(os.path.join(golden_dir, "reference_costs.json")) as f:
+        goldc = np.array(json.load(f)["stored_cost_curves"][key]["values"])
+    cfg = ec.CONFIGS[name]()
+    s = make_system(api, name)
+    solver = api.IrsLqrExact(s, make_params(api, cfg))
+    assert abs(solver.cost - goldc[0]) <= 1e-12 * goldc[0]
+    solver.iterate(len(goldc) - 2, verbose=False)
+    assert len(solver.cost_lst) == len(goldc)
+    assert len(solver.x_trj_lst) == len(goldc) and len(solver.u_trj_lst) == len(goldc)
+    np.testing.assert_allclose(np.array(solver.cost_lst), goldc, rtol=rtol)
+
+
+@pytest.mark.parametrize("name,T,N", [("pendulum", 200, 1000), ("quadrotor", 40, 2000),
+                                      ("three_cart", 30, 2000)])
+def test_local_descent_teacher_forced_matches_oracle(api, name, T, N):
+    """One descent from the same nominal trajectory with the same deltas: trajectory and cost
+    within 1e-4 relative (BASELINE.json:north_star)."""
+    cfg = ec.CONFIGS[name](T=T)
+    s = make_system(api, name)
+    n = s.dim_x
+    proj = "absolute" if cfg["projection"] else None
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=2021,
+                                   projection=proj)
+    solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=T), sampler)
+    x_new, u_new = solver.local_descent(solver.x_trj, solver.u_trj)
+    cost = solver.evaluate_cost(x_new, u_new)
+    deltas = sampler.deltas(T, solver.iter).astype(np.float64)
+    orc = cr.SYSTEMS[name](s.h)
+    if proj:
+        for t in range(T):
+            xp, up = orc.projection(solver.x_trj[t], deltas[t][:, :n], solver.u_trj[t], deltas[t][:, n:])
+            deltas[t] = np.hstack((xp, up))
+    At, Bt, ct = cr.zero_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    K, k = cr.tvlqr_riccati(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["xd_trj"])
+    x_o, u_o = cr.closed_loop_descent(orc, K, k, solver.x_trj[0])
+    cost_o = cr.evaluate_cost(x_o, u_o, cfg["xd_trj"], cfg["Q"], cfg["R"])
+    assert rel_err(x_new, x_o) < FP32_RTOL
+    assert rel_err(u_new, u_o) < 5 * FP32_RTOL
+    assert abs(cost - cost_o) / abs(cost_o) < FP32_RTOL
+    assert abs(solver._last_descent_cost - cost) <= 1e-12 * abs(cost)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json configs 3 and 4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,N", [("quadrotor", 100000), ("three_cart", 200000)])
+def test_full_size_properties(api, name, N):
+    import torch
+    from irs_mpc_b200 import _device, smoothing
+    T = 100
+    cfg = ec.CONFIGS[name](T=T)
+    s = make_system(api, name)
+    n = s.dim_x
+    solver = api.IrsLqrExact(s, make_params(api, cfg, T=T)) if name != "three_cart" else None
+    x_trj = cr.rollout(cr.SYSTEMS[name](s.h), cfg["x0"], cfg["u_trj_initial"])
+    x_nom = _device.to_device(x_trj[:T])
+    u_nom = _device.to_device(cfg["u_trj_initial"])
+    kw = dict(sigma=cfg["sigma"], seed=0x1255, it=1)
+
+    def run(xn, un, Ns, **extra):
+        k = dict(kw)
+        k.update(extra)
+        At, Bt, ct, status, ws = smoothing.linearize(s, smoothing.ZERO_ORDER, xn, un, Ns, **k)
+        assert int(status.sum().item()) == 0
+        return At.clone(), Bt.clone(), ct.clone(), ws
+
+    A1, B1, c1, ws = run(x_nom, u_nom, N)
+    # (i) determinism: bit-identical on repeat
+    A2, B2, c2, _ = run(x_nom, u_nom, N)
+    assert torch.equal(A1, A2) and torch.equal(B1, B2) and torch.equal(c1, c2)
+    # (ii) timestep sharding: computing the two halves of the horizon separately with the global
+    #      point offset p0 reproduces the full result bit-for-bit (what the all-gather relies on)
+    h = T // 2
+    Aa, Ba, ca, _ = run(x_nom[:h].contiguous(), u_nom[:h].contiguous(), N, p0=0)
+    Ab, Bb, cb, _ = run(x_nom[h:].contiguous(), u_nom[h:].contiguous(), N, p0=h)
+    assert torch.equal(torch.cat((Aa, Ab)), A1) and torch.equal(torch.cat((Ba, Bb)), B1)
+    assert torch.equal(torch.cat((ca, cb)), c1)
+    # (iii) sample sharding: two half-size sample ranges (offset i0) summed by the finalize
+    #       kernel's multi-buffer path agree with the single-range result to fp32 summation noise
+    half = N // 2
+    wsA = smoothing.Workspace(s, smoothing.ZERO_ORDER, T, half)
+    both = _device.empty((2,) + tuple(wsA.partials.shape), torch.float32)
+    for r in range(2):
+        smoothing.accumulate(s, smoothing.ZERO_ORDER, x_nom, u_nom, half, wsA, i0=r * half, **kw)
+        both[r].copy_(wsA.partials)
+    A3, B3, c3, st3 = smoothing.finalize(s, smoothing.ZERO_ORDER, x_nom, u_nom, wsA, N, partials=both,
+                                         nranks=2, rank_stride=wsA.partials.numel())
+    assert int(st3.sum().item()) == 0
+    assert rel_err(_device.to_numpy(A3), _device.to_numpy(A1)) < 1e-5
+    assert rel_err(_device.to_numpy(B3), _device.to_numpy(B1)) < 1e-5
+    # (iv) smoothing converges to the exact Jacobian as sigma -> 0 (quadrotor is smooth)
+    if name == "quadrotor":
+        A4, B4, c4, _ = run(x_nom, u_nom, N, sigma=1e-2 * np.ones(16))
+        Ae, Be, ce = solver.get_TV_matrices(x_trj, cfg["u_trj_initial"])
+        assert rel_err(_device.to_numpy(A4), Ae) < 2e-3
+        assert rel_err(_device.to_numpy(B4), Be) < 2e-3

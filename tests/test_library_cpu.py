@@ -1,0 +1,100 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/irs_mpc_b200.h
+declares, host-only entry points work, and compute entry points fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "irs_mpc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(irs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(built_lib):
+    from irs_mpc_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(built_lib, name), "library does not export %s" % name
+        assert name in _lib.SIGNATURES, "no ctypes signature for %s" % name
+    assert sorted(_lib.SIGNATURES) == names
+    assert built_lib.irs_abi_version() == 1
+
+
+def test_system_dims_and_partial_width(built_lib):
+    expect = {0: (2, 1), 1: (5, 2), 2: (12, 4), 3: (6, 2)}
+    for sid, (n, m) in expect.items():
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert built_lib.irs_system_dims(sid, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 0
+        assert (a.value, b.value) == (n, m)
+        d = n + m
+        assert built_lib.irs_partial_width(sid, 0) == d * (d + 1) // 2 + d * n
+    assert built_lib.irs_system_dims(9, None, None, None) != 0
+    assert b"unknown system" in built_lib.irs_last_error()
+
+
+@pytest.mark.parametrize("P,N", [(1, 1), (200, 1000), (100, 10000), (100, 100000), (100, 1000000),
+                                 (409600, 1000), (3, 77)])
+def test_smooth_plan_covers_all_samples(built_lib, P, N):
+    from irs_mpc_b200 import smoothing
+    for sid in range(4):
+        C, S = smoothing.plan(sid, 0, P, N)
+        assert C >= 1 and S >= 1 and S % 128 == 0
+        assert C * S >= N and (C - 1) * S < N      # no empty chunk
+        assert P * C < 2 ** 31
+
+
+def test_compute_fails_loudly_without_gpu(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from irs_mpc_b200 import _lib
+    from irs_mpc_b200.all import PendulumDynamics
+    with pytest.raises(_lib.IrsCudaError, match="no CPU fallback"):
+        PendulumDynamics(0.05).dynamics(np.zeros(2), np.zeros(1))
+
+
+def test_get_solver_and_sampling_schedule(built_lib):
+    from irs_mpc_b200.all import GaussianSampling, get_solver
+    assert get_solver("osqp").name == "osqp"
+    with pytest.raises(ValueError, match="Do not recognize solver"):
+        get_solver("nope")
+    s = GaussianSampling([2.0, 4.0], [1.0], 100, power=0.5)
+    np.testing.assert_allclose(s.sigma(4), [1.0, 2.0, 0.5])
+    assert s.flags() == 0
+    assert GaussianSampling([1.0], [1.0], 1, projection="absolute").flags() == 2
+    with pytest.raises(ValueError):
+        GaussianSampling([1.0], [1.0], 1, projection="bogus")
+
+
+def test_drop_in_import_path(built_lib):
+    # same import lines as examples/pendulum/pendulum_zero_order.py:8 of the reference
+    import subprocess
+    import sys
+    code = ("from irs_lqr.all import IrsLqrParameters, IrsLqrZeroOrder, IrsLqrFirstOrder, IrsLqrExact;"
+            "from irs_lqr.tv_lqr import solve_tvlqr, get_solver;"
+            "from irs_lqr.dynamical_system import DynamicalSystem;"
+            "p = IrsLqrParameters(); assert p.solver_name == 'osqp'; print('ok')")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_argument_validation_messages(built_lib):
+    """Host-side validation runs before any launch, so it is testable without a GPU."""
+    prm = (ctypes.c_double * 1)(0.05)
+    rc = built_lib.irs_smooth_zero_order_accumulate(0, prm, 1, 0, None, None, 1, 10, None, None,
+                                                    0, 1, 0, 0, 0, 1, 128, None, None)
+    assert rc != 0 and b"null pointer" in built_lib.irs_last_error()
+    rc = built_lib.irs_smooth_zero_order_accumulate(0, prm, 2, 0, None, None, 1, 10, None, None,
+                                                    0, 1, 0, 0, 0, 1, 128, None, None)
+    assert rc != 0 and b"expects 1 parameters" in built_lib.irs_last_error()
+    rc = built_lib.irs_jacobian_xu_batch_f64(3, (ctypes.c_double * 2)(0.05, 0.2), 2, None, None, None, 4, None)
+    assert rc != 0 and b"no Jacobian" in built_lib.irs_last_error()
+    rc = built_lib.irs_tvlqr_riccati(3, 3, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, None)
+    assert rc != 0 and b"unsupported TVLQR dims" in built_lib.irs_last_error()
