@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the iRS-MPC hot path (BASELINE.json: smoothed-dynamics samples/s and iRS-LQR
+iterations/s at 1/2/4/8 B200 vs the numpy CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[2] — quadrotor 12-state, IrsLqrZeroOrder,
+T=100, N=1e5 samples/step per GPU.  A "step" is one full smoothing linearization
+(IrsLqrZeroOrder.get_TV_matrices: T x N perturbed dynamics evaluations + least-squares fits).
+For N GPUs the SAMPLE axis is sharded (weak scaling: every GPU draws 1e5 samples per step, the
+global fit uses N*1e5) with one all-gather of the per-step fp64 Gram blocks.
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_STEPS = 100
+N_SAMPLES = 100000
+FLOPS_PER_SAMPLE = 838        # quadrotor zero-order, algorithmic, FMA = 2
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+SEED0 = 0x1255 + 3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception as e:       # nvidia-smi missing: report it, do not fail the bench
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, name in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def quadrotor_problem(for_cpu=False):
+    if for_cpu:
+        from oracle import example_configs as ec          # CPU baseline leg only
+    else:
+        from irs_mpc_b200 import example_configs as ec
+    return ec.quadrotor(T=T_STEPS)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the float64 numpy port of the reference path (oracle), timed on
+# the host cores.  The unmodified reference cannot travel to the GPU box (pure Python tree at
+# /root/reference, needs pydrake) -> kind "port".
+# ------------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    t0, t1, n_samples, seed = args
+    from oracle import cpu_restatement as cr
+    cfg = quadrotor_problem(for_cpu=True)
+    orc = cr.QuadrotorOracle(cfg["h"])
+    x_trj = cr.rollout(orc, cfg["x0"], cfg["u_trj_initial"])
+    rng = np.random.default_rng(seed + t0)
+    # the reference draws its normals inside the timed loop too (sampling closure)
+    deltas = rng.standard_normal((t1 - t0, n_samples, 16)) * cfg["sigma"]
+    cr.zero_order_tv_matrices(orc, x_trj[t0:t1 + 1], cfg["u_trj_initial"][t0:t1], deltas)
+    return (t1 - t0) * n_samples
+
+
+def cpu_pass(n_samples, procs, seed=0, pool=None):
+    """One smoothing pass (T=100 timesteps x n_samples) on `procs` host processes, sharded by
+    timestep like the reference's ZeroMQ task farm.  Returns (samples, seconds)."""
+    bounds = np.linspace(0, T_STEPS, procs + 1).astype(int)
+    jobs = [(int(bounds[i]), int(bounds[i + 1]), n_samples, seed) for i in range(procs)
+            if bounds[i + 1] > bounds[i]]
+    t = time.perf_counter()
+    if pool is None:
+        done = sum(_cpu_chunk(j) for j in jobs)
+    else:
+        done = sum(pool.map(_cpu_chunk, jobs))
+    return done, time.perf_counter() - t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    procs = max(1, min(os.cpu_count() or 1, T_STEPS))
+    n_samples = 20000          # bounded sample of the 1e5-samples/step workload (per-sample cost is flat in N)
+    # one BLAS thread per worker process (the workers already cover every core)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        for _ in range(max(1, min(args.warmup, 1))):
+            cpu_pass(2000, procs, pool=pool)
+        total, secs = 0, 0.0
+        for k in range(args.steps):
+            done, dt = cpu_pass(n_samples, procs, seed=k, pool=pool)
+            total += done
+            secs += dt
+    value = total / secs
+    sample = ("float64 numpy port (oracle/cpu_restatement.py) of IrsLqrZeroOrder.get_TV_matrices, quadrotor "
+              "T=100, N=%d samples/step (bounded from 1e5; cost per sample is flat in N), %d host processes "
+              "sharded by timestep; the reference's own QuadrotorDynamics.dynamics_batch is a per-sample Python "
+              "loop (6.7e3 samples/s single-thread, SURVEY.md section 6)" % (n_samples, procs))
+    out = {
+        "impl": "reference", "metric": "smoothed_dynamics_samples_per_s", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "quadrotor zero-order T=100 N=%d/step (CPU sample of cfg3)" % n_samples},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from irs_mpc_b200 import _device, _lib, smoothing
+    from irs_mpc_b200.all import (GaussianSampling, IrsLqrParameters, IrsLqrZeroOrder,
+                                  QuadrotorDynamics)
+    from irs_mpc_b200.distributed import ShardedLinearizer
+
+    cfg = quadrotor_problem()
+    system = QuadrotorDynamics(cfg["h"])
+    params = IrsLqrParameters()
+    for key in ("Q", "Qd", "R", "x0", "xd_trj", "u_trj_initial", "xbound", "ubound"):
+        setattr(params, key, cfg[key])
+    sampler = GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], N_SAMPLES, power=cfg["power"], seed=SEED0)
+    solver = IrsLqrZeroOrder(system, params, sampler)
+    x_host, u_host = solver.x_trj, solver.u_trj
+    x_nom = _device.to_device(x_host[:T_STEPS])
+    u_nom = _device.to_device(u_host)
+    sigma = sampler.sigma(1)
+    ws = smoothing.Workspace(system, smoothing.ZERO_ORDER, T_STEPS, N_SAMPLES)
+    sharded = ShardedLinearizer(system, smoothing.ZERO_ORDER) if world > 1 else None
+    launches_per_step = 2 if world == 1 else 3
+
+    def step_device(k):
+        """Inputs resident in HBM; the seed changes every step so nothing can be cached."""
+        if world == 1:
+            smoothing.accumulate(system, smoothing.ZERO_ORDER, x_nom, u_nom, N_SAMPLES, ws, sigma=sigma,
+                                 seed=SEED0 + k, it=1)
+            return smoothing.finalize(system, smoothing.ZERO_ORDER, x_nom, u_nom, ws, N_SAMPLES)
+        return sharded.linearize_n(x_nom, u_nom, N_SAMPLES, sigma=sigma, seed=SEED0 + k, it=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for k in range(warmup):
+            fn(k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            fn(warmup + k)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+
+    # 1. headline: device-resident throughput of the whole smoothing pass
+    ms = timed(step_device, args.steps, args.warmup)
+    samples_per_step = world * T_STEPS * N_SAMPLES
+    value = samples_per_step * args.steps / (ms * 1e-3)
+
+    # 2. dominant kernel alone (accumulate), CUDA events on the launching stream
+    def only_accumulate(k):
+        smoothing.accumulate(system, smoothing.ZERO_ORDER, x_nom, u_nom, N_SAMPLES, ws, sigma=sigma,
+                             seed=SEED0 + 1000 + k, it=1)
+    ms_kernel = timed(only_accumulate, args.steps, 1) / args.steps
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # 3. measured FP32 FMA peak (roofline denominator), best of 5
+    scratch = _device.empty((148 * 8 * 256,), torch.float32)
+    import ctypes
+    flops = ctypes.c_double(0.0)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("irs_fp32_fma_peak", 20000, _device.ptr(scratch), scratch.numel(), ctypes.byref(flops),
+                  _device.stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    achieved_tflops = T_STEPS * N_SAMPLES * FLOPS_PER_SAMPLE / (ms_kernel * 1e-3) / 1e12
+
+    # 4. end to end through the public API: numpy in -> get_TV_matrices -> numpy out
+    if world == 1:
+        def step_e2e(k):
+            sampler.seed = SEED0 + 5000 + k
+            return solver.get_TV_matrices(x_host, u_host)
+    else:
+        def step_e2e(k):
+            xn = _device.to_device(x_host[:T_STEPS])
+            un = _device.to_device(u_host)
+            At, Bt, ct, st = sharded.linearize_n(xn, un, N_SAMPLES, sigma=sigma, seed=SEED0 + 5000 + k, it=1)
+            return _device.to_numpy(At), _device.to_numpy(Bt), _device.to_numpy(ct), _device.to_numpy(st)
+    ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 3))
+    e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
+    n, m = 12, 4
+    h2d = T_STEPS * (n + m) * 8 + (n + m) * 4
+    d2h = T_STEPS * (n * n + n * m + n) * 8 + T_STEPS * 4
+
+    # 5. iRS-LQR iterations/s: local_descent (smoothing + Riccati + closed-loop rollout) + evaluate_cost,
+    #    teacher-forced from the initial trajectory, through the public numpy API (replicated per rank)
+    def one_iteration(k):
+        sampler.seed = SEED0 + 9000 + k
+        xn, un = solver.local_descent(x_host, u_host)
+        return solver.evaluate_cost(xn, un)
+    it_steps = max(3, min(args.steps, 20))
+    ms_iter = timed(one_iteration, it_steps, 2)
+    iters_per_s = it_steps / (ms_iter * 1e-3)
+
+    # 6. CPU baseline on this box's host cores (rank 0, single GPU run only), bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_pass(2000, 1)
+        done, secs = cpu_pass(N_SAMPLES, 1)
+        cpu = {"value": done / secs, "unit": "samples/s", "cores": 1, "kind": "port",
+               "sample": "float64 numpy port (oracle) of IrsLqrZeroOrder.get_TV_matrices, quadrotor T=100 N=1e5 "
+                         "(one full step, %.1f s, single process; numpy elementwise is single-threaded, only "
+                         "lstsq may use BLAS threads); reference's own quadrotor dynamics_batch is a Python "
+                         "per-sample loop (6.7e3 samples/s, SURVEY.md section 6)" % secs}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        out = {
+            "metric": "smoothed_dynamics_samples_per_s", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "quadrotor zero-order T=100 N=1e5/step/GPU (BASELINE.json configs[2])",
+                       "system": "quadrotor n=12 m=4", "mode": "zero_order", "T": T_STEPS,
+                       "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-10 in-kernel",
+                       "sharding": "none" if world == 1 else "sample axis, all_gather of fp64 Gram blocks",
+                       "l2": "no per-sample HBM input (noise generated in registers); seed changes every step"},
+            "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_kernel<Quadrotor,G>",
+                         "achieved": achieved_tflops, "peak": best, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / best if best > 0 else None,
+                         "peak_source": "measured on this box: dependent-chain FFMA microbenchmark (irs_fp32_fma_peak); "
+                                        "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % FP32_NOMINAL_TFLOPS,
+                         "frac_of_nominal": achieved_tflops / FP32_NOMINAL_TFLOPS,
+                         "flops_per_sample": FLOPS_PER_SAMPLE, "kernel_ms": ms_kernel,
+                         "traffic": None,
+                         "hbm_gbs_measured_peak": peaks.get("hbm_gbs")},
+            "cpu_baseline": cpu,
+            "clocks": clock_info,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        log("note: warmup raised to 3 (timing rules)")
+        args.warmup = 3
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,13 +75,22 @@ int irs_smooth_first_order_accumulate(int system, const double* params_host, int
                                       unsigned p0, unsigned long long i0,
                                       int C, long long S, float* partials, void* stream);
 
-/* Fit / mean + affine offset (irs_lqr_zero_order.py:27-36,:59-62; irs_lqr_first_order.py:48-53):
- * sums `nranks` partial buffers (partials + r*rank_stride floats, r = 0..nranks-1; peer-mapped
- * pointers are fine) in fixed order, solves the normal equations (order 0) or divides by n_total
- * (order 1), writes At [P,n,n], Bt [P,n,m], ct [P,n] (f64) and status [P] (0 ok, 1 rank deficient). */
+/* Chunk reduction of the accumulation stage: partials [P,C,width] fp32 -> reduced [P,width] fp64,
+ * fixed chunk order.  This is the block one rank contributes when the SAMPLE axis is sharded
+ * across GPUs (the per-point blocks are then all-gathered and summed in rank order). */
+int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P, int C,
+                             double* reduced, void* stream);
+
+/* Fit / mean + affine offset (irs_lqr_zero_order.py:27-36,:59-62; irs_lqr_first_order.py:48-53).
+ * Input is EITHER `partials` (fp32 [nranks][P,C,width], other NULL) OR `reduced` (fp64
+ * [nranks][P,width]); the `nranks` buffers lie `rank_stride` elements apart (peer-mapped pointers
+ * are fine) and are summed in rank order, then chunk order — deterministic.  Solves the normal
+ * equations (order 0; identical to lstsq for full column rank) or divides by n_total (order 1),
+ * writes At [P,n,n], Bt [P,n,m], ct [P,n] (f64) and status [P] (0 ok, 1 rank deficient). */
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
-                        const float* partials, int nranks, long long rank_stride, double n_total,
+                        const float* partials, const double* reduced, int nranks,
+                        long long rank_stride, double n_total,
                         double* At, double* Bt, double* ct, int* status, void* stream);
 
 /* IrsLqrExact.get_TV_matrices (irs_lqr/irs_lqr_exact.py:15-31), all fp64: [A|B] = jacobian_xu at
@@ -145,6 +154,11 @@ int irs_rollout_open_loop(int system, const double* params_host, int nparams,
                           const double* u_in, const double* x0,
                           const double* xd, long long xd_stride, const double* Q, const double* R,
                           int I, int T, double* x_trj, double* cost, void* stream);
+
+/* Measurement aid (no reference counterpart): dependent-chain FP32 FMA microbenchmark used by
+ * bench.py as the measured FP32 roofline denominator.  out: device scratch of >= 148*8*256 floats;
+ * *flops_host receives the flop count of one launch. */
+int irs_fp32_fma_peak(int iters, float* out, long long out_len, double* flops_host, void* stream);
 
 /* IrsLqr.evaluate_cost (irs_lqr/irs_lqr.py:121-137) for given trajectories x_trj [I,T+1,n],
  * u_trj [I,T,m]: sum_t e'Qe + u'Ru + terminal e'Qe (Q, not Qd, :135-136).  cost [I]. */

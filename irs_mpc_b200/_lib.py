@@ -58,7 +58,8 @@ SIGNATURES = {
                                          _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
     "irs_smooth_first_order_accumulate": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _ll, _vp, _vp,
                                           _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
-    "irs_smooth_finalize": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _i, _ll,
+    "irs_smooth_reduce_chunks": [_i, _i, _vp, _i, _i, _vp, _vp],
+    "irs_smooth_finalize": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _ll,
                             ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
     "irs_exact_linearize": [_i, _c_double_p, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "irs_philox_dump": [_i, _ll, _i, _vp, _ull, _u, _u, _u, _ull, _vp, _vp, _vp],
@@ -73,6 +74,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp],
     "irs_rollout_open_loop": [_i, _c_double_p, _i, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i,
                               _vp, _vp, _vp],
+    "irs_fp32_fma_peak": [_i, _vp, _ll, _c_double_p, _vp],
     "irs_evaluate_cost": [_i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"irs_last_error": ctypes.c_char_p}

@@ -141,6 +141,22 @@ __global__ void __launch_bounds__(128) project_batch_kernel(SysParams prm, R* x,
     }
 }
 
+// FP32 FMA peak microbenchmark (roofline denominator measured on the box): 8 independent
+// dependent-FMA chains per thread, 148*8 blocks of 256 threads.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float b, float c) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = (float)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(acc[k], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = s;
+}
+
 static unsigned grid_for(long long work, int threads) {
     long long g = (work + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -213,16 +229,15 @@ int irs_partial_width(int system, int order) {
 int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long* S) {
     IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
     IRS_REQUIRE(P >= 1 && N >= 1 && C && S, "bad plan arguments");
-    // samples per chunk: large enough to amortise the end-of-chunk reduction, small enough that
-    // P*C blocks give several waves over 148 SMs
+    // Samples per chunk: large enough to amortise the end-of-chunk reduction, small enough that
+    // P*C blocks give several waves over 148 SMs.  The plan depends on N ONLY, never on P, so
+    // that a timestep-sharded run (P split over ranks) sums in exactly the same order as the
+    // single-GPU run and reproduces it bit for bit.
     const long long tile = 128;
     long long target = 4096;
     const char* e = getenv("IRS_CHUNK_SAMPLES");
     if (e && atoll(e) > 0) target = atoll(e);
     long long c = (N + target - 1) / target;
-    // keep at least ~4 waves worth of blocks when N allows it
-    const long long want_blocks = 148ll * 12;
-    while (c * P < want_blocks && (N + c) / (c + 1) >= 1024) ++c;
     long long s = (N + c - 1) / c;
     s = (s + tile - 1) / tile * tile;
     c = (N + s - 1) / s;
@@ -281,14 +296,28 @@ int irs_smooth_first_order_accumulate(int system, const double* params_host, int
     return check_launch("smooth_first_order_kernel");
 }
 
+int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P, int C,
+                             double* reduced, void* stream) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    IRS_REQUIRE(partials && reduced && P >= 1 && C >= 1, "bad reduce arguments");
+    const int width = irs_partial_width(system, order);
+    reduce_chunks_kernel<<<grid_for((long long)P * width, 256), 256, 0, (cudaStream_t)stream>>>(
+        partials, P, C, width, reduced);
+    return check_launch("reduce_chunks_kernel");
+}
+
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
-                        const float* partials, int nranks, long long rank_stride, double n_total,
+                        const float* partials, const double* reduced, int nranks,
+                        long long rank_stride, double n_total,
                         double* At, double* Bt, double* ct, int* status, void* stream) {
     FinalizeArgs a;
     if (load_params(system, params_host, nparams, &a.prm)) return 1;
     IRS_REQUIRE(order == 0 || order == 1, "order must be 0 or 1");
-    IRS_REQUIRE(x_nom && u_nom && partials && At && Bt && ct && status, "null pointer argument");
+    IRS_REQUIRE(x_nom && u_nom && At && Bt && ct && status, "null pointer argument");
+    IRS_REQUIRE((partials != nullptr) != (reduced != nullptr),
+                "exactly one of partials (fp32 per-chunk) and reduced (fp64) must be given");
+    a.reduced = reduced;
     IRS_REQUIRE(P >= 1 && C >= 1 && nranks >= 1 && n_total >= 1.0, "bad finalize arguments");
     IRS_REQUIRE(!(order == 1 && system == kThreeCart), "three_cart has no Jacobian");
     a.x_nom = x_nom;  a.u_nom = u_nom;  a.partials = partials;  a.rank_stride = rank_stride;
@@ -426,6 +455,15 @@ int irs_rollout_open_loop(int system, const double* params_host, int nparams,
     cudaStream_t st = (cudaStream_t)stream;
     IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, false><<<(I + 63) / 64, 64, 0, st>>>(a)));
     return check_launch("rollout_kernel<open>");
+}
+
+int irs_fp32_fma_peak(int iters, float* out, long long out_len, double* flops_host, void* stream) {
+    const int blocks = 148 * 8, threads = 256;
+    IRS_REQUIRE(out != nullptr && out_len >= (long long)blocks * threads, "scratch buffer too small");
+    IRS_REQUIRE(iters >= 1, "iters must be positive");
+    fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999999f, 1e-6f);
+    if (flops_host) *flops_host = 2.0 * 8.0 * (double)iters * blocks * threads;
+    return check_launch("fma_peak_kernel");
 }
 
 int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,

@@ -78,23 +78,34 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
         }
     }
     float x[n], u[m];
-    if (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) {
-        // three_cart: project the perturbed state onto non-penetration
-        // (three_cart_dynamics.py:196-264 called from three_cart_zero_order.py:38-43)
-        float xp[n];
+    if constexpr (Sys::kHasProjection) {
+        if (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) {
+            // three_cart: project the perturbed state onto non-penetration
+            // (three_cart_dynamics.py:196-264 called from three_cart_zero_order.py:38-43).
+            // Done in fp64: the reference re-evaluates its masks on the partially projected point,
+            // so whether a second push-out fires can hinge on the last bit of a gap that is
+            // nominally exactly d; only the same arithmetic reproduces those decisions.
+            using SysD = typename Sys::template Rebind<double>;
+            const SysD sysd(a.prm);
+            double xb[n], xp[n];
 #pragma unroll
-        for (int c = 0; c < n; ++c) xp[c] = xbar[c] + w[c];
-        sys.project(xp);
-        if (a.flags & kFlagProjectAbsolute) {
-            // the reference closure returns ABSOLUTE points which the solver adds to the nominal
-            // again and uses as regressors — reproduced literally
+            for (int c = 0; c < n; ++c) {
+                xb[c] = a.x_nom[(long long)p * n + c];
+                xp[c] = xb[c] + (double)w[c];
+            }
+            sysd.project(xp);
+            if (a.flags & kFlagProjectAbsolute) {
+                // the reference closure returns ABSOLUTE points which the solver adds to the
+                // nominal again and uses as regressors — reproduced literally
 #pragma unroll
-            for (int c = 0; c < n; ++c) w[c] = xp[c];
+                for (int c = 0; c < n; ++c) w[c] = (float)xp[c];
 #pragma unroll
-            for (int c = 0; c < m; ++c) w[n + c] = ubar[c] + w[n + c];
-        } else {
+                for (int c = 0; c < m; ++c)
+                    w[n + c] = (float)(a.u_nom[(long long)p * m + c] + (double)w[n + c]);
+            } else {
 #pragma unroll
-            for (int c = 0; c < n; ++c) w[c] = xp[c] - xbar[c];
+                for (int c = 0; c < n; ++c) w[c] = (float)(xp[c] - xb[c]);
+            }
         }
     }
 #pragma unroll
@@ -334,8 +345,9 @@ __global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArg
 struct FinalizeArgs {
     const double* x_nom;     // [P, n]
     const double* u_nom;     // [P, m]
-    const float* partials;   // [R][P, C, NACC or NJ]  (R = number of rank buffers summed in order)
-    long long rank_stride;   // floats between rank buffers
+    const float* partials;   // [R][P, C, width] fp32 per-chunk partials (width = NACC or NJ), or
+    const double* reduced;   // [R][P, width] fp64 chunk-reduced sums (exactly one of the two is set)
+    long long rank_stride;   // elements between rank buffers (R buffers are summed in rank order)
     int R;
     int P, C;
     double n_total;          // total samples per point (first order: divisor of the mean)
@@ -389,8 +401,12 @@ __global__ void __launch_bounds__(128) finalize_zero_order_kernel(const Finalize
     for (int e = lane; e < NACC; e += 32) {
         double s = 0.0;
         for (int r = 0; r < a.R; ++r) {
-            const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NACC + e;
-            for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NACC];
+            if (a.reduced != nullptr) {
+                s += a.reduced[r * a.rank_stride + (long long)p * NACC + e];
+            } else {
+                const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NACC + e;
+                for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NACC];
+            }
         }
         // unpack (i, j)
         int i = 0;
@@ -469,8 +485,12 @@ __global__ void __launch_bounds__(128) finalize_first_order_kernel(const Finaliz
     for (int e = lane; e < NJ; e += 32) {
         double s = 0.0;
         for (int r = 0; r < a.R; ++r) {
-            const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NJ + e;
-            for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NJ];
+            if (a.reduced != nullptr) {
+                s += a.reduced[r * a.rank_stride + (long long)p * NJ + e];
+            } else {
+                const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NJ + e;
+                for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NJ];
+            }
         }
         sV[warp][e] = s / a.n_total;
     }
@@ -484,6 +504,22 @@ __global__ void __launch_bounds__(128) finalize_first_order_kernel(const Finaliz
     }
     __syncwarp();
     write_abc<Sys>(sys, a, p, sAB[warp], lane);
+}
+
+// Chunk reduction [P, C, width] fp32 -> [P, width] fp64 in fixed chunk order: the block a rank
+// contributes to the sample-sharded exchange (all-gather of per-point Gram blocks).
+__global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* partials, int P, int C,
+                                                           int width, double* reduced) {
+    const long long total = (long long)P * width;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / width;
+        const int e = (int)(idx % width);
+        const float* src = partials + (p * C) * width + e;
+        double s = 0.0;
+        for (int c = 0; c < C; ++c) s += (double)src[(long long)c * width];
+        reduced[idx] = s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -23,8 +23,10 @@ enum SystemId { kPendulum = 0, kBicycle = 1, kQuadrotor = 2, kThreeCart = 3, kNu
 // ---------------------------------------------------------------------------------------------
 template <typename R>
 struct Pendulum {
+    template <typename S> using Rebind = Pendulum<S>;
     static constexpr int N = 2, M = 1, D = 3, NJ = 1;
     static constexpr bool kHasJacobian = true;
+    static constexpr bool kHasProjection = false;
     R h;
     __device__ explicit Pendulum(const SysParams& p) : h(R(p.v[0])) {}
 
@@ -54,8 +56,10 @@ struct Pendulum {
 // ---------------------------------------------------------------------------------------------
 template <typename R>
 struct Bicycle {
+    template <typename S> using Rebind = Bicycle<S>;
     static constexpr int N = 5, M = 2, D = 7, NJ = 6;
     static constexpr bool kHasJacobian = true;
+    static constexpr bool kHasProjection = false;
     R h;
     __device__ explicit Bicycle(const SysParams& p) : h(R(p.v[0])) {}
 
@@ -109,8 +113,10 @@ struct Bicycle {
 
 template <typename R>
 struct Quadrotor {
+    template <typename S> using Rebind = Quadrotor<S>;
     static constexpr int N = 12, M = 4, D = 16, NJ = IRS_QUAD_NJ;
     static constexpr bool kHasJacobian = true;
+    static constexpr bool kHasProjection = false;
     R h, mass, L, g, I0, I1, I2, kF, kM;
     __device__ explicit Quadrotor(const SysParams& p)
         : h(R(p.v[0])), mass(R(p.v[1])), L(R(p.v[2])), g(R(p.v[3])), I0(R(p.v[4])),
@@ -194,8 +200,10 @@ struct Quadrotor {
 // ---------------------------------------------------------------------------------------------
 template <typename R>
 struct ThreeCart {
+    template <typename S> using Rebind = ThreeCart<S>;
     static constexpr int N = 6, M = 2, D = 8, NJ = 0;
     static constexpr bool kHasJacobian = false;   // three_cart_dynamics.py:20
+    static constexpr bool kHasProjection = true;
     R h, d;
     __device__ explicit ThreeCart(const SysParams& p) : h(R(p.v[0])), d(R(p.v[1])) {}
 

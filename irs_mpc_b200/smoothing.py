@@ -56,14 +56,26 @@ def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=
               int(p0), int(i0), ws.C, ws.S, _device.ptr(ws.partials), _device.stream_ptr())
 
 
-def finalize(system, order, x_nom, u_nom, ws, n_total, partials=None, nranks=1, rank_stride=0):
+def reduce_chunks(system, order, ws, out=None):
+    """[P, C, width] fp32 partials -> [P, width] fp64 (the block exchanged between ranks)."""
+    P = ws.partials.shape[0]
+    if out is None:
+        out = _device.empty((P, ws.width))
+    _lib.call("irs_smooth_reduce_chunks", system.system_id, order, _device.ptr(ws.partials), P, ws.C,
+              _device.ptr(out), _device.stream_ptr())
+    return out
+
+
+def finalize(system, order, x_nom, u_nom, ws, n_total, partials=None, reduced=None, nranks=1,
+             rank_stride=0):
+    """Fit from fp32 per-chunk partials (default: ws.partials) or from fp64 reduced blocks."""
     P = x_nom.shape[0]
     prm, nprm = system._params()
-    part = ws.partials if partials is None else partials
+    part = None if reduced is not None else (ws.partials if partials is None else partials)
     _lib.call("irs_smooth_finalize", system.system_id, prm, nprm, order, _device.ptr(x_nom),
-              _device.ptr(u_nom), P, ws.C, _device.ptr(part), nranks, int(rank_stride),
-              float(n_total), _device.ptr(ws.At), _device.ptr(ws.Bt), _device.ptr(ws.ct),
-              _device.ptr(ws.status), _device.stream_ptr())
+              _device.ptr(u_nom), P, ws.C, _device.ptr(part), _device.ptr(reduced), nranks,
+              int(rank_stride), float(n_total), _device.ptr(ws.At), _device.ptr(ws.Bt),
+              _device.ptr(ws.ct), _device.ptr(ws.status), _device.stream_ptr())
     return ws.At, ws.Bt, ws.ct, ws.status
 
 
