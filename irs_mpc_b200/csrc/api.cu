@@ -53,7 +53,7 @@ template <class Sys, int G>
 static int launch_zero_order(const SmoothArgs& a, cudaStream_t st) {
     using C = ZeroOrderCfg<Sys, G>;
     const size_t smem = G == 1 ? sizeof(float) * (C::kThreads / 32) * C::NACC
-                               : sizeof(float) * C::kTile * C::RS;
+                               : sizeof(float) * 2 * C::kTile * C::RS;      // double-buffered tile
     auto kern = smooth_zero_order_kernel<Sys, G>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

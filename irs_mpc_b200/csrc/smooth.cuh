@@ -197,71 +197,107 @@ __device__ __forceinline__ void gram_flush(float2 (&acc)[NP], float* out, int la
     }
 }
 
-template <class Sys, int G, int g, bool BATCH>
-__device__ __forceinline__ void zero_order_role(const Sys& sys, const SmoothArgs& a, int p,
-                                                long long s_begin, long long s_end,
-                                                const float* xbar, const float* ubar,
-                                                const float* fbar, float* tile, float* out) {
+// Role g's share of the Gram update for the G*32 samples of one smem tile (lane = sample).
+template <class Sys, int G, int g, int NP>
+__device__ __forceinline__ void gram_update_tile(const float* tile, int lane, float2 (&acc)[NP]) {
     using C = ZeroOrderCfg<Sys, G>;
-    constexpr int NP = role_pairs(C::d, C::Wp, G, g);
+#pragma unroll 1
+    for (int q = 0; q < G; ++q) {
+        float w[C::RS];
+        const float4* src = reinterpret_cast<const float4*>(tile + (q * 32 + lane) * C::RS);
+#pragma unroll
+        for (int c = 0; c < C::RS / 4; ++c) {
+            const float4 v = src[c];
+            w[4 * c] = v.x;  w[4 * c + 1] = v.y;  w[4 * c + 2] = v.z;  w[4 * c + 3] = v.w;
+        }
+        gram_update<Sys, G, g, NP>(w, acc);
+    }
+}
+
+// G == 1: every thread keeps the whole Gram block of its own samples in registers.
+template <class Sys, bool BATCH>
+__device__ __forceinline__ void zero_order_registers(const Sys& sys, const SmoothArgs& a, int p,
+                                                     long long s_begin, long long s_end,
+                                                     const float* xbar, const float* ubar,
+                                                     const float* fbar, float* slabs, float* out) {
+    using C = ZeroOrderCfg<Sys, 1>;
+    constexpr int NP = role_pairs(C::d, C::Wp, 1, 0);
     float2 acc[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
     const int lane = threadIdx.x & 31;
+    for (long long s = s_begin + threadIdx.x; s < s_end; s += C::kThreads) {
+        float w[C::RS];
+#pragma unroll
+        for (int c = 0; c < C::RS; ++c) w[c] = 0.f;
+        make_sample<Sys, BATCH, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
+        gram_update<Sys, 1, 0, NP>(w, acc);
+    }
+    // cross-warp: each warp flushes into its own smem slab, then the block sums the slabs
+    float* slab = slabs + (threadIdx.x >> 5) * C::NACC;
+    gram_flush<Sys, 1, 0, NP>(acc, slab, lane);
+    __syncthreads();
+    for (int e = threadIdx.x; e < C::NACC; e += C::kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < C::kThreads / 32; ++wq) s += slabs[wq * C::NACC + e];
+        out[e] = s;
+    }
+}
 
-    if constexpr (G == 1) {
-        for (long long s = s_begin + threadIdx.x; s < s_end; s += C::kThreads) {
+// G > 1: the Gram rows are split over the G warps of the block.  Sample generation is COMMON code
+// (one copy in the instruction stream); only the short accumulate/flush sections are specialised
+// per warp role, so the hot loop stays inside the instruction cache.  The sample tile is double
+// buffered: one __syncthreads per round.
+template <class Sys, int G>
+__device__ __forceinline__ void zero_order_split(const Sys& sys, const SmoothArgs& a, int p,
+                                                 long long s_begin, long long s_end,
+                                                 const float* xbar, const float* ubar,
+                                                 const float* fbar, float* tiles, float* out) {
+    using C = ZeroOrderCfg<Sys, G>;
+    constexpr int NP = role_pairs(C::d, C::Wp, G, 0);
+    static_assert(G == 2 || G == 4, "supported group sizes");
+    static_assert(role_pairs(C::d, C::Wp, G, G - 1) == NP && role_pairs(C::d, C::Wp, G, 1) == NP,
+                  "row split must be balanced");
+    float2 acc[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;
+    int buf = 0;
+    for (long long base = s_begin; base < s_end; base += C::kTile) {
+        float* tile = tiles + buf * (C::kTile * C::RS);
+        {
             float w[C::RS];
 #pragma unroll
             for (int c = 0; c < C::RS; ++c) w[c] = 0.f;
-            make_sample<Sys, BATCH, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
-            gram_update<Sys, G, g, NP>(w, acc);
+            const long long s = base + threadIdx.x;
+            if (s < s_end) make_sample<Sys, false, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
+            float4* dst = reinterpret_cast<float4*>(tile + threadIdx.x * C::RS);
+#pragma unroll
+            for (int c = 0; c < C::RS / 4; ++c)
+                dst[c] = make_float4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         }
-        // cross-warp: each warp flushes into its own smem slab, then the block sums the slabs
-        float* slab = tile + (threadIdx.x >> 5) * C::NACC;
-        gram_flush<Sys, G, g, NP>(acc, slab, lane);
         __syncthreads();
-        for (int e = threadIdx.x; e < C::NACC; e += C::kThreads) {
-            float s = 0.f;
-#pragma unroll
-            for (int wq = 0; wq < C::kThreads / 32; ++wq) s += tile[wq * C::NACC + e];
-            out[e] = s;
+        switch (role) {
+            case 0: gram_update_tile<Sys, G, 0, NP>(tile, lane, acc); break;
+            case 1: gram_update_tile<Sys, G, 1, NP>(tile, lane, acc); break;
+            case 2: gram_update_tile<Sys, G, 2 % G, NP>(tile, lane, acc); break;
+            default: gram_update_tile<Sys, G, 3 % G, NP>(tile, lane, acc); break;
         }
-    } else {
-        for (long long base = s_begin; base < s_end; base += C::kTile) {
-            {
-                float w[C::RS];
-#pragma unroll
-                for (int c = 0; c < C::RS; ++c) w[c] = 0.f;
-                const long long s = base + threadIdx.x;
-                if (s < s_end) make_sample<Sys, BATCH, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
-                float4* dst = reinterpret_cast<float4*>(tile + threadIdx.x * C::RS);
-#pragma unroll
-                for (int c = 0; c < C::RS / 4; ++c)
-                    dst[c] = make_float4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < G; ++q) {
-                float w[C::RS];
-                const float4* src = reinterpret_cast<const float4*>(tile + (q * 32 + lane) * C::RS);
-#pragma unroll
-                for (int c = 0; c < C::RS / 4; ++c) {
-                    const float4 v = src[c];
-                    w[4 * c] = v.x;  w[4 * c + 1] = v.y;  w[4 * c + 2] = v.z;  w[4 * c + 3] = v.w;
-                }
-                gram_update<Sys, G, g, NP>(w, acc);
-            }
-            __syncthreads();
-        }
-        gram_flush<Sys, G, g, NP>(acc, out, lane);
+        buf ^= 1;
+    }
+    switch (role) {
+        case 0: gram_flush<Sys, G, 0, NP>(acc, out, lane); break;
+        case 1: gram_flush<Sys, G, 1, NP>(acc, out, lane); break;
+        case 2: gram_flush<Sys, G, 2 % G, NP>(acc, out, lane); break;
+        default: gram_flush<Sys, G, 3 % G, NP>(acc, out, lane); break;
     }
 }
 
 template <class Sys, int G>
-__global__ void __launch_bounds__(ZeroOrderCfg<Sys, G>::kThreads)
+__global__ void __launch_bounds__(ZeroOrderCfg<Sys, G>::kThreads, G == 1 ? 1 : 3)
 smooth_zero_order_kernel(const SmoothArgs a) {
-    using C = ZeroOrderCfg<Sys, G>;
     constexpr int n = Sys::N, m = Sys::M;
     extern __shared__ __align__(16) float tile[];
     const Sys sys(a.prm);
@@ -276,22 +312,16 @@ smooth_zero_order_kernel(const SmoothArgs a) {
     for (int q = 0; q < m; ++q) ubar[q] = (float)a.u_nom[(long long)p * m + q];
     // nominal response: the reference uses the SCALAR dynamics here (irs_lqr_zero_order.py:52)
     sys.template step<false>(xbar, ubar, fbar);
-    float* out = a.partials + ((long long)p * a.C + c) * C::NACC;
-    const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
+    float* out = a.partials + ((long long)p * a.C + c) * ZeroOrderCfg<Sys, G>::NACC;
     if constexpr (G == 1) {
-        if (batch) zero_order_role<Sys, 1, 0, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
-        else       zero_order_role<Sys, 1, 0, false>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+        if (a.flags & kFlagSamplesBatchVariant)
+            zero_order_registers<Sys, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
+        else
+            zero_order_registers<Sys, false>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
     } else {
-        // warp-uniform role dispatch: each warp owns a fixed subset of the Gram rows
-        const int role = threadIdx.x >> 5;
-        static_assert(G == 1 || G == 2 || G == 4, "supported group sizes");
-        if (role == 0) zero_order_role<Sys, G, 0, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
-        if constexpr (G >= 2)
-            if (role == 1) zero_order_role<Sys, G, 1 % G, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
-        if constexpr (G >= 4) {
-            if (role == 2) zero_order_role<Sys, G, 2 % G, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
-            if (role == 3) zero_order_role<Sys, G, 3 % G, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
-        }
+        // the split path is only instantiated for systems whose batch and scalar dynamics agree
+        static_assert(!Sys::kHasProjection, "split path assumes step<true> == step<false>");
+        zero_order_split<Sys, G>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
     }
 }
 
