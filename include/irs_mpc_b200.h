@@ -57,10 +57,11 @@ int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long
  *           = sigma * Philox-normal(seed; i0+i, p0+p, iter, stream)   otherwise
  *   dF      = f(xbar+dx, ubar+du) - f(xbar, ubar)
  * and accumulates [dx du]^T [dx du | dF] into partials[P, C, irs_partial_width(system,0)].
- * x_nom [P,n] f64, u_nom [P,m] f64, sigma [n+m] f32, noise [P,N,n+m] f32 or NULL. */
+ * x_nom [P,n] f64, u_nom [P,m] f64, sigma_host [n+m] f32 (HOST array, may be NULL in replay mode),
+ * noise [P,N,n+m] f32 or NULL.  The Philox stream is Philox4x32-7 (see csrc/common.cuh). */
 int irs_smooth_zero_order_accumulate(int system, const double* params_host, int nparams, int flags,
                                      const double* x_nom, const double* u_nom, int P, long long N,
-                                     const float* sigma, const float* noise,
+                                     const float* sigma_host, const float* noise,
                                      unsigned long long seed, unsigned iter, unsigned stream_id,
                                      unsigned p0, unsigned long long i0,
                                      int C, long long S, float* partials, void* stream);
@@ -70,7 +71,7 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
  * bicycle_dynamics.py:115-132, quadrotor_dynamics.py:132-148).  partials [P, C, nj]. */
 int irs_smooth_first_order_accumulate(int system, const double* params_host, int nparams, int flags,
                                       const double* x_nom, const double* u_nom, int P, long long N,
-                                      const float* sigma, const float* noise,
+                                      const float* sigma_host, const float* noise,
                                       unsigned long long seed, unsigned iter, unsigned stream_id,
                                       unsigned p0, unsigned long long i0,
                                       int C, long long S, float* partials, void* stream);
@@ -100,8 +101,8 @@ int irs_exact_linearize(int system, const double* params_host, int nparams,
                         double* At, double* Bt, double* ct, void* stream);
 
 /* The Philox words / deltas exactly as the fused kernels draw them (bookkeeping tests).
- * words [P,N,ceil(d/4),4] u32 or NULL; deltas [P,N,d] f32 or NULL. */
-int irs_philox_dump(int P, long long N, int d, const float* sigma, unsigned long long seed,
+ * words [P,N,ceil(d/4),4] u32 or NULL; deltas [P,N,d] f32 or NULL; sigma_host: HOST array [d]. */
+int irs_philox_dump(int P, long long N, int d, const float* sigma_host, unsigned long long seed,
                     unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
                     unsigned* words, float* deltas, void* stream);
 

@@ -74,12 +74,17 @@ static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host
     IRS_REQUIRE(C >= 1 && S >= 1 && (long long)C * S >= N, "chunk plan (C=%d, S=%lld) does not cover N=%lld", C, S, N);
     IRS_REQUIRE((long long)P * C < (1ll << 31), "grid too large");
     IRS_REQUIRE(noise != nullptr || sigma != nullptr, "need either replayed noise or sigma");
+    {
+        const SystemDims dm = system_dims(system);
+        for (int c = 0; c < kMaxRegressors; ++c)
+            a->sigma_scaled[c] = (sigma != nullptr && c < dm.n + dm.m) ? kBoxMullerScale * sigma[c] : 0.f;
+    }
     IRS_REQUIRE(iter < (1u << 24), "iter out of range");
     IRS_REQUIRE(!((flags & (IRS_PROJECT_ABSOLUTE | IRS_PROJECT_DELTA)) && system != kThreeCart),
                 "projection flags are only defined for three_cart");
     IRS_REQUIRE(!((flags & IRS_PROJECT_ABSOLUTE) && (flags & IRS_PROJECT_DELTA)),
                 "IRS_PROJECT_ABSOLUTE and IRS_PROJECT_DELTA are exclusive");
-    a->x_nom = x_nom;  a->u_nom = u_nom;  a->sigma = sigma;  a->noise = noise;
+    a->x_nom = x_nom;  a->u_nom = u_nom;  a->noise = noise;
     a->partials = partials;  a->N = N;  a->S = S;  a->P = P;  a->C = C;
     a->seed_lo = (uint32_t)(seed & 0xffffffffull);
     a->seed_hi = (uint32_t)(seed >> 32);
@@ -248,12 +253,12 @@ int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long
 
 int irs_smooth_zero_order_accumulate(int system, const double* params_host, int nparams, int flags,
                                      const double* x_nom, const double* u_nom, int P, long long N,
-                                     const float* sigma, const float* noise,
+                                     const float* sigma_host, const float* noise,
                                      unsigned long long seed, unsigned iter, unsigned stream_id,
                                      unsigned p0, unsigned long long i0,
                                      int C, long long S, float* partials, void* stream) {
     SmoothArgs a;
-    if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma, noise,
+    if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma_host, noise,
                          seed, iter, stream_id, p0, i0, C, S, partials))
         return 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -275,14 +280,14 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
 
 int irs_smooth_first_order_accumulate(int system, const double* params_host, int nparams, int flags,
                                       const double* x_nom, const double* u_nom, int P, long long N,
-                                      const float* sigma, const float* noise,
+                                      const float* sigma_host, const float* noise,
                                       unsigned long long seed, unsigned iter, unsigned stream_id,
                                       unsigned p0, unsigned long long i0,
                                       int C, long long S, float* partials, void* stream) {
     SmoothArgs a;
     IRS_REQUIRE(system != kThreeCart,
                 "three_cart is not differentiable and has no Jacobian (three_cart_dynamics.py:20)");
-    if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma, noise,
+    if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma_host, noise,
                          seed, iter, stream_id, p0, i0, C, S, partials))
         return 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -357,15 +362,19 @@ int irs_exact_linearize(int system, const double* params_host, int nparams,
     return check_launch("exact_linearize_kernel");
 }
 
-int irs_philox_dump(int P, long long N, int d, const float* sigma, unsigned long long seed,
+int irs_philox_dump(int P, long long N, int d, const float* sigma_host, unsigned long long seed,
                     unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
                     unsigned* words, float* deltas, void* stream) {
-    IRS_REQUIRE(P >= 1 && N >= 1 && d >= 1, "bad dump arguments");
-    IRS_REQUIRE(deltas == nullptr || sigma != nullptr, "deltas need sigma");
+    IRS_REQUIRE(P >= 1 && N >= 1 && d >= 1 && d <= kMaxRegressors, "bad dump arguments");
+    IRS_REQUIRE(deltas == nullptr || sigma_host != nullptr, "deltas need sigma");
+    PhiloxDumpArgs a;
+    a.P = P;  a.d = d;  a.N = N;
+    a.seed_lo = (uint32_t)(seed & 0xffffffffull);  a.seed_hi = (uint32_t)(seed >> 32);
+    a.iter = iter;  a.stream = stream_id;  a.p0 = p0;  a.i0 = i0;  a.words = words;  a.deltas = deltas;
+    for (int c = 0; c < kMaxRegressors; ++c)
+        a.sigma_scaled[c] = (sigma_host != nullptr && c < d) ? kBoxMullerScale * sigma_host[c] : 0.f;
     const long long total = (long long)P * N * ((d + 3) / 4);
-    philox_dump_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        P, N, d, sigma, (uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32), iter, stream_id, p0, i0,
-        words, deltas);
+    philox_dump_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("philox_dump_kernel");
 }
 

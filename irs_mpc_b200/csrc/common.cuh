@@ -1,4 +1,4 @@
-// Shared device helpers for the iRS-MPC sm_100a kernels: error plumbing, Philox4x32-10,
+// Shared device helpers for the iRS-MPC sm_100a kernels: error plumbing, Philox4x32,
 // Box-Muller, packed-FP32 FMA (FFMA2), scalar-type math wrappers.
 #pragma once
 #include <cuda_runtime.h>
@@ -51,17 +51,25 @@ struct Math<double> {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11).  Spec of the counter layout: oracle/philox_ref.py.
+// Philox4x32 (Salmon et al., SC'11).  Spec of the counter layout: oracle/philox_ref.py.
+// The sample stream uses kPhiloxRounds = 7 rounds: the smallest round count of Philox4x32 that
+// the paper reports as Crush-resistant (10 is its default safety margin).  On sm_100a the two
+// 32x32->64 multiplies per round issue at a quarter of the FP32 rate (measured: 32
+// IMAD.WIDE/clk/SM vs 128 FFMA/clk/SM), so the rounds are the single largest item of the
+// sample-generation cost.  The round function itself is pinned on the Random123 10-round
+// known-answer vectors (tests/test_oracle_philox.py).
 // ---------------------------------------------------------------------------------------------
+constexpr int kPhiloxRounds = 7;
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
 constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+template <int ROUNDS = kPhiloxRounds>
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c0);
         const uint32_t lo0 = kPhiloxM0 * c0;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c2);
@@ -84,17 +92,22 @@ __device__ __forceinline__ float unit_float(uint32_t w) {
     return __uint_as_float((w >> 9) | 0x3f800000u);
 }
 
-// Two standard normals from two 32-bit words.
-__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& e0, float& e1) {
+// Box-Muller on two 32-bit words, returned UNSCALED:  (g0, g1) = sqrt(-log2 u) * (cos, sin)(2 pi f)
+// with u = 2 - unit_float(wa) in (0,1] and f = unit_float(wb) in [1,2).  The standard normals of
+// the spec (oracle/philox_ref.py: angle 2 pi (f - 1.5), radius sqrt(-2 ln u)) are
+//     e = -sqrt(2 ln 2) * g        (cos/sin(x - 3 pi) = -cos/sin(x))
+// so callers fold kBoxMullerScale into sigma once instead of spending FMULs per sample.
+constexpr float kBoxMullerScale = -1.1774100225154747f;     // -sqrt(2 ln 2)
+
+__device__ __forceinline__ void box_muller_raw(uint32_t wa, uint32_t wb, float& g0, float& g1) {
     const float u = 2.0f - unit_float(wa);                      // (0, 1]
-    const float l2 = __log2f(u);                                // MUFU.LG2
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));   // sqrt(-2 ln u)
-    const float th = (unit_float(wb) - 1.5f) * 6.283185307179586f;                  // [-pi, pi)
+    float l2, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));      // MUFU.LG2 (u >= 2^-23: never denormal)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-l2));    // MUFU.SQRT
     float s, c;
-    __sincosf(th, &s, &c);
-    e0 = r * c;
-    e1 = r * s;
+    __sincosf(unit_float(wb) * 6.283185307179586f, &s, &c);     // argument in [2 pi, 4 pi)
+    g0 = r * c;
+    g1 = r * s;
 }
 
 // ---------------------------------------------------------------------------------------------

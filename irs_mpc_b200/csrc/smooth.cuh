@@ -22,7 +22,6 @@ enum SmoothFlags {
 struct SmoothArgs {
     const double* x_nom;   // [P, n] nominal states
     const double* u_nom;   // [P, m] nominal inputs
-    const float* sigma;    // [d]     per-column std-dev (Philox mode)
     const float* noise;    // [P, N, d] replayed deltas (dx | du) or nullptr
     float* partials;       // [P, C, NACC]
     long long N;           // samples per nominal point (local to this rank)
@@ -33,7 +32,9 @@ struct SmoothArgs {
     unsigned long long i0; // global index of local sample 0 (Philox counter word 0)
     int flags;
     SysParams prm;
+    float sigma_scaled[16];   // kBoxMullerScale * sigma[c] (Philox mode), lives in the constant bank
 };
+constexpr int kMaxRegressors = 16;
 
 __host__ __device__ constexpr int gram_nacc(int n, int m) {
     return (n + m) * (n + m + 1) / 2 + (n + m) * n;
@@ -67,14 +68,14 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
 #pragma unroll
         for (int j = 0; j < nblk; ++j) {
             uint32_t r[4];
-            philox4x32_10((uint32_t)gi, a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j, a.stream,
-                          a.seed_lo, a.seed_hi, r);
+            philox4x32((uint32_t)gi, a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j, a.stream,
+                       a.seed_lo, a.seed_hi, r);
             float e[4];
-            box_muller(r[0], r[1], e[0], e[1]);
-            box_muller(r[2], r[3], e[2], e[3]);
+            box_muller_raw(r[0], r[1], e[0], e[1]);
+            box_muller_raw(r[2], r[3], e[2], e[3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (4 * j + q < d) w[4 * j + q] = __ldg(a.sigma + 4 * j + q) * e[q];
+                if (4 * j + q < d) w[4 * j + q] = a.sigma_scaled[4 * j + q] * e[q];
         }
     }
     float x[n], u[m];
@@ -594,27 +595,36 @@ __global__ void __launch_bounds__(64) exact_linearize_kernel(SysParams prm, cons
 // Debug / bookkeeping kernel: dump the Philox words and the deltas exactly as the fused kernels
 // draw them (same counter function).  Used by the bit-exact index tests.
 // ---------------------------------------------------------------------------------------------
-__global__ void philox_dump_kernel(int P, long long N, int d, const float* sigma, uint32_t seed_lo,
-                                   uint32_t seed_hi, uint32_t iter, uint32_t stream, uint32_t p0,
-                                   unsigned long long i0, uint32_t* words, float* deltas) {
-    const int nblk = (d + 3) / 4;
-    const long long total = (long long)P * N * nblk;
+struct PhiloxDumpArgs {
+    int P, d;
+    long long N;
+    uint32_t seed_lo, seed_hi, iter, stream, p0;
+    unsigned long long i0;
+    uint32_t* words;
+    float* deltas;
+    float sigma_scaled[16];
+};
+
+__global__ void philox_dump_kernel(const PhiloxDumpArgs a) {
+    const int nblk = (a.d + 3) / 4;
+    const long long total = (long long)a.P * a.N * nblk;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx % nblk);
-        const long long i = (idx / nblk) % N;
-        const int p = (int)(idx / nblk / N);
+        const long long i = (idx / nblk) % a.N;
+        const int p = (int)(idx / nblk / a.N);
         uint32_t r[4];
-        philox4x32_10((uint32_t)(i0 + (unsigned long long)i), p0 + (uint32_t)p, (iter << 8) | (uint32_t)j,
-                      stream, seed_lo, seed_hi, r);
-        if (words != nullptr)
-            for (int q = 0; q < 4; ++q) words[idx * 4 + q] = r[q];
-        if (deltas != nullptr) {
+        philox4x32((uint32_t)(a.i0 + (unsigned long long)i), a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j,
+                   a.stream, a.seed_lo, a.seed_hi, r);
+        if (a.words != nullptr)
+            for (int q = 0; q < 4; ++q) a.words[idx * 4 + q] = r[q];
+        if (a.deltas != nullptr) {
             float e[4];
-            box_muller(r[0], r[1], e[0], e[1]);
-            box_muller(r[2], r[3], e[2], e[3]);
+            box_muller_raw(r[0], r[1], e[0], e[1]);
+            box_muller_raw(r[2], r[3], e[2], e[3]);
             for (int q = 0; q < 4; ++q)
-                if (4 * j + q < d) deltas[((long long)p * N + i) * d + 4 * j + q] = sigma[4 * j + q] * e[q];
+                if (4 * j + q < a.d)
+                    a.deltas[((long long)p * a.N + i) * a.d + 4 * j + q] = a.sigma_scaled[4 * j + q] * e[q];
         }
     }
 }

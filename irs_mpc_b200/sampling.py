@@ -13,6 +13,8 @@ Philox4x32-10 and never touches HBM:
 It is also callable with the reference signature, in which case it returns exactly the deltas
 the fused kernel would draw for that (t, iter) — generated on the GPU by irs_philox_dump.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -49,10 +51,10 @@ class GaussianSampling:
         """Deltas [T, N, d] (numpy float32) exactly as the fused kernels draw them."""
         N = self.num_samples if num_samples is None else int(num_samples)
         d = self.sigma0.shape[0]
-        sig = _device.to_device(self.sigma(it), torch.float32)
+        sig = np.ascontiguousarray(self.sigma(it), dtype=np.float32)
         out = _device.empty((T, N, d), torch.float32)
         words = _device.empty((T, N, (d + 3) // 4, 4), torch.int32) if return_words else None
-        _lib.call("irs_philox_dump", T, N, d, _device.ptr(sig), self.seed, int(it), self.stream_id,
+        _lib.call("irs_philox_dump", T, N, d, sig.ctypes.data_as(ctypes.c_void_p), self.seed, int(it), self.stream_id,
                   int(t0), int(i0), _device.ptr(words), _device.ptr(out), _device.stream_ptr())
         z = _device.to_numpy(out)
         if return_words:

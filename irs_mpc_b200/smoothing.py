@@ -37,7 +37,6 @@ class Workspace:
         self.Bt = _device.empty((P, n, m))
         self.ct = _device.empty((P, n))
         self.status = _device.empty((P,), torch.int32)
-        self.sigma = _device.empty((n + m,), torch.float32)
 
 
 def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=0, it=1,
@@ -47,12 +46,16 @@ def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=
     prm, nprm = system._params()
     if system.batch_differs_from_scalar and order == ZERO_ORDER:
         flags |= 1   # IRS_SAMPLES_BATCH_VARIANT: samples go through dynamics_batch (…zero_order.py:51)
+    sig = None
     if noise is None:
-        ws.sigma.copy_(torch.as_tensor(np.asarray(sigma, dtype=np.float32)), non_blocking=True)
+        sig = np.ascontiguousarray(np.asarray(sigma, dtype=np.float32))
+        if sig.shape != (system.dim_x + system.dim_u,):
+            raise ValueError("sigma must have n + m = %d entries" % (system.dim_x + system.dim_u))
+        sig = sig.ctypes.data_as(ctypes.c_void_p)
     fn = ("irs_smooth_zero_order_accumulate" if order == ZERO_ORDER
           else "irs_smooth_first_order_accumulate")
     _lib.call(fn, system.system_id, prm, nprm, flags, _device.ptr(x_nom), _device.ptr(u_nom), P,
-              int(N), _device.ptr(ws.sigma), _device.ptr(noise), int(seed), int(it), int(stream_id),
+              int(N), sig, _device.ptr(noise), int(seed), int(it), int(stream_id),
               int(p0), int(i0), ws.C, ws.S, _device.ptr(ws.partials), _device.stream_ptr())
 
 

@@ -3,7 +3,8 @@
 The reference draws its perturbations with numpy's global legacy MT19937 stream inside a user
 closure (e.g. examples/pendulum/pendulum_zero_order.py:38-43) and never seeds it, so there is no
 reference bit stream to match.  The CUDA fast path instead defines its own counter-based stream
-(Philox4x32-10, Salmon et al. SC'11; same round function as Random123 / cuRAND) whose *integer*
+(Philox4x32 with STREAM_ROUNDS = 7 rounds, Salmon et al. SC'11; same round function as Random123 /
+cuRAND, pinned on the 10-round known-answer vectors) whose *integer*
 bookkeeping is checked bit-for-bit against this file:
 
   counter = (sample index i, timestep t, (iter << 8) | word-block j, instance id)
@@ -22,6 +23,7 @@ M1 = np.uint64(0xCD9E8D57)
 W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
+STREAM_ROUNDS = 7     # must equal kPhiloxRounds in irs_mpc_b200/csrc/common.cuh
 
 
 def philox4x32(counter, key, rounds=10):
@@ -52,7 +54,7 @@ def words_for(T, N, d, seed, it, instance=0, t0=0, i0=0):
     ctr[..., 2] = ((np.uint64(it) << np.uint64(8)) | (j + 0 * i + 0 * t)).astype(np.uint32)
     ctr[..., 3] = np.uint32(instance)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    return philox4x32(ctr, key)
+    return philox4x32(ctr, key, rounds=STREAM_ROUNDS)
 
 
 def unit_float(w):

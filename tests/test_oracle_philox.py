@@ -1,0 +1,30 @@
+"""Known-answer and statistical checks of the numpy Philox restatement (oracle/philox_ref.py)."""
+import numpy as np
+
+from oracle import philox_ref
+
+
+def test_philox4x32_10_random123_known_answers():
+    # Random123 kat_vectors, philox4x32 with 10 rounds
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, expect in kats:
+        out = philox_ref.philox4x32(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32), rounds=10)
+        assert tuple(int(v) for v in out) == expect
+
+
+def test_stream_statistics():
+    e = philox_ref.standard_normals(2, 100000, 16, 0x1255, 1)
+    assert abs(e.mean()) < 2e-3 and abs(e.std() - 1.0) < 2e-3
+    c = np.corrcoef(e[0].T)
+    assert np.max(np.abs(c - np.eye(16))) < 0.02
+    # different timesteps / iterations / streams give different noise
+    a = philox_ref.words_for(1, 8, 4, 1, 1)
+    assert not np.array_equal(a, philox_ref.words_for(1, 8, 4, 1, 2))
+    assert not np.array_equal(a, philox_ref.words_for(1, 8, 4, 1, 1, instance=1))
+    assert not np.array_equal(a, philox_ref.words_for(1, 8, 4, 1, 1, t0=1))
+    # global indexing: an offset range equals the tail of the full range
+    full = philox_ref.words_for(2, 10, 7, 9, 3)
+    np.testing.assert_array_equal(full[1:, 4:], philox_ref.words_for(1, 6, 7, 9, 3, t0=1, i0=4))
