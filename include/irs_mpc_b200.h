@@ -41,6 +41,12 @@ enum {
 int irs_abi_version(void);
 const char* irs_last_error(void);
 
+/* Selects where the zero-order kernel accumulates the Gram blocks [dx du]^T[dx du | dF]:
+ * -1 auto (default: tcgen05 tensor cores for quadrotor and three_cart, CUDA cores otherwise), 0 CUDA cores
+ * (packed FFMA2), 1 tcgen05 (bf16x2-split operands, fp32 accumulation in TMEM).  Both engines
+ * implement irs_lqr/irs_lqr_zero_order.py:54-57 and are parity-tested against each other. */
+int irs_set_gram_engine(int engine);
+
 /* DynamicalSystem.dim_x / dim_u (irs_lqr/dynamical_system.py:8-10); nj = varying Jacobian scalars */
 int irs_system_dims(int system, int* n, int* m, int* nj);
 

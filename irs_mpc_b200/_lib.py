@@ -51,6 +51,7 @@ _u = ctypes.c_uint
 SIGNATURES = {
     "irs_abi_version": [],
     "irs_last_error": [],
+    "irs_set_gram_engine": [_i],
     "irs_system_dims": [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)],
     "irs_partial_width": [_i, _i],
     "irs_smooth_plan": [_i, _i, _i, _ll, ctypes.POINTER(_i), ctypes.POINTER(_ll)],

@@ -6,6 +6,7 @@
 
 #include "../../include/irs_mpc_b200.h"
 #include "smooth.cuh"
+#include "smooth_tc.cuh"
 #include "tvlqr.cuh"
 
 namespace irs {
@@ -61,6 +62,50 @@ static int launch_zero_order(const SmoothArgs& a, cudaStream_t st) {
     }
     kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
     return check_launch("smooth_zero_order_kernel");
+}
+
+// Gram engine of the zero-order kernel: -1 = auto (tensor cores when the regressor dimension is
+// large enough to pay for the operand staging: quadrotor, three_cart), 0 = CUDA cores (FFMA2), 1 = tcgen05.
+static int g_gram_engine = -2;
+static int gram_engine() {
+    if (g_gram_engine == -2) {
+        const char* e = getenv("IRS_GRAM_ENGINE");
+        g_gram_engine = e ? atoi(e) : -1;
+        if (g_gram_engine < -1 || g_gram_engine > 1) g_gram_engine = -1;
+    }
+    return g_gram_engine;
+}
+static bool use_tensor_cores(int system) {
+    const int e = gram_engine();
+    if (e == -1) return system == kQuadrotor || system == kThreeCart;   // measured: see DESIGN.md
+    return e == 1;
+}
+static int tc_stages() {
+    static int g = -1;
+    if (g < 0) {
+        const char* e = getenv("IRS_TC_STAGES");
+        g = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return g;
+}
+
+template <class Sys>
+static int launch_zero_order_tc(const SmoothArgs& a, cudaStream_t st) {
+    using C = TcCfg<Sys>;
+    const int stages = tc_stages();
+    const size_t smem = (size_t)stages * C::kStageBytes;
+    if (stages == 2) {
+        auto kern = smooth_zero_order_tc_kernel<Sys, 2>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(smooth_zero_order_tc)");
+        kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
+    } else {
+        auto kern = smooth_zero_order_tc_kernel<Sys, 1>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(smooth_zero_order_tc)");
+        kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
+    }
+    return check_launch("smooth_zero_order_tc_kernel");
 }
 
 static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host, int nparams,
@@ -216,6 +261,12 @@ int irs_abi_version(void) { return IRS_ABI_VERSION; }
 
 const char* irs_last_error(void) { return g_error; }
 
+int irs_set_gram_engine(int engine) {
+    IRS_REQUIRE(engine >= -1 && engine <= 1, "engine must be -1 (auto), 0 (CUDA cores) or 1 (tensor cores)");
+    g_gram_engine = engine;
+    return 0;
+}
+
 int irs_system_dims(int system, int* n, int* m, int* nj) {
     IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
     const SystemDims d = system_dims(system);
@@ -262,6 +313,14 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
                          seed, iter, stream_id, p0, i0, C, S, partials))
         return 1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_tensor_cores(system)) {
+        switch (system) {
+            case kPendulum: return launch_zero_order_tc<Pendulum<float>>(a, st);
+            case kBicycle: return launch_zero_order_tc<Bicycle<float>>(a, st);
+            case kThreeCart: return launch_zero_order_tc<ThreeCart<float>>(a, st);
+            case kQuadrotor: return launch_zero_order_tc<Quadrotor<float>>(a, st);
+        }
+    }
     switch (system) {
         case kPendulum: return launch_zero_order<Pendulum<float>, 1>(a, st);
         case kBicycle: return launch_zero_order<Bicycle<float>, 1>(a, st);

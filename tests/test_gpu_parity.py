@@ -214,6 +214,33 @@ def test_zero_order_three_cart_inkernel_projection_matches_reference(api, golden
     assert rel_err(_device.to_numpy(ct), g["ct"]) < FP32_RTOL
 
 
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_zero_order_both_gram_engines_match_reference(api, golden_dir, name, engine):
+    """CUDA-core (FFMA2) and tensor-core (tcgen05, bf16x2 split) Gram engines against the
+    reference's own (At, Bt, ct) on the replayed deltas."""
+    import torch
+    from irs_mpc_b200 import _device, _lib, smoothing
+    g = gold(golden_dir, "zero_order_%s.npz" % name)
+    s = make_system(api, name)
+    T = g["u_trj"].shape[0]
+    x_nom = _device.to_device(g["x_trj"][:T])
+    u_nom = _device.to_device(g["u_trj"])
+    noise = _device.to_device(g["deltas"], torch.float32)
+    _lib.call("irs_set_gram_engine", engine)
+    try:
+        At, Bt, ct, status, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, x_nom, u_nom, noise.shape[1],
+                                                    noise=noise, flags=2 if bool(g["projection"]) else 0)
+        assert int(status.sum().item()) == 0
+        At, Bt, ct = _device.to_numpy(At), _device.to_numpy(Bt), _device.to_numpy(ct)
+    finally:
+        _lib.call("irs_set_gram_engine", -1)
+    scale = max(1.0, float(np.max(np.abs(g["x_trj"]))))
+    assert rel_err(At, g["At"]) < FP32_RTOL
+    assert rel_err(Bt, g["Bt"]) < FP32_RTOL
+    assert float(np.max(np.abs(ct - g["ct"]))) < FP32_RTOL * scale
+
+
 # ------------------------------------------------------------------------------------------------
 # Philox fast path vs the oracle fed with the very same deltas
 # ------------------------------------------------------------------------------------------------
