@@ -35,7 +35,21 @@ static int load_params(int system, const double* params_host, int nparams, SysPa
     IRS_REQUIRE(params_host != nullptr && nparams == expected[system],
                 "system %d expects %d parameters, got %d", system, expected[system], nparams);
     memset(out, 0, sizeof(*out));
-    for (int i = 0; i < nparams; ++i) out->v[i] = params_host[i];
+    for (int i = 0; i < nparams; ++i) {
+        out->v[i] = params_host[i];
+        out->f[i] = (float)params_host[i];
+    }
+    if (system == kQuadrotor) {      // derived invariants of Quadrotor<float>::step, rounded once
+        const double* v = out->v;    // [h, mass, L, g, Ixx, Iyy, Izz, kF, kM]
+        out->f[9] = (float)(1.0 / v[1]);
+        out->f[10] = (float)(1.0 / v[4]);
+        out->f[11] = (float)(1.0 / v[5]);
+        out->f[12] = (float)(1.0 / v[6]);
+        out->f[13] = (float)(v[2] * v[7]);
+        out->f[14] = (float)(v[5] - v[6]);
+        out->f[15] = (float)(v[6] - v[4]);
+        out->f[16] = (float)(v[4] - v[5]);
+    }
     return 0;
 }
 
@@ -89,23 +103,54 @@ static int tc_stages() {
     return g;
 }
 
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <class Sys, int NSTAGE>
+static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
+    using C = TcCfg<Sys>;
+    const size_t smem = (size_t)NSTAGE * C::kStageBytes;
+    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(smooth_zero_order_tc)");
+        // resident blocks per SM from the kernel's own resource usage (the occupancy API answers for
+        // the *current* shared-memory carve-out, which is not the one the launch will configure)
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return check_launch("cudaFuncGetAttributes");
+        const int regs_per_block = ((fa.numRegs * 32 + 255) / 256 * 256) * (C::kThreads / 32);
+        const int by_regs = 65536 / regs_per_block;
+        const int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+        const int by_tmem = 512 / C::kTmemCols;
+        int occ = by_regs < by_smem ? by_regs : by_smem;
+        if (by_tmem < occ) occ = by_tmem;
+        if (occ > 32) occ = 32;
+        blocks_per_sm = occ < 1 ? 1 : occ;
+    }
+    // persistent grid: every resident block walks the (point, chunk) item list with stride gridDim.x
+    const long long items = (long long)a.P * a.C;
+    long long grid = (long long)num_sms() * blocks_per_sm;
+    if (grid > items) grid = items;
+    if (getenv("IRS_DEBUG"))
+        fprintf(stderr, "[irs] smooth_zero_order_tc: items=%lld grid=%lld blocks/SM=%d smem=%zu stages=%d\n", items, grid,
+                blocks_per_sm, smem, NSTAGE);
+    if (const char* g = getenv("IRS_TC_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, C::kThreads, smem, st>>>(a);
+    return check_launch("smooth_zero_order_tc_kernel");
+}
+
 template <class Sys>
 static int launch_zero_order_tc(const SmoothArgs& a, cudaStream_t st) {
-    using C = TcCfg<Sys>;
-    const int stages = tc_stages();
-    const size_t smem = (size_t)stages * C::kStageBytes;
-    if (stages == 2) {
-        auto kern = smooth_zero_order_tc_kernel<Sys, 2>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("cudaFuncSetAttribute(smooth_zero_order_tc)");
-        kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
-    } else {
-        auto kern = smooth_zero_order_tc_kernel<Sys, 1>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("cudaFuncSetAttribute(smooth_zero_order_tc)");
-        kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
-    }
-    return check_launch("smooth_zero_order_tc_kernel");
+    return tc_stages() == 2 ? launch_zero_order_tc_stages<Sys, 2>(a, st) : launch_zero_order_tc_stages<Sys, 1>(a, st);
 }
 
 static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host, int nparams,
@@ -290,7 +335,8 @@ int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long
     // that a timestep-sharded run (P split over ranks) sums in exactly the same order as the
     // single-GPU run and reproduces it bit for bit.
     const long long tile = 128;
-    long long target = 4096;
+    // tensor-core path = persistent kernel: small items cost almost nothing and balance the SMs
+    long long target = (order == 0 && use_tensor_cores(system)) ? 1024 : 4096;
     const char* e = getenv("IRS_CHUNK_SAMPLES");
     if (e && atoll(e) > 0) target = atoll(e);
     long long c = (N + target - 1) / target;

@@ -20,9 +20,13 @@ int check_launch(const char* what);
         }                                 \
     } while (0)
 
-// System parameters travel by value into the kernels (<= 10 doubles).
+// System parameters travel by value into the kernels (<= 10 doubles).  `f` mirrors `v` in fp32
+// followed by the derived loop invariants of the system (filled on the host in double precision,
+// load_params in api.cu), so that the fp32 sample kernels read them as constant-bank operands
+// instead of converting doubles (F2F runs on the XU pipe, the busiest one in the sample loop).
 struct SysParams {
     double v[10];
+    float f[20];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -37,7 +41,11 @@ struct Math<float> {
     static __device__ __forceinline__ void sincos(float a, float& s, float& c) {
         __sincosf(a, &s, &c);
     }
-    static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
+    static __device__ __forceinline__ float rcp(float a) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));      // one MUFU.RCP, no slow path
+        return r;
+    }
     static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
 };
 

@@ -45,11 +45,10 @@ __host__ __device__ constexpr int gram_row_offset(int i, int W) { return i * W -
 // ---------------------------------------------------------------------------------------------
 // One sample: regressors w[0..D) = (dx | du), responses w[D..D+N) = f(xbar+dx, ubar+du) - fbar.
 // ---------------------------------------------------------------------------------------------
-template <class Sys, bool BATCH, int RS>
-__device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a, int p, long long i,
-                                            const float* xbar, const float* ubar,
-                                            const float* fbar, float (&w)[RS], bool want_df = true) {
-    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+// Deltas of sample i of nominal point p: replayed from a.noise or drawn from the Philox stream.
+template <class Sys, int RS>
+__device__ __forceinline__ void draw_deltas(const SmoothArgs& a, int p, long long i, float (&w)[RS]) {
+    constexpr int d = Sys::D;
     if (a.noise != nullptr) {
         const float* src = a.noise + ((long long)p * a.N + i) * d;
         if constexpr (d % 4 == 0) {
@@ -78,14 +77,18 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
                 if (4 * j + q < d) w[4 * j + q] = a.sigma_scaled[4 * j + q] * e[q];
         }
     }
-    float x[n], u[m];
+}
+
+// three_cart: project the perturbed state onto non-penetration
+// (three_cart_dynamics.py:196-264 called from three_cart_zero_order.py:38-43).
+// Done in fp64: the reference re-evaluates its masks on the partially projected point,
+// so whether a second push-out fires can hinge on the last bit of a gap that is
+// nominally exactly d; only the same arithmetic reproduces those decisions.
+template <class Sys, int RS>
+__device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, float (&w)[RS]) {
+    constexpr int n = Sys::N, m = Sys::M;
     if constexpr (Sys::kHasProjection) {
         if (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) {
-            // three_cart: project the perturbed state onto non-penetration
-            // (three_cart_dynamics.py:196-264 called from three_cart_zero_order.py:38-43).
-            // Done in fp64: the reference re-evaluates its masks on the partially projected point,
-            // so whether a second push-out fires can hinge on the last bit of a gap that is
-            // nominally exactly d; only the same arithmetic reproduces those decisions.
             using SysD = typename Sys::template Rebind<double>;
             const SysD sysd(a.prm);
             double xb[n], xp[n];
@@ -109,6 +112,16 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
             }
         }
     }
+}
+
+template <class Sys, bool BATCH, int RS>
+__device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a, int p, long long i,
+                                            const float* xbar, const float* ubar,
+                                            const float* fbar, float (&w)[RS], bool want_df = true) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    draw_deltas<Sys, RS>(a, p, i, w);
+    project_deltas<Sys, RS>(a, p, w);
+    float x[n], u[m];
 #pragma unroll
     for (int c = 0; c < n; ++c) x[c] = xbar[c] + w[c];
 #pragma unroll

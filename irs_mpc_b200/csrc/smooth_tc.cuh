@@ -23,6 +23,13 @@
 #pragma once
 #include "smooth.cuh"
 
+#ifndef IRS_TC_POLL_NS
+#define IRS_TC_POLL_NS 100      // back-off of the UMMA warp while it waits for a stage
+#endif
+#ifndef IRS_TC_MIN_BLOCKS
+#define IRS_TC_MIN_BLOCKS 4
+#endif
+
 namespace irs {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -42,14 +49,22 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Wait for the phase with the given parity to complete.  try_wait suspends the thread in hardware
+// for at most a short, implementation-defined time; without a back-off a warp that waits for
+// thousands of cycles (the UMMA warp waiting for a stage) polls every ~25 cycles and its
+// SYNCS/BRA pairs take issue slots away from the sample producers (ncu: 18 % of all issued
+// instructions).  SLEEP_NS > 0 inserts a nanosleep between polls.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
-    while (!done) {
+    while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (done) break;
+        if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     }
 }
 
@@ -62,18 +77,18 @@ struct TcCfg {
     static constexpr int kN = 2 * dq;                    // UMMA N (columns of D): [z_1 | z_2]
     static constexpr int kRows = 2 * dq + 2 * nq;        // used rows of A (<= 64)
     static constexpr int kM = 64;
-    static constexpr int kThreads = 128;                 // 4 warps, lane = sample
+    static constexpr int kThreads = 160;                 // 4 producer warps (lane = sample) + 1 UMMA warp
     static constexpr int kTile = 128;                    // samples per stage
     static constexpr int kLBO = 128;                     // bytes between k-groups (8 samples)
     static constexpr int kSBO = (kTile / 8) * kLBO;      // bytes between 8-feature groups (2048)
     static constexpr int kGroups = kM / 8;
     static constexpr int kStageBytes = kGroups * kSBO;   // 16,384
-    static constexpr int kTmemCols = kN < 32 ? 32 : kN;
+    static constexpr int kTmemCols = 2 * kN < 32 ? 32 : 2 * kN;   // two accumulators (double buffered)
     static constexpr int NACC = gram_nacc(n, m);
     static constexpr int RS = (W + 1) / 2 * 2;
     static_assert(kRows <= kM, "operand rows must fit one M = 64 UMMA");
     static_assert(kN % 8 == 0 && kN >= 8 && kN <= 256, "invalid UMMA N");
-    static_assert(kM * kN * 4 <= kStageBytes, "read-back scratch must fit a stage");
+    static_assert(kN % 16 == 0, "accumulator read-back uses 16-column TMEM loads");
     // instruction descriptor: D fp32, A/B bf16, both MN-major, N >> 3, M >> 4
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
@@ -91,149 +106,278 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& p1, u
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void producer_bar_sync() {      // named barrier 1: the 4 producer warps only
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// Persistent kernel.  A work item is one (nominal point p, sample chunk c); blocks walk the item
+// list with stride gridDim.x, so the result layout (partials[p][c]) does not depend on the grid.
+//
+// Warp roles
+//   warps 0-3  sample producers (lane = sample): Philox / replay -> perturb -> dynamics -> bf16x2
+//              split -> stage in shared memory -> arrive on the stage's "full" mbarrier.  With
+//              NSTAGE = 2 they run one stage ahead of the tensor core and never meet a block-wide
+//              barrier inside the sample loop.
+//   warp 4     owns the tensor core: waits for "full", issues the UMMAs of the stage from one lane and
+//              commits them to the stage's "empty" mbarrier.  It also prepares the NEXT item's nominal
+//              point (xbar, ubar, f(xbar, ubar) as fp32) in shared memory, so the producers start an
+//              item with 40 LDS instead of a chain of global loads and a dynamics evaluation.
+// The accumulator is double buffered in TMEM (item k uses buffer k & 1): the producers read item
+// k's Gram block back after they have staged the FIRST tile of item k + 1, when its UMMAs have long
+// retired, so the item switch costs neither a pipeline drain nor a wait.
 template <class Sys, int NSTAGE>
-__global__ void __launch_bounds__(128) smooth_zero_order_tc_kernel(const SmoothArgs a) {
+__global__ void __launch_bounds__(160, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_kernel(const SmoothArgs a) {
     using C = TcCfg<Sys>;
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    constexpr int kXU = (n + m + 3) / 4 * 4;             // xbar | ubar, padded to float4
+    constexpr int kNom = kXU + (n + 3) / 4 * 4;          // ... | fbar, padded to float4
+    constexpr int kScr = C::dq + 1;                      // padded scratch row (bank-conflict free)
     extern __shared__ __align__(1024) unsigned char stage_mem[];
-    __shared__ uint64_t mbar_empty[NSTAGE];
-    __shared__ uint64_t mbar_done;
+    __shared__ uint64_t mbar_full[NSTAGE];               // producers -> UMMA warp: stage staged
+    __shared__ uint64_t mbar_empty[NSTAGE];              // UMMA commit -> producers: stage drained
+    __shared__ uint64_t mbar_done[2];                    // UMMA commit -> producers: accumulator complete
+    __shared__ uint64_t mbar_acc_free[2];                // producers -> UMMA warp: accumulator read back
+    __shared__ uint64_t mbar_nom[2];                     // UMMA warp -> producers: nominal point ready
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float nom_s[2][kNom];
+    __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][i] + D[r][dq + i]
+    __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
 
-    const Sys sys(a.prm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int p = blockIdx.x / a.C;
-    const int c = blockIdx.x % a.C;
-    const long long s_begin = (long long)c * a.S;
-    const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+    const long long num_items = (long long)a.P * a.C;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&mbar_empty[s], 1);
-        mbar_init(&mbar_done, 1);
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&mbar_full[s], C::kTile);      // every producer thread arrives
+            mbar_init(&mbar_empty[s], 1);            // one tcgen05.commit arrives
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&mbar_done[b], 1);
+            mbar_init(&mbar_acc_free[b], C::kTile);
+            mbar_init(&mbar_nom[b], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    if (warp == 0) {
+    for (int e = tid; e < C::NACC; e += C::kThreads) {
+        int i = 0;
+        while (i + 1 < d && gram_row_offset(i + 1, C::W) <= e) ++i;
+        idx_s[e] = (uint16_t)((i << 8) | (i + (e - gram_row_offset(i, C::W))));
+    }
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(C::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    float xbar[n], ubar[m], fbar[n];
-#pragma unroll
-    for (int q = 0; q < n; ++q) xbar[q] = (float)a.x_nom[(long long)p * n + q];
-#pragma unroll
-    for (int q = 0; q < m; ++q) ubar[q] = (float)a.u_nom[(long long)p * m + q];
-    sys.template step<false>(xbar, ubar, fbar);      // scalar dynamics at the nominal (…zero_order.py:52)
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t stage_base = smem_u32(stage_mem);
-    const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
+    const Sys sys(a.prm);
 
-    // byte offset of this thread's sample inside a stage (feature group 0): (k/8)*LBO + (k%8)*16
-    const uint32_t my_off = (uint32_t)(tid >> 3) * C::kLBO + (uint32_t)(tid & 7) * 16;
-
-    int round = 0;
-    for (long long base = s_begin; base < s_end; base += C::kTile, ++round) {
-        const int stage = round % NSTAGE;
-        if (round >= NSTAGE) mbar_wait(&mbar_empty[stage], (uint32_t)((round / NSTAGE - 1) & 1));
-        unsigned char* sm = stage_mem + stage * C::kStageBytes + my_off;
-        {
-            float w[C::RS];
+    if (warp == 4) {
+        // ===== UMMA issuer + nominal-point prefetcher =====
+        const uint32_t stage_base = smem_u32(stage_mem);
+        // nominal point of item `item` -> nom_s[buf]; the buffer was last read by the producers two
+        // items ago, and every producer has arrived on a "full" barrier of the item in between
+        auto prepare_nominal = [&](long long item, int buf) {
+            const int p = (int)(item / a.C);
+            float* dst = nom_s[buf];
+            if (lane < n) dst[lane] = (float)a.x_nom[(long long)p * n + lane];
+            else if (lane < n + m) dst[lane] = (float)a.u_nom[(long long)p * m + (lane - n)];
+            __syncwarp();
+            if (lane == 0) {
+                float xb[n], ub[m], fb[n];
 #pragma unroll
-            for (int q = 0; q < C::RS; ++q) w[q] = 0.f;
-            const long long s = base + tid;
-            if (s < s_end) {
-                if (batch) make_sample<Sys, true, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
-                else make_sample<Sys, false, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
+                for (int q = 0; q < n; ++q) xb[q] = dst[q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) ub[q] = dst[n + q];
+                sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
+#pragma unroll
+                for (int q = 0; q < n; ++q) dst[kXU + q] = fb[q];
+                mbar_arrive(&mbar_nom[buf]);            // release: the stores above are visible to waiters
             }
-            // regressors: dq/8 groups of 8 features, first and second bf16 pieces
-#pragma unroll
-            for (int g = 0; g < C::dq / 8; ++g) {
-                uint32_t p1[4], p2[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
-                    split_bf16x2(c0 < d ? w[c0] : 0.f, c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
+            __syncwarp();
+        };
+        static_assert(n + m <= 32, "one lane per nominal coordinate");
+        if ((long long)blockIdx.x < num_items) prepare_nominal(blockIdx.x, 0);
+        int round = 0;                                    // running round counter of this block
+        int it = 0;                                       // running item counter of this block
+        for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            if (item + gridDim.x < num_items) prepare_nominal(item + gridDim.x, (it + 1) & 1);
+            if (lane == 0) {
+                const int buf = it & 1;
+                const int c = (int)(item % a.C);
+                const long long s_begin = (long long)c * a.S;
+                const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+                const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * C::kN);
+                if (it >= 2) {       // the producers must have read this buffer's previous item back
+                    mbar_wait(&mbar_acc_free[buf], (uint32_t)(((it >> 1) - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;");
                 }
-                *reinterpret_cast<uint4*>(sm + (C::grp_z1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                *reinterpret_cast<uint4*>(sm + (C::grp_z2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-            }
-            // responses
+                for (int r = 0; r < rounds; ++r, ++round) {
+                    const int stage = round % NSTAGE;
+                    mbar_wait<IRS_TC_POLL_NS>(&mbar_full[stage], (uint32_t)((round / NSTAGE) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint64_t desc0 = umma_smem_desc(stage_base + stage * C::kStageBytes, C::kLBO, C::kSBO);
 #pragma unroll
-            for (int g = 0; g < C::nq / 8; ++g) {
-                uint32_t p1[4], p2[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
-                    split_bf16x2(c0 < n ? w[d + c0] : 0.f, c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
+                    for (int kb = 0; kb < C::kTile / 16; ++kb) {   // one UMMA = K 16 = two k-groups of 8 samples
+                        const uint64_t desc = desc0 + (uint64_t)((kb * 2 * C::kLBO) >> 4);
+                        const uint32_t acc = (r > 0 || kb > 0) ? 1u : 0u;   // first UMMA of an item overwrites
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_acc),
+                            "l"(desc), "l"(desc), "r"(C::kIdesc), "r"(acc)
+                            : "memory");
+                    }
+                    // frees the stage once these UMMAs have read it (commit implies fence::before_thread_sync)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     smem_u32(&mbar_empty[stage]))
+                                 : "memory");
                 }
-                *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 smem_u32(&mbar_done[buf]))
+                             : "memory");
             }
+            __syncwarp();
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
-        __syncthreads();
-        if (tid == 0) {
+    } else {
+        // ===== sample producers =====
+        [[maybe_unused]] const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
+        // byte offset of this thread's sample inside a stage (feature group 0): (k/8)*LBO + (k%8)*16
+        const uint32_t my_off = (uint32_t)(tid >> 3) * C::kLBO + (uint32_t)(tid & 7) * 16;
+
+        // Read item (`item`, local index `it`)'s accumulator back and write its packed Gram block.
+        // Row r of D lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64 layout): lanes 0-15 of warp w
+        // hold rows 16 w .. 16 w + 15.
+        auto epilogue = [&](long long item, int it) {
+            const int buf = it & 1;
+            mbar_wait(&mbar_done[buf], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t sbase = stage_base + stage * C::kStageBytes;
-#pragma unroll 4
-            for (int kb = 0; kb < C::kTile / 16; ++kb) {       // one UMMA = K 16 = two k-groups of 8 samples
-                const uint64_t desc = umma_smem_desc(sbase + kb * 2 * C::kLBO, C::kLBO, C::kSBO);
-                const uint32_t acc = (round > 0 || kb > 0) ? 1u : 0u;
+            uint32_t v[C::kN];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(buf * C::kN);
+#pragma unroll
+            for (int c0 = 0; c0 < C::kN; c0 += 16) {
                 asm volatile(
-                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
-                    "l"(desc), "l"(desc), "r"(C::kIdesc), "r"(acc)
-                    : "memory");
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]),
+                      "=r"(v[c0 + 5]), "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]),
+                      "=r"(v[c0 + 10]), "=r"(v[c0 + 11]), "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]),
+                      "=r"(v[c0 + 15])
+                    : "r"(taddr + c0));
             }
-            // frees the stage for the round that reuses it (tcgen05.commit implies fence::before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             smem_u32(&mbar_empty[stage]))
-                         : "memory");
-        }
-    }
-    if (tid == 0)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(&mbar_done))
-                     : "memory");
-    mbar_wait(&mbar_done, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;");
-
-    // ---- read the accumulator back: row r lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64) ----
-    float* scratch = reinterpret_cast<float*>(stage_mem);            // [64][kN], all UMMAs are done
-    {
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
-        const int row = 16 * warp + lane;
-#pragma unroll
-        for (int c0 = 0; c0 < C::kN; c0 += 8) {
-            uint32_t v[8];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                         : "r"(taddr + c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (lane < 16) {
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(&mbar_acc_free[buf]);             // the UMMA warp may overwrite this buffer now
+            const int row = 16 * warp + lane;
+            if (lane < 16 && row < C::kRows) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) scratch[row * C::kN + c0 + q] = __uint_as_float(v[q]);
+                for (int i = 0; i < C::dq; ++i)
+                    scratch[row * kScr + i] = __uint_as_float(v[i]) + __uint_as_float(v[C::dq + i]);
             }
+            producer_bar_sync();
+            // G[i][j] = sum_k z_i w_j = sum over the two pieces of w_j of s_row[i]
+            float* out = a.partials + item * C::NACC;
+            for (int e = tid; e < C::NACC; e += C::kTile) {
+                const int ij = idx_s[e];
+                const int i = ij >> 8, j = ij & 0xff;
+                out[e] = scratch[C::row_1(j) * kScr + i] + scratch[C::row_2(j) * kScr + i];
+            }
+            producer_bar_sync();      // the next epilogue overwrites the scratch
+        };
+
+        int round = 0;
+        int it = 0;
+        long long prev_item = -1;
+        for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            const int p = (int)(item / a.C);
+            const int c = (int)(item % a.C);
+            const long long s_begin = (long long)c * a.S;
+            const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+            const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
+            // The nominal point stays in shared memory: xbar/ubar/fbar are re-read (7 broadcast
+            // LDS.128 per sample) instead of living in 28 registers per thread.
+            mbar_wait(&mbar_nom[it & 1], (uint32_t)((it >> 1) & 1));
+            const float4* nom4 = reinterpret_cast<const float4*>(nom_s[it & 1]);
+            for (int r = 0; r < rounds; ++r, ++round) {
+                const int stage = round % NSTAGE;
+                const long long s = s_begin + (long long)r * C::kTile + tid;
+                float w[C::RS];
+                if (s < s_end) {
+                    if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
+                    draw_deltas<Sys, C::RS>(a, p, s, w);
+                    project_deltas<Sys, C::RS>(a, p, w);
+                    float xu[kXU], f[n];
+#pragma unroll
+                    for (int q = 0; q < kXU / 4; ++q) {
+                        const float4 v = nom4[q];
+                        xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < d; ++q) xu[q] += w[q];
+                    if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar
+                        if (batch) sys.template step<true>(xu, xu + n, f);
+                        else sys.template step<false>(xu, xu + n, f);
+                    } else {
+                        sys.template step<false>(xu, xu + n, f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < (n + 3) / 4; ++q) {
+                        const float4 v = nom4[kXU / 4 + q];
+                        const float fb[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (4 * q + k < n) w[d + 4 * q + k] = f[4 * q + k] - fb[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
+                }
+                // the stage must have been drained by the UMMAs that last read it
+                if (round >= NSTAGE) mbar_wait(&mbar_empty[stage], (uint32_t)((round / NSTAGE - 1) & 1));
+                unsigned char* sm = stage_mem + stage * C::kStageBytes + my_off;
+                // regressors: dq/8 groups of 8 features, first and second bf16 pieces
+#pragma unroll
+                for (int g = 0; g < C::dq / 8; ++g) {
+                    uint32_t p1[4], p2[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
+                        split_bf16x2(c0 < d ? w[c0] : 0.f, c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
+                    }
+                    *reinterpret_cast<uint4*>(sm + (C::grp_z1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                    *reinterpret_cast<uint4*>(sm + (C::grp_z2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                }
+                // responses
+#pragma unroll
+                for (int g = 0; g < C::nq / 8; ++g) {
+                    uint32_t p1[4], p2[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
+                        split_bf16x2(c0 < n ? w[d + c0] : 0.f, c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
+                    }
+                    *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                    *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
+                mbar_arrive(&mbar_full[stage]);
+                if (r == 0 && prev_item >= 0) epilogue(prev_item, it - 1);
+            }
+            prev_item = item;
         }
+        if (prev_item >= 0) epilogue(prev_item, it - 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0)
+    if (warp == 4)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols));
-    // G[i][j] = sum_k z_i w_j = D[w_j rows][z_i cols], hi and lo blocks added
-    float* out = a.partials + ((long long)p * a.C + c) * C::NACC;
-    for (int e = tid; e < C::NACC; e += C::kThreads) {
-        int i = 0;
-        while (i + 1 < d && gram_row_offset(i + 1, C::W) <= e) ++i;
-        const int j = i + (e - gram_row_offset(i, C::W));
-        const int rh = C::row_1(j), rl = C::row_2(j);
-        const int ch = i, cl = C::dq + i;
-        out[e] = (scratch[rh * C::kN + ch] + scratch[rl * C::kN + cl]) +
-                 (scratch[rh * C::kN + cl] + scratch[rl * C::kN + ch]);
-    }
 }
 
 }  // namespace irs

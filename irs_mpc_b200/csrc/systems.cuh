@@ -11,11 +11,21 @@
 //                        affine in v, so mean(J) == assemble(mean(v))
 //   project(x)           non-penetration projection of a sample (three_cart); no-op otherwise
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace irs {
 
 enum SystemId { kPendulum = 0, kBicycle = 1, kQuadrotor = 2, kThreeCart = 3, kNumSystems = 4 };
+
+// ---------------------------------------------------------------------------------------------
+// parameter i in the functor's scalar type: fp32 reads the host-rounded mirror
+template <typename R>
+__device__ __forceinline__ R prm(const SysParams& p, int i) {
+    if constexpr (std::is_same<R, float>::value) return p.f[i];
+    else return R(p.v[i]);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Pendulum — examples/pendulum/pendulum_dynamics.py:46-81 (dynamics), :110-127 (Jacobian).
@@ -28,7 +38,7 @@ struct Pendulum {
     static constexpr bool kHasJacobian = true;
     static constexpr bool kHasProjection = false;
     R h;
-    __device__ explicit Pendulum(const SysParams& p) : h(R(p.v[0])) {}
+    __device__ explicit Pendulum(const SysParams& p) : h(prm<R>(p, 0)) {}
 
     template <bool BATCH>
     __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
@@ -61,7 +71,7 @@ struct Bicycle {
     static constexpr bool kHasJacobian = true;
     static constexpr bool kHasProjection = false;
     R h;
-    __device__ explicit Bicycle(const SysParams& p) : h(R(p.v[0])) {}
+    __device__ explicit Bicycle(const SysParams& p) : h(prm<R>(p, 0)) {}
 
     template <bool BATCH>
     __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
@@ -118,9 +128,19 @@ struct Quadrotor {
     static constexpr bool kHasJacobian = true;
     static constexpr bool kHasProjection = false;
     R h, mass, L, g, I0, I1, I2, kF, kM;
+    // loop invariants (fp32: computed on the host in double precision, SysParams::f[9..16])
+    R inv_mass, inv_I0, inv_I1, inv_I2, LkF, dI12, dI20, dI01;
     __device__ explicit Quadrotor(const SysParams& p)
-        : h(R(p.v[0])), mass(R(p.v[1])), L(R(p.v[2])), g(R(p.v[3])), I0(R(p.v[4])),
-          I1(R(p.v[5])), I2(R(p.v[6])), kF(R(p.v[7])), kM(R(p.v[8])) {}
+        : h(prm<R>(p, 0)), mass(prm<R>(p, 1)), L(prm<R>(p, 2)), g(prm<R>(p, 3)), I0(prm<R>(p, 4)),
+          I1(prm<R>(p, 5)), I2(prm<R>(p, 6)), kF(prm<R>(p, 7)), kM(prm<R>(p, 8)) {
+        if constexpr (std::is_same<R, float>::value) {
+            inv_mass = p.f[9];  inv_I0 = p.f[10];  inv_I1 = p.f[11];  inv_I2 = p.f[12];
+            LkF = p.f[13];  dI12 = p.f[14];  dI20 = p.f[15];  dI01 = p.f[16];
+        } else {
+            inv_mass = R(1.0 / p.v[1]);  inv_I0 = R(1.0 / p.v[4]);  inv_I1 = R(1.0 / p.v[5]);
+            inv_I2 = R(1.0 / p.v[6]);  LkF = L * kF;  dI12 = I1 - I2;  dI20 = I2 - I0;  dI01 = I0 - I1;
+        }
+    }
 
     template <bool BATCH>
     __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
@@ -133,11 +153,11 @@ struct Quadrotor {
         // thrust and moments (:43-49)
         const R s03 = u[0] + u[3], s12 = u[1] + u[2];
         const R Fz = kF * (s03 + s12);
-        const R M0 = (L * kF) * ((u[2] + u[3]) - (u[0] + u[1]));
-        const R M1 = (L * kF) * (s12 - s03);
+        const R M0 = LkF * ((u[2] + u[3]) - (u[0] + u[1]));
+        const R M1 = LkF * (s12 - s03);
         const R M2 = kM * ((u[1] + u[3]) - (u[0] + u[2]));
         // translational acceleration: third column of Rz Ry Rx times Fz (:51-54, :150-189)
-        const R a = Fz * Math<R>::rcp(mass);
+        const R a = Fz * inv_mass;
         const R spcr = sp * cr;
         o[6] = x[6] + h * (a * (cy * spcr + sy * sr));
         o[7] = x[7] + h * (a * (sy * spcr - cy * sr));
@@ -148,9 +168,9 @@ struct Quadrotor {
         const R q = cr * rd1 + sr * cprd2;
         const R r = cr * cprd2 - sr * rd1;
         // pqr_d = I^-1 (M - pqr x I pqr) (:59)
-        const R pd = (M0 + (I1 - I2) * (q * r)) * Math<R>::rcp(I0);
-        const R qd = (M1 + (I2 - I0) * (r * p)) * Math<R>::rcp(I1);
-        const R rdd = (M2 + (I0 - I1) * (p * q)) * Math<R>::rcp(I2);
+        const R pd = (M0 + dI12 * (q * r)) * inv_I0;
+        const R qd = (M1 + dI20 * (r * p)) * inv_I1;
+        const R rdd = (M2 + dI01 * (p * q)) * inv_I2;
         // rpy_dd = Phi pqr_d + (dPhi/dt) pqr (:61-68, :204-231)
         const R tp = sp * icp;
         const R icp2 = icp * icp;
@@ -205,7 +225,7 @@ struct ThreeCart {
     static constexpr bool kHasJacobian = false;   // three_cart_dynamics.py:20
     static constexpr bool kHasProjection = true;
     R h, d;
-    __device__ explicit ThreeCart(const SysParams& p) : h(R(p.v[0])), d(R(p.v[1])) {}
+    __device__ explicit ThreeCart(const SysParams& p) : h(prm<R>(p, 0)), d(prm<R>(p, 1)) {}
 
     // case id: 0 none, 1 all three, 2 carts 1-2, 3 carts 2-3  (:146-157)
     __device__ __forceinline__ int contact_case(R q1, R q2, R q3) const {

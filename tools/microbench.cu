@@ -30,6 +30,12 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float fb, float 
             if (OP == 13) { float r; asm volatile("lg2.approx.ftz.f32 %0,%1;" : "=f"(r) : "f"(a[i])); a[i] = r; }
             if (OP == 14) { float r; asm volatile("sin.approx.ftz.f32 %0,%1;" : "=f"(r) : "f"(a[i])); a[i] = r; }
             if (OP == 15) { float r; asm volatile("rsqrt.approx.ftz.f32 %0,%1;" : "=f"(r) : "f"(a[i])); a[i] = r; }
+            if (OP == 16) { float r; asm volatile("cos.approx.ftz.f32 %0,%1;" : "=f"(r) : "f"(a[i])); a[i] = r; }
+            if (OP == 17) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0,%1,%2;" : "=r"(r) : "f"(a[i]), "f"(fb)); a[i] = __uint_as_float(r); }
+            if (OP == 18) { double dd = (double)a[i] * (double)fc; float r; asm volatile("cvt.rn.f32.f64 %0,%1;" : "=f"(r) : "d"(dd)); a[i] = r; }
+            if (OP == 19) { uint32_t r; asm volatile("prmt.b32 %0,%1,%2,0x7632;" : "=r"(r) : "r"(u[i]), "r"(ub)); u[i] = r + 1u; }
+            if (OP == 20) { uint32_t r; asm volatile("cvt.rna.tf32.f32 %0,%1;" : "=r"(r) : "f"(a[i])); a[i] = __uint_as_float(r); }
+            if (OP == 21) { uint32_t r; asm volatile("cvt.rn.f16x2.f32 %0,%1,%2;" : "=r"(r) : "f"(a[i]), "f"(fb)); a[i] = __uint_as_float(r); }
         }
     }
     float s = 0; for (int i = 0; i < CHAINS; ++i) s += a[i] + (float)u[i]; for (int i = 0; i < CHAINS / 2; ++i) s += p[i].x + p[i].y;
@@ -75,10 +81,10 @@ int main() {
     const int blocks = 148 * 8, threads = 256, iters = 4000;
     float* out; cudaMalloc(&out, blocks * threads * sizeof(float));
     const double clk = 1.965e9;
-    const char* names[] = {"FFMA", "FFMA2(instr)", "IMAD.lo", "IMAD.HI", "IMAD.WIDE+xor", "sinf(MUFU+FMUL)", "__log2f", "sqrt.approx", "rcp.approx", "LOP3+SHF+IADD(3 ops)", "FMUL", "FADD", "ex2.approx", "lg2.approx.ftz", "sin.approx.ftz", "rsqrt.approx"};
+    const char* names[] = {"FFMA", "FFMA2(instr)", "IMAD.lo", "IMAD.HI", "IMAD.WIDE+xor", "sinf(MUFU+FMUL)", "__log2f", "sqrt.approx", "rcp.approx", "LOP3+SHF+IADD(3 ops)", "FMUL", "FADD", "ex2.approx", "lg2.approx.ftz", "sin.approx.ftz", "rsqrt.approx", "cos.approx.ftz", "cvt.bf16x2(F2FP)", "DMUL+cvt.f32.f64", "PRMT+IADD", "cvt.rna.tf32", "cvt.f16x2(F2FP)"};
 #define RUN(OP, PER) { double t = timeit([&] { k<OP><<<blocks, threads>>>(out, iters, 0.999f, 1e-3f, 2654435761u); }); \
         double ops = (double)blocks * threads * iters * PER; printf("%-24s %8.3f ms  %7.2f thread-ops/clk/SM\n", names[OP], t * 1e3, ops / (t * clk * 148)); }
-    RUN(0, 8) RUN(1, 4) RUN(2, 8) RUN(3, 8) RUN(4, 8) RUN(5, 8) RUN(6, 8) RUN(7, 8) RUN(8, 8) RUN(9, 8) RUN(10, 8) RUN(11, 8) RUN(12, 8) RUN(13, 8) RUN(14, 8) RUN(15, 8)
+    RUN(0, 8) RUN(1, 4) RUN(2, 8) RUN(3, 8) RUN(4, 8) RUN(5, 8) RUN(6, 8) RUN(7, 8) RUN(8, 8) RUN(9, 8) RUN(10, 8) RUN(11, 8) RUN(12, 8) RUN(13, 8) RUN(14, 8) RUN(15, 8) RUN(16, 8) RUN(17, 8) RUN(18, 8) RUN(19, 8) RUN(20, 8) RUN(21, 8)
     const char* mn[] = {"8 FFMA", "8 FFMA + 2 EX2", "8 FFMA + 4 IMAD.WIDE", "8 FFMA + 4x(3 ALU)"};
 #define RUNM(M) { double t = timeit([&] { mix<M><<<blocks, threads>>>(out, iters, 0.999f, 1e-3f, 2654435761u); }); \
         printf("%-24s %8.3f ms  (FFMA-only equivalent %.2f FFMA/clk/SM)\n", mn[M], t * 1e3, (double)blocks * threads * iters * 8 / (t * clk * 148)); }
