@@ -98,7 +98,7 @@ static int tc_stages() {
     static int g = -1;
     if (g < 0) {
         const char* e = getenv("IRS_TC_STAGES");
-        g = (e && atoi(e) == 1) ? 1 : 2;
+        g = (e && atoi(e) == 2) ? 2 : 1;      // measured: one tile per warp is fastest
     }
     return g;
 }
@@ -116,7 +116,7 @@ static int num_sms() {
 template <class Sys, int NSTAGE>
 static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
     using C = TcCfg<Sys>;
-    const size_t smem = (size_t)NSTAGE * C::kStageBytes;
+    const size_t smem = (size_t)NSTAGE * C::kWarps * C::kStageBytes;
     auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -335,8 +335,7 @@ int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long
     // that a timestep-sharded run (P split over ranks) sums in exactly the same order as the
     // single-GPU run and reproduces it bit for bit.
     const long long tile = 128;
-    // tensor-core path = persistent kernel: small items cost almost nothing and balance the SMs
-    long long target = (order == 0 && use_tensor_cores(system)) ? 1024 : 4096;
+    long long target = 4096;
     const char* e = getenv("IRS_CHUNK_SAMPLES");
     if (e && atoll(e) > 0) target = atoll(e);
     long long c = (N + target - 1) / target;

@@ -8,24 +8,23 @@
 //     D[64 x N] (TMEM, fp32)  +=  A[64 x 16] (smem)  *  B[16 x N] (smem),     kind::f16 (bf16), MN-major
 //
 // A rows ("features") = [ z_1 | z_2 | dF_1 | dF_2 ],  B = the first N = 2*dq rows of the SAME smem
-// array = [ z_1 | z_2 ].  Every fp32 value x is split into two bf16 pieces, x ~ x_1 + x_2 with
-// x_1 = bf16_rn(x), x_2 = bf16_rn(x - x_1)  (|x - x_1 - x_2| <= 2^-18 |x|, round-to-nearest, so the
-// residual is zero-mean and averages out over the samples); D then holds all four partial products
-// and their sum reproduces the fp32 product to ~2^-17 relative — far inside the 1e-4 budget, and the
-// bf16 operands halve the shared-memory traffic of a tf32 split (the UMMA operand reads were the
-// bottleneck of the tf32 variant: 3 KB per 8 samples against 128 B/clk of smem bandwidth).
+// array = [ z_1 | z_2 ].  Every fp32 value x is split into two bf16 pieces, x ~ x_1 - x_2' with
+// x_1 = bf16_rn(x), x_2' = bf16_rn(x_1 - x)  (|x - x_1 + x_2'| <= 2^-18 |x|, round-to-nearest, so
+// the residual is zero-mean and averages out over the samples; the second piece is stored negated
+// because the sm_100 mixed-precision subtract FHADD.BF16 yields x_1 - x without unpacking).  D then
+// holds all four partial products and their signed sum reproduces the fp32 product to ~2^-17
+// relative — far inside the 1e-4 budget, and the bf16 operands halve the shared-memory traffic of a
+// tf32 split (the UMMA operand reads were the bottleneck of the tf32 variant: 3 KB per 8 samples
+// against 128 B/clk of smem bandwidth).
 //
 // MN-major canonical layout without swizzle (conventions verified on hardware by
 // tools/test_umma3.cu):
 //     byte address of (feature f, sample k) = (f/8)*SBO + (k/8)*LBO + (k%8)*16 + (f%8)*2
-// with LBO = 128 B, SBO = (samples per stage / 8) * 128 B: a thread (lane = sample) stores 8
+// with LBO = 128 B, SBO = (samples per tile / 8) * 128 B: a thread (lane = sample) stores 8
 // consecutive features with one 16-byte STS and a warp's store covers 512 contiguous bytes.
 #pragma once
 #include "smooth.cuh"
 
-#ifndef IRS_TC_POLL_NS
-#define IRS_TC_POLL_NS 100      // back-off of the UMMA warp while it waits for a stage
-#endif
 #ifndef IRS_TC_MIN_BLOCKS
 #define IRS_TC_MIN_BLOCKS 4
 #endif
@@ -49,22 +48,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-// Wait for the phase with the given parity to complete.  try_wait suspends the thread in hardware
-// for at most a short, implementation-defined time; without a back-off a warp that waits for
-// thousands of cycles (the UMMA warp waiting for a stage) polls every ~25 cycles and its
-// SYNCS/BRA pairs take issue slots away from the sample producers (ncu: 18 % of all issued
-// instructions).  SLEEP_NS > 0 inserts a nanosleep between polls.
-template <int SLEEP_NS = 0>
+// Wait for the phase with the given parity to complete (try_wait suspends the thread in hardware
+// for a short, implementation-defined time; the loop re-arms it).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
-    while (true) {
+    while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-        if (done) break;
-        if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     }
 }
 
@@ -77,13 +70,15 @@ struct TcCfg {
     static constexpr int kN = 2 * dq;                    // UMMA N (columns of D): [z_1 | z_2]
     static constexpr int kRows = 2 * dq + 2 * nq;        // used rows of A (<= 64)
     static constexpr int kM = 64;
-    static constexpr int kThreads = 160;                 // 4 producer warps (lane = sample) + 1 UMMA warp
-    static constexpr int kTile = 128;                    // samples per stage
+    static constexpr int kWarps = 4;                     // self-contained warp pipelines per block
+    static constexpr int kThreads = 32 * kWarps;         // lane = sample
+    static constexpr int kTile = kThreads;               // samples per block round
+    static constexpr int kWarpTile = 32;                 // samples per warp tile (two K = 16 UMMAs)
     static constexpr int kLBO = 128;                     // bytes between k-groups (8 samples)
-    static constexpr int kSBO = (kTile / 8) * kLBO;      // bytes between 8-feature groups (2048)
+    static constexpr int kSBO = (kWarpTile / 8) * kLBO;  // bytes between 8-feature groups (512)
     static constexpr int kGroups = kM / 8;
-    static constexpr int kStageBytes = kGroups * kSBO;   // 16,384
-    static constexpr int kTmemCols = 2 * kN < 32 ? 32 : 2 * kN;   // two accumulators (double buffered)
+    static constexpr int kStageBytes = kGroups * kSBO;   // 4,096 per warp tile
+    static constexpr int kTmemCols = kWarps * kN < 32 ? 32 : kWarps * kN;   // one accumulator per warp
     static constexpr int NACC = gram_nacc(n, m);
     static constexpr int RS = (W + 1) / 2 * 2;
     static_assert(kRows <= kM, "operand rows must fit one M = 64 UMMA");
@@ -98,52 +93,43 @@ struct TcCfg {
     __host__ __device__ static constexpr int row_2(int j) { return j < d ? dq + j : 2 * dq + nq + (j - d); }
 };
 
-// fp32 pair -> two packed bf16x2 words: first pieces and second pieces (low half = v0, high half = v1)
+// fp32 pair -> two packed bf16x2 words (low half = v0, high half = v1): first pieces p1 = bf16_rn(v)
+// and NEGATED second pieces p2 = bf16_rn(p1 - v).  The residual uses the mixed-precision subtract of
+// sm_100 (sub.f32.bf16 -> FHADD.BF16 with a half-register selector), so no unpacking instructions:
+// 4 instructions per pair.  The sign of the second pieces is undone when the accumulator is read.
 __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& p1, uint32_t& p2) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v1), "f"(v0));
-    const float r0 = v0 - __uint_as_float(p1 << 16);
-    const float r1 = v1 - __uint_as_float(p1 & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void producer_bar_sync() {      // named barrier 1: the 4 producer warps only
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float n0, n1;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+        "sub.rn.f32.bf16 %0, lo, %3;\n\tsub.rn.f32.bf16 %1, hi, %4;\n\t}"
+        : "=f"(n0), "=f"(n1)
+        : "r"(p1), "f"(v0), "f"(v1));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(n1), "f"(n0));
 }
 
 // Persistent kernel.  A work item is one (nominal point p, sample chunk c); blocks walk the item
 // list with stride gridDim.x, so the result layout (partials[p][c]) does not depend on the grid.
 //
-// Warp roles
-//   warps 0-3  sample producers (lane = sample): Philox / replay -> perturb -> dynamics -> bf16x2
-//              split -> stage in shared memory -> arrive on the stage's "full" mbarrier.  With
-//              NSTAGE = 2 they run one stage ahead of the tensor core and never meet a block-wide
-//              barrier inside the sample loop.
-//   warp 4     owns the tensor core: waits for "full", issues the UMMAs of the stage from one lane and
-//              commits them to the stage's "empty" mbarrier.  It also prepares the NEXT item's nominal
-//              point (xbar, ubar, f(xbar, ubar) as fp32) in shared memory, so the producers start an
-//              item with 40 LDS instead of a chain of global loads and a dynamics evaluation.
-// The accumulator is double buffered in TMEM (item k uses buffer k & 1): the producers read item
-// k's Gram block back after they have staged the FIRST tile of item k + 1, when its UMMAs have long
-// retired, so the item switch costs neither a pipeline drain nor a wait.
+// Every warp is a self-contained pipeline: it generates 32 samples per round (lane = sample:
+// Philox / replay -> perturb -> dynamics -> bf16x2 split), stages them in its OWN ring of
+// shared-memory tiles, and one elected lane issues the two UMMAs (K = 16 samples each) of the tile
+// into the warp's OWN accumulator in TMEM, committing them to the tile's "empty" mbarrier.  There
+// is no cross-warp synchronisation inside an item: no "full" barrier, no dedicated MMA warp, no
+// block barrier.  (tcgen05.mma from different threads are not ordered against each other, hence one
+// accumulator per issuing warp.)  At the end of an item the block meets once: every warp reads its
+// TMEM lane quarter of all four accumulators, adds them and the packed Gram block is written.
 template <class Sys, int NSTAGE>
-__global__ void __launch_bounds__(160, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_kernel(const SmoothArgs a) {
+__global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_kernel(const SmoothArgs a) {
     using C = TcCfg<Sys>;
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int kXU = (n + m + 3) / 4 * 4;             // xbar | ubar, padded to float4
     constexpr int kNom = kXU + (n + 3) / 4 * 4;          // ... | fbar, padded to float4
     constexpr int kScr = C::dq + 1;                      // padded scratch row (bank-conflict free)
-    extern __shared__ __align__(1024) unsigned char stage_mem[];
-    __shared__ uint64_t mbar_full[NSTAGE];               // producers -> UMMA warp: stage staged
-    __shared__ uint64_t mbar_empty[NSTAGE];              // UMMA commit -> producers: stage drained
-    __shared__ uint64_t mbar_done[2];                    // UMMA commit -> producers: accumulator complete
-    __shared__ uint64_t mbar_acc_free[2];                // producers -> UMMA warp: accumulator read back
-    __shared__ uint64_t mbar_nom[2];                     // UMMA warp -> producers: nominal point ready
+    extern __shared__ __align__(128) unsigned char stage_mem[];   // [warp][stage][kStageBytes]
+    __shared__ uint64_t mbar_empty[C::kWarps][NSTAGE];   // UMMA commit -> owning warp: tile drained
+    __shared__ uint64_t mbar_done[C::kWarps];            // UMMA commit -> owning warp: accumulator complete
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float nom_s[2][kNom];
+    __shared__ __align__(16) float nom_s[kNom];          // nominal point of the current item (fp32)
     __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][i] + D[r][dq + i]
     __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
 
@@ -152,15 +138,10 @@ __global__ void __launch_bounds__(160, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&mbar_full[s], C::kTile);      // every producer thread arrives
-            mbar_init(&mbar_empty[s], 1);            // one tcgen05.commit arrives
-        }
+        for (int w = 0; w < C::kWarps; ++w) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&mbar_done[b], 1);
-            mbar_init(&mbar_acc_free[b], C::kTile);
-            mbar_init(&mbar_nom[b], 1);
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&mbar_empty[w][s], 1);
+            mbar_init(&mbar_done[w], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -169,214 +150,195 @@ __global__ void __launch_bounds__(160, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         while (i + 1 < d && gram_row_offset(i + 1, C::W) <= e) ++i;
         idx_s[e] = (uint16_t)((i << 8) | (i + (e - gram_row_offset(i, C::W))));
     }
-    if (warp == 4) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(C::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    const Sys sys(a.prm);
+    // nominal point of an item -> nom_s (two block barriers inside; all threads call it)
+    auto load_nominal = [&](long long item) {
+        const int p = (int)(item / a.C);
+        if (tid < n) nom_s[tid] = (float)a.x_nom[(long long)p * n + tid];
+        else if (tid < n + m) nom_s[tid] = (float)a.u_nom[(long long)p * m + (tid - n)];
+        __syncthreads();
+        if (tid == 0) {
+            float xb[n], ub[m], fb[n];
+#pragma unroll
+            for (int q = 0; q < n; ++q) xb[q] = nom_s[q];
+#pragma unroll
+            for (int q = 0; q < m; ++q) ub[q] = nom_s[n + q];
+            sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
+#pragma unroll
+            for (int q = 0; q < n; ++q) nom_s[kXU + q] = fb[q];
+        }
+        __syncthreads();
+    };
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = tmem_base_s;
-    const Sys sys(a.prm);
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(warp * C::kN);      // this warp's accumulator
 
-    if (warp == 4) {
-        // ===== UMMA issuer + nominal-point prefetcher =====
-        const uint32_t stage_base = smem_u32(stage_mem);
-        // nominal point of item `item` -> nom_s[buf]; the buffer was last read by the producers two
-        // items ago, and every producer has arrived on a "full" barrier of the item in between
-        auto prepare_nominal = [&](long long item, int buf) {
-            const int p = (int)(item / a.C);
-            float* dst = nom_s[buf];
-            if (lane < n) dst[lane] = (float)a.x_nom[(long long)p * n + lane];
-            else if (lane < n + m) dst[lane] = (float)a.u_nom[(long long)p * m + (lane - n)];
-            __syncwarp();
-            if (lane == 0) {
-                float xb[n], ub[m], fb[n];
-#pragma unroll
-                for (int q = 0; q < n; ++q) xb[q] = dst[q];
-#pragma unroll
-                for (int q = 0; q < m; ++q) ub[q] = dst[n + q];
-                sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
-#pragma unroll
-                for (int q = 0; q < n; ++q) dst[kXU + q] = fb[q];
-                mbar_arrive(&mbar_nom[buf]);            // release: the stores above are visible to waiters
-            }
-            __syncwarp();
-        };
-        static_assert(n + m <= 32, "one lane per nominal coordinate");
-        if ((long long)blockIdx.x < num_items) prepare_nominal(blockIdx.x, 0);
-        int round = 0;                                    // running round counter of this block
-        int it = 0;                                       // running item counter of this block
-        for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-            if (item + gridDim.x < num_items) prepare_nominal(item + gridDim.x, (it + 1) & 1);
-            if (lane == 0) {
-                const int buf = it & 1;
-                const int c = (int)(item % a.C);
-                const long long s_begin = (long long)c * a.S;
-                const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
-                const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * C::kN);
-                if (it >= 2) {       // the producers must have read this buffer's previous item back
-                    mbar_wait(&mbar_acc_free[buf], (uint32_t)(((it >> 1) - 1) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                }
-                for (int r = 0; r < rounds; ++r, ++round) {
-                    const int stage = round % NSTAGE;
-                    mbar_wait<IRS_TC_POLL_NS>(&mbar_full[stage], (uint32_t)((round / NSTAGE) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint64_t desc0 = umma_smem_desc(stage_base + stage * C::kStageBytes, C::kLBO, C::kSBO);
-#pragma unroll
-                    for (int kb = 0; kb < C::kTile / 16; ++kb) {   // one UMMA = K 16 = two k-groups of 8 samples
-                        const uint64_t desc = desc0 + (uint64_t)((kb * 2 * C::kLBO) >> 4);
-                        const uint32_t acc = (r > 0 || kb > 0) ? 1u : 0u;   // first UMMA of an item overwrites
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_acc),
-                            "l"(desc), "l"(desc), "r"(C::kIdesc), "r"(acc)
-                            : "memory");
-                    }
-                    // frees the stage once these UMMAs have read it (commit implies fence::before_thread_sync)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     smem_u32(&mbar_empty[stage]))
-                                 : "memory");
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                 smem_u32(&mbar_done[buf]))
-                             : "memory");
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== sample producers =====
-        [[maybe_unused]] const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
-        // byte offset of this thread's sample inside a stage (feature group 0): (k/8)*LBO + (k%8)*16
-        const uint32_t my_off = (uint32_t)(tid >> 3) * C::kLBO + (uint32_t)(tid & 7) * 16;
+    [[maybe_unused]] const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
+    // this warp's tile ring; byte offset of this lane's sample inside a tile (feature group 0)
+    unsigned char* my_ring = stage_mem + (size_t)warp * NSTAGE * C::kStageBytes;
+    const uint32_t ring_u32 = smem_u32(my_ring);
+    const uint32_t my_off = (uint32_t)(lane >> 3) * C::kLBO + (uint32_t)(lane & 7) * 16;
+    const float4* nom4 = reinterpret_cast<const float4*>(nom_s);
 
-        // Read item (`item`, local index `it`)'s accumulator back and write its packed Gram block.
-        // Row r of D lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64 layout): lanes 0-15 of warp w
-        // hold rows 16 w .. 16 w + 15.
-        auto epilogue = [&](long long item, int it) {
-            const int buf = it & 1;
-            mbar_wait(&mbar_done[buf], (uint32_t)((it >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            uint32_t v[C::kN];
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(buf * C::kN);
+    // Issue the UMMAs of a staged tile (all lanes call it; one lane issues).
+    auto issue_tile = [&](int stage, bool first, bool last) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
+        __syncwarp();
+        if (lane == 0) {
+            const uint64_t desc0 = umma_smem_desc(ring_u32 + stage * C::kStageBytes, C::kLBO, C::kSBO);
 #pragma unroll
-            for (int c0 = 0; c0 < C::kN; c0 += 16) {
+            for (int kb = 0; kb < C::kWarpTile / 16; ++kb) {   // one UMMA = K 16 = two k-groups of 8 samples
+                const uint64_t desc = desc0 + (uint64_t)((kb * 2 * C::kLBO) >> 4);
+                const uint32_t acc = (!first || kb > 0) ? 1u : 0u;   // first UMMA of an item overwrites
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]),
-                      "=r"(v[c0 + 5]), "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]),
-                      "=r"(v[c0 + 10]), "=r"(v[c0 + 11]), "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]),
-                      "=r"(v[c0 + 15])
-                    : "r"(taddr + c0));
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_acc),
+                    "l"(desc), "l"(desc), "r"(C::kIdesc), "r"(acc)
+                    : "memory");
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(&mbar_acc_free[buf]);             // the UMMA warp may overwrite this buffer now
+            // frees the tile once these UMMAs have read it (commit implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(&mbar_empty[warp][stage]))
+                         : "memory");
+            if (last)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 smem_u32(&mbar_done[warp]))
+                             : "memory");
+        }
+        __syncwarp();
+    };
+
+    int round = 0;      // running round counter of this warp (tile ring position)
+    int it = 0;         // running item counter of this block
+    for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int p = (int)(item / a.C);
+        const int c = (int)(item % a.C);
+        const long long s_begin = (long long)c * a.S;
+        const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+        const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
+        load_nominal(item);
+        for (int r = 0; r < rounds; ++r, ++round) {
+            const int stage = round % NSTAGE;
+            const long long s = s_begin + (long long)r * C::kTile + tid;
+            float w[C::RS];
+            if (s < s_end) {
+                if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
+                draw_deltas<Sys, C::RS>(a, p, s, w);
+                project_deltas<Sys, C::RS>(a, p, w);
+                float xu[kXU], f[n];
+                // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers:
+                // measured faster than the register copy, which costs occupancy-neutral spills)
+#pragma unroll
+                for (int q = 0; q < kXU / 4; ++q) {
+                    const float4 v = nom4[q];
+                    xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < d; ++q) xu[q] += w[q];
+                if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar
+                    if (batch) sys.template step<true>(xu, xu + n, f);
+                    else sys.template step<false>(xu, xu + n, f);
+                } else {
+                    sys.template step<false>(xu, xu + n, f);
+                }
+#pragma unroll
+                for (int q = 0; q < (n + 3) / 4; ++q) {
+                    const float4 v = nom4[kXU / 4 + q];
+                    const float fb[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (4 * q + k < n) w[d + 4 * q + k] = f[4 * q + k] - fb[k];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
+            }
+            // the tile must have been drained by the UMMAs that last read it
+            if (round >= NSTAGE) mbar_wait(&mbar_empty[warp][stage], (uint32_t)((round / NSTAGE - 1) & 1));
+            unsigned char* sm = my_ring + stage * C::kStageBytes + my_off;
+            // regressors: dq/8 groups of 8 features, first and second bf16 pieces
+#pragma unroll
+            for (int g = 0; g < C::dq / 8; ++g) {
+                uint32_t p1[4], p2[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
+                    split_bf16x2(c0 < d ? w[c0] : 0.f, c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
+                }
+                *reinterpret_cast<uint4*>(sm + (C::grp_z1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                *reinterpret_cast<uint4*>(sm + (C::grp_z2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+            }
+            // responses
+#pragma unroll
+            for (int g = 0; g < C::nq / 8; ++g) {
+                uint32_t p1[4], p2[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
+                    split_bf16x2(c0 < n ? w[d + c0] : 0.f, c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
+                }
+                *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+            }
+            issue_tile(stage, r == 0, r == rounds - 1);
+        }
+        // ---- item finished: wait for this warp's UMMAs, meet the other warps, read all four
+        //      accumulators back.  Row r of D lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64
+        //      layout): lanes 0-15 of warp w hold rows 16 w .. 16 w + 15 of every accumulator. ----
+        mbar_wait(&mbar_done[warp], (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        {
+            float sum[C::kN];
+#pragma unroll
+            for (int q = 0; q < C::kN; ++q) sum[q] = 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+#pragma unroll
+            for (int wa = 0; wa < C::kWarps; ++wa) {
+                uint32_t v[C::kN];
+#pragma unroll
+                for (int c0 = 0; c0 < C::kN; c0 += 16) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]),
+                          "=r"(v[c0 + 5]), "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]),
+                          "=r"(v[c0 + 10]), "=r"(v[c0 + 11]), "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]),
+                          "=r"(v[c0 + 15])
+                        : "r"(taddr + (uint32_t)(wa * C::kN + c0)));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < C::kN; ++q) sum[q] += __uint_as_float(v[q]);    // fixed warp order
+            }
             const int row = 16 * warp + lane;
             if (lane < 16 && row < C::kRows) {
 #pragma unroll
-                for (int i = 0; i < C::dq; ++i)
-                    scratch[row * kScr + i] = __uint_as_float(v[i]) + __uint_as_float(v[C::dq + i]);
+                for (int i = 0; i < C::dq; ++i) scratch[row * kScr + i] = sum[i] - sum[C::dq + i];   // z_2 columns are negated
             }
-            producer_bar_sync();
-            // G[i][j] = sum_k z_i w_j = sum over the two pieces of w_j of s_row[i]
-            float* out = a.partials + item * C::NACC;
-            for (int e = tid; e < C::NACC; e += C::kTile) {
-                const int ij = idx_s[e];
-                const int i = ij >> 8, j = ij & 0xff;
-                out[e] = scratch[C::row_1(j) * kScr + i] + scratch[C::row_2(j) * kScr + i];
-            }
-            producer_bar_sync();      // the next epilogue overwrites the scratch
-        };
-
-        int round = 0;
-        int it = 0;
-        long long prev_item = -1;
-        for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-            const int p = (int)(item / a.C);
-            const int c = (int)(item % a.C);
-            const long long s_begin = (long long)c * a.S;
-            const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
-            const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
-            // The nominal point stays in shared memory: xbar/ubar/fbar are re-read (7 broadcast
-            // LDS.128 per sample) instead of living in 28 registers per thread.
-            mbar_wait(&mbar_nom[it & 1], (uint32_t)((it >> 1) & 1));
-            const float4* nom4 = reinterpret_cast<const float4*>(nom_s[it & 1]);
-            for (int r = 0; r < rounds; ++r, ++round) {
-                const int stage = round % NSTAGE;
-                const long long s = s_begin + (long long)r * C::kTile + tid;
-                float w[C::RS];
-                if (s < s_end) {
-                    if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
-                    draw_deltas<Sys, C::RS>(a, p, s, w);
-                    project_deltas<Sys, C::RS>(a, p, w);
-                    float xu[kXU], f[n];
-#pragma unroll
-                    for (int q = 0; q < kXU / 4; ++q) {
-                        const float4 v = nom4[q];
-                        xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
-                    }
-#pragma unroll
-                    for (int q = 0; q < d; ++q) xu[q] += w[q];
-                    if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar
-                        if (batch) sys.template step<true>(xu, xu + n, f);
-                        else sys.template step<false>(xu, xu + n, f);
-                    } else {
-                        sys.template step<false>(xu, xu + n, f);
-                    }
-#pragma unroll
-                    for (int q = 0; q < (n + 3) / 4; ++q) {
-                        const float4 v = nom4[kXU / 4 + q];
-                        const float fb[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (4 * q + k < n) w[d + 4 * q + k] = f[4 * q + k] - fb[k];
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
-                }
-                // the stage must have been drained by the UMMAs that last read it
-                if (round >= NSTAGE) mbar_wait(&mbar_empty[stage], (uint32_t)((round / NSTAGE - 1) & 1));
-                unsigned char* sm = stage_mem + stage * C::kStageBytes + my_off;
-                // regressors: dq/8 groups of 8 features, first and second bf16 pieces
-#pragma unroll
-                for (int g = 0; g < C::dq / 8; ++g) {
-                    uint32_t p1[4], p2[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
-                        split_bf16x2(c0 < d ? w[c0] : 0.f, c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
-                    }
-                    *reinterpret_cast<uint4*>(sm + (C::grp_z1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                    *reinterpret_cast<uint4*>(sm + (C::grp_z2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-                }
-                // responses
-#pragma unroll
-                for (int g = 0; g < C::nq / 8; ++g) {
-                    uint32_t p1[4], p2[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
-                        split_bf16x2(c0 < n ? w[d + c0] : 0.f, c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
-                    }
-                    *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                    *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
-                mbar_arrive(&mbar_full[stage]);
-                if (r == 0 && prev_item >= 0) epilogue(prev_item, it - 1);
-            }
-            prev_item = item;
         }
-        if (prev_item >= 0) epilogue(prev_item, it - 1);
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();      // scratch complete; every accumulator read back (next item may overwrite)
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        // G[i][j] = sum_k z_i w_j = sum over the two pieces of w_j of s_row[i] (second-piece rows negated)
+        float* out = a.partials + item * C::NACC;
+        for (int e = tid; e < C::NACC; e += C::kThreads) {
+            const int ij = idx_s[e];
+            const int i = ij >> 8, j = ij & 0xff;
+            out[e] = scratch[C::row_1(j) * kScr + i] - scratch[C::row_2(j) * kScr + i];
+        }
+        // (the two barriers of the next load_nominal order these scratch reads before its next writes)
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 4)
+    if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols));
 }
 
