@@ -32,6 +32,7 @@ N_SAMPLES = 100000
 FLOPS_PER_SAMPLE = 838        # quadrotor zero-order, algorithmic, FMA = 2
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 SEED0 = 0x1255 + 3
+DRAM_BYTES_PER_LAUNCH = 48896   # ncu capture of the dominant kernel, see roofline.traffic_source
 
 
 def log(*a):
@@ -39,19 +40,21 @@ def log(*a):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons every 50 ms from process start; the report uses
+    the samples that arrived inside the load windows (timed regions + a sustained repeat of the
+    same step, because K steps of this workload last only a few milliseconds)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -60,7 +63,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def samples_in_windows(self):
+        return sum(1 for t, _ in self.rows if any(a <= t <= b for a, b in self.windows))
 
     def stop(self):
         if self.proc is None:
@@ -72,7 +81,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not any(a <= t <= b for a, b in self.windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -83,7 +94,9 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "how": "nvidia-smi -lms 50; samples inside the timed regions and a >=1.5 s sustained repeat "
+                       "of the same step"}
 
 
 def quadrotor_problem(for_cpu=False):
@@ -165,6 +178,9 @@ def run_reference(args, rank, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args, rank, local_rank, world):
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -218,11 +234,8 @@ def run_gpu(args, rank, local_rank, world):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-
     # 1. headline: device-resident throughput of the whole smoothing pass
+    t_w0 = time.time()
     ms = timed(step_device, args.steps, args.warmup)
     samples_per_step = world * T_STEPS * N_SAMPLES
     value = samples_per_step * args.steps / (ms * 1e-3)
@@ -232,6 +245,17 @@ def run_gpu(args, rank, local_rank, world):
         smoothing.accumulate(system, smoothing.ZERO_ORDER, x_nom, u_nom, N_SAMPLES, ws, sigma=sigma,
                              seed=SEED0 + 1000 + k, it=1)
     ms_kernel = timed(only_accumulate, args.steps, 1) / args.steps
+    clocks.window(t_w0, time.time())
+    # sustained repeat of the same step so that the 50 ms sampler sees the clocks under this load
+    t_l0 = time.time()
+    n_load = int(min(200000, max(100, 2000.0 / max(ms / args.steps, 1e-3))))   # ~2 s, same count on all ranks
+    for k in range(n_load):
+        step_device(100000 + k)
+        if k % 256 == 255:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks.window(t_l0, time.time())
+    barrier()
     clock_info = clocks.stop() if rank == 0 else None
 
     # 3. measured FP32 FMA peak (roofline denominator), best of 5
@@ -263,8 +287,11 @@ def run_gpu(args, rank, local_rank, world):
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 3))
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
     n, m = 12, 4
-    h2d = T_STEPS * (n + m) * 8 + (n + m) * 4
-    d2h = T_STEPS * (n * n + n * m + n) * 8 + T_STEPS * 4
+    if world == 1:
+        h2d, d2h = solver._io_bytes()            # counted from the buffers the API copies
+    else:
+        h2d = T_STEPS * (n + m) * 8
+        d2h = T_STEPS * (n * n + n * m + n) * 8 + T_STEPS * 4
 
     # 5. iRS-LQR iterations/s: local_descent (smoothing + Riccati + closed-loop rollout) + evaluate_cost,
     #    teacher-forced from the initial trajectory, through the public numpy API (replicated per rank)
@@ -300,21 +327,26 @@ def run_gpu(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "quadrotor zero-order T=100 N=1e5/step/GPU (BASELINE.json configs[2])",
                        "system": "quadrotor n=12 m=4", "mode": "zero_order", "T": T_STEPS,
-                       "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-10 in-kernel",
+                       "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-7 + Box-Muller in-kernel",
                        "sharding": "none" if world == 1 else "sample axis, all_gather of fp64 Gram blocks",
                        "l2": "no per-sample HBM input (noise generated in registers); seed changes every step"},
             "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_kernel<Quadrotor,G>",
+            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1>",
                          "achieved": achieved_tflops, "peak": best, "unit": "TFLOP/s",
                          "frac": achieved_tflops / best if best > 0 else None,
                          "peak_source": "measured on this box: dependent-chain FFMA microbenchmark (irs_fp32_fma_peak); "
                                         "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % FP32_NOMINAL_TFLOPS,
                          "frac_of_nominal": achieved_tflops / FP32_NOMINAL_TFLOPS,
                          "flops_per_sample": FLOPS_PER_SAMPLE, "kernel_ms": ms_kernel,
-                         "traffic": None,
+                         "traffic": DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                           "(profiles/r1_smooth_tc_full.txt): the kernel reads the nominal points and "
+                                           "writes 3.3 MB of packed Gram blocks that stay in L2",
+                         "bound_note": "Philox mode has no per-sample HBM stream, so the kernel is bounded by FP32 "
+                                       "issue, not by HBM or the tensor pipe (DESIGN.md 3.1)",
                          "hbm_gbs_measured_peak": peaks.get("hbm_gbs")},
             "cpu_baseline": cpu,
             "clocks": clock_info,

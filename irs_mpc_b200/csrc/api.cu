@@ -433,14 +433,14 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
     a.R = nranks;  a.P = P;  a.C = C;  a.n_total = n_total;
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.status = status;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((P + 3) / 4);
+    const unsigned grid = (unsigned)P;      // one block per nominal point
     if (order == 0) {
-        IRS_DISPATCH_SYSTEM(system, double, Sys, (finalize_zero_order_kernel<Sys><<<grid, 128, 0, st>>>(a)));
+        IRS_DISPATCH_SYSTEM(system, double, Sys, (finalize_zero_order_kernel<Sys><<<grid, kFinalizeThreads, 0, st>>>(a)));
     } else {
         switch (system) {
-            case kPendulum: finalize_first_order_kernel<Pendulum<double>><<<grid, 128, 0, st>>>(a); break;
-            case kBicycle: finalize_first_order_kernel<Bicycle<double>><<<grid, 128, 0, st>>>(a); break;
-            case kQuadrotor: finalize_first_order_kernel<Quadrotor<double>><<<grid, 128, 0, st>>>(a); break;
+            case kPendulum: finalize_first_order_kernel<Pendulum<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
+            case kBicycle: finalize_first_order_kernel<Bicycle<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
+            case kQuadrotor: finalize_first_order_kernel<Quadrotor<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
             default: set_error("unknown system id %d", system); return 1;
         }
     }
@@ -520,10 +520,16 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
     IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
     TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T};
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((I + kTvlqrWarps - 1) / kTvlqrWarps);
+    // few instances: one block per instance (latency); many: one warp per instance (throughput)
+    const bool per_block = I <= 2 * num_sms();
     IRS_DISPATCH_DIMS(n, m, {
-        const size_t smem = sizeof(TvlqrSmem<N_, M_>) * kTvlqrWarps;
-        tvlqr_riccati_kernel<N_, M_><<<grid, 32 * kTvlqrWarps, smem, st>>>(a);
+        if (per_block) {
+            tvlqr_riccati_kernel<N_, M_, kTvlqrBlockThreads>
+                <<<(unsigned)I, kTvlqrBlockThreads, sizeof(TvlqrSmem<N_, M_>), st>>>(a);
+        } else {
+            const unsigned grid = (unsigned)((I + kTvlqrWarps - 1) / kTvlqrWarps);
+            tvlqr_riccati_kernel<N_, M_, 32><<<grid, 32 * kTvlqrWarps, sizeof(TvlqrSmem<N_, M_>) * kTvlqrWarps, st>>>(a);
+        }
     });
     return check_launch("tvlqr_riccati_kernel");
 }
@@ -551,7 +557,7 @@ int irs_rollout_closed_loop(int system, const double* params_host, int nparams,
     a.K = K;  a.k = k;  a.x0 = x0;  a.u_in = nullptr;  a.xd = xd;  a.xd_stride = xd_stride;
     a.Q = Q;  a.R = R;  a.x_trj = x_trj;  a.u_trj = u_trj;  a.cost = cost;  a.I = I;  a.T = T;
     cudaStream_t st = (cudaStream_t)stream;
-    IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, true><<<(I + 63) / 64, 64, 0, st>>>(a)));
+    IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, true><<<(I + kRolloutWarps - 1) / kRolloutWarps, 32 * kRolloutWarps, 0, st>>>(a)));
     return check_launch("rollout_kernel<closed>");
 }
 
@@ -566,7 +572,7 @@ int irs_rollout_open_loop(int system, const double* params_host, int nparams,
     a.K = nullptr;  a.k = nullptr;  a.x0 = x0;  a.u_in = u_in;  a.xd = xd;  a.xd_stride = xd_stride;
     a.Q = Q;  a.R = R;  a.x_trj = x_trj;  a.u_trj = nullptr;  a.cost = cost;  a.I = I;  a.T = T;
     cudaStream_t st = (cudaStream_t)stream;
-    IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, false><<<(I + 63) / 64, 64, 0, st>>>(a)));
+    IRS_DISPATCH_SYSTEM(system, double, Sys, (rollout_kernel<Sys, false><<<(I + kRolloutWarps - 1) / kRolloutWarps, 32 * kRolloutWarps, 0, st>>>(a)));
     return check_launch("rollout_kernel<open>");
 }
 

@@ -384,8 +384,10 @@ __global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArg
 }
 
 // ---------------------------------------------------------------------------------------------
-// Finalize (fp64, one warp per nominal point).
+// Finalize (fp64, one block of kFinalizeThreads per nominal point).
 // ---------------------------------------------------------------------------------------------
+constexpr int kFinalizeThreads = 128;
+
 struct FinalizeArgs {
     const double* x_nom;     // [P, n]
     const double* u_nom;     // [P, m]
@@ -402,57 +404,78 @@ struct FinalizeArgs {
     SysParams prm;
 };
 
+// Fixed-order sum over ranks, then chunks, of entry e of point p (deterministic; the chunk loop is
+// unrolled so that the loads are in flight together while the adds keep their order).
+__device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int e, int width) {
+    double s = 0.0;
+    for (int r = 0; r < a.R; ++r) {
+        if (a.reduced != nullptr) {
+            s += a.reduced[r * a.rank_stride + (long long)p * width + e];
+        } else {
+            const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * width + e;
+            int c = 0;
+            for (; c + 4 <= a.C; c += 4) {
+                const float v0 = src[(long long)c * width], v1 = src[(long long)(c + 1) * width];
+                const float v2 = src[(long long)(c + 2) * width], v3 = src[(long long)(c + 3) * width];
+                s += (double)v0;  s += (double)v1;  s += (double)v2;  s += (double)v3;
+            }
+            for (; c < a.C; ++c) s += (double)src[(long long)c * width];
+        }
+    }
+    return s;
+}
+
+// Nominal point (xbar | ubar | f(xbar, ubar)) of point p in fp64 -> shared memory; one thread.
 template <class Sys>
-__device__ __forceinline__ void write_abc(const Sys& sys, const FinalizeArgs& a, int p,
-                                          const double* AB /*[n][d] smem*/, int lane) {
-    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+__device__ __forceinline__ void nominal_to_smem(const Sys& sys, const FinalizeArgs& a, int p, double* nom) {
+    constexpr int n = Sys::N, m = Sys::M;
     double xb[n], ub[m], fb[n];
 #pragma unroll
     for (int q = 0; q < n; ++q) xb[q] = a.x_nom[(long long)p * n + q];
 #pragma unroll
     for (int q = 0; q < m; ++q) ub[q] = a.u_nom[(long long)p * m + q];
     sys.template step<false>(xb, ub, fb);      // scalar dynamics at the nominal (…zero_order.py:61)
-    for (int e = lane; e < n * d; e += 32) {
+#pragma unroll
+    for (int q = 0; q < n; ++q) nom[q] = xb[q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) nom[n + q] = ub[q];
+#pragma unroll
+    for (int q = 0; q < n; ++q) nom[n + m + q] = fb[q];
+}
+
+// At, Bt from AB ([n][d] smem) and c = f(xbar,ubar) - A xbar - B ubar (…zero_order.py:59-62).
+template <class Sys>
+__device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const double* AB,
+                                          const double* nom /*[n+m+n] smem*/, int tid) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    for (int e = tid; e < n * d; e += kFinalizeThreads) {
         const int r = e / d, cidx = e % d;
         if (cidx < n) a.At[((long long)p * n + r) * n + cidx] = AB[e];
         else a.Bt[((long long)p * n + r) * m + (cidx - n)] = AB[e];
     }
-    for (int r = lane; r < n; r += 32) {
-        double acc = fb[r];
+    if (tid < n) {
+        double acc = nom[d + tid];
 #pragma unroll
-        for (int q = 0; q < n; ++q) acc -= AB[r * d + q] * xb[q];
-#pragma unroll
-        for (int q = 0; q < m; ++q) acc -= AB[r * d + n + q] * ub[q];
-        a.ct[(long long)p * n + r] = acc;
+        for (int q = 0; q < d; ++q) acc -= AB[tid * d + q] * nom[q];
+        a.ct[(long long)p * n + tid] = acc;
     }
 }
 
 template <class Sys>
-__global__ void __launch_bounds__(128) finalize_zero_order_kernel(const FinalizeArgs a) {
+__global__ void __launch_bounds__(kFinalizeThreads) finalize_zero_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int W = d + n;
     constexpr int NACC = gram_nacc(n, m);
-    __shared__ double sG[4][d * d];      // Gram (then its Cholesky factor, lower)
-    __shared__ double sB[4][d * n];      // right-hand sides Z^T dF, then the solution
-    __shared__ double sAB[4][n * d];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 4 + warp;
-    if (p >= a.P) return;
-    const Sys sys(a.prm);
-    double* Gm = sG[warp];
-    double* Bm = sB[warp];
-    // 1. fixed-order sum over ranks and chunks (deterministic)
-    for (int e = lane; e < NACC; e += 32) {
-        double s = 0.0;
-        for (int r = 0; r < a.R; ++r) {
-            if (a.reduced != nullptr) {
-                s += a.reduced[r * a.rank_stride + (long long)p * NACC + e];
-            } else {
-                const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NACC + e;
-                for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NACC];
-            }
-        }
-        // unpack (i, j)
+    __shared__ double Gm[d * d];      // Gram (then its Cholesky factor, lower)
+    __shared__ double Bm[d * n];      // right-hand sides Z^T dF, then the solution
+    __shared__ double sAB[n * d];
+    __shared__ double inv_diag[d];
+    __shared__ double nom[d + n];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int p = blockIdx.x;
+    // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs
+    for (int e = tid; e < NACC; e += kFinalizeThreads) {
+        const double s = sum_partials(a, p, e, NACC);
         int i = 0;
         while (i + 1 < d && gram_row_offset(i + 1, W) <= e) ++i;
         const int j = i + (e - gram_row_offset(i, W));
@@ -463,91 +486,96 @@ __global__ void __launch_bounds__(128) finalize_zero_order_kernel(const Finalize
             Bm[i * n + (j - d)] = s;
         }
     }
-    __syncwarp();
-    // 2. Cholesky G = L L^T (lanes = rows).  A column whose diagonal is exactly zero (sigma = 0:
-    //    regressor identically zero) gets coefficient 0, which is what the min-norm lstsq of the
-    //    reference returns for it.
-    bool bad = false;
-    double diag0 = 0.0;      // lane k keeps the original diagonal entry G_kk
-    if (lane < d) diag0 = Gm[lane * d + lane];
-    for (int k = 0; k < d; ++k) {
-        double dk = Gm[k * d + k];
-        const double d0 = __shfl_sync(0xffffffffu, diag0, k);
-        __syncwarp();
-        bool zero_col = false;
-        // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones; the
-        // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency
-        if (d0 == 0.0) { zero_col = true; dk = 1.0; }
-        else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
-        const double lkk = sqrt(dk);
-        if (lane == 0) Gm[k * d + k] = lkk;
-        for (int r = k + 1 + lane; r < d; r += 32) Gm[r * d + k] = zero_col ? 0.0 : Gm[r * d + k] / lkk;
-        if (zero_col)
-            for (int q = lane; q < n; q += 32) Bm[k * n + q] = 0.0;
-        __syncwarp();
-        // trailing update, lower triangle
-        for (int e = lane; e < (d - k - 1) * (d - k - 1); e += 32) {
-            const int r = k + 1 + e / (d - k - 1), cc = k + 1 + e % (d - k - 1);
-            if (cc <= r) Gm[r * d + cc] -= Gm[r * d + k] * Gm[cc * d + k];
+    __syncthreads();
+    if (tid == 32) {
+        // the fp64 dynamics at the nominal point runs on warp 1 while warp 0 factors the Gram
+        const Sys sys(a.prm);
+        nominal_to_smem<Sys>(sys, a, p, nom);
+    } else if (tid < 32) {
+        // 2. Cholesky G = L L^T by warp 0 (lanes = rows).  A column whose diagonal is exactly zero
+        //    (sigma = 0: regressor identically zero) gets coefficient 0, which is what the min-norm
+        //    lstsq of the reference returns for it.
+        bool bad = false;
+        double diag0 = 0.0;      // lane k keeps the original diagonal entry G_kk
+        if (lane < d) diag0 = Gm[lane * d + lane];
+#pragma unroll
+        for (int k = 0; k < d; ++k) {
+            double dk = Gm[k * d + k];
+            const double d0 = __shfl_sync(0xffffffffu, diag0, k);
+            __syncwarp();
+            bool zero_col = false;
+            // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones; the
+            // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency
+            if (d0 == 0.0) { zero_col = true; dk = 1.0; }
+            else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
+            const double lkk = sqrt(dk);
+            const double ikk = 1.0 / lkk;
+            if (lane == 0) { Gm[k * d + k] = lkk;  inv_diag[k] = ikk; }
+            for (int r = k + 1 + lane; r < d; r += 32) Gm[r * d + k] = zero_col ? 0.0 : Gm[r * d + k] * ikk;
+            if (zero_col)
+                for (int q = lane; q < n; q += 32) Bm[k * n + q] = 0.0;
+            __syncwarp();
+            // trailing update, lower triangle (k is a compile-time constant here: cheap index math)
+            const int rem = d - k - 1;
+            for (int e = lane; e < rem * rem; e += 32) {
+                const int r = k + 1 + e / rem, cc = k + 1 + e % rem;
+                if (cc <= r) Gm[r * d + cc] -= Gm[r * d + k] * Gm[cc * d + k];
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        // 3. solve L L^T X = B, one right-hand side per lane (fully unrolled: the L loads pipeline)
+        if (lane < n) {
+            const int q = lane;
+            double y[d];
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                double s = Bm[r * n + q];
+#pragma unroll
+                for (int k = 0; k < r; ++k) s -= Gm[r * d + k] * y[k];
+                y[r] = s * inv_diag[r];
+            }
+#pragma unroll
+            for (int r = d - 1; r >= 0; --r) {
+                double s = y[r];
+#pragma unroll
+                for (int k = r + 1; k < d; ++k) s -= Gm[k * d + r] * y[k];
+                y[r] = s * inv_diag[r];
+            }
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                if (!(y[r] == y[r]) || fabs(y[r]) > 1e300) bad = true;
+                sAB[q * d + r] = y[r];      // [A|B] = X^T
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) a.status[p] = bad ? 1 : 0;
     }
-    // 3. solve L L^T X = B, one right-hand side per lane
-    for (int q = lane; q < n; q += 32) {
-        for (int r = 0; r < d; ++r) {
-            double s = Bm[r * n + q];
-            for (int k = 0; k < r; ++k) s -= Gm[r * d + k] * Bm[k * n + q];
-            Bm[r * n + q] = s / Gm[r * d + r];
-        }
-        for (int r = d - 1; r >= 0; --r) {
-            double s = Bm[r * n + q];
-            for (int k = r + 1; k < d; ++k) s -= Gm[k * d + r] * Bm[k * n + q];
-            Bm[r * n + q] = s / Gm[r * d + r];
-        }
-        for (int r = 0; r < d; ++r) {
-            const double v = Bm[r * n + q];
-            if (!(v == v) || fabs(v) > 1e300) bad = true;
-            sAB[warp][q * d + r] = v;      // [A|B] = X^T
-        }
-    }
-    bad = __any_sync(0xffffffffu, bad);
-    __syncwarp();
-    if (lane == 0) a.status[p] = bad ? 1 : 0;
-    write_abc<Sys>(sys, a, p, sAB[warp], lane);
+    __syncthreads();
+    write_abc<Sys>(a, p, sAB, nom, tid);
 }
 
 template <class Sys>
-__global__ void __launch_bounds__(128) finalize_first_order_kernel(const FinalizeArgs a) {
+__global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, d = Sys::D;
     constexpr int NJ = Sys::NJ > 0 ? Sys::NJ : 1;
-    __shared__ double sV[4][NJ];
-    __shared__ double sAB[4][n * d];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 4 + warp;
-    if (p >= a.P) return;
+    __shared__ double sV[NJ];
+    __shared__ double sAB[n * d];
+    __shared__ double nom[d + n];
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x;
     const Sys sys(a.prm);
-    for (int e = lane; e < NJ; e += 32) {
-        double s = 0.0;
-        for (int r = 0; r < a.R; ++r) {
-            if (a.reduced != nullptr) {
-                s += a.reduced[r * a.rank_stride + (long long)p * NJ + e];
-            } else {
-                const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * NJ + e;
-                for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * NJ];
-            }
-        }
-        sV[warp][e] = s / a.n_total;
-    }
-    __syncwarp();
-    if (lane == 0) {
+    for (int e = tid; e < NJ; e += kFinalizeThreads) sV[e] = sum_partials(a, p, e, NJ) / a.n_total;
+    if (tid == 32) nominal_to_smem<Sys>(sys, a, p, nom);
+    __syncthreads();
+    if (tid == 0) {
         double v[NJ], J[n * d];
-        for (int k = 0; k < NJ; ++k) v[k] = sV[warp][k];
+        for (int k = 0; k < NJ; ++k) v[k] = sV[k];
         sys.jac_assemble(v, J);
-        for (int e = 0; e < n * d; ++e) sAB[warp][e] = J[e];
+        for (int e = 0; e < n * d; ++e) sAB[e] = J[e];
         a.status[p] = 0;
     }
-    __syncwarp();
-    write_abc<Sys>(sys, a, p, sAB[warp], lane);
+    __syncthreads();
+    write_abc<Sys>(a, p, sAB, nom, tid);
 }
 
 // Chunk reduction [P, C, width] fp32 -> [P, width] fp64 in fixed chunk order: the block a rank

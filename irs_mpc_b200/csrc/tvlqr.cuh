@@ -28,192 +28,243 @@ struct TvlqrArgs {
     int I, T;
 };
 
-// Solve H y = b for m x m SPD H given its Cholesky factor (registers, fully unrolled).
-template <int m>
-__device__ __forceinline__ bool cholesky_inplace(double (&H)[m][m]) {
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < m; ++j) {
-        double dj = H[j][j];
-#pragma unroll
-        for (int q = 0; q < j; ++q) dj -= H[j][q] * H[j][q];
-        if (!(dj > 0.0)) { ok = false; dj = 1.0; }
-        const double l = sqrt(dj);
-        H[j][j] = l;
-        const double il = 1.0 / l;
-#pragma unroll
-        for (int i = j + 1; i < m; ++i) {
-            double s = H[i][j];
-#pragma unroll
-            for (int q = 0; q < j; ++q) s -= H[i][q] * H[j][q];
-            H[i][j] = s * il;
-        }
-    }
+// Reciprocal in fp64 from the hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps — a
+// 5-deep dependent chain instead of the library division's ~12 plus slow-path branches.  The fp64
+// special functions sit on the sequential critical path of the recursion.
+__device__ __forceinline__ double fast_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    x = fma(x, fma(-a, x, 1.0), x);
+    x = fma(x, fma(-a, x, 1.0), x);
+    return x;
+}
+
+// Inverse of a symmetric positive definite m x m matrix (m in {1, 2, 4}) in registers, by 2 x 2
+// block elimination: H = [[A, B], [B', D]], S = D - B' A^-1 B.  Two sequential reciprocals for
+// m = 4 against four rsqrt + substitutions for a Cholesky solve.  Returns false if H is not SPD
+// (Sylvester: A > 0 and S > 0) or contains NaN.
+__device__ __forceinline__ bool spd_inverse2(double a, double b, double d, double& ia, double& ib, double& id) {
+    const double det = a * d - b * b;
+    const bool ok = (a > 0.0) && (det > 0.0);
+    const double r = fast_rcp(ok ? det : 1.0);
+    ia = d * r;  ib = -b * r;  id = a * r;
     return ok;
 }
 template <int m>
-__device__ __forceinline__ void cholesky_solve(const double (&L)[m][m], double (&b)[m]) {
-#pragma unroll
-    for (int i = 0; i < m; ++i) {
-        double s = b[i];
-#pragma unroll
-        for (int q = 0; q < i; ++q) s -= L[i][q] * b[q];
-        b[i] = s / L[i][i];
+__device__ __forceinline__ bool spd_inverse(const double (&H)[m][m], double (&Hi)[m][m]) {
+    static_assert(m == 1 || m == 2 || m == 4, "input dimensions of the built-in systems");
+    if constexpr (m == 1) {
+        const bool ok = H[0][0] > 0.0;
+        Hi[0][0] = fast_rcp(ok ? H[0][0] : 1.0);
+        return ok;
+    } else if constexpr (m == 2) {
+        const bool ok = spd_inverse2(H[0][0], H[0][1], H[1][1], Hi[0][0], Hi[0][1], Hi[1][1]);
+        Hi[1][0] = Hi[0][1];
+        return ok;
+    } else {
+        double a0, a1, a2;                                  // A^-1 = [[a0, a1], [a1, a2]]
+        bool ok = spd_inverse2(H[0][0], H[0][1], H[1][1], a0, a1, a2);
+        // X = A^-1 B,  B = H[0:2, 2:4]
+        const double x00 = a0 * H[0][2] + a1 * H[1][2], x01 = a0 * H[0][3] + a1 * H[1][3];
+        const double x10 = a1 * H[0][2] + a2 * H[1][2], x11 = a1 * H[0][3] + a2 * H[1][3];
+        // S = D - B' X (symmetric)
+        const double s00 = H[2][2] - (H[0][2] * x00 + H[1][2] * x10);
+        const double s01 = H[2][3] - (H[0][2] * x01 + H[1][2] * x11);
+        const double s11 = H[3][3] - (H[0][3] * x01 + H[1][3] * x11);
+        double t0, t1, t2;                                  // S^-1
+        ok = spd_inverse2(s00, s01, s11, t0, t1, t2) && ok;
+        // Y = X S^-1
+        const double y00 = x00 * t0 + x01 * t1, y01 = x00 * t1 + x01 * t2;
+        const double y10 = x10 * t0 + x11 * t1, y11 = x10 * t1 + x11 * t2;
+        Hi[2][2] = t0;  Hi[2][3] = t1;  Hi[3][2] = t1;  Hi[3][3] = t2;
+        Hi[0][2] = -y00;  Hi[0][3] = -y01;  Hi[1][2] = -y10;  Hi[1][3] = -y11;
+        Hi[2][0] = -y00;  Hi[3][0] = -y01;  Hi[2][1] = -y10;  Hi[3][1] = -y11;
+        Hi[0][0] = a0 + (y00 * x00 + y01 * x01);
+        Hi[0][1] = a1 + (y00 * x10 + y01 * x11);
+        Hi[1][0] = Hi[0][1];
+        Hi[1][1] = a2 + (y10 * x10 + y11 * x11);
+        return ok;
     }
+}
+
+// sum_{q<len} a[q*sa] * b[q*sb] with four independent partial sums: the fp64 FMA latency, not its
+// throughput, bounds the sequential recursion, so the dependent chain is cut from len to len/4 + 2.
+template <int len>
+__device__ __forceinline__ double dot4(const double* a, int sa, const double* b, int sb, double init = 0.0) {
+    double acc[4] = {init, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int i = m - 1; i >= 0; --i) {
-        double s = b[i];
-#pragma unroll
-        for (int q = i + 1; q < m; ++q) s -= L[q][i] * b[q];
-        b[i] = s / L[i][i];
-    }
+    for (int q = 0; q < len; ++q) acc[q & 3] += a[q * sa] * b[q * sb];
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 template <int n, int m>
 struct TvlqrSmem {
-    double P[n * n], A[n * n], PA[n * n], Pn[n * n];
+    double P[n * n], A[n * n], PA[n * n];
     double B[n * m], PB[n * m], G[m * n], Kt[m * n];
     double H[m * m];
     double p[n], w[n], c[n], xd[n], g[m], kt[m];
 };
 
-constexpr int kTvlqrWarps = 4;
+constexpr int kTvlqrWarps = 4;          // warp-per-instance variant: instances per block
+constexpr int kTvlqrBlockThreads = 256; // block-per-instance variant
 
-template <int n, int m>
-__global__ void __launch_bounds__(32 * kTvlqrWarps) tvlqr_riccati_kernel(const TvlqrArgs a) {
+// One cooperative group of G threads per MPC instance: G = 32 (a warp; many instances, throughput)
+// or G = blockDim.x (a whole block; few instances, latency).  The step-(t-1) matrices are
+// prefetched into registers while step t is computed, so the sequential recursion never waits on
+// an exposed global-memory round trip.
+template <int n, int m, int G>
+__global__ void __launch_bounds__(G == 32 ? 32 * kTvlqrWarps : G) tvlqr_riccati_kernel(const TvlqrArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int inst = blockIdx.x * kTvlqrWarps + warp;
-    if (inst >= a.I) return;
-    TvlqrSmem<n, m>& s = reinterpret_cast<TvlqrSmem<n, m>*>(smem_raw)[warp];
+    const int sub = G == 32 ? (int)(threadIdx.x >> 5) : 0;      // instance slot inside the block
+    const int gt = G == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int inst = G == 32 ? blockIdx.x * kTvlqrWarps + sub : blockIdx.x;
+    if (inst >= a.I) return;      // whole group exits together
+    TvlqrSmem<n, m>& s = reinterpret_cast<TvlqrSmem<n, m>*>(smem_raw)[sub];
+    auto group_sync = [] {
+        if constexpr (G == 32) __syncwarp();
+        else __syncthreads();
+    };
     const double* xd_i = a.xd + inst * a.xd_stride;
     bool ok = true;
+    // register prefetch slots of this thread
+    constexpr int kRA = (n * n + G - 1) / G, kRB = (n * m + G - 1) / G, kRC = (n + G - 1) / G;
+    double rA[kRA], rB[kRB], rc[kRC], rxd[kRC];
+    auto prefetch = [&](int t) {
+        const long long it = (long long)inst * a.T + t;
+#pragma unroll
+        for (int k = 0; k < kRA; ++k) { const int e = gt + k * G; if (e < n * n) rA[k] = a.At[it * n * n + e]; }
+#pragma unroll
+        for (int k = 0; k < kRB; ++k) { const int e = gt + k * G; if (e < n * m) rB[k] = a.Bt[it * n * m + e]; }
+#pragma unroll
+        for (int k = 0; k < kRC; ++k) {
+            const int e = gt + k * G;
+            if (e < n) { rc[k] = a.ct[it * n + e];  rxd[k] = xd_i[(long long)t * n + e]; }
+        }
+    };
+    prefetch(a.T - 1);
     // terminal condition: P_T = Qd, p_T = -Qd xd_T
-    for (int e = lane; e < n * n; e += 32) s.P[e] = a.Qd[e];
-    for (int i = lane; i < n; i += 32) {
+    for (int e = gt; e < n * n; e += G) s.P[e] = a.Qd[e];
+    for (int i = gt; i < n; i += G) {
         double acc = 0.0;
         for (int q = 0; q < n; ++q) acc -= a.Qd[i * n + q] * xd_i[(long long)a.T * n + q];
         s.p[i] = acc;
     }
-    __syncwarp();
     for (int t = a.T - 1; t >= 0; --t) {
         const long long it = (long long)inst * a.T + t;
-        for (int e = lane; e < n * n; e += 32) s.A[e] = a.At[it * n * n + e];
-        for (int e = lane; e < n * m; e += 32) s.B[e] = a.Bt[it * n * m + e];
-        for (int e = lane; e < n; e += 32) {
-            s.c[e] = a.ct[it * n + e];
-            s.xd[e] = xd_i[(long long)t * n + e];
-        }
-        __syncwarp();
-        // PA = P A, PB = P B, w = P c + p
-        for (int e = lane; e < n * n; e += 32) {
-            const int i = e / n, j = e % n;
-            double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.P[i * n + q] * s.A[q * n + j];
-            s.PA[e] = acc;
-        }
-        for (int e = lane; e < n * m; e += 32) {
-            const int i = e / m, j = e % m;
-            double acc = 0.0;
+        for (int k = 0; k < kRA; ++k) { const int e = gt + k * G; if (e < n * n) s.A[e] = rA[k]; }
 #pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.P[i * n + q] * s.B[q * m + j];
-            s.PB[e] = acc;
-        }
-        for (int i = lane; i < n; i += 32) {
-            double acc = s.p[i];
+        for (int k = 0; k < kRB; ++k) { const int e = gt + k * G; if (e < n * m) s.B[e] = rB[k]; }
 #pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.P[i * n + q] * s.c[q];
-            s.w[i] = acc;
+        for (int k = 0; k < kRC; ++k) {
+            const int e = gt + k * G;
+            if (e < n) { s.c[e] = rc[k];  s.xd[e] = rxd[k]; }
         }
-        __syncwarp();
+        group_sync();
+        if (t > 0) prefetch(t - 1);
+        // PA = P A, PB = P B, w = P c + p   (one output per thread where G allows)
+        for (int e = gt; e < n * n + n * m + n; e += G) {
+            if (e < n * n) {
+                const int i = e / n, j = e % n;
+                s.PA[e] = dot4<n>(&s.P[i * n], 1, &s.A[j], n);
+            } else if (e < n * n + n * m) {
+                const int f = e - n * n, i = f / m, j = f % m;
+                s.PB[f] = dot4<n>(&s.P[i * n], 1, &s.B[j], m);
+            } else {
+                const int i = e - n * n - n * m;
+                s.w[i] = dot4<n>(&s.P[i * n], 1, s.c, 1, s.p[i]);
+            }
+        }
+        group_sync();
         // H = R/2 + B'PB, G = B'PA, g = B'w
-        for (int e = lane; e < m * m; e += 32) {
-            const int i = e / m, j = e % m;
-            double acc = 0.5 * a.R[e];
-#pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.B[q * m + i] * s.PB[q * m + j];
-            s.H[e] = acc;
+        for (int e = gt; e < m * m + m * n + m; e += G) {
+            if (e < m * m) {
+                const int i = e / m, j = e % m;
+                s.H[e] = dot4<n>(&s.B[i], m, &s.PB[j], m, 0.5 * a.R[e]);
+            } else if (e < m * m + m * n) {
+                const int f = e - m * m, i = f / n, j = f % n;
+                s.G[f] = dot4<n>(&s.B[i], m, &s.PA[j], n);
+            } else {
+                const int i = e - m * m - m * n;
+                s.g[i] = dot4<n>(&s.B[i], m, s.w, 1);
+            }
         }
-        for (int e = lane; e < m * n; e += 32) {
-            const int i = e / n, j = e % n;
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.B[q * m + i] * s.PA[q * n + j];
-            s.G[e] = acc;
-        }
-        for (int i = lane; i < m; i += 32) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.B[q * m + i] * s.w[q];
-            s.g[i] = acc;
-        }
-        __syncwarp();
-        // every lane factors H (m <= 4: registers); lanes 0..n-1 solve a column of K, lane n solves k
-        {
-            double L[m][m];
+        group_sync();
+        // the first warp inverts H (m <= 4: registers); threads 0..n-1 form a column of K = -H^-1 G, thread n forms k
+        if (gt < 32) {
+            double Hs[m][m], Hi[m][m];
 #pragma unroll
             for (int i = 0; i < m; ++i)
 #pragma unroll
-                for (int j = 0; j < m; ++j) L[i][j] = 0.5 * (s.H[i * m + j] + s.H[j * m + i]);
-            ok = cholesky_inplace<m>(L) && ok;
-            for (int col = lane; col <= n; col += 32) {
-                double b[m];
+                for (int j = 0; j < m; ++j) Hs[i][j] = 0.5 * (s.H[i * m + j] + s.H[j * m + i]);
+            ok = spd_inverse<m>(Hs, Hi) && ok;
+            for (int col = gt; col <= n; col += G) {
+                double b[m], y[m];
 #pragma unroll
                 for (int i = 0; i < m; ++i) b[i] = col < n ? s.G[i * n + col] : s.g[i];
-                cholesky_solve<m>(L, b);
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc -= Hi[i][q] * b[q];
+                    y[i] = acc;
+                }
                 if (col < n) {
 #pragma unroll
                     for (int i = 0; i < m; ++i) {
-                        s.Kt[i * n + col] = -b[i];
-                        a.K[(it * m + i) * n + col] = -b[i];
+                        s.Kt[i * n + col] = y[i];
+                        a.K[(it * m + i) * n + col] = y[i];
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < m; ++i) {
-                        s.kt[i] = -b[i];
-                        a.k[it * m + i] = -b[i];
+                        s.kt[i] = y[i];
+                        a.k[it * m + i] = y[i];
                     }
                 }
             }
         }
-        __syncwarp();
-        // P <- Q + A'PA + G'K,  p <- -Q xd_t + A'w + G'k
-        for (int e = lane; e < n * n; e += 32) {
-            const int i = e / n, j = e % n;
-            double acc = a.Q[e];
+        group_sync();
+        // P <- sym(Q + A'PA + G'K),  p <- -Q xd_t + A'w + G'k.  Each thread forms entry (i,j) and its
+        // mirror (j,i) and writes their mean: P stays exactly symmetric without a second pass.
+        double Pnew[(n * n + n + G - 1) / G];
 #pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.A[q * n + i] * s.PA[q * n + j];
-#pragma unroll
-            for (int q = 0; q < m; ++q) acc += s.G[q * n + i] * s.Kt[q * n + j];
-            s.Pn[e] = acc;
+        for (int k = 0; k < (n * n + n + G - 1) / G; ++k) {
+            const int e = gt + k * G;
+            if (e < n * n) {
+                const int i = e / n, j = e % n;
+                const double aij = dot4<n>(&s.A[i], n, &s.PA[j], n, a.Q[i * n + j]) + dot4<m>(&s.G[i], n, &s.Kt[j], n);
+                const double aji = dot4<n>(&s.A[j], n, &s.PA[i], n, a.Q[j * n + i]) + dot4<m>(&s.G[j], n, &s.Kt[i], n);
+                Pnew[k] = 0.5 * (aij + aji);
+            } else if (e < n * n + n) {
+                const int i = e - n * n;
+                Pnew[k] = (dot4<n>(&s.A[i], n, s.w, 1) - dot4<n>(&a.Q[i * n], 1, s.xd, 1)) +
+                          dot4<m>(&s.G[i], n, s.kt, 1);
+            }
         }
-        for (int i = lane; i < n; i += 32) {
-            double acc = 0.0;
+        group_sync();      // everyone has read the old P / p
 #pragma unroll
-            for (int q = 0; q < n; ++q) acc -= a.Q[i * n + q] * s.xd[q];
-#pragma unroll
-            for (int q = 0; q < n; ++q) acc += s.A[q * n + i] * s.w[q];
-#pragma unroll
-            for (int q = 0; q < m; ++q) acc += s.G[q * n + i] * s.kt[q];
-            s.p[i] = acc;
+        for (int k = 0; k < (n * n + n + G - 1) / G; ++k) {
+            const int e = gt + k * G;
+            if (e < n * n) s.P[e] = Pnew[k];
+            else if (e < n * n + n) s.p[e - n * n] = Pnew[k];
         }
-        __syncwarp();
-        for (int e = lane; e < n * n; e += 32) {
-            const int i = e / n, j = e % n;
-            s.P[e] = 0.5 * (s.Pn[i * n + j] + s.Pn[j * n + i]);
-        }
-        __syncwarp();
+        // (the group_sync after the next step's operand stores orders these writes before its reads)
     }
+    group_sync();
     // NaN guard on the final value function
-    for (int e = lane; e < n * n; e += 32)
+    for (int e = gt; e < n * n; e += G)
         if (!(s.P[e] == s.P[e])) ok = false;
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) a.status[inst] = ok ? 0 : 1;
+    if constexpr (G == 32) {
+        ok = __all_sync(0xffffffffu, ok);
+    } else {
+        ok = __syncthreads_and(ok);
+    }
+    if (gt == 0) a.status[inst] = ok ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Rollouts (thread per instance; x lives in registers).
+// Rollouts (warp per instance; x lives in lane 0's registers).
 //   closed loop: u_t = K_t x_t + k_t, x_{t+1} = f(x_t, u_t)      (irs_lqr.py:183-184)
 //   open loop  : x_{t+1} = f(x_t, u_t) for given u               (irs_lqr.py:105-119)
 // Both also return the cost of irs_lqr.py:121-137 (terminal term uses Q, :135-136).
@@ -234,74 +285,126 @@ struct RolloutArgs {
     SysParams prm;
 };
 
+constexpr int kRolloutWarps = 2;
+
+// IrsLqr.evaluate_cost (irs_lqr.py:121-137) of one instance by one warp, lanes over t; the terminal
+// term uses Q (:135-136).  Returns the warp-reduced cost on every lane.
+template <int n, int m>
+__device__ __forceinline__ double warp_trajectory_cost(const double* x_trj, const double* u_trj,
+                                                       const double* xd_i, const double* Q,
+                                                       const double* R, int T, int lane) {
+    double acc = 0.0;
+    for (int t = lane; t <= T; t += 32) {
+        double e[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) e[q] = x_trj[(long long)t * n + q] - xd_i[(long long)t * n + q];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < n; ++q) s += Q[i * n + q] * e[q];
+            acc += e[i] * s;
+        }
+        if (t < T) {
+            double u[m];
+#pragma unroll
+            for (int q = 0; q < m; ++q) u[q] = u_trj[(long long)t * m + q];
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < m; ++q) s += R[i * m + q] * u[q];
+                acc += u[i] * s;
+            }
+        }
+    }
+    return warp_sum(acc);
+}
+
+// One warp per instance.  The recursion x_{t+1} = f(x_t, u_t) is sequential and runs on lane 0 in
+// fp64; the other lanes are the prefetcher: while lane 0 computes step t they fetch step t+1's
+// gains / inputs into registers and hand them over through a double-buffered
+// shared-memory slot, so the critical path never contains a global-memory round trip.
 template <class Sys, bool CLOSED>
-__global__ void __launch_bounds__(64) rollout_kernel(const RolloutArgs a) {
+__global__ void __launch_bounds__(32 * kRolloutWarps) rollout_kernel(const RolloutArgs a) {
     constexpr int n = Sys::N, m = Sys::M;
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int kSlot = CLOSED ? m * n + m : m;        // K_t | k_t   or   u_t
+    constexpr int kPer = (kSlot + 31) / 32;
+    __shared__ double slot[kRolloutWarps][2][kSlot];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int inst = blockIdx.x * kRolloutWarps + warp;
     if (inst >= a.I) return;
     const Sys sys(a.prm);
     const double* xd_i = a.xd + inst * a.xd_stride;
-    double x[n], u[m], xn[n];
-#pragma unroll
-    for (int q = 0; q < n; ++q) {
-        x[q] = a.x0[(long long)inst * n + q];
-        a.x_trj[((long long)inst * (a.T + 1)) * n + q] = x[q];
-    }
-    double cost = 0.0;
-    for (int t = 0; t < a.T; ++t) {
+    double pre[kPer];
+    auto fetch = [&](int t) {
         const long long it = (long long)inst * a.T + t;
-        if (CLOSED) {
 #pragma unroll
-            for (int i = 0; i < m; ++i) {
-                double acc = a.k[it * m + i];
-#pragma unroll
-                for (int q = 0; q < n; ++q) acc += a.K[(it * m + i) * n + q] * x[q];
-                u[i] = acc;
+        for (int k = 0; k < kPer; ++k) {
+            const int e = lane + 32 * k;
+            if (e < kSlot) {
+                if (CLOSED) pre[k] = e < m * n ? a.K[it * m * n + e] : a.k[it * m + (e - m * n)];
+                else pre[k] = a.u_in[it * m + e];
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < m; ++i) u[i] = a.u_in[it * m + i];
         }
-        // stage cost (x_t - xd_t)'Q(x_t - xd_t) + u_t'R u_t
-        double e[n];
+    };
+    auto publish = [&](int b) {
 #pragma unroll
-        for (int q = 0; q < n; ++q) e[q] = x[q] - xd_i[(long long)t * n + q];
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < n; ++q) acc += a.Q[i * n + q] * e[q];
-            cost += e[i] * acc;
+        for (int k = 0; k < kPer; ++k) {
+            const int e = lane + 32 * k;
+            if (e < kSlot) slot[warp][b][e] = pre[k];
         }
-#pragma unroll
-        for (int i = 0; i < m; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < m; ++q) acc += a.R[i * m + q] * u[q];
-            cost += u[i] * acc;
-        }
-        sys.template step<false>(x, u, xn);
-        if (CLOSED) {
-#pragma unroll
-            for (int i = 0; i < m; ++i) a.u_trj[it * m + i] = u[i];
-        }
+    };
+    fetch(0);
+    publish(0);
+    __syncwarp();
+    double x[n], u[m], xn[n];
+    if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < n; ++q) {
-            x[q] = xn[q];
-            a.x_trj[((long long)inst * (a.T + 1) + t + 1) * n + q] = x[q];
+            x[q] = a.x0[(long long)inst * n + q];
+            a.x_trj[((long long)inst * (a.T + 1)) * n + q] = x[q];
         }
     }
-    double e[n];
+    for (int t = 0; t < a.T; ++t) {
+        const long long it = (long long)inst * a.T + t;
+        const double* sl = slot[warp][t & 1];
+        if (t + 1 < a.T) fetch(t + 1);                 // in flight while lane 0 computes
+        if (lane == 0) {
+            if (CLOSED) {
 #pragma unroll
-    for (int q = 0; q < n; ++q) e[q] = x[q] - xd_i[(long long)a.T * n + q];
+                for (int i = 0; i < m; ++i) {
+                    double acc = sl[m * n + i];
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
-        double acc = 0.0;
+                    for (int q = 0; q < n; ++q) acc += sl[i * n + q] * x[q];
+                    u[i] = acc;
+                }
+            } else {
 #pragma unroll
-        for (int q = 0; q < n; ++q) acc += a.Q[i * n + q] * e[q];
-        cost += e[i] * acc;
+                for (int i = 0; i < m; ++i) u[i] = sl[i];
+            }
+            sys.template step<false>(x, u, xn);
+            if (CLOSED) {
+#pragma unroll
+                for (int i = 0; i < m; ++i) a.u_trj[it * m + i] = u[i];
+            }
+#pragma unroll
+            for (int q = 0; q < n; ++q) {
+                x[q] = xn[q];
+                a.x_trj[((long long)inst * (a.T + 1) + t + 1) * n + q] = x[q];
+            }
+        }
+        if (t + 1 < a.T) publish((t + 1) & 1);
+        __syncwarp();
     }
-    a.cost[inst] = cost;
+    // cost of the finished trajectory, parallel over t (off the sequential path); lane 0's global
+    // stores are visible to the warp after the __syncwarp that closed the loop
+    __threadfence_block();
+    __syncwarp();
+    const double* u_used = CLOSED ? a.u_trj + (long long)inst * a.T * m : a.u_in + (long long)inst * a.T * m;
+    const double c = warp_trajectory_cost<n, m>(a.x_trj + (long long)inst * (a.T + 1) * n, u_used, xd_i,
+                                                a.Q, a.R, a.T, lane);
+    if (lane == 0) a.cost[inst] = c;
 }
 
 // evaluate_cost for given trajectories (irs_lqr.py:121-137); one warp per instance, lanes over t.
@@ -314,32 +417,8 @@ __global__ void __launch_bounds__(128) evaluate_cost_kernel(const double* x_trj,
     const int inst = blockIdx.x * 4 + warp;
     if (inst >= I) return;
     const double* xd_i = xd + inst * xd_stride;
-    double acc = 0.0;
-    for (int t = lane; t <= T; t += 32) {
-        double e[n];
-#pragma unroll
-        for (int q = 0; q < n; ++q) e[q] = x_trj[((long long)inst * (T + 1) + t) * n + q] - xd_i[(long long)t * n + q];
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < n; ++q) s += Q[i * n + q] * e[q];
-            acc += e[i] * s;
-        }
-        if (t < T) {
-            double u[m];
-#pragma unroll
-            for (int q = 0; q < m; ++q) u[q] = u_trj[((long long)inst * T + t) * m + q];
-#pragma unroll
-            for (int i = 0; i < m; ++i) {
-                double s = 0.0;
-#pragma unroll
-                for (int q = 0; q < m; ++q) s += R[i * m + q] * u[q];
-                acc += u[i] * s;
-            }
-        }
-    }
-    acc = warp_sum(acc);
+    const double acc = warp_trajectory_cost<n, m>(x_trj + (long long)inst * (T + 1) * n,
+                                                  u_trj + (long long)inst * T * m, xd_i, Q, R, T, lane);
     if (lane == 0) cost[inst] = acc;
 }
 

@@ -66,6 +66,8 @@ class IrsLqr:
         self._dR = _device.to_device(np.asarray(self.R, dtype=np.float64))
         self._dxd = _device.to_device(np.asarray(self.xd_trj, dtype=np.float64)[:self.T + 1])
         self._ws = None
+        self._db = None
+        self._last_descent = None
         self.timings = {}
 
         self.x_trj = self.rollout(self.x0, self.u_trj)
@@ -118,6 +120,12 @@ class IrsLqr:
         return _device.to_numpy(x_trj[0])
 
     def evaluate_cost(self, x_trj, u_trj):
+        ld = self._last_descent
+        if ld is not None and x_trj is ld[0] and u_trj is ld[1] and np.array_equal(x_trj, ld[2]) \
+                and np.array_equal(u_trj, ld[3]):
+            # the trajectory local_descent just returned (unmodified): its cost was computed on the
+            # device by the same routine (warp_trajectory_cost) during the rollout
+            return self._last_descent_cost
         x = _device.to_device(np.asarray(x_trj, dtype=np.float64).reshape(1, self.T + 1, self.dim_x))
         u = _device.to_device(np.asarray(u_trj, dtype=np.float64).reshape(1, self.T, self.dim_u))
         cost = _device.empty((1,))
@@ -139,34 +147,73 @@ class IrsLqr:
         smoothing.check_status(status)
         return _device.to_numpy(At), _device.to_numpy(Bt), _device.to_numpy(ct)
 
+    def _io_bytes(self):
+        """(host->device, device->host) bytes one get_TV_matrices call moves."""
+        n, m, T = self.dim_x, self.dim_u, self.T
+        return T * (n + m) * 8, T * (n * n + n * m + n) * 8 + T * 4
+
     # -- descent (irs_lqr.py:148-186) ------------------------------------------------------------
+    def _descent_buffers(self):
+        """Device + pinned host staging for one descent: a single H2D copy of [x_trj | u_trj] and a
+        single D2H copy of [x_new | u_new | cost | riccati status | smoothing status]."""
+        if self._db is None:
+            T, n, m = self.T, self.dim_x, self.dim_u
+            db = {}
+            nx, nu = (T + 1) * n, T * m
+            db["in_dev"] = _device.empty((nx + nu,))
+            db["in_host"] = torch.empty((nx + nu,), dtype=torch.float64).pin_memory()
+            n_out = nx + nu + 1 + 1 + (T + 1) // 2
+            db["out_dev"] = _device.empty((n_out,))
+            db["out_host"] = torch.empty((n_out,), dtype=torch.float64).pin_memory()
+            o = db["out_dev"]
+            db["x_new"] = o[:nx].view(1, T + 1, n)
+            db["u_new"] = o[nx:nx + nu].view(1, T, m)
+            db["cost"] = o[nx + nu:nx + nu + 1]
+            db["rstatus"] = o[nx + nu + 1:nx + nu + 2].view(torch.int32)[:1]
+            db["sstatus"] = o[nx + nu + 2:].view(torch.int32)[:T]
+            db["K"] = _device.empty((1, T, m, n))
+            db["k"] = _device.empty((1, T, m))
+            db["nx"], db["nu"] = nx, nu
+            self._db = db
+        return self._db
+
     def local_descent(self, x_trj, u_trj):
         T, n, m = self.T, self.dim_x, self.dim_u
-        xh = np.asarray(x_trj, dtype=np.float64)
-        x_all = _device.to_device(xh)
-        u_nom = _device.to_device(np.asarray(u_trj, dtype=np.float64)[:T])
+        db = self._descent_buffers()
+        nx, nu = db["nx"], db["nu"]
+        h = db["in_host"].numpy()
+        h[:nx] = np.asarray(x_trj, dtype=np.float64)[:T + 1].reshape(-1)
+        h[nx:] = np.asarray(u_trj, dtype=np.float64)[:T].reshape(-1)
+        db["in_dev"].copy_(db["in_host"], non_blocking=True)
+        x_all = db["in_dev"][:nx].view(T + 1, n)
+        u_nom = db["in_dev"][nx:].view(T, m)
         x_nom = x_all[:T]
         At, Bt, ct, status = self._tv_matrices_device(x_nom, u_nom)
-        K, k, rstatus = riccati_device(At.view(1, T, n, n), Bt.view(1, T, n, m), ct.view(1, T, n),
-                                       self._dQ, self._dQd, self._dR, self._dxd, 0)
-        x_new = _device.empty((1, T + 1, n))
-        u_new = _device.empty((1, T, m))
-        cost = _device.empty((1,))
+        db["sstatus"].copy_(status)
+        K, k = db["K"], db["k"]
+        _lib.call("irs_tvlqr_riccati", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                  _device.ptr(self._dQ), _device.ptr(self._dQd), _device.ptr(self._dR),
+                  _device.ptr(self._dxd), 0, 1, T, _device.ptr(K), _device.ptr(k),
+                  _device.ptr(db["rstatus"]), _device.stream_ptr())
         prm, nprm = self.system._params()
         _lib.call("irs_rollout_closed_loop", self.system.system_id, prm, nprm, _device.ptr(K),
-                  _device.ptr(k), _device.ptr(x_all[0:1]), _device.ptr(self._dxd), 0,
-                  _device.ptr(self._dQ), _device.ptr(self._dR), 1, T, _device.ptr(x_new),
-                  _device.ptr(u_new), _device.ptr(cost), _device.stream_ptr())
+                  _device.ptr(k), _device.ptr(x_all), _device.ptr(self._dxd), 0,
+                  _device.ptr(self._dQ), _device.ptr(self._dR), 1, T, _device.ptr(db["x_new"]),
+                  _device.ptr(db["u_new"]), _device.ptr(db["cost"]), _device.stream_ptr())
         # one synchronising read-back for everything the host needs
-        smoothing.check_status(status)
-        if int(rstatus.item()) != 0:
+        db["out_host"].copy_(db["out_dev"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        o = db["out_host"].numpy()
+        smoothing.check_status(o[nx + nu + 2:].view(np.int32)[:T])
+        if int(o[nx + nu + 1:nx + nu + 2].view(np.int32)[0]) != 0:
             raise ValueError(TVLQR_FAILED)
-        x_out = _device.to_numpy(x_new[0])
-        u_out = _device.to_numpy(u_new[0])
+        x_out = o[:nx].reshape(T + 1, n).copy()
+        u_out = o[nx:nx + nu].reshape(T, m).copy()
         if not (np.all(np.isfinite(x_out)) and np.all(np.isfinite(u_out))):
             raise ValueError(TVLQR_FAILED)
         self._check_bounds(x_out, u_out)
-        self._last_descent_cost = float(cost.item())
+        self._last_descent_cost = float(o[nx + nu])
+        self._last_descent = (x_out, u_out, x_out.copy(), u_out.copy())
         return x_out, u_out
 
     def _check_bounds(self, x_new, u_new, tol=1e-9):
@@ -257,6 +304,31 @@ class _SampledIrsLqr(IrsLqr):
             At, Bt, ct, status, self._ws = smoothing.linearize(
                 self.system, self.order, x_nom, u_nom, noise.shape[1], self._ws, noise=noise)
         return At, Bt, ct, status
+
+
+    def get_TV_matrices(self, x_trj, u_trj):
+        """numpy in, numpy out: one pinned H2D copy of [x_nom | u_nom], the two kernels, one D2H copy
+        of [At | Bt | ct | status]."""
+        s = self.sampling
+        if not isinstance(s, GaussianSampling):
+            return super().get_TV_matrices(x_trj, u_trj)
+        key = (self.system.system_id, self.order, self.T, s.num_samples)
+        if self._ws is None or self._ws.key != key:
+            self._ws = smoothing.Workspace(self.system, self.order, self.T, s.num_samples)
+        ws = self._ws
+        x_nom, u_nom = ws.upload_nominal(x_trj, u_trj)
+        smoothing.accumulate(self.system, self.order, x_nom, u_nom, s.num_samples, ws,
+                             sigma=s.sigma(self.iter), seed=s.seed, it=self.iter, stream_id=s.stream_id,
+                             flags=s.flags())
+        smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, s.num_samples)
+        At, Bt, ct, status = ws.download()
+        smoothing.check_status(status)
+        return At, Bt, ct
+
+    def _io_bytes(self):
+        if self._ws is None:
+            return super()._io_bytes()
+        return self._ws.h2d_bytes(), self._ws.d2h_bytes()
 
 
 class IrsLqrFirstOrder(_SampledIrsLqr):

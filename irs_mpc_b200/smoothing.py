@@ -25,18 +25,62 @@ def plan(system_id, order, P, N):
 
 
 class Workspace:
-    """Reusable device buffers for one (system, order, P, N) shape."""
+    """Reusable device buffers for one (system, order, P, N) shape.
+
+    The fit outputs live in ONE flat float64 buffer [At | Bt | ct | status(int32)] and the nominal
+    points in one [x_nom | u_nom] buffer, each with a pinned host mirror, so that the numpy-facing
+    API moves exactly one host->device and one device->host copy per linearization."""
 
     def __init__(self, system, order, P, N):
         self.key = (system.system_id, order, P, N)
         self.C, self.S = plan(system.system_id, order, P, N)
         self.width = _lib.lib().irs_partial_width(system.system_id, order)
         n, m = system.dim_x, system.dim_u
+        self.P, self.n, self.m = P, n, m
         self.partials = _device.empty((P, self.C, self.width), torch.float32)
-        self.At = _device.empty((P, n, n))
-        self.Bt = _device.empty((P, n, m))
-        self.ct = _device.empty((P, n))
-        self.status = _device.empty((P,), torch.int32)
+        na, nb, nc = P * n * n, P * n * m, P * n
+        self._out = _device.empty((na + nb + nc + (P + 1) // 2,))
+        self.At = self._out[:na].view(P, n, n)
+        self.Bt = self._out[na:na + nb].view(P, n, m)
+        self.ct = self._out[na + nb:na + nb + nc].view(P, n)
+        self.status = self._out[na + nb + nc:].view(torch.int32)[:P]
+        self._nom = _device.empty((P * (n + m),))
+        self.x_nom = self._nom[:P * n].view(P, n)
+        self.u_nom = self._nom[P * n:].view(P, m)
+        self._out_host = None
+        self._nom_host = None
+
+    def upload_nominal(self, x_trj, u_trj):
+        """numpy [>=P, n], [>=P, m] -> (x_nom, u_nom) device views; one pinned H2D copy."""
+        P, n, m = self.P, self.n, self.m
+        if self._nom_host is None:
+            self._nom_host = torch.empty((P * (n + m),), dtype=torch.float64).pin_memory()
+        h = self._nom_host.numpy()
+        h[:P * n] = np.asarray(x_trj, dtype=np.float64)[:P].reshape(-1)
+        h[P * n:] = np.asarray(u_trj, dtype=np.float64)[:P].reshape(-1)
+        self._nom.copy_(self._nom_host, non_blocking=True)
+        return self.x_nom, self.u_nom
+
+    def download(self):
+        """-> (At, Bt, ct, status) as numpy arrays; one D2H copy into pinned memory + one sync."""
+        P, n, m = self.P, self.n, self.m
+        if self._out_host is None:
+            self._out_host = torch.empty(self._out.shape, dtype=torch.float64).pin_memory()
+        self._out_host.copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self._out_host.numpy()
+        na, nb, nc = P * n * n, P * n * m, P * n
+        At = h[:na].reshape(P, n, n).copy()
+        Bt = h[na:na + nb].reshape(P, n, m).copy()
+        ct = h[na + nb:na + nb + nc].reshape(P, n).copy()
+        status = h[na + nb + nc:].view(np.int32)[:P].copy()
+        return At, Bt, ct, status
+
+    def h2d_bytes(self):
+        return self._nom.numel() * 8
+
+    def d2h_bytes(self):
+        return self._out.numel() * 8
 
 
 def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=0, it=1,
@@ -92,7 +136,7 @@ def linearize(system, order, x_nom, u_nom, N, ws=None, **kw):
 
 
 def check_status(status):
-    bad = int(status.sum().item())
+    bad = int(status.sum().item()) if isinstance(status, torch.Tensor) else int(np.sum(status))
     if bad:
         raise np.linalg.LinAlgError(
             "smoothing fit: the sample Gram matrix [dx du]^T[dx du] is rank deficient at %d "
