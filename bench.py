@@ -303,6 +303,43 @@ def run_gpu(args, rank, local_rank, world):
     ms_iter = timed(one_iteration, it_steps, 2)
     iters_per_s = it_steps / (ms_iter * 1e-3)
 
+    # 5b. BASELINE.json configs[4]: 4096 independent quadrotor MPC instances (T=100, N=1e3 samples/step as
+    #     in examples/quadrotor/quadrotor_zero_order.py:44), instances sharded over the ranks, no
+    #     collective on the data path.  One step = one local_descent of every instance, device resident.
+    batched = None
+    if not args.no_batched:
+        from irs_mpc_b200.all import BatchedIrsLqrZeroOrder
+        I_total = 4096
+        lo, hi = rank * I_total // world, (rank + 1) * I_total // world
+        ph = 2.0 * np.pi * np.arange(lo, hi) / I_total
+        tt = np.arange(T_STEPS + 1, dtype=np.float64)
+        xdb = np.zeros((hi - lo, T_STEPS + 1, 12))
+        xdb[:, :, 0] = 1.5 * np.cos(0.05 * tt[None, :] + ph[:, None])
+        xdb[:, :, 1] = 1.5 * np.sin(0.05 * tt[None, :] + ph[:, None])
+        xdb[:, :, 2] = 0.02 * tt[None, :]
+        # instance b starts on its own helix (phase 2 pi b / 4096) plus N(0, diag(X0_SCALE^2)) from
+        # default_rng(5000 + b): 0.1 on positions / velocities, 0.01 on angles / angular rates (larger tilt
+        # noise makes the uncontrolled initial rollout tumble, which is not a meaningful MPC start)
+        X0_SCALE = np.array([0.1] * 3 + [0.01] * 3 + [0.1] * 3 + [0.01] * 3)
+        x0b = xdb[:, 0, :] + np.stack([X0_SCALE * np.random.default_rng(5000 + b).standard_normal(12)
+                                       for b in range(lo, hi)])
+        smp = GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], 1000, power=cfg["power"], seed=SEED0 + 77)
+        bat = BatchedIrsLqrZeroOrder(system, cfg["Q"], cfg["Qd"], cfg["R"], x0b, xdb, cfg["u_trj_initial"], smp,
+                                     instance_offset=lo)
+
+        def batched_step(k):
+            smp.seed = SEED0 + 77 + k
+            return bat.local_descent()
+        b_steps = max(3, min(args.steps, 5))
+        ms_b = timed(batched_step, b_steps, 2) / b_steps
+        bat.check()
+        batched = {"workload": "BASELINE.json configs[4]: 4096 quadrotor MPC instances, T=100, N=1000 samples/step, "
+                               "zero-order smoothing + Riccati + closed-loop rollout per step",
+                   "instances": I_total, "instances_per_gpu": hi - lo, "ms_per_batch_iteration": ms_b,
+                   "instance_iterations_per_s": I_total / (ms_b * 1e-3),
+                   "samples_per_s": I_total * T_STEPS * 1000 / (ms_b * 1e-3)}
+        del bat
+
     # 6. CPU baseline on this box's host cores (rank 0, single GPU run only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -331,6 +368,7 @@ def run_gpu(args, rank, local_rank, world):
                        "sharding": "none" if world == 1 else "sample axis, all_gather of fp64 Gram blocks",
                        "l2": "no per-sample HBM input (noise generated in registers); seed changes every step"},
             "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,
+            "batched_mpc": batched,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
@@ -363,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the 4096-instance leg (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

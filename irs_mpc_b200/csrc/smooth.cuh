@@ -384,9 +384,13 @@ __global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArg
 }
 
 // ---------------------------------------------------------------------------------------------
-// Finalize (fp64, one block of kFinalizeThreads per nominal point).
+// Finalize (fp64, one block of BT threads per nominal point).  BT = 128 when there are few points
+// (latency: the sum over chunks and the nominal dynamics run beside the warp that factors the
+// Gram); BT = 32 when there are many (throughput: the factorisation is a one-warp job, idle warps
+// would only hold registers).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinalizeThreads = 128;
+constexpr int kFinalizeThreadsMany = 32;
 
 struct FinalizeArgs {
     const double* x_nom;     // [P, n]
@@ -425,30 +429,25 @@ __device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int
     return s;
 }
 
-// Nominal point (xbar | ubar | f(xbar, ubar)) of point p in fp64 -> shared memory; one thread.
-template <class Sys>
-__device__ __forceinline__ void nominal_to_smem(const Sys& sys, const FinalizeArgs& a, int p, double* nom) {
+// Nominal point (xbar | ubar | f(xbar, ubar)) of point p in fp64 -> shared memory.  f(xbar, ubar)
+// (scalar dynamics, …zero_order.py:61) was written into ct[p] by the dynamics kernel that
+// irs_smooth_finalize launches first, which keeps the fp64 dynamics (and its ~250 registers) out of
+// this kernel.
+template <class Sys, int BT>
+__device__ __forceinline__ void nominal_to_smem(const FinalizeArgs& a, int p, double* nom, int tid) {
     constexpr int n = Sys::N, m = Sys::M;
-    double xb[n], ub[m], fb[n];
-#pragma unroll
-    for (int q = 0; q < n; ++q) xb[q] = a.x_nom[(long long)p * n + q];
-#pragma unroll
-    for (int q = 0; q < m; ++q) ub[q] = a.u_nom[(long long)p * m + q];
-    sys.template step<false>(xb, ub, fb);      // scalar dynamics at the nominal (…zero_order.py:61)
-#pragma unroll
-    for (int q = 0; q < n; ++q) nom[q] = xb[q];
-#pragma unroll
-    for (int q = 0; q < m; ++q) nom[n + q] = ub[q];
-#pragma unroll
-    for (int q = 0; q < n; ++q) nom[n + m + q] = fb[q];
+    for (int q = tid; q < 2 * n + m; q += BT) {
+        nom[q] = q < n ? a.x_nom[(long long)p * n + q]
+                       : (q < n + m ? a.u_nom[(long long)p * m + (q - n)] : a.ct[(long long)p * n + (q - n - m)]);
+    }
 }
 
 // At, Bt from AB ([n][d] smem) and c = f(xbar,ubar) - A xbar - B ubar (…zero_order.py:59-62).
-template <class Sys>
+template <class Sys, int BT>
 __device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const double* AB,
                                           const double* nom /*[n+m+n] smem*/, int tid) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
-    for (int e = tid; e < n * d; e += kFinalizeThreads) {
+    for (int e = tid; e < n * d; e += BT) {
         const int r = e / d, cidx = e % d;
         if (cidx < n) a.At[((long long)p * n + r) * n + cidx] = AB[e];
         else a.Bt[((long long)p * n + r) * m + (cidx - n)] = AB[e];
@@ -461,8 +460,8 @@ __device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const do
     }
 }
 
-template <class Sys>
-__global__ void __launch_bounds__(kFinalizeThreads) finalize_zero_order_kernel(const FinalizeArgs a) {
+template <class Sys, int BT>
+__global__ void __launch_bounds__(BT, BT == 32 ? 16 : 4) finalize_zero_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int W = d + n;
     constexpr int NACC = gram_nacc(n, m);
@@ -474,7 +473,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_zero_order_kernel(c
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
     // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs
-    for (int e = tid; e < NACC; e += kFinalizeThreads) {
+    for (int e = tid; e < NACC; e += BT) {
         const double s = sum_partials(a, p, e, NACC);
         int i = 0;
         while (i + 1 < d && gram_row_offset(i + 1, W) <= e) ++i;
@@ -486,19 +485,16 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_zero_order_kernel(c
             Bm[i * n + (j - d)] = s;
         }
     }
+    nominal_to_smem<Sys, BT>(a, p, nom, tid);
     __syncthreads();
-    if (tid == 32) {
-        // the fp64 dynamics at the nominal point runs on warp 1 while warp 0 factors the Gram
-        const Sys sys(a.prm);
-        nominal_to_smem<Sys>(sys, a, p, nom);
-    } else if (tid < 32) {
+    if (tid < 32) {
         // 2. Cholesky G = L L^T by warp 0 (lanes = rows).  A column whose diagonal is exactly zero
         //    (sigma = 0: regressor identically zero) gets coefficient 0, which is what the min-norm
         //    lstsq of the reference returns for it.
         bool bad = false;
         double diag0 = 0.0;      // lane k keeps the original diagonal entry G_kk
         if (lane < d) diag0 = Gm[lane * d + lane];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < d; ++k) {
             double dk = Gm[k * d + k];
             const double d0 = __shfl_sync(0xffffffffu, diag0, k);
@@ -515,43 +511,52 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_zero_order_kernel(c
             if (zero_col)
                 for (int q = lane; q < n; q += 32) Bm[k * n + q] = 0.0;
             __syncwarp();
-            // trailing update, lower triangle (k is a compile-time constant here: cheap index math)
-            const int rem = d - k - 1;
-            for (int e = lane; e < rem * rem; e += 32) {
-                const int r = k + 1 + e / rem, cc = k + 1 + e % rem;
-                if (cc <= r) Gm[r * d + cc] -= Gm[r * d + k] * Gm[cc * d + k];
+            // trailing update, lower triangle: lane = row, loop over the columns (no integer division)
+            for (int r = k + 1 + lane; r < d; r += 32) {
+                const double lrk = Gm[r * d + k];
+                for (int cc = k + 1; cc <= r; ++cc) Gm[r * d + cc] -= lrk * Gm[cc * d + k];
             }
             __syncwarp();
         }
-        // 3. solve L L^T X = B, one right-hand side per lane (fully unrolled: the L loads pipeline)
+        // 3. solve L L^T X = B, one right-hand side per lane (reciprocal diagonal: no divisions)
         if (lane < n) {
             const int q = lane;
-            double y[d];
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < d; ++r) {
-                double s = Bm[r * n + q];
-#pragma unroll
-                for (int k = 0; k < r; ++k) s -= Gm[r * d + k] * y[k];
-                y[r] = s * inv_diag[r];
+                double s0 = Bm[r * n + q], s1 = 0.0;
+                int k = 0;
+#pragma unroll 4
+                for (; k + 1 < r; k += 2) {
+                    s0 -= Gm[r * d + k] * Bm[k * n + q];
+                    s1 -= Gm[r * d + k + 1] * Bm[(k + 1) * n + q];
+                }
+                if (k < r) s0 -= Gm[r * d + k] * Bm[k * n + q];
+                Bm[r * n + q] = (s0 + s1) * inv_diag[r];
             }
-#pragma unroll
+#pragma unroll 1
             for (int r = d - 1; r >= 0; --r) {
-                double s = y[r];
-#pragma unroll
-                for (int k = r + 1; k < d; ++k) s -= Gm[k * d + r] * y[k];
-                y[r] = s * inv_diag[r];
+                double s0 = Bm[r * n + q], s1 = 0.0;
+                int k = r + 1;
+#pragma unroll 4
+                for (; k + 1 < d; k += 2) {
+                    s0 -= Gm[k * d + r] * Bm[k * n + q];
+                    s1 -= Gm[(k + 1) * d + r] * Bm[(k + 1) * n + q];
+                }
+                if (k < d) s0 -= Gm[k * d + r] * Bm[k * n + q];
+                Bm[r * n + q] = (s0 + s1) * inv_diag[r];
             }
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < d; ++r) {
-                if (!(y[r] == y[r]) || fabs(y[r]) > 1e300) bad = true;
-                sAB[q * d + r] = y[r];      // [A|B] = X^T
+                const double v = Bm[r * n + q];
+                if (!(v == v) || fabs(v) > 1e300) bad = true;
+                sAB[q * d + r] = v;      // [A|B] = X^T
             }
         }
         bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) a.status[p] = bad ? 1 : 0;
     }
     __syncthreads();
-    write_abc<Sys>(a, p, sAB, nom, tid);
+    write_abc<Sys, BT>(a, p, sAB, nom, tid);
 }
 
 template <class Sys>
@@ -565,7 +570,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
     const int p = blockIdx.x;
     const Sys sys(a.prm);
     for (int e = tid; e < NJ; e += kFinalizeThreads) sV[e] = sum_partials(a, p, e, NJ) / a.n_total;
-    if (tid == 32) nominal_to_smem<Sys>(sys, a, p, nom);
+    nominal_to_smem<Sys, kFinalizeThreads>(a, p, nom, tid);
     __syncthreads();
     if (tid == 0) {
         double v[NJ], J[n * d];
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
         a.status[p] = 0;
     }
     __syncthreads();
-    write_abc<Sys>(a, p, sAB, nom, tid);
+    write_abc<Sys, kFinalizeThreads>(a, p, sAB, nom, tid);
 }
 
 // Chunk reduction [P, C, width] fp32 -> [P, width] fp64 in fixed chunk order: the block a rank

@@ -484,3 +484,53 @@ def test_full_size_properties(api, name, N):
         Ae, Be, ce = solver.get_TV_matrices(x_trj, cfg["u_trj_initial"])
         assert rel_err(_device.to_numpy(A4), Ae) < 2e-3
         assert rel_err(_device.to_numpy(B4), Be) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# batched MPC instances (BASELINE.json configs[4])
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,I,T,N", [("quadrotor", 5, 24, 1500), ("pendulum", 300, 30, 600)])
+def test_batched_instances_match_oracle_and_shard(api, name, I, T, N):
+    """Every instance of a batch equals the single-problem oracle pipeline on the deltas the kernel
+    drew for it (1e-4), and a shard of the batch (instance_offset) is bit-identical to the same
+    instances inside the full batch — what instance sharding over GPUs relies on."""
+    import torch
+    from irs_mpc_b200 import _device
+    cfg = ec.CONFIGS[name](T=T)
+    s = make_system(api, name)
+    n, m = s.dim_x, s.dim_u
+    rng = np.random.default_rng(5000)
+    x0 = cfg["x0"] + 0.02 * rng.standard_normal((I, n))
+    shift = np.zeros(n)
+    shift[0] = 1.0
+    xd = np.stack([cfg["xd_trj"] + (0.2 * b / I) * shift for b in range(I)])   # per-instance targets
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=77)
+    batch = api.BatchedIrsLqrZeroOrder(s, cfg["Q"], cfg["Qd"], cfg["R"], x0, xd, cfg["u_trj_initial"], sampler)
+    x_init = _device.to_numpy(batch.x_trj)
+    x_new, u_new, cost_new = batch.local_descent()
+    batch.check()
+    x_new, u_new, cost_new = _device.to_numpy(x_new), _device.to_numpy(u_new), _device.to_numpy(cost_new)
+    orc = cr.SYSTEMS[name](s.h)
+    for b in sorted(set([0, 1, I // 2, I - 1])):
+        np.testing.assert_allclose(x_init[b], cr.rollout(orc, x0[b], cfg["u_trj_initial"]), rtol=1e-12, atol=1e-12)
+        deltas = sampler.deltas(T, 1, t0=b * T).astype(np.float64)
+        At, Bt, ct = cr.zero_order_tv_matrices(orc, x_init[b], cfg["u_trj_initial"], deltas)
+        K, k = cr.tvlqr_riccati(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], xd[b])
+        x_o, u_o = cr.closed_loop_descent(orc, K, k, x_init[b][0])
+        cost_o = cr.evaluate_cost(x_o, u_o, xd[b], cfg["Q"], cfg["R"])
+        assert rel_err(x_new[b], x_o) < FP32_RTOL
+        assert rel_err(u_new[b], u_o) < 5 * FP32_RTOL
+        assert abs(cost_new[b] - cost_o) / abs(cost_o) < FP32_RTOL
+    # shard [lo, hi) with instance_offset = lo
+    lo, hi = 1, min(I, 4)
+    shard = api.BatchedIrsLqrZeroOrder(s, cfg["Q"], cfg["Qd"], cfg["R"], x0[lo:hi], xd[lo:hi],
+                                       cfg["u_trj_initial"], sampler, instance_offset=lo)
+    xs, us, cs = shard.local_descent()
+    shard.check()
+    assert np.array_equal(_device.to_numpy(xs), x_new[lo:hi])
+    assert np.array_equal(_device.to_numpy(us), u_new[lo:hi])
+    assert np.array_equal(_device.to_numpy(cs), cost_new[lo:hi])
+    # iterate() keeps the reference's bookkeeping: k + 1 descents, k + 2 cost entries
+    xk, uk, ck = batch.iterate(1)
+    assert len(batch.cost_lst) == 3 and xk.shape == (I, T + 1, n) and ck.shape == (I,)
+    assert np.all(np.isfinite(ck))
