@@ -173,6 +173,20 @@ int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,
                       const double* xd, long long xd_stride, const double* Q, const double* R,
                       int I, int T, double* cost, void* stream);
 
+/* CUDA-graph replay of a fixed call sequence (no reference counterpart; the reference's per-iteration
+ * Python loop, irs_lqr/irs_lqr.py:148-186 and :188-218, re-issues the same calls every iteration).
+ * Everything submitted to `stream` between irs_graph_begin and irs_graph_end — entry points of this
+ * library and cudaMemcpyAsync alike — is captured into one graph instead of being executed.
+ * irs_graph_update_smoothing rewrites seed / iter / stream_id / sigma (HOST array [n+m], NULL = keep)
+ * of the captured accumulate kernel before a replay; pointers and shapes are fixed at capture.
+ * sigma = 0 entries at capture time stay 0 (they mark the unused regressor slots). */
+int irs_graph_begin(void* stream);
+int irs_graph_end(void* stream, void** graph_out);
+int irs_graph_update_smoothing(void* graph, const float* sigma_host, unsigned long long seed,
+                               unsigned iter, unsigned stream_id);
+int irs_graph_launch(void* graph, void* stream);
+int irs_graph_destroy(void* graph);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,11 @@ SIGNATURES = {
                               _vp, _vp, _vp],
     "irs_fp32_fma_peak": [_i, _vp, _ll, _c_double_p, _vp],
     "irs_evaluate_cost": [_i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp],
+    "irs_graph_begin": [_vp],
+    "irs_graph_end": [_vp, ctypes.POINTER(_vp)],
+    "irs_graph_update_smoothing": [_vp, _vp, _ull, _u, _u],
+    "irs_graph_launch": [_vp, _vp],
+    "irs_graph_destroy": [_vp],
 }
 _RESTYPES = {"irs_last_error": ctypes.c_char_p}
 

@@ -64,6 +64,10 @@ static int quadrotor_group() {
     return g;
 }
 
+// The accumulate kernel launched last on this thread: irs_graph_end looks its node up in a captured
+// graph so that irs_graph_update_smoothing can re-parameterise it (seed, iter, sigma) per replay.
+static thread_local const void* g_last_smooth_func = nullptr;
+
 template <class Sys, int G>
 static int launch_zero_order(const SmoothArgs& a, cudaStream_t st) {
     using C = ZeroOrderCfg<Sys, G>;
@@ -74,6 +78,7 @@ static int launch_zero_order(const SmoothArgs& a, cudaStream_t st) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(smooth_zero_order)");
     }
+    g_last_smooth_func = (const void*)kern;
     kern<<<(unsigned)((long long)a.P * a.C), C::kThreads, smem, st>>>(a);
     return check_launch("smooth_zero_order_kernel");
 }
@@ -144,6 +149,7 @@ static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
                 blocks_per_sm, smem, NSTAGE);
     if (const char* g = getenv("IRS_TC_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
     if (grid > items) grid = items;
+    g_last_smooth_func = (const void*)kern;
     kern<<<(unsigned)grid, C::kThreads, smem, st>>>(a);
     return check_launch("smooth_zero_order_tc_kernel");
 }
@@ -397,9 +403,18 @@ int irs_smooth_first_order_accumulate(int system, const double* params_host, int
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((long long)P * C);
     switch (system) {
-        case kPendulum: smooth_first_order_kernel<Pendulum<float>><<<grid, 128, 0, st>>>(a); break;
-        case kBicycle: smooth_first_order_kernel<Bicycle<float>><<<grid, 128, 0, st>>>(a); break;
-        case kQuadrotor: smooth_first_order_kernel<Quadrotor<float>><<<grid, 128, 0, st>>>(a); break;
+        case kPendulum:
+            g_last_smooth_func = (const void*)smooth_first_order_kernel<Pendulum<float>>;
+            smooth_first_order_kernel<Pendulum<float>><<<grid, 128, 0, st>>>(a);
+            break;
+        case kBicycle:
+            g_last_smooth_func = (const void*)smooth_first_order_kernel<Bicycle<float>>;
+            smooth_first_order_kernel<Bicycle<float>><<<grid, 128, 0, st>>>(a);
+            break;
+        case kQuadrotor:
+            g_last_smooth_func = (const void*)smooth_first_order_kernel<Quadrotor<float>>;
+            smooth_first_order_kernel<Quadrotor<float>><<<grid, 128, 0, st>>>(a);
+            break;
         default: set_error("unknown system id %d", system); return 1;
     }
     return check_launch("smooth_first_order_kernel");
@@ -604,6 +619,107 @@ int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,
     IRS_DISPATCH_DIMS(n, m, (evaluate_cost_kernel<N_, M_><<<(I + 3) / 4, 128, 0, st>>>(
                                 x_trj, u_trj, xd, xd_stride, Q, R, I, T, cost)));
     return check_launch("evaluate_cost_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph replay of a fixed call sequence (one iRS-LQR descent, or one linearization with its
+// host<->device copies).  Everything submitted to `stream` between irs_graph_begin and
+// irs_graph_end — entry points of this library and plain cudaMemcpyAsync alike — becomes one
+// graph; irs_graph_update_smoothing rewrites the arguments of the captured accumulate kernel
+// (seed, iteration, sigma change between replays; pointers and shapes must not).
+// ------------------------------------------------------------------------------------------------
+struct IrsGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t smooth_node = nullptr;
+    cudaKernelNodeParams smooth_params{};
+    SmoothArgs args{};
+    void* arg_ptrs[1] = {nullptr};
+};
+
+int irs_graph_begin(void* stream) {
+    g_last_smooth_func = nullptr;
+    if (cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return check_launch("cudaStreamBeginCapture");
+    return 0;
+}
+
+int irs_graph_end(void* stream, void** graph_out) {
+    IRS_REQUIRE(graph_out != nullptr, "null pointer argument");
+    IrsGraph* g = new IrsGraph();
+    if (cudaStreamEndCapture((cudaStream_t)stream, &g->graph) != cudaSuccess || g->graph == nullptr) {
+        delete g;
+        return check_launch("cudaStreamEndCapture") ? 1 : (set_error("stream capture produced no graph"), 1);
+    }
+    // locate the accumulate kernel node
+    size_t nn = 0;
+    cudaGraphGetNodes(g->graph, nullptr, &nn);
+    cudaGraphNode_t* nodes = new cudaGraphNode_t[nn ? nn : 1];
+    cudaGraphGetNodes(g->graph, nodes, &nn);
+    for (size_t i = 0; i < nn && g_last_smooth_func != nullptr; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+        if (kp.func == g_last_smooth_func) {
+            g->smooth_node = nodes[i];
+            g->smooth_params = kp;
+            g->args = *reinterpret_cast<const SmoothArgs*>(kp.kernelParams[0]);
+        }
+    }
+    delete[] nodes;
+    cudaGetLastError();
+    if (cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) {
+        const int rc = check_launch("cudaGraphInstantiate");
+        cudaGraphDestroy(g->graph);
+        delete g;
+        return rc ? rc : 1;
+    }
+    *graph_out = g;
+    return 0;
+}
+
+int irs_graph_update_smoothing(void* graph, const float* sigma_host, unsigned long long seed, unsigned iter,
+                               unsigned stream_id) {
+    IrsGraph* g = reinterpret_cast<IrsGraph*>(graph);
+    IRS_REQUIRE(g != nullptr && g->exec != nullptr, "invalid graph handle");
+    IRS_REQUIRE(g->smooth_node != nullptr, "the captured sequence contains no smoothing accumulate kernel");
+    IRS_REQUIRE(iter < (1u << 24), "iter out of range");
+    SmoothArgs& a = g->args;
+    a.seed_lo = (uint32_t)(seed & 0xffffffffull);
+    a.seed_hi = (uint32_t)(seed >> 32);
+    a.iter = iter;
+    a.stream = stream_id;
+    if (sigma_host != nullptr) {
+        // sigma holds n + m entries; the remaining slots stay zero as in fill_smooth_args
+        int live = 0;
+        for (int c = 0; c < kMaxRegressors; ++c) live = a.sigma_scaled[c] != 0.f ? c + 1 : live;
+        for (int c = 0; c < kMaxRegressors; ++c)
+            if (c < live) a.sigma_scaled[c] = kBoxMullerScale * sigma_host[c];
+    }
+    g->arg_ptrs[0] = &a;
+    cudaKernelNodeParams kp = g->smooth_params;
+    kp.kernelParams = g->arg_ptrs;
+    kp.extra = nullptr;
+    if (cudaGraphExecKernelNodeSetParams(g->exec, g->smooth_node, &kp) != cudaSuccess)
+        return check_launch("cudaGraphExecKernelNodeSetParams");
+    return 0;
+}
+
+int irs_graph_launch(void* graph, void* stream) {
+    IrsGraph* g = reinterpret_cast<IrsGraph*>(graph);
+    IRS_REQUIRE(g != nullptr && g->exec != nullptr, "invalid graph handle");
+    if (cudaGraphLaunch(g->exec, (cudaStream_t)stream) != cudaSuccess) return check_launch("cudaGraphLaunch");
+    return 0;
+}
+
+int irs_graph_destroy(void* graph) {
+    IrsGraph* g = reinterpret_cast<IrsGraph*>(graph);
+    if (g == nullptr) return 0;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
 }
 
 }  // extern "C"

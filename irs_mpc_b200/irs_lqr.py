@@ -13,6 +13,8 @@ Differences a user can observe, all deliberate:
     Any other callable is honoured through the replay path.
   * only systems derived from `CudaDynamicalSystem` are accepted (no CPU fallback).
 """
+import ctypes
+import os
 import time
 
 import numpy as np
@@ -22,6 +24,10 @@ from . import _device, _lib, smoothing
 from .dynamical_system import CudaDynamicalSystem
 from .sampling import GaussianSampling
 from .tv_lqr import TVLQR_FAILED, get_solver, riccati_device
+
+
+# CUDA-graph replay of the per-iteration call sequence (IRS_CUDA_GRAPH=0 forces eager launches)
+_USE_GRAPHS = os.environ.get("IRS_CUDA_GRAPH", "1") != "0"
 
 
 class IrsLqrParameters:
@@ -67,6 +73,7 @@ class IrsLqr:
         self._dxd = _device.to_device(np.asarray(self.xd_trj, dtype=np.float64)[:self.T + 1])
         self._ws = None
         self._db = None
+        self._graphs = {}
         self._last_descent = None
         self.timings = {}
 
@@ -177,13 +184,11 @@ class IrsLqr:
             self._db = db
         return self._db
 
-    def local_descent(self, x_trj, u_trj):
+    def _enqueue_descent(self, db):
+        """All device work of one descent on the current stream, bracketed by the two staging copies;
+        no host synchronisation (this is the sequence the CUDA graph captures)."""
         T, n, m = self.T, self.dim_x, self.dim_u
-        db = self._descent_buffers()
-        nx, nu = db["nx"], db["nu"]
-        h = db["in_host"].numpy()
-        h[:nx] = np.asarray(x_trj, dtype=np.float64)[:T + 1].reshape(-1)
-        h[nx:] = np.asarray(u_trj, dtype=np.float64)[:T].reshape(-1)
+        nx = db["nx"]
         db["in_dev"].copy_(db["in_host"], non_blocking=True)
         x_all = db["in_dev"][:nx].view(T + 1, n)
         u_nom = db["in_dev"][nx:].view(T, m)
@@ -200,8 +205,57 @@ class IrsLqr:
                   _device.ptr(k), _device.ptr(x_all), _device.ptr(self._dxd), 0,
                   _device.ptr(self._dQ), _device.ptr(self._dR), 1, T, _device.ptr(db["x_new"]),
                   _device.ptr(db["u_new"]), _device.ptr(db["cost"]), _device.stream_ptr())
-        # one synchronising read-back for everything the host needs
         db["out_host"].copy_(db["out_dev"], non_blocking=True)
+
+    def _graph_key(self):
+        """None when this call sequence cannot be replayed from a CUDA graph (see _SampledIrsLqr)."""
+        return None
+
+    def _graph_update(self, graph):
+        pass
+
+    def _run(self, name, enqueue):
+        """Run `enqueue()` eagerly, or — from the third call of the same shape on — replay it from a
+        CUDA graph captured through the library (one launch instead of ~8 API calls)."""
+        key = self._graph_key()
+        if key is None or not _USE_GRAPHS:
+            enqueue()
+            return
+        key = (name,) + key
+        slot = self._graphs.get(name)
+        if slot is None or slot[0] != key:
+            if slot is not None and slot[1] is not None:
+                _lib.call("irs_graph_destroy", slot[1])
+            self._graphs[name] = [key, None, 1]       # key, graph handle, eager calls so far
+            enqueue()
+            return
+        if slot[1] is None:
+            if slot[2] < 2:                           # let every workspace be allocated and warm first
+                slot[2] += 1
+                enqueue()
+                return
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                _lib.call("irs_graph_begin", side.cuda_stream)
+                try:
+                    enqueue()
+                finally:
+                    handle = ctypes.c_void_p()
+                    _lib.call("irs_graph_end", side.cuda_stream, ctypes.byref(handle))
+            slot[1] = handle
+        self._graph_update(slot[1])
+        _lib.call("irs_graph_launch", slot[1], _device.stream_ptr())
+
+    def local_descent(self, x_trj, u_trj):
+        T, n, m = self.T, self.dim_x, self.dim_u
+        db = self._descent_buffers()
+        nx, nu = db["nx"], db["nu"]
+        h = db["in_host"].numpy()
+        h[:nx] = np.asarray(x_trj, dtype=np.float64)[:T + 1].reshape(-1)
+        h[nx:] = np.asarray(u_trj, dtype=np.float64)[:T].reshape(-1)
+        self._run("descent", lambda: self._enqueue_descent(db))
+        # one synchronising read-back for everything the host needs
         torch.cuda.current_stream().synchronize()
         o = db["out_host"].numpy()
         smoothing.check_status(o[nx + nu + 2:].view(np.int32)[:T])
@@ -306,9 +360,30 @@ class _SampledIrsLqr(IrsLqr):
         return At, Bt, ct, status
 
 
+    def _graph_key(self):
+        s = self.sampling
+        if not isinstance(s, GaussianSampling):
+            return None           # a Python closure is called T times per iteration: nothing to replay
+        return (self.system.system_id, self.order, self.T, s.num_samples, s.flags())
+
+    def _graph_update(self, graph):
+        s = self.sampling
+        sig = np.ascontiguousarray(s.sigma(self.iter), dtype=np.float32)
+        _lib.call("irs_graph_update_smoothing", graph, sig.ctypes.data_as(ctypes.c_void_p), int(s.seed),
+                  int(self.iter), int(s.stream_id))
+
+    def _enqueue_linearize(self, ws):
+        s = self.sampling
+        ws.enqueue_upload()
+        smoothing.accumulate(self.system, self.order, ws.x_nom, ws.u_nom, s.num_samples, ws,
+                             sigma=s.sigma(self.iter), seed=s.seed, it=self.iter, stream_id=s.stream_id,
+                             flags=s.flags())
+        smoothing.finalize(self.system, self.order, ws.x_nom, ws.u_nom, ws, s.num_samples)
+        ws.enqueue_download()
+
     def get_TV_matrices(self, x_trj, u_trj):
-        """numpy in, numpy out: one pinned H2D copy of [x_nom | u_nom], the two kernels, one D2H copy
-        of [At | Bt | ct | status]."""
+        """numpy in, numpy out: one pinned H2D copy of [x_nom | u_nom], the kernels, one D2H copy
+        of [At | Bt | ct | status] — replayed from a CUDA graph once warm."""
         s = self.sampling
         if not isinstance(s, GaussianSampling):
             return super().get_TV_matrices(x_trj, u_trj)
@@ -316,12 +391,9 @@ class _SampledIrsLqr(IrsLqr):
         if self._ws is None or self._ws.key != key:
             self._ws = smoothing.Workspace(self.system, self.order, self.T, s.num_samples)
         ws = self._ws
-        x_nom, u_nom = ws.upload_nominal(x_trj, u_trj)
-        smoothing.accumulate(self.system, self.order, x_nom, u_nom, s.num_samples, ws,
-                             sigma=s.sigma(self.iter), seed=s.seed, it=self.iter, stream_id=s.stream_id,
-                             flags=s.flags())
-        smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, s.num_samples)
-        At, Bt, ct, status = ws.download()
+        ws.stage_nominal(x_trj, u_trj)
+        self._run("linearize", lambda: self._enqueue_linearize(ws))
+        At, Bt, ct, status = ws.read_download()
         smoothing.check_status(status)
         return At, Bt, ct
 

@@ -50,23 +50,30 @@ class Workspace:
         self._out_host = None
         self._nom_host = None
 
-    def upload_nominal(self, x_trj, u_trj):
-        """numpy [>=P, n], [>=P, m] -> (x_nom, u_nom) device views; one pinned H2D copy."""
-        P, n, m = self.P, self.n, self.m
+    def _host_buffers(self):
         if self._nom_host is None:
-            self._nom_host = torch.empty((P * (n + m),), dtype=torch.float64).pin_memory()
+            self._nom_host = torch.empty(self._nom.shape, dtype=torch.float64).pin_memory()
+            self._out_host = torch.empty(self._out.shape, dtype=torch.float64).pin_memory()
+
+    def stage_nominal(self, x_trj, u_trj):
+        """numpy [>=P, n], [>=P, m] -> the pinned host mirror of [x_nom | u_nom] (no device work)."""
+        P, n, m = self.P, self.n, self.m
+        self._host_buffers()
         h = self._nom_host.numpy()
         h[:P * n] = np.asarray(x_trj, dtype=np.float64)[:P].reshape(-1)
         h[P * n:] = np.asarray(u_trj, dtype=np.float64)[:P].reshape(-1)
-        self._nom.copy_(self._nom_host, non_blocking=True)
-        return self.x_nom, self.u_nom
 
-    def download(self):
-        """-> (At, Bt, ct, status) as numpy arrays; one D2H copy into pinned memory + one sync."""
-        P, n, m = self.P, self.n, self.m
-        if self._out_host is None:
-            self._out_host = torch.empty(self._out.shape, dtype=torch.float64).pin_memory()
+    def enqueue_upload(self):
+        self._host_buffers()
+        self._nom.copy_(self._nom_host, non_blocking=True)
+
+    def enqueue_download(self):
+        self._host_buffers()
         self._out_host.copy_(self._out, non_blocking=True)
+
+    def read_download(self):
+        """Synchronise and unpack the pinned mirror -> (At, Bt, ct, status) numpy arrays."""
+        P, n, m = self.P, self.n, self.m
         torch.cuda.current_stream().synchronize()
         h = self._out_host.numpy()
         na, nb, nc = P * n * n, P * n * m, P * n
@@ -75,6 +82,17 @@ class Workspace:
         ct = h[na + nb:na + nb + nc].reshape(P, n).copy()
         status = h[na + nb + nc:].view(np.int32)[:P].copy()
         return At, Bt, ct, status
+
+    def upload_nominal(self, x_trj, u_trj):
+        """One pinned H2D copy; returns the (x_nom, u_nom) device views."""
+        self.stage_nominal(x_trj, u_trj)
+        self.enqueue_upload()
+        return self.x_nom, self.u_nom
+
+    def download(self):
+        """One D2H copy into pinned memory + one sync -> (At, Bt, ct, status) numpy arrays."""
+        self.enqueue_download()
+        return self.read_download()
 
     def h2d_bytes(self):
         return self._nom.numel() * 8

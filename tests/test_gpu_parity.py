@@ -534,3 +534,43 @@ def test_batched_instances_match_oracle_and_shard(api, name, I, T, N):
     xk, uk, ck = batch.iterate(1)
     assert len(batch.cost_lst) == 3 and xk.shape == (I, T + 1, n) and ck.shape == (I,)
     assert np.all(np.isfinite(ck))
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the per-iteration call sequence
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,T,N", [("pendulum", 60, 1000), ("quadrotor", 30, 2000)])
+def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
+    """From the third call on, local_descent / get_TV_matrices are replayed from a CUDA graph whose
+    accumulate node is re-parameterised (iter, seed, sigma) — the results must equal the eager
+    launches bit for bit, iteration after iteration."""
+    from irs_mpc_b200 import irs_lqr as mod
+    cfg = ec.CONFIGS[name](T=T)
+    n = cfg["x0"].shape[0]
+
+    def run(use_graphs):
+        old = mod._USE_GRAPHS
+        mod._USE_GRAPHS = use_graphs
+        try:
+            s = make_system(api, name)
+            sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=11)
+            solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=T), sampler)
+            solver.iterate(5, verbose=False)
+            tv = []
+            for k in range(4):
+                sampler.seed = 100 + k
+                tv.append(solver.get_TV_matrices(solver.x_trj, solver.u_trj))
+            return solver, tv
+        finally:
+            mod._USE_GRAPHS = old
+
+    eager, tv_e = run(False)
+    graph, tv_g = run(True)
+    assert "descent" in graph._graphs and graph._graphs["descent"][1] is not None      # really replayed
+    assert "linearize" in graph._graphs and graph._graphs["linearize"][1] is not None
+    assert not eager._graphs
+    assert eager.cost_lst == graph.cost_lst
+    for a, b in zip(eager.x_trj_lst, graph.x_trj_lst):
+        assert np.array_equal(a, b)
+    for (A1, B1, c1), (A2, B2, c2) in zip(tv_e, tv_g):
+        assert np.array_equal(A1, A2) and np.array_equal(B1, B2) and np.array_equal(c1, c2)
