@@ -259,6 +259,19 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     clock_info = clocks.stop() if rank == 0 else None
 
+    # 2b. the same kernel in replay mode (pre-generated noise streamed from HBM, the parity path):
+    #     64 B/sample of algorithmic traffic; buffer (640 MB) is far larger than the 126 MB L2
+    replay = None
+    if world == 1:
+        noise = torch.empty((T_STEPS, N_SAMPLES, 16), dtype=torch.float32, device="cuda").normal_(0.0, 0.1)
+
+        def only_replay(k):
+            smoothing.accumulate(system, smoothing.ZERO_ORDER, x_nom, u_nom, N_SAMPLES, ws, noise=noise)
+        ms_replay = timed(only_replay, args.steps, 2) / args.steps
+        gbs = T_STEPS * N_SAMPLES * 64 / (ms_replay * 1e-3) / 1e9
+        del noise
+        torch.cuda.empty_cache()
+
     # 3. measured FP32 FMA peak (roofline denominator), best of 5
     scratch = _device.empty((148 * 8 * 256,), torch.float32)
     import ctypes
@@ -387,6 +400,13 @@ def run_gpu(args, rank, local_rank, world):
                          "bound_note": "Philox mode has no per-sample HBM stream, so the kernel is bounded by FP32 "
                                        "issue, not by HBM or the tensor pipe (DESIGN.md 3.1)",
                          "hbm_gbs_measured_peak": peaks.get("hbm_gbs")},
+            "roofline_replay_mode": None if world > 1 else {
+                "bound": "hbm", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1> (noise replayed from HBM)",
+                "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)", "bytes_per_sample": 64,
+                "kernel_ms": ms_replay, "samples_per_s": T_STEPS * N_SAMPLES / (ms_replay * 1e-3),
+                "note": "parity/compat path; still bounded by FP32 issue, not by HBM"},
             "cpu_baseline": cpu,
             "clocks": clock_info,
         }

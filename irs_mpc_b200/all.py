@@ -4,6 +4,7 @@ from .dynamical_system import CudaDynamicalSystem, DynamicalSystem  # noqa: F401
 from .irs_lqr import (IrsLqr, IrsLqrExact, IrsLqrFirstOrder, IrsLqrParameters,  # noqa: F401
                       IrsLqrZeroOrder)
 from .batched import BatchedIrsLqrZeroOrder  # noqa: F401
+from .cem import CemParameters, CrossEntropyMethod  # noqa: F401
 from .sampling import GaussianSampling  # noqa: F401
 from .systems import (BicycleDynamics, PendulumDynamics, QuadrotorDynamics,  # noqa: F401
                       ThreeCartDynamics)

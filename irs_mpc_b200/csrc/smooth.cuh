@@ -81,34 +81,42 @@ __device__ __forceinline__ void draw_deltas(const SmoothArgs& a, int p, long lon
 
 // three_cart: project the perturbed state onto non-penetration
 // (three_cart_dynamics.py:196-264 called from three_cart_zero_order.py:38-43).
-// Done in fp64: the reference re-evaluates its masks on the partially projected point,
-// so whether a second push-out fires can hinge on the last bit of a gap that is
-// nominally exactly d; only the same arithmetic reproduces those decisions.
+// The POSITIONS are projected in fp64: the reference re-evaluates its masks on the partially
+// projected point, and after a pair push-out the gap it re-tests is exactly d in exact arithmetic,
+// so whether the next push-out (which has a real depth) fires is decided by the rounding of the
+// reference's float64 operations; only the same arithmetic on the same values reproduces those
+// decisions.  Everything that no branch depends on (velocities, inputs) stays in fp32.
+// pos64: the kProj leading nominal coordinates in fp64 (shared memory), or nullptr = read a.x_nom.
 template <class Sys, int RS>
-__device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, float (&w)[RS]) {
+__device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, const float* xbar,
+                                               const float* ubar, const double* pos64, float (&w)[RS]) {
     constexpr int n = Sys::N, m = Sys::M;
     if constexpr (Sys::kHasProjection) {
+        constexpr int kProj = Sys::kProjDims;
         if (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) {
             using SysD = typename Sys::template Rebind<double>;
             const SysD sysd(a.prm);
-            double xb[n], xp[n];
+            double xb[kProj], xp[n];
 #pragma unroll
-            for (int c = 0; c < n; ++c) {
-                xb[c] = a.x_nom[(long long)p * n + c];
+            for (int c = 0; c < kProj; ++c) {
+                xb[c] = pos64 != nullptr ? pos64[c] : a.x_nom[(long long)p * n + c];
                 xp[c] = xb[c] + (double)w[c];
             }
+#pragma unroll
+            for (int c = kProj; c < n; ++c) xp[c] = 0.0;      // untouched by project()
             sysd.project(xp);
             if (a.flags & kFlagProjectAbsolute) {
                 // the reference closure returns ABSOLUTE points which the solver adds to the
                 // nominal again and uses as regressors — reproduced literally
 #pragma unroll
-                for (int c = 0; c < n; ++c) w[c] = (float)xp[c];
+                for (int c = 0; c < kProj; ++c) w[c] = (float)xp[c];
 #pragma unroll
-                for (int c = 0; c < m; ++c)
-                    w[n + c] = (float)(a.u_nom[(long long)p * m + c] + (double)w[n + c]);
+                for (int c = kProj; c < n; ++c) w[c] = xbar[c] + w[c];
+#pragma unroll
+                for (int c = 0; c < m; ++c) w[n + c] = ubar[c] + w[n + c];
             } else {
 #pragma unroll
-                for (int c = 0; c < n; ++c) w[c] = (float)(xp[c] - xb[c]);
+                for (int c = 0; c < kProj; ++c) w[c] = (float)(xp[c] - xb[c]);
             }
         }
     }
@@ -120,7 +128,7 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
                                             const float* fbar, float (&w)[RS], bool want_df = true) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     draw_deltas<Sys, RS>(a, p, i, w);
-    project_deltas<Sys, RS>(a, p, w);
+    project_deltas<Sys, RS>(a, p, xbar, ubar, nullptr, w);
     float x[n], u[m];
 #pragma unroll
     for (int c = 0; c < n; ++c) x[c] = xbar[c] + w[c];

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     __shared__ uint64_t mbar_done[C::kWarps];            // UMMA commit -> owning warp: accumulator complete
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float nom_s[kNom];          // nominal point of the current item (fp32)
+    __shared__ double pos64_s[4];                        // its leading coordinates in fp64 (projection)
     __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][i] + D[r][dq + i]
     __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
 
@@ -159,8 +160,13 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     // nominal point of an item -> nom_s (two block barriers inside; all threads call it)
     auto load_nominal = [&](long long item) {
         const int p = (int)(item / a.C);
-        if (tid < n) nom_s[tid] = (float)a.x_nom[(long long)p * n + tid];
-        else if (tid < n + m) nom_s[tid] = (float)a.u_nom[(long long)p * m + (tid - n)];
+        if (tid < n) {
+            const double v = a.x_nom[(long long)p * n + tid];
+            nom_s[tid] = (float)v;
+            if (tid < 4) pos64_s[tid] = v;
+        } else if (tid < n + m) {
+            nom_s[tid] = (float)a.u_nom[(long long)p * m + (tid - n)];
+        }
         __syncthreads();
         if (tid == 0) {
             float xb[n], ub[m], fb[n];
@@ -231,15 +237,15 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             if (s < s_end) {
                 if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
                 draw_deltas<Sys, C::RS>(a, p, s, w);
-                project_deltas<Sys, C::RS>(a, p, w);
-                float xu[kXU], f[n];
                 // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers:
-                // measured faster than the register copy, which costs occupancy-neutral spills)
+                // measured faster than the register copy)
+                float xu[kXU], f[n];
 #pragma unroll
                 for (int q = 0; q < kXU / 4; ++q) {
                     const float4 v = nom4[q];
                     xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
                 }
+                project_deltas<Sys, C::RS>(a, p, xu, xu + n, pos64_s, w);
 #pragma unroll
                 for (int q = 0; q < d; ++q) xu[q] += w[q];
                 if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar

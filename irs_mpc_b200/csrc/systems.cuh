@@ -224,6 +224,7 @@ struct ThreeCart {
     static constexpr int N = 6, M = 2, D = 8, NJ = 0;
     static constexpr bool kHasJacobian = false;   // three_cart_dynamics.py:20
     static constexpr bool kHasProjection = true;
+    static constexpr int kProjDims = 3;           // project() touches the cart positions only
     R h, d;
     __device__ explicit ThreeCart(const SysParams& p) : h(prm<R>(p, 0)), d(prm<R>(p, 1)) {}
 

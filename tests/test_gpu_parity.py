@@ -574,3 +574,35 @@ def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
         assert np.array_equal(a, b)
     for (A1, B1, c1), (A2, B2, c2) in zip(tv_e, tv_g):
         assert np.array_equal(A1, A2) and np.array_equal(B1, B2) and np.array_equal(c1, c2)
+
+
+# ------------------------------------------------------------------------------------------------
+# CEM baseline (irs_lqr/cem.py) — SURVEY.md section 8f row 2
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,T,B", [("pendulum", 60, 200), ("three_cart", 40, 128)])
+def test_cem_matches_numpy_restatement(api, name, T, B):
+    """Same seed -> same candidates (np.random.normal, as the reference); costs from the batched
+    rollout kernel equal the float64 loop of cem.py:165-169, so the elite set and the refit agree."""
+    cfg = ec.CONFIGS[name](T=T)
+    s = make_system(api, name)
+    m = s.dim_u
+    p = api.CemParameters()
+    p.Q, p.Qd, p.R, p.x0, p.xd_trj, p.u_trj_initial = (cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"],
+                                                       cfg["u_trj_initial"])
+    p.n_elite, p.batch_size, p.initial_std = 20, B, 0.5 * np.ones(m)
+    np.random.seed(1234)
+    solver = api.CrossEntropyMethod(s, p)
+    x_new, u_new = solver.local_descent(solver.x_trj, solver.u_trj)
+    # restatement of cem.py:151-184 on the oracle dynamics
+    orc = cr.SYSTEMS[name](s.h)
+    np.random.seed(1234)
+    cand = np.random.normal(cfg["u_trj_initial"], np.tile(p.initial_std, (T, 1)), (B, T, m))
+    costs = np.array([cr.evaluate_cost(cr.rollout(orc, cfg["x0"], cand[k]), cand[k], cfg["xd_trj"], cfg["Q"],
+                                       cfg["R"]) for k in range(B)])
+    best = np.argpartition(costs, p.n_elite)[:p.n_elite]
+    u_o = cand[best].mean(axis=0)
+    np.testing.assert_allclose(u_new, u_o, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(solver.std_trj, cand[best].std(axis=0), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(x_new, cr.rollout(orc, cfg["x0"], u_o), rtol=1e-9, atol=1e-9)
+    x, u, c = solver.iterate(2, verbose=False)
+    assert len(solver.cost_lst) == 4 and np.isfinite(c)
