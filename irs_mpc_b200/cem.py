@@ -98,8 +98,7 @@ class CrossEntropyMethod:
         u = np.ascontiguousarray(np.asarray(u_candidates, dtype=np.float64))
         B = u.shape[0]
         ud = _device.to_device(u)
-        x0d = _device.to_device(np.ascontiguousarray(np.broadcast_to(
-            np.asarray(x0, dtype=np.float64), (B, self.dim_x))))
+        x0d = _device.to_device(np.tile(np.asarray(x0, dtype=np.float64), (B, 1)))
         x_trj = _device.empty((B, self.T + 1, self.dim_x))
         cost = _device.empty((B,))
         prm, nprm = self.system._params()

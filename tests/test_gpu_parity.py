@@ -606,3 +606,37 @@ def test_cem_matches_numpy_restatement(api, name, T, B):
     np.testing.assert_allclose(x_new, cr.rollout(orc, cfg["x0"], u_o), rtol=1e-9, atol=1e-9)
     x, u, c = solver.iterate(2, verbose=False)
     assert len(solver.cost_lst) == 4 and np.isfinite(c)
+
+
+# ------------------------------------------------------------------------------------------------
+# ragged / edge sample counts through both Gram engines
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("name,N", [("quadrotor", 17), ("quadrotor", 127), ("quadrotor", 128), ("quadrotor", 129),
+                                    ("quadrotor", 4097), ("pendulum", 4), ("pendulum", 33), ("bicycle", 300),
+                                    ("three_cart", 257)])
+def test_ragged_sample_counts_match_oracle(api, name, N, engine):
+    """Sample counts that do not fill a 32-sample warp tile, a 128-sample block round or a 4096-sample
+    chunk: the padded lanes must contribute nothing (fit vs the fp64 oracle on the same deltas)."""
+    from irs_mpc_b200 import _device, _lib, smoothing
+    T = 3
+    cfg, s, u_trj = _nominal(api, name, T)
+    n = s.dim_x
+    x_trj = cr.rollout(cr.SYSTEMS[name](s.h), cfg["x0"], u_trj)
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=5)
+    _lib.call("irs_set_gram_engine", engine)
+    try:
+        At, Bt, ct, status, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, _device.to_device(x_trj[:T]),
+                                                    _device.to_device(u_trj), N, sigma=sampler.sigma(1),
+                                                    seed=sampler.seed, it=1)
+        assert int(status.sum().item()) == 0
+        At, Bt, ct = _device.to_numpy(At), _device.to_numpy(Bt), _device.to_numpy(ct)
+    finally:
+        _lib.call("irs_set_gram_engine", -1)
+    deltas = sampler.deltas(T, 1).astype(np.float64)
+    Ao, Bo, co = cr.zero_order_tv_matrices(cr.SYSTEMS[name](s.h), x_trj, u_trj, deltas)
+    # few samples -> ill-conditioned normal equations amplify the fp32 Gram noise
+    tol = FP32_RTOL * (30.0 if N < 3 * (n + s.dim_u) else 1.0)
+    assert rel_err(At, Ao) < tol
+    assert rel_err(Bt, Bo) < tol
+    assert float(np.max(np.abs(ct - co))) < tol * max(1.0, float(np.max(np.abs(x_trj))))
