@@ -410,9 +410,29 @@ def run_gpu(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "clocks": clock_info,
         }
-        print(json.dumps(out), flush=True)
+        result_line = json.dumps(out)
+    else:
+        result_line = None
     if world > 1:
         dist.destroy_process_group()
+    return result_line
+
+
+class StdoutGuard:
+    """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner to
+    stdout; native libraries may too) so that stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -433,7 +453,10 @@ def main():
     if args.warmup < 3:
         log("note: warmup raised to 3 (timing rules)")
         args.warmup = 3
-    run_gpu(args, rank, local_rank, world)
+    with StdoutGuard():
+        line = run_gpu(args, rank, local_rank, world)
+    if line is not None:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
