@@ -547,8 +547,16 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
     cudaStream_t st = (cudaStream_t)stream;
     // few instances: one block per instance (latency); many: one warp per instance (throughput)
     const bool per_block = I <= 2 * num_sms();
+    static const bool no_tiles = getenv("IRS_TVLQR_NO_TILES") != nullptr;
     IRS_DISPATCH_DIMS(n, m, {
         if (per_block) {
+            if constexpr (N_ % 2 == 0 && M_ % 2 == 0) {
+                if (!no_tiles) {
+                    tvlqr_riccati_tiled_kernel<N_, M_>
+                        <<<(unsigned)I, kTvlqrTiledThreads, sizeof(TvlqrTiledSmem<N_, M_>), st>>>(a);
+                    return check_launch("tvlqr_riccati_tiled_kernel");
+                }
+            }
             tvlqr_riccati_kernel<N_, M_, kTvlqrBlockThreads>
                 <<<(unsigned)I, kTvlqrBlockThreads, sizeof(TvlqrSmem<N_, M_>), st>>>(a);
         } else {

@@ -264,6 +264,218 @@ __global__ void __launch_bounds__(G == 32 ? 32 * kTvlqrWarps : G) tvlqr_riccati_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-tiled variant for few instances and even n, m (quadrotor 12/4, three_cart 6/2): one block
+// of 128 threads per instance, every thread owns a 2 x 2 tile of a matrix product and streams the
+// operand rows as 16-byte shared-memory loads (24 LDS.128 for 48 DFMA per tile).  The generic
+// kernel above spends most of a step in the LSU: one thread per output needs 2 loads per FMA and
+// ~1200 of its ~3150 cycles per step are shared-memory issue; tiling halves the loads per FMA
+// twice over (2 x 2 tile, 128-bit loads).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTvlqrTiledThreads = 128;
+
+template <int n, int m>
+struct TvlqrTiledSmem {
+    double P[n * n], A[n * n], PA[n * n], Pn[n * n], Q[n * n];
+    double B[n * m], PB[n * m], G[m * n], Kt[m * n];
+    double H[m * m], Rh[m * m];
+    double p[n], w[n], c[n], xd[n], g[m], kt[m];
+};
+
+// acc[r][c] += sum_{q < len} X[q][x0 + r] * Y[q][y0 + c], X and Y row-major with leading dimensions
+// ldx, ldy; x0, y0 even (16-byte aligned pairs).
+template <int len>
+__device__ __forceinline__ void tile_atb(const double* X, int ldx, int x0, const double* Y, int ldy, int y0,
+                                         double (&acc)[2][2]) {
+    double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};      // second partial sums: halves the dependent chain
+#pragma unroll
+    for (int q = 0; q < len; ++q) {
+        const double2 x = *reinterpret_cast<const double2*>(X + q * ldx + x0);
+        const double2 y = *reinterpret_cast<const double2*>(Y + q * ldy + y0);
+        if (q & 1) {
+            a2[0][0] += x.x * y.x;  a2[0][1] += x.x * y.y;  a2[1][0] += x.y * y.x;  a2[1][1] += x.y * y.y;
+        } else {
+            acc[0][0] += x.x * y.x;  acc[0][1] += x.x * y.y;  acc[1][0] += x.y * y.x;  acc[1][1] += x.y * y.y;
+        }
+    }
+    acc[0][0] += a2[0][0];  acc[0][1] += a2[0][1];  acc[1][0] += a2[1][0];  acc[1][1] += a2[1][1];
+}
+// acc[r][c] += sum_{q < len} X[x0 + r][q] * Y[q][y0 + c]   (rows of X, columns of Y; len even)
+template <int len>
+__device__ __forceinline__ void tile_ab(const double* X, int ldx, int x0, const double* Y, int ldy, int y0,
+                                        double (&acc)[2][2]) {
+    double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int q = 0; q < len; q += 2) {
+        const double2 x0v = *reinterpret_cast<const double2*>(X + (x0 + 0) * ldx + q);
+        const double2 x1v = *reinterpret_cast<const double2*>(X + (x0 + 1) * ldx + q);
+        const double2 ya = *reinterpret_cast<const double2*>(Y + q * ldy + y0);
+        const double2 yb = *reinterpret_cast<const double2*>(Y + (q + 1) * ldy + y0);
+        acc[0][0] += x0v.x * ya.x;  acc[0][1] += x0v.x * ya.y;  acc[1][0] += x1v.x * ya.x;  acc[1][1] += x1v.x * ya.y;
+        a2[0][0] += x0v.y * yb.x;   a2[0][1] += x0v.y * yb.y;   a2[1][0] += x1v.y * yb.x;   a2[1][1] += x1v.y * yb.y;
+    }
+    acc[0][0] += a2[0][0];  acc[0][1] += a2[0][1];  acc[1][0] += a2[1][0];  acc[1][1] += a2[1][1];
+}
+
+template <int n, int m>
+__global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel(const TvlqrArgs a) {
+    static_assert(n % 2 == 0 && m % 2 == 0, "2 x 2 tiles");
+    constexpr int G = kTvlqrTiledThreads;
+    constexpr int hn = n / 2, hm = m / 2;
+    static_assert(hn * hn <= 64 && hn * hm <= 32 && hm * hm <= 32 && n + 1 <= 32, "tile-to-warp mapping");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TvlqrTiledSmem<n, m>& s = *reinterpret_cast<TvlqrTiledSmem<n, m>*>(smem_raw);
+    const int gt = threadIdx.x, warp = gt >> 5, lane = gt & 31;
+    const int inst = blockIdx.x;
+    const double* xd_i = a.xd + inst * a.xd_stride;
+    bool ok = true;
+    // Work is assigned to warps by ROLE (one code path per warp and phase: no intra-warp divergence
+    // between the tile kinds); tile origins are loop invariants.
+    const int pa_r0 = 2 * (gt / hn), pa_c0 = 2 * (gt % hn);            // n x n tiles: threads 0 .. hn*hn-1
+    const int pb_r0 = 2 * (lane / hm), pb_c0 = 2 * (lane % hm);        // n x m tiles: warp 2
+    const int g_r0 = 2 * (lane / hn), g_c0 = 2 * (lane % hn);          // m x n tiles: warp 0
+    const int h_r0 = 2 * (lane / hm), h_c0 = 2 * (lane % hm);          // m x m tiles: warp 1
+    // running global pointers of step t (stepped back once per iteration: no 64-bit index math inside)
+    constexpr int kRA = (n * n + G - 1) / G;
+    const double* pA = a.At + ((long long)inst * a.T + (a.T - 1)) * n * n + gt;
+    const double* pB = a.Bt + ((long long)inst * a.T + (a.T - 1)) * n * m + gt;
+    const double* pc = a.ct + ((long long)inst * a.T + (a.T - 1)) * n + gt;
+    const double* pxd = xd_i + (long long)(a.T - 1) * n + gt;
+    double* pK = a.K + ((long long)inst * a.T + (a.T - 1)) * m * n;
+    double* pk = a.k + ((long long)inst * a.T + (a.T - 1)) * m;
+    static_assert(n * m <= G && n <= G, "one prefetch slot per thread for B, c, xd");
+    double rA[kRA], rB = 0.0, rc = 0.0, rxd = 0.0;
+    auto prefetch = [&] {
+#pragma unroll
+        for (int k = 0; k < kRA; ++k) if (gt + k * G < n * n) rA[k] = pA[k * G];
+        if (gt < n * m) rB = *pB;
+        if (gt < n) { rc = *pc;  rxd = *pxd; }
+        pA -= n * n;  pB -= n * m;  pc -= n;  pxd -= n;
+    };
+    auto publish = [&] {
+#pragma unroll
+        for (int k = 0; k < kRA; ++k) if (gt + k * G < n * n) s.A[gt + k * G] = rA[k];
+        if (gt < n * m) s.B[gt] = rB;
+        if (gt < n) { s.c[gt] = rc;  s.xd[gt] = rxd; }
+    };
+    prefetch();
+    // terminal condition: P_T = Qd, p_T = -Qd xd_T; constants into shared memory
+    for (int e = gt; e < n * n; e += G) { s.P[e] = a.Qd[e];  s.Q[e] = a.Q[e]; }
+    for (int e = gt; e < m * m; e += G) s.Rh[e] = 0.5 * a.R[e];
+    for (int i = gt; i < n; i += G) {
+        double acc = 0.0;
+        for (int q = 0; q < n; ++q) acc -= a.Qd[i * n + q] * xd_i[(long long)a.T * n + q];
+        s.p[i] = acc;
+    }
+    publish();
+    __syncthreads();
+    for (int t = a.T - 1; t >= 0; --t) {
+        if (t > 0) prefetch();
+        // ---- phase 1: PA = P A (warps 0-1), PB = P B (warp 2), w = P c + p (warp 3) ----
+        if (gt < hn * hn) {
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            tile_ab<n>(s.P, n, pa_r0, s.A, n, pa_c0, acc);
+            *reinterpret_cast<double2*>(&s.PA[pa_r0 * n + pa_c0]) = make_double2(acc[0][0], acc[0][1]);
+            *reinterpret_cast<double2*>(&s.PA[(pa_r0 + 1) * n + pa_c0]) = make_double2(acc[1][0], acc[1][1]);
+        } else if (warp == 2) {
+            if (lane < hn * hm) {
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                tile_ab<n>(s.P, n, pb_r0, s.B, m, pb_c0, acc);
+                *reinterpret_cast<double2*>(&s.PB[pb_r0 * m + pb_c0]) = make_double2(acc[0][0], acc[0][1]);
+                *reinterpret_cast<double2*>(&s.PB[(pb_r0 + 1) * m + pb_c0]) = make_double2(acc[1][0], acc[1][1]);
+            }
+        } else if (warp == 3) {
+            if (lane < n) s.w[lane] = dot4<n>(&s.P[lane * n], 1, s.c, 1, s.p[lane]);
+        }
+        __syncthreads();
+        // ---- phase 2: G = B' PA (warp 0), H = R/2 + B' PB (warp 1), g = B' w (warp 2) ----
+        if (warp == 0) {
+            if (lane < hm * hn) {
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                tile_atb<n>(s.B, m, g_r0, s.PA, n, g_c0, acc);
+                *reinterpret_cast<double2*>(&s.G[g_r0 * n + g_c0]) = make_double2(acc[0][0], acc[0][1]);
+                *reinterpret_cast<double2*>(&s.G[(g_r0 + 1) * n + g_c0]) = make_double2(acc[1][0], acc[1][1]);
+            }
+        } else if (warp == 1) {
+            if (lane < hm * hm) {
+                double acc[2][2] = {{s.Rh[h_r0 * m + h_c0], s.Rh[h_r0 * m + h_c0 + 1]},
+                                    {s.Rh[(h_r0 + 1) * m + h_c0], s.Rh[(h_r0 + 1) * m + h_c0 + 1]}};
+                tile_atb<n>(s.B, m, h_r0, s.PB, m, h_c0, acc);
+                *reinterpret_cast<double2*>(&s.H[h_r0 * m + h_c0]) = make_double2(acc[0][0], acc[0][1]);
+                *reinterpret_cast<double2*>(&s.H[(h_r0 + 1) * m + h_c0]) = make_double2(acc[1][0], acc[1][1]);
+            }
+        } else if (warp == 2) {
+            if (lane < m) s.g[lane] = dot4<n>(&s.B[lane], m, s.w, 1);
+        }
+        __syncthreads();
+        // ---- phase 3: K = -H^-1 G, k = -H^-1 g (warp 0; H inverted redundantly in registers) ----
+        if (gt <= n) {
+            double Hs[m][m], Hi[m][m];
+#pragma unroll
+            for (int i = 0; i < m; ++i)
+#pragma unroll
+                for (int j = 0; j < m; ++j) Hs[i][j] = 0.5 * (s.H[i * m + j] + s.H[j * m + i]);
+            ok = spd_inverse<m>(Hs, Hi) && ok;
+            const int col = gt;
+            double b[m], y[m];
+#pragma unroll
+            for (int i = 0; i < m; ++i) b[i] = col < n ? s.G[i * n + col] : s.g[i];
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < m; ++q) acc -= Hi[i][q] * b[q];
+                y[i] = acc;
+            }
+            if (col < n) {
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    s.Kt[i * n + col] = y[i];
+                    pK[i * n + col] = y[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    s.kt[i] = y[i];
+                    pk[i] = y[i];
+                }
+            }
+        }
+        pK -= m * n;
+        pk -= m;
+        __syncthreads();
+        // ---- phase 4: Pn = Q + A' PA + G' K (warps 0-1; raw, symmetrised when stored),
+        //               p <- -Q xd_t + A' w + G' k (warp 2) ----
+        double pnew = 0.0;
+        if (gt < hn * hn) {
+            double acc[2][2] = {{s.Q[pa_r0 * n + pa_c0], s.Q[pa_r0 * n + pa_c0 + 1]},
+                                {s.Q[(pa_r0 + 1) * n + pa_c0], s.Q[(pa_r0 + 1) * n + pa_c0 + 1]}};
+            tile_atb<n>(s.A, n, pa_r0, s.PA, n, pa_c0, acc);
+            tile_atb<m>(s.G, n, pa_r0, s.Kt, n, pa_c0, acc);
+            *reinterpret_cast<double2*>(&s.Pn[pa_r0 * n + pa_c0]) = make_double2(acc[0][0], acc[0][1]);
+            *reinterpret_cast<double2*>(&s.Pn[(pa_r0 + 1) * n + pa_c0]) = make_double2(acc[1][0], acc[1][1]);
+        } else if (warp == 2) {
+            if (lane < n)
+                pnew = (dot4<n>(&s.A[lane], n, s.w, 1) - dot4<n>(&s.Q[lane * n], 1, s.xd, 1)) +
+                       dot4<m>(&s.G[lane], n, s.kt, 1);
+        }
+        __syncthreads();
+        // ---- phase 5: P = sym(Pn), p, and the prefetched operands of step t-1 ----
+        for (int e = gt; e < n * n; e += G) {
+            const int i = e / n, j = e % n;
+            s.P[e] = 0.5 * (s.Pn[i * n + j] + s.Pn[j * n + i]);
+        }
+        if (warp == 2 && lane < n) s.p[lane] = pnew;
+        if (t > 0) publish();
+        __syncthreads();
+    }
+    // NaN guard on the final value function
+    for (int e = gt; e < n * n; e += G)
+        if (!(s.P[e] == s.P[e])) ok = false;
+    ok = __syncthreads_and(ok);
+    if (gt == 0) a.status[inst] = ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Rollouts (warp per instance; x lives in lane 0's registers).
 //   closed loop: u_t = K_t x_t + k_t, x_{t+1} = f(x_t, u_t)      (irs_lqr.py:183-184)
 //   open loop  : x_{t+1} = f(x_t, u_t) for given u               (irs_lqr.py:105-119)
