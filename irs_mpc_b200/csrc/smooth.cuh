@@ -417,7 +417,7 @@ struct FinalizeArgs {
 };
 
 // Fixed-order sum over ranks, then chunks, of entry e of point p (deterministic; the chunk loop is
-// unrolled so that the loads are in flight together while the adds keep their order).
+// unrolled by eight so that the loads are in flight together while the adds keep their order).
 __device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int e, int width) {
     double s = 0.0;
     for (int r = 0; r < a.R; ++r) {
@@ -426,10 +426,12 @@ __device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int
         } else {
             const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * width + e;
             int c = 0;
-            for (; c + 4 <= a.C; c += 4) {
-                const float v0 = src[(long long)c * width], v1 = src[(long long)(c + 1) * width];
-                const float v2 = src[(long long)(c + 2) * width], v3 = src[(long long)(c + 3) * width];
-                s += (double)v0;  s += (double)v1;  s += (double)v2;  s += (double)v3;
+            for (; c + 8 <= a.C; c += 8) {       // eight loads in flight, adds in chunk order
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = src[(long long)(c + k) * width];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += (double)v[k];
             }
             for (; c < a.C; ++c) s += (double)src[(long long)c * width];
         }
@@ -469,7 +471,7 @@ __device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const do
 }
 
 template <class Sys, int BT>
-__global__ void __launch_bounds__(BT, BT == 32 ? 16 : 4) finalize_zero_order_kernel(const FinalizeArgs a) {
+__global__ void __launch_bounds__(BT, BT == 32 ? 16 : 1) finalize_zero_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int W = d + n;
     constexpr int NACC = gram_nacc(n, m);
@@ -478,8 +480,15 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 16 : 4) finalize_zero_order_ker
     __shared__ double sAB[n * d];
     __shared__ double inv_diag[d];
     __shared__ double nom[d + n];
+    __shared__ unsigned char tri_r[d * (d + 1) / 2], tri_c[d * (d + 1) / 2];   // packed lower triangle -> (row, col)
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
+    for (int e = tid; e < d * (d + 1) / 2; e += BT) {
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= e) ++r;
+        tri_r[e] = (unsigned char)r;
+        tri_c[e] = (unsigned char)(e - r * (r + 1) / 2);
+    }
     // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs
     for (int e = tid; e < NACC; e += BT) {
         const double s = sum_partials(a, p, e, NACC);
@@ -512,52 +521,78 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 16 : 4) finalize_zero_order_ker
             // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency
             if (d0 == 0.0) { zero_col = true; dk = 1.0; }
             else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
-            const double lkk = sqrt(dk);
-            const double ikk = 1.0 / lkk;
-            if (lane == 0) { Gm[k * d + k] = lkk;  inv_diag[k] = ikk; }
+            const double ikk = rsqrt(dk);           // one special function on the critical path, not two
+            if (lane == 0) { Gm[k * d + k] = dk * ikk;  inv_diag[k] = ikk; }
             for (int r = k + 1 + lane; r < d; r += 32) Gm[r * d + k] = zero_col ? 0.0 : Gm[r * d + k] * ikk;
             if (zero_col)
                 for (int q = lane; q < n; q += 32) Bm[k * n + q] = 0.0;
             __syncwarp();
-            // trailing update, lower triangle: lane = row, loop over the columns (no integer division)
-            for (int r = k + 1 + lane; r < d; r += 32) {
-                const double lrk = Gm[r * d + k];
-                for (int cc = k + 1; cc <= r; ++cc) Gm[r * d + cc] -= lrk * Gm[cc * d + k];
+            // trailing update of the lower triangle: the packed entries (r, cc), cc <= r, are dealt
+            // round-robin to the lanes (table built once per block), entries outside the trailing
+            // block are skipped — at most 5 short steps per column instead of a 15-long row loop
+            for (int e = lane; e < d * (d + 1) / 2; e += 32) {
+                const int r = tri_r[e], cc = tri_c[e];
+                if (cc > k) Gm[r * d + cc] -= Gm[r * d + k] * Gm[cc * d + k];
             }
             __syncwarp();
         }
         // 3. solve L L^T X = B, one right-hand side per lane (reciprocal diagonal: no divisions)
         if (lane < n) {
             const int q = lane;
-#pragma unroll 1
-            for (int r = 0; r < d; ++r) {
-                double s0 = Bm[r * n + q], s1 = 0.0;
-                int k = 0;
-#pragma unroll 4
-                for (; k + 1 < r; k += 2) {
-                    s0 -= Gm[r * d + k] * Bm[k * n + q];
-                    s1 -= Gm[r * d + k + 1] * Bm[(k + 1) * n + q];
+            if constexpr (BT > 32) {
+                // latency variant: fully unrolled, solution in registers, the L loads pipeline
+                double y[d];
+#pragma unroll
+                for (int r = 0; r < d; ++r) {
+                    double s0 = Bm[r * n + q];
+#pragma unroll
+                    for (int k = 0; k < r; ++k) s0 -= Gm[r * d + k] * y[k];
+                    y[r] = s0 * inv_diag[r];
                 }
-                if (k < r) s0 -= Gm[r * d + k] * Bm[k * n + q];
-                Bm[r * n + q] = (s0 + s1) * inv_diag[r];
-            }
-#pragma unroll 1
-            for (int r = d - 1; r >= 0; --r) {
-                double s0 = Bm[r * n + q], s1 = 0.0;
-                int k = r + 1;
-#pragma unroll 4
-                for (; k + 1 < d; k += 2) {
-                    s0 -= Gm[k * d + r] * Bm[k * n + q];
-                    s1 -= Gm[(k + 1) * d + r] * Bm[(k + 1) * n + q];
+#pragma unroll
+                for (int r = d - 1; r >= 0; --r) {
+                    double s0 = y[r];
+#pragma unroll
+                    for (int k = r + 1; k < d; ++k) s0 -= Gm[k * d + r] * y[k];
+                    y[r] = s0 * inv_diag[r];
                 }
-                if (k < d) s0 -= Gm[k * d + r] * Bm[k * n + q];
-                Bm[r * n + q] = (s0 + s1) * inv_diag[r];
-            }
+#pragma unroll
+                for (int r = 0; r < d; ++r) {
+                    if (!(y[r] == y[r]) || fabs(y[r]) > 1e300) bad = true;
+                    sAB[q * d + r] = y[r];      // [A|B] = X^T
+                }
+            } else {
+                // throughput variant: compact loops, solution in shared memory (56 registers)
 #pragma unroll 1
-            for (int r = 0; r < d; ++r) {
-                const double v = Bm[r * n + q];
-                if (!(v == v) || fabs(v) > 1e300) bad = true;
-                sAB[q * d + r] = v;      // [A|B] = X^T
+                for (int r = 0; r < d; ++r) {
+                    double s0 = Bm[r * n + q], s1 = 0.0;
+                    int k = 0;
+#pragma unroll 4
+                    for (; k + 1 < r; k += 2) {
+                        s0 -= Gm[r * d + k] * Bm[k * n + q];
+                        s1 -= Gm[r * d + k + 1] * Bm[(k + 1) * n + q];
+                    }
+                    if (k < r) s0 -= Gm[r * d + k] * Bm[k * n + q];
+                    Bm[r * n + q] = (s0 + s1) * inv_diag[r];
+                }
+#pragma unroll 1
+                for (int r = d - 1; r >= 0; --r) {
+                    double s0 = Bm[r * n + q], s1 = 0.0;
+                    int k = r + 1;
+#pragma unroll 4
+                    for (; k + 1 < d; k += 2) {
+                        s0 -= Gm[k * d + r] * Bm[k * n + q];
+                        s1 -= Gm[(k + 1) * d + r] * Bm[(k + 1) * n + q];
+                    }
+                    if (k < d) s0 -= Gm[k * d + r] * Bm[k * n + q];
+                    Bm[r * n + q] = (s0 + s1) * inv_diag[r];
+                }
+#pragma unroll 1
+                for (int r = 0; r < d; ++r) {
+                    const double v = Bm[r * n + q];
+                    if (!(v == v) || fabs(v) > 1e300) bad = true;
+                    sAB[q * d + r] = v;      // [A|B] = X^T
+                }
             }
         }
         bad = __any_sync(0xffffffffu, bad);
