@@ -142,6 +142,38 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
                       const double* xd, long long xd_stride, int I, int T,
                       double* K, double* k, int* status, void* stream);
 
+/* Box-constrained solve_tvlqr / local_descent (irs_lqr/tv_lqr.py:113-118,:132-134 absolute bounds;
+ * irs_lqr/irs_lqr.py:160-184 re-solve at every timestep).  Three pieces:
+ *  - irs_tvlqr_riccati_ex: irs_tvlqr_riccati that also returns Hinv [I,T,m,m] = (R/2 + B'PB)^-1 and
+ *    P [I,T+1,n,n]; called with the penalty-augmented weights (Q + diag(dx)/2, Qd + diag(dx)/2,
+ *    R + diag(du)) it yields the matrix part of the ADMM's equality-constrained step;
+ *  - irs_tvlqr_plan_check: for every start time t0 rolls the affine model forward from the actual
+ *    state x_trj[t0] under the unconstrained gains (K, k) and sets violated[i] = 1 if any planned
+ *    state (t0 < t <= T) or input leaves [lo - tol, hi + tol].  violated == 0 means every QP of the
+ *    reference's loop had inactive bounds, i.e. the one-pass Riccati descent is its exact result;
+ *  - irs_tvlqr_box_solve: ADMM on the box split.  mpc = 1: the reference's closed loop (QP over the
+ *    remaining horizon at every t0 from the actual state, first input applied to the TRUE dynamics of
+ *    `system`); mpc = 0: one QP from x0 (solve_tvlqr), x_trj/u_trj receive the plan.  Bounds are per
+ *    coordinate, constant in time (xlo/xhi [n], ulo/uhi [m]); dx [n], du [m] are the ADMM penalties;
+ *    status[i] = 1 if a solve did not reach eps within max_iter (-> the reference's ValueError).
+ *    Algorithm and its check against a dense QP solve: oracle/box_tvlqr.py. */
+int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const double* ct,
+                         const double* Q, const double* Qd, const double* R,
+                         const double* xd, long long xd_stride, int I, int T,
+                         double* K, double* k, int* status, double* Hinv_out, double* P_out, void* stream);
+int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const double* ct,
+                         const double* K, const double* k, const double* x_trj,
+                         const double* xlo, const double* xhi, const double* ulo, const double* uhi,
+                         double tol, int I, int T, int* violated, void* stream);
+int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int mpc,
+                        const double* At, const double* Bt, const double* ct,
+                        const double* K, const double* Hinv, const double* P,
+                        const double* Q, const double* Qd, const double* R,
+                        const double* xd, long long xd_stride, const double* dx, const double* du,
+                        const double* xlo, const double* xhi, const double* ulo, const double* uhi,
+                        const double* x0, double alpha, double eps, int max_iter, int I, int T,
+                        double* x_trj, double* u_trj, double* cost, int* status, int* iters, void* stream);
+
 /* (x*, u*) of solve_tvlqr: rollout of the affine model under u = K x + k (tv_lqr.py:142-145).
  * x0 [I,n]; xs [I,T+1,n]; us [I,T,m]. */
 int irs_tvlqr_linear_rollout(int n, int m, const double* At, const double* Bt, const double* ct,

@@ -8,6 +8,7 @@
 #include "smooth.cuh"
 #include "smooth_tc.cuh"
 #include "tvlqr.cuh"
+#include "tvlqr_box.cuh"
 
 namespace irs {
 
@@ -306,6 +307,17 @@ static int jacobian_batch_impl(int system, const double* params_host, int nparam
 
 using namespace irs;
 
+template <class Sys>
+static int launch_box_mpc(const BoxMpcArgs& a, cudaStream_t st) {
+    const size_t smem = box_mpc_smem_bytes<Sys::N, Sys::M>(a.T);
+    IRS_REQUIRE(smem <= 200 * 1024, "horizon T=%d too long for the shared-memory resident ADMM state", a.T);
+    auto kern = box_mpc_kernel<Sys>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(box_mpc_kernel)");
+    kern<<<(unsigned)a.I, 32, smem, st>>>(a);
+    return check_launch("box_mpc_kernel");
+}
+
 extern "C" {
 
 int irs_abi_version(void) { return IRS_ABI_VERSION; }
@@ -537,21 +549,22 @@ int irs_project_batch_f64(int system, const double* params_host, int nparams, do
     return check_launch("project_batch_kernel");
 }
 
-int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const double* ct,
-                      const double* Q, const double* Qd, const double* R,
-                      const double* xd, long long xd_stride, int I, int T,
-                      double* K, double* k, int* status, void* stream) {
+static int tvlqr_riccati_impl(int n, int m, const double* At, const double* Bt, const double* ct,
+                              const double* Q, const double* Qd, const double* R,
+                              const double* xd, long long xd_stride, int I, int T,
+                              double* K, double* k, int* status, double* Hinv_out, double* P_out, void* stream) {
     IRS_REQUIRE(At && Bt && ct && Q && Qd && R && xd && K && k && status, "null pointer argument");
     IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
-    TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T};
+    TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T, Hinv_out, P_out};
     cudaStream_t st = (cudaStream_t)stream;
     // few instances: one block per instance (latency); many: one warp per instance (throughput)
     const bool per_block = I <= 2 * num_sms();
+    const bool extra = Hinv_out != nullptr || P_out != nullptr;     // only the generic kernel writes them
     static const bool no_tiles = getenv("IRS_TVLQR_NO_TILES") != nullptr;
     IRS_DISPATCH_DIMS(n, m, {
         if (per_block) {
             if constexpr (N_ % 2 == 0 && M_ % 2 == 0) {
-                if (!no_tiles) {
+                if (!no_tiles && !extra) {
                     tvlqr_riccati_tiled_kernel<N_, M_>
                         <<<(unsigned)I, kTvlqrTiledThreads, sizeof(TvlqrTiledSmem<N_, M_>), st>>>(a);
                     return check_launch("tvlqr_riccati_tiled_kernel");
@@ -565,6 +578,62 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
         }
     });
     return check_launch("tvlqr_riccati_kernel");
+}
+
+int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const double* ct,
+                      const double* Q, const double* Qd, const double* R,
+                      const double* xd, long long xd_stride, int I, int T,
+                      double* K, double* k, int* status, void* stream) {
+    return tvlqr_riccati_impl(n, m, At, Bt, ct, Q, Qd, R, xd, xd_stride, I, T, K, k, status, nullptr, nullptr, stream);
+}
+
+int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const double* ct,
+                         const double* Q, const double* Qd, const double* R,
+                         const double* xd, long long xd_stride, int I, int T,
+                         double* K, double* k, int* status, double* Hinv_out, double* P_out, void* stream) {
+    return tvlqr_riccati_impl(n, m, At, Bt, ct, Q, Qd, R, xd, xd_stride, I, T, K, k, status, Hinv_out, P_out, stream);
+}
+
+int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const double* ct,
+                         const double* K, const double* k, const double* x_trj,
+                         const double* xlo, const double* xhi, const double* ulo, const double* uhi,
+                         double tol, int I, int T, int* violated, void* stream) {
+    IRS_REQUIRE(At && Bt && ct && K && k && x_trj && xlo && xhi && ulo && uhi && violated, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1 && I <= 65535, "need 1 <= I <= 65535 and T >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(violated, 0, sizeof(int) * I, st) != cudaSuccess) return check_launch("cudaMemsetAsync");
+    PlanCheckArgs a{At, Bt, ct, K, k, x_trj, xlo, xhi, ulo, uhi, tol, violated, I, T};
+    IRS_DISPATCH_DIMS(n, m, (plan_check_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a)));
+    return check_launch("plan_check_kernel");
+}
+
+int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int mpc,
+                        const double* At, const double* Bt, const double* ct,
+                        const double* K, const double* Hinv, const double* P,
+                        const double* Q, const double* Qd, const double* R,
+                        const double* xd, long long xd_stride, const double* dx, const double* du,
+                        const double* xlo, const double* xhi, const double* ulo, const double* uhi,
+                        const double* x0, double alpha, double eps, int max_iter, int I, int T,
+                        double* x_trj, double* u_trj, double* cost, int* status, int* iters, void* stream) {
+    BoxMpcArgs a;
+    if (load_params(system, params_host, nparams, &a.prm)) return 1;
+    IRS_REQUIRE(At && Bt && ct && K && Hinv && P && Q && Qd && R && xd && dx && du && xlo && xhi && ulo && uhi &&
+                    x0 && x_trj && u_trj && cost && status && iters, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1 && max_iter >= 1, "need I >= 1, T >= 1, max_iter >= 1");
+    IRS_REQUIRE(alpha > 0.0 && alpha < 2.0 && eps > 0.0, "need 0 < alpha < 2 and eps > 0");
+    a.At = At;  a.Bt = Bt;  a.ct = ct;  a.K = K;  a.Hinv = Hinv;  a.P = P;  a.Q = Q;  a.Qd = Qd;  a.R = R;
+    a.xd = xd;  a.xd_stride = xd_stride;  a.dx = dx;  a.du = du;  a.xlo = xlo;  a.xhi = xhi;  a.ulo = ulo;
+    a.uhi = uhi;  a.x0 = x0;  a.alpha = alpha;  a.eps = eps;  a.max_iter = max_iter;  a.mpc = mpc ? 1 : 0;
+    a.x_trj = x_trj;  a.u_trj = u_trj;  a.cost = cost;  a.status = status;  a.iters = iters;  a.I = I;  a.T = T;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (system) {
+        case kPendulum: return launch_box_mpc<Pendulum<double>>(a, st);
+        case kBicycle: return launch_box_mpc<Bicycle<double>>(a, st);
+        case kQuadrotor: return launch_box_mpc<Quadrotor<double>>(a, st);
+        case kThreeCart: return launch_box_mpc<ThreeCart<double>>(a, st);
+    }
+    set_error("unknown system id %d", system);
+    return 1;
 }
 
 int irs_tvlqr_linear_rollout(int n, int m, const double* At, const double* Bt, const double* ct,

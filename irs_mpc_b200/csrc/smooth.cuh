@@ -562,30 +562,22 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 16 : 1) finalize_zero_order_ker
                     sAB[q * d + r] = y[r];      // [A|B] = X^T
                 }
             } else {
-                // throughput variant: compact loops, solution in shared memory (56 registers)
+                // throughput variant: compact loops, solution in shared memory (56 registers); the
+                // SAME operations in the same order as the latency variant, so that a point's result
+                // does not depend on how many points the launch holds (sharding reproducibility)
 #pragma unroll 1
                 for (int r = 0; r < d; ++r) {
-                    double s0 = Bm[r * n + q], s1 = 0.0;
-                    int k = 0;
+                    double s0 = Bm[r * n + q];
 #pragma unroll 4
-                    for (; k + 1 < r; k += 2) {
-                        s0 -= Gm[r * d + k] * Bm[k * n + q];
-                        s1 -= Gm[r * d + k + 1] * Bm[(k + 1) * n + q];
-                    }
-                    if (k < r) s0 -= Gm[r * d + k] * Bm[k * n + q];
-                    Bm[r * n + q] = (s0 + s1) * inv_diag[r];
+                    for (int k = 0; k < r; ++k) s0 -= Gm[r * d + k] * Bm[k * n + q];
+                    Bm[r * n + q] = s0 * inv_diag[r];
                 }
 #pragma unroll 1
                 for (int r = d - 1; r >= 0; --r) {
-                    double s0 = Bm[r * n + q], s1 = 0.0;
-                    int k = r + 1;
+                    double s0 = Bm[r * n + q];
 #pragma unroll 4
-                    for (; k + 1 < d; k += 2) {
-                        s0 -= Gm[k * d + r] * Bm[k * n + q];
-                        s1 -= Gm[(k + 1) * d + r] * Bm[(k + 1) * n + q];
-                    }
-                    if (k < d) s0 -= Gm[k * d + r] * Bm[k * n + q];
-                    Bm[r * n + q] = (s0 + s1) * inv_diag[r];
+                    for (int k = r + 1; k < d; ++k) s0 -= Gm[k * d + r] * Bm[k * n + q];
+                    Bm[r * n + q] = s0 * inv_diag[r];
                 }
 #pragma unroll 1
                 for (int r = 0; r < d; ++r) {

@@ -26,6 +26,8 @@ struct TvlqrArgs {
     double* k;           // [I, T, m]
     int* status;         // [I] 0 ok, 1 H not SPD / NaN
     int I, T;
+    double* Hinv;        // optional [I, T, m, m]: (R/2 + B'PB)^-1 of every step (bounded solve)
+    double* Pout;        // optional [I, T+1, n, n]: value-function Hessians P_t
 };
 
 // Reciprocal in fp64 from the hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps — a
@@ -143,7 +145,10 @@ __global__ void __launch_bounds__(G == 32 ? 32 * kTvlqrWarps : G) tvlqr_riccati_
     };
     prefetch(a.T - 1);
     // terminal condition: P_T = Qd, p_T = -Qd xd_T
-    for (int e = gt; e < n * n; e += G) s.P[e] = a.Qd[e];
+    for (int e = gt; e < n * n; e += G) {
+        s.P[e] = a.Qd[e];
+        if (a.Pout != nullptr) a.Pout[((long long)inst * (a.T + 1) + a.T) * n * n + e] = a.Qd[e];
+    }
     for (int i = gt; i < n; i += G) {
         double acc = 0.0;
         for (int q = 0; q < n; ++q) acc -= a.Qd[i * n + q] * xd_i[(long long)a.T * n + q];
@@ -198,6 +203,12 @@ __global__ void __launch_bounds__(G == 32 ? 32 * kTvlqrWarps : G) tvlqr_riccati_
 #pragma unroll
                 for (int j = 0; j < m; ++j) Hs[i][j] = 0.5 * (s.H[i * m + j] + s.H[j * m + i]);
             ok = spd_inverse<m>(Hs, Hi) && ok;
+            if (a.Hinv != nullptr && gt == 0) {
+#pragma unroll
+                for (int i = 0; i < m; ++i)
+#pragma unroll
+                    for (int j = 0; j < m; ++j) a.Hinv[(it * m + i) * m + j] = Hi[i][j];
+            }
             for (int col = gt; col <= n; col += G) {
                 double b[m], y[m];
 #pragma unroll
@@ -246,8 +257,12 @@ __global__ void __launch_bounds__(G == 32 ? 32 * kTvlqrWarps : G) tvlqr_riccati_
 #pragma unroll
         for (int k = 0; k < (n * n + n + G - 1) / G; ++k) {
             const int e = gt + k * G;
-            if (e < n * n) s.P[e] = Pnew[k];
-            else if (e < n * n + n) s.p[e - n * n] = Pnew[k];
+            if (e < n * n) {
+                s.P[e] = Pnew[k];
+                if (a.Pout != nullptr) a.Pout[((long long)inst * (a.T + 1) + t) * n * n + e] = Pnew[k];
+            } else if (e < n * n + n) {
+                s.p[e - n * n] = Pnew[k];
+            }
         }
         // (the group_sync after the next step's operand stores orders these writes before its reads)
     }

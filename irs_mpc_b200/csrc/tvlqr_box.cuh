@@ -1,0 +1,295 @@
+// Box-constrained TVLQR.
+//
+// The reference re-solves, at every timestep t0 of IrsLqr.local_descent (irs_lqr/irs_lqr.py:169-184),
+// the QP of irs_lqr/tv_lqr.py:69-137 over the remaining horizon with absolute box bounds on states
+// and inputs (:113-118, :132-134), and applies the first input to the true dynamics.
+//
+//   plan_check_kernel   for every start time t0 in parallel: roll the affine model forward from the
+//                       ACTUAL state x_{t0} under the unconstrained gains and test the bounds.  If no
+//                       plan touches a bound, every one of the reference's QPs had inactive
+//                       constraints and the one-pass Riccati descent IS the reference's result.
+//   box_mpc_kernel      otherwise: the reference's loop itself.  Each QP is solved by ADMM on the box
+//                       split (y = z, y = states and inputs, z in the box); the equality-constrained
+//                       step is an affine Riccati recursion whose MATRIX part (K_t, H_t^-1, P_t for
+//                       the penalty-augmented cost) does not depend on the iterate nor on t0 and is
+//                       computed once by tvlqr_riccati_kernel; only the vector recursion and the
+//                       affine rollout run per iteration.  Consecutive QPs warm-start each other
+//                       (split and dual variables are indexed by absolute time).
+// Oracle: oracle/box_tvlqr.py (same algorithm in numpy, checked against a dense QP solve).
+#pragma once
+#include "tvlqr.cuh"
+
+namespace irs {
+
+struct PlanCheckArgs {
+    const double* At;     // [I, T, n, n]
+    const double* Bt;     // [I, T, n, m]
+    const double* ct;     // [I, T, n]
+    const double* K;      // [I, T, m, n]  unconstrained gains
+    const double* k;      // [I, T, m]
+    const double* x_trj;  // [I, T+1, n]   actual closed-loop states
+    const double* xlo;    // [n]
+    const double* xhi;
+    const double* ulo;    // [m]
+    const double* uhi;
+    double tol;
+    int* violated;        // [I] set to 1 if any plan leaves the box (must be zeroed by the caller)
+    int I, T;
+};
+
+// grid = (T, I), one warp per (start time, instance); lanes = state / input coordinates
+template <int n, int m>
+__global__ void __launch_bounds__(32) plan_check_kernel(const PlanCheckArgs a) {
+    static_assert(n <= 32 && m <= 32, "one lane per coordinate");
+    __shared__ double xs[n], us[m];
+    const int lane = threadIdx.x;
+    const int t0 = blockIdx.x, inst = blockIdx.y;
+    const long long base = (long long)inst * a.T;
+    if (lane < n) xs[lane] = a.x_trj[((long long)inst * (a.T + 1) + t0) * n + lane];
+    __syncwarp();
+    bool bad = false;
+    for (int t = t0; t < a.T; ++t) {
+        if (lane < m) {
+            const double* Kr = a.K + ((base + t) * m + lane) * n;
+            double u = a.k[(base + t) * m + lane];
+#pragma unroll
+            for (int q = 0; q < n; ++q) u += Kr[q] * xs[q];
+            us[lane] = u;
+            bad |= !(u >= a.ulo[lane] - a.tol && u <= a.uhi[lane] + a.tol);
+        }
+        __syncwarp();
+        double xn = 0.0;
+        if (lane < n) {
+            const double* Ar = a.At + ((base + t) * n + lane) * n;
+            const double* Br = a.Bt + ((base + t) * n + lane) * m;
+            xn = a.ct[(base + t) * n + lane];
+#pragma unroll
+            for (int q = 0; q < n; ++q) xn += Ar[q] * xs[q];
+#pragma unroll
+            for (int q = 0; q < m; ++q) xn += Br[q] * us[q];
+            bad |= !(xn >= a.xlo[lane] - a.tol && xn <= a.xhi[lane] + a.tol);
+        }
+        __syncwarp();
+        if (lane < n) xs[lane] = xn;
+        __syncwarp();
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&a.violated[inst], 1);
+}
+
+struct BoxMpcArgs {
+    const double* At;     // [I, T, n, n]
+    const double* Bt;     // [I, T, n, m]
+    const double* ct;     // [I, T, n]
+    const double* K;      // [I, T, m, n]   gains of the penalty-augmented problem
+    const double* Hinv;   // [I, T, m, m]
+    const double* P;      // [I, T+1, n, n]
+    const double* Q;      // [n, n]  (original weights)
+    const double* Qd;
+    const double* R;      // [m, m]
+    const double* xd;     // [I or 1, T+1, n]
+    long long xd_stride;
+    const double* dx;     // [n] ADMM penalties on the states
+    const double* du;     // [m] ... on the inputs
+    const double* xlo;    // [n]
+    const double* xhi;
+    const double* ulo;    // [m]
+    const double* uhi;
+    const double* x0;     // [I, n]
+    double alpha, eps;
+    int max_iter;
+    int mpc;              // 1: closed loop on the true dynamics (local_descent); 0: one QP from x0 (solve_tvlqr)
+    double* x_trj;        // [I, T+1, n]
+    double* u_trj;        // [I, T, m]
+    double* cost;         // [I] evaluate_cost of the result (irs_lqr.py:121-137)
+    int* status;          // [I] 0 ok, 1 ADMM did not converge / NaN
+    int* iters;           // [I] total ADMM iterations
+    int I, T;
+    SysParams prm;
+};
+
+// One warp per instance; lanes = coordinates.  Dynamic shared memory (doubles):
+//   zx, wx, x : (T+1) n each     zu, wu, u, kk : T m each     Pc : T n     scratch
+template <class Sys>
+__global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
+    constexpr int n = Sys::N, m = Sys::M;
+    static_assert(n <= 32 && m <= 32, "one lane per coordinate");
+    extern __shared__ __align__(16) double sm[];
+    const int T = a.T;
+    double* zx = sm;
+    double* wx = zx + (T + 1) * n;
+    double* x = wx + (T + 1) * n;
+    double* zu = x + (T + 1) * n;
+    double* wu = zu + T * m;
+    double* u = wu + T * m;
+    double* kk = u + T * m;
+    double* Pc = kk + T * m;
+    double* pv = Pc + T * n;      // [2][n] rolling p_{t+1}, p_t
+    double* ww = pv + 2 * n;      // [n]
+    double* gv = ww + n;          // [m]
+    const int lane = threadIdx.x;
+    const int inst = blockIdx.x;
+    const long long base = (long long)inst * T;
+    const double* xd_i = a.xd + inst * a.xd_stride;
+    const Sys sys(a.prm);
+    const double dxl = lane < n ? a.dx[lane] : 0.0, dul = lane < m ? a.du[lane] : 0.0;
+    // Pc_t = P_{t+1} c_t; cold start of the split variables: z = clip(target), w = 0
+    for (int e = lane; e < T * n; e += 32) {
+        const int t = e / n, i = e % n;
+        const double* Pr = a.P + ((long long)inst * (T + 1) + t + 1) * n * n + i * n;
+        double acc = 0.0;
+        for (int q = 0; q < n; ++q) acc += Pr[q] * a.ct[(base + t) * n + q];
+        Pc[e] = acc;
+    }
+    for (int e = lane; e < (T + 1) * n; e += 32) {
+        const int i = e % n;
+        zx[e] = fmin(fmax(xd_i[e], a.xlo[i]), a.xhi[i]);
+        wx[e] = 0.0;
+        x[e] = 0.0;
+    }
+    for (int e = lane; e < T * m; e += 32) {
+        const int j = e % m;
+        zu[e] = fmin(fmax(0.0, a.ulo[j]), a.uhi[j]);
+        wu[e] = 0.0;
+        u[e] = 0.0;
+    }
+    if (lane < n) x[lane] = a.x0[(long long)inst * n + lane];
+    __syncwarp();
+    int total_iters = 0;
+    bool failed = false;
+    const int n_starts = a.mpc ? T : 1;
+    for (int t0 = 0; t0 < n_starts; ++t0) {
+        bool converged = false;
+        for (int it = 0; it < a.max_iter && !converged; ++it) {
+            // ---- backward vector recursion: p_T, then kk_t, p_t for t = T-1 .. t0 ----
+            int cur = 0;
+            if (lane < n) {
+                double acc = 0.5 * dxl * (zx[T * n + lane] - wx[T * n + lane]);
+                for (int q = 0; q < n; ++q) acc += a.Qd[lane * n + q] * xd_i[(long long)T * n + q];
+                pv[lane] = -acc;
+            }
+            __syncwarp();
+            for (int t = T - 1; t >= t0; --t) {
+                if (lane < n) ww[lane] = Pc[t * n + lane] + pv[cur * n + lane];
+                __syncwarp();
+                if (lane < m) {
+                    double g = -0.5 * dul * (zu[t * m + lane] - wu[t * m + lane]);
+                    const double* Bc = a.Bt + (base + t) * n * m + lane;
+#pragma unroll
+                    for (int q = 0; q < n; ++q) g += Bc[q * m] * ww[q];
+                    gv[lane] = g;
+                }
+                __syncwarp();
+                if (lane < m) {
+                    const double* Hr = a.Hinv + ((base + t) * m + lane) * m;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc -= Hr[q] * gv[q];
+                    kk[t * m + lane] = acc;
+                }
+                if (t > t0 && lane < n) {
+                    double acc = -0.5 * dxl * (zx[t * n + lane] - wx[t * n + lane]);
+                    for (int q = 0; q < n; ++q) acc -= a.Q[lane * n + q] * xd_i[(long long)t * n + q];
+                    const double* Ac = a.At + (base + t) * n * n + lane;
+#pragma unroll
+                    for (int q = 0; q < n; ++q) acc += Ac[q * n] * ww[q];
+                    const double* Kc = a.K + (base + t) * m * n + lane;
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc += Kc[q * n] * gv[q];
+                    pv[(cur ^ 1) * n + lane] = acc;
+                }
+                cur ^= 1;
+                __syncwarp();
+            }
+            // ---- forward affine rollout from the fixed x_{t0} ----
+            for (int t = t0; t < T; ++t) {
+                if (lane < m) {
+                    const double* Kr = a.K + ((base + t) * m + lane) * n;
+                    double acc = kk[t * m + lane];
+#pragma unroll
+                    for (int q = 0; q < n; ++q) acc += Kr[q] * x[t * n + q];
+                    u[t * m + lane] = acc;
+                }
+                __syncwarp();
+                if (lane < n) {
+                    const double* Ar = a.At + ((base + t) * n + lane) * n;
+                    const double* Br = a.Bt + ((base + t) * n + lane) * m;
+                    double acc = a.ct[(base + t) * n + lane];
+#pragma unroll
+                    for (int q = 0; q < n; ++q) acc += Ar[q] * x[t * n + q];
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc += Br[q] * u[t * m + q];
+                    x[(t + 1) * n + lane] = acc;
+                }
+                __syncwarp();
+            }
+            // ---- relaxed projection, dual update, residuals (element-wise over the horizon) ----
+            double r_prim = 0.0, r_dual = 0.0, scale = 1.0;
+            for (int e = (t0 + 1) * n + lane; e < (T + 1) * n; e += 32) {
+                const int i = e % n;
+                const double xh = a.alpha * x[e] + (1.0 - a.alpha) * zx[e];
+                const double zn = fmin(fmax(xh + wx[e], a.xlo[i]), a.xhi[i]);
+                wx[e] += xh - zn;
+                r_prim = fmax(r_prim, fabs(x[e] - zn));
+                r_dual = fmax(r_dual, fabs(a.dx[i] * (zn - zx[e])));
+                scale = fmax(scale, fabs(zn));
+                zx[e] = zn;
+            }
+            for (int e = t0 * m + lane; e < T * m; e += 32) {
+                const int j = e % m;
+                const double uh = a.alpha * u[e] + (1.0 - a.alpha) * zu[e];
+                const double zn = fmin(fmax(uh + wu[e], a.ulo[j]), a.uhi[j]);
+                wu[e] += uh - zn;
+                r_prim = fmax(r_prim, fabs(u[e] - zn));
+                r_dual = fmax(r_dual, fabs(a.du[j] * (zn - zu[e])));
+                scale = fmax(scale, fabs(zn));
+                zu[e] = zn;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                r_prim = fmax(r_prim, __shfl_xor_sync(0xffffffffu, r_prim, o));
+                r_dual = fmax(r_dual, __shfl_xor_sync(0xffffffffu, r_dual, o));
+                scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, o));
+            }
+            ++total_iters;
+            // NaN-safe: a NaN residual never satisfies the test and the solve ends as "failed"
+            converged = (r_prim <= a.eps * scale) && (r_dual <= a.eps * scale);
+            __syncwarp();
+        }
+        if (!converged) failed = true;
+        if (a.mpc) {
+            // apply the first input (the feasible split variable) to the TRUE dynamics (irs_lqr.py:183-184)
+            if (lane == 0) {
+                double xs[n], us[m], xn[n];
+#pragma unroll
+                for (int q = 0; q < n; ++q) xs[q] = x[t0 * n + q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) us[q] = zu[t0 * m + q];
+                sys.template step<false>(xs, us, xn);
+#pragma unroll
+                for (int q = 0; q < n; ++q) x[(t0 + 1) * n + q] = xn[q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) u[t0 * m + q] = us[q];
+            }
+            __syncwarp();
+        }
+    }
+    // results: closed-loop trajectory (mpc) or the QP plan (states consistent with the dynamics)
+    for (int e = lane; e < (T + 1) * n; e += 32) a.x_trj[(long long)inst * (T + 1) * n + e] = x[e];
+    for (int e = lane; e < T * m; e += 32) a.u_trj[base * m + e] = u[e];
+    __threadfence_block();
+    __syncwarp();
+    const double c = warp_trajectory_cost<n, m>(a.x_trj + (long long)inst * (T + 1) * n, a.u_trj + base * m, xd_i,
+                                                a.Q, a.R, T, lane);
+    if (lane == 0) {
+        a.cost[inst] = c;
+        a.status[inst] = (failed || !(c == c)) ? 1 : 0;
+        a.iters[inst] = total_iters;
+    }
+}
+
+template <int n, int m>
+inline size_t box_mpc_smem_bytes(int T) {
+    return sizeof(double) * ((size_t)3 * (T + 1) * n + (size_t)4 * T * m + (size_t)T * n + 2 * n + n + m);
+}
+
+}  // namespace irs

@@ -6,9 +6,10 @@ arithmetic runs in the sm_100a kernels of libirs_mpc_b200.so.  numpy float64 at 
 
 Differences a user can observe, all deliberate:
   * `local_descent` performs ONE Riccati backward pass + closed-loop rollout instead of T QP
-    solves; identical results while the box bounds are inactive.  If the new
-    trajectory touches `xbound`/`ubound`, NotImplementedError is raised (box-constrained TVLQR is
-    the next row of SURVEY.md section 8f) — there is no silent clamping.
+    solves and then verifies, for every start time in parallel, that no planned trajectory touches
+    `xbound`/`ubound` — in which case it IS the result of the reference's T QPs.
+    Otherwise it runs the reference's loop itself with a box-constrained QP at every timestep
+    (ADMM with Riccati-structured solves, csrc/tvlqr_box.cuh) — there is no silent clamping.
   * `sampling` may be a `GaussianSampling` object: the noise is then generated inside the kernel.
     Any other callable is honoured through the replay path.
   * only systems derived from `CudaDynamicalSystem` are accepted (no CPU fallback).
@@ -23,7 +24,7 @@ import torch
 from . import _device, _lib, smoothing
 from .dynamical_system import CudaDynamicalSystem
 from .sampling import GaussianSampling
-from .tv_lqr import TVLQR_FAILED, get_solver, riccati_device
+from .tv_lqr import BOUND_TOL, TVLQR_FAILED, box_solve_device, get_solver, riccati_device
 
 
 # CUDA-graph replay of the per-iteration call sequence (IRS_CUDA_GRAPH=0 forces eager launches)
@@ -169,7 +170,7 @@ class IrsLqr:
             nx, nu = (T + 1) * n, T * m
             db["in_dev"] = _device.empty((nx + nu,))
             db["in_host"] = torch.empty((nx + nu,), dtype=torch.float64).pin_memory()
-            n_out = nx + nu + 1 + 1 + (T + 1) // 2
+            n_out = nx + nu + 1 + 1 + 1 + (T + 1) // 2
             db["out_dev"] = _device.empty((n_out,))
             db["out_host"] = torch.empty((n_out,), dtype=torch.float64).pin_memory()
             o = db["out_dev"]
@@ -177,7 +178,18 @@ class IrsLqr:
             db["u_new"] = o[nx:nx + nu].view(1, T, m)
             db["cost"] = o[nx + nu:nx + nu + 1]
             db["rstatus"] = o[nx + nu + 1:nx + nu + 2].view(torch.int32)[:1]
-            db["sstatus"] = o[nx + nu + 2:].view(torch.int32)[:T]
+            db["violated"] = o[nx + nu + 2:nx + nu + 3].view(torch.int32)[:1]
+            db["sstatus"] = o[nx + nu + 3:].view(torch.int32)[:T]
+            if self.xbound is not None or self.ubound is not None:
+                big = 1e30
+                xlo, xhi = ((np.asarray(self.xbound[0], dtype=np.float64), np.asarray(self.xbound[1], dtype=np.float64))
+                            if self.xbound is not None else (-big * np.ones(n), big * np.ones(n)))
+                ulo, uhi = ((np.asarray(self.ubound[0], dtype=np.float64), np.asarray(self.ubound[1], dtype=np.float64))
+                            if self.ubound is not None else (-big * np.ones(m), big * np.ones(m)))
+                db["box_host"] = (xlo, xhi, ulo, uhi)
+                db["box"] = tuple(_device.to_device(np.ascontiguousarray(v)) for v in (xlo, xhi, ulo, uhi))
+            else:
+                db["box"] = None
             db["K"] = _device.empty((1, T, m, n))
             db["k"] = _device.empty((1, T, m))
             db["nx"], db["nu"] = nx, nu
@@ -205,6 +217,16 @@ class IrsLqr:
                   _device.ptr(k), _device.ptr(x_all), _device.ptr(self._dxd), 0,
                   _device.ptr(self._dQ), _device.ptr(self._dR), 1, T, _device.ptr(db["x_new"]),
                   _device.ptr(db["u_new"]), _device.ptr(db["cost"]), _device.stream_ptr())
+        if db["box"] is not None:
+            # would any of the reference's T re-solved QPs (irs_lqr.py:169-182) have had an active bound?
+            xlo, xhi, ulo, uhi = db["box"]
+            _lib.call("irs_tvlqr_plan_check", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                      _device.ptr(K), _device.ptr(k), _device.ptr(db["x_new"]), _device.ptr(xlo),
+                      _device.ptr(xhi), _device.ptr(ulo), _device.ptr(uhi), BOUND_TOL, 1, T,
+                      _device.ptr(db["violated"]), _device.stream_ptr())
+        else:
+            db["violated"].zero_()
+        db["lin"] = (At, Bt, ct)
         db["out_host"].copy_(db["out_dev"], non_blocking=True)
 
     def _graph_key(self):
@@ -258,31 +280,36 @@ class IrsLqr:
         # one synchronising read-back for everything the host needs
         torch.cuda.current_stream().synchronize()
         o = db["out_host"].numpy()
-        smoothing.check_status(o[nx + nu + 2:].view(np.int32)[:T])
+        smoothing.check_status(o[nx + nu + 3:].view(np.int32)[:T])
         if int(o[nx + nu + 1:nx + nu + 2].view(np.int32)[0]) != 0:
             raise ValueError(TVLQR_FAILED)
-        x_out = o[:nx].reshape(T + 1, n).copy()
-        u_out = o[nx:nx + nu].reshape(T, m).copy()
+        if int(o[nx + nu + 2:nx + nu + 3].view(np.int32)[0]) != 0:
+            # some planned trajectory touches a bound: the reference's loop with the bounded QP
+            x_out, u_out, cost = self._bounded_descent(db)
+        else:
+            x_out = o[:nx].reshape(T + 1, n).copy()
+            u_out = o[nx:nx + nu].reshape(T, m).copy()
+            cost = float(o[nx + nu])
         if not (np.all(np.isfinite(x_out)) and np.all(np.isfinite(u_out))):
             raise ValueError(TVLQR_FAILED)
-        self._check_bounds(x_out, u_out)
-        self._last_descent_cost = float(o[nx + nu])
+        self._last_descent_cost = cost
         self._last_descent = (x_out, u_out, x_out.copy(), u_out.copy())
         return x_out, u_out
 
-    def _check_bounds(self, x_new, u_new, tol=1e-9):
-        if self.xbound is not None:
-            lo, hi = np.asarray(self.xbound[0]), np.asarray(self.xbound[1])
-            if np.any(x_new[1:] < lo - tol) or np.any(x_new[1:] > hi + tol):
-                raise NotImplementedError(
-                    "a state bound (params.xbound) is active on the new trajectory: the "
-                    "box-constrained TVLQR of the reference (tv_lqr.py:113-124) is not implemented")
-        if self.ubound is not None:
-            lo, hi = np.asarray(self.ubound[0]), np.asarray(self.ubound[1])
-            if np.any(u_new < lo - tol) or np.any(u_new > hi + tol):
-                raise NotImplementedError(
-                    "an input bound (params.ubound) is active on the new trajectory: the "
-                    "box-constrained TVLQR of the reference (tv_lqr.py:113-124) is not implemented")
+    def _bounded_descent(self, db):
+        """irs_lqr.py:169-184 with active bounds: a box QP over the remaining horizon at every timestep
+        (ADMM, csrc/tvlqr_box.cuh), first input applied to the true dynamics."""
+        T, n, m = self.T, self.dim_x, self.dim_u
+        At, Bt, ct = db["lin"]
+        xlo, xhi, ulo, uhi = db["box_host"]
+        x0 = db["in_dev"][:n].view(1, n)
+        xb, ub, cost, status, iters = box_solve_device(
+            self.system, True, At.view(1, T, n, n), Bt.view(1, T, n, m), ct.view(1, T, n), self._dQ, self._dQd,
+            self._dR, self.Q, self.Qd, self.R, self._dxd, 0, x0, xlo, xhi, ulo, uhi)
+        if int(status.item()) != 0:
+            raise ValueError(TVLQR_FAILED)
+        self.bounded_admm_iterations = int(iters.item())
+        return _device.to_numpy(xb[0]), _device.to_numpy(ub[0]), float(cost.item())
 
     # -- iteration (irs_lqr.py:188-218): runs max_iterations + 1 descents ------------------------
     def iterate(self, max_iterations, verbose=True):

@@ -2,8 +2,10 @@
 
 The reference builds a Drake MathematicalProgram QP and calls OSQP.  Here the same optimisation
 problem is solved by an affine Riccati recursion on the GPU (csrc/tvlqr.cuh) — exact, not
-iterative — which is the QP's minimiser whenever no box bound is active.  Active bounds and the
-position-controlled / relative-bound variants are not implemented.
+iterative — which is the QP's minimiser whenever no box bound is active.  When an absolute bound
+IS active, the QP is solved by ADMM on the box split with Riccati-structured linear solves
+(csrc/tvlqr_box.cuh; same algorithm as oracle/box_tvlqr.py, which is checked against a dense QP
+solve).  The position-controlled / relative-bound variants are not implemented.
 """
 import numpy as np
 import torch
@@ -44,7 +46,88 @@ def riccati_device(At, Bt, ct, Q, Qd, R, xd, xd_stride):
     return K, k, status
 
 
-def _violates(v, lo, hi, tol=1e-9):
+# ADMM parameters of the bounded solve (csrc/tvlqr_box.cuh)
+BOX_RHO0 = 1.0
+BOX_ALPHA = 1.6
+BOX_EPS = 1e-8
+BOX_MAX_ITER = 4000
+BOUND_TOL = 1e-9
+
+
+def box_penalties(Q, R, rho0=BOX_RHO0):
+    """Per-coordinate ADMM penalties: rho0 times the cost curvature of the coordinate, floored at the
+    mean curvature (a coordinate with zero weight still gets a usable penalty)."""
+    qd = np.diag(np.asarray(Q, dtype=np.float64)).copy()
+    rd = 0.5 * np.diag(np.asarray(R, dtype=np.float64))
+    return rho0 * np.maximum(qd, qd.mean()), rho0 * np.maximum(rd, rd.mean())
+
+
+def box_solve_device(system, mpc, At, Bt, ct, dQ, dQd, dR, Q, Qd, R, dxd, xd_stride, x0, xlo, xhi, ulo, uhi,
+                     rho0=BOX_RHO0, alpha=BOX_ALPHA, eps=BOX_EPS, max_iter=BOX_MAX_ITER):
+    """Bounded solve on the device.  At [I,T,n,n] ... CUDA float64; Q, Qd, R numpy (for the penalty
+    augmentation).  mpc=True: the reference's closed loop on the true dynamics of `system`
+    (irs_lqr.py:169-184); mpc=False: one QP from x0 (tv_lqr.py:69-145).  Returns device tensors
+    (x_trj [I,T+1,n], u_trj [I,T,m], cost [I], status [I], iters [I])."""
+    I, T, n, _ = At.shape
+    m = Bt.shape[3]
+    dx, du = box_penalties(Q, R, rho0)
+    Qe = _device.to_device(np.asarray(Q, dtype=np.float64) + 0.5 * np.diag(dx))
+    Qde = _device.to_device(np.asarray(Qd, dtype=np.float64) + 0.5 * np.diag(dx))
+    Re = _device.to_device(np.asarray(R, dtype=np.float64) + np.diag(du))      # halved inside the kernel
+    K = _device.empty((I, T, m, n))
+    k = _device.empty((I, T, m))
+    Hinv = _device.empty((I, T, m, m))
+    P = _device.empty((I, T + 1, n, n))
+    rstatus = _device.empty((I,), torch.int32)
+    _lib.call("irs_tvlqr_riccati_ex", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+              _device.ptr(Qe), _device.ptr(Qde), _device.ptr(Re), _device.ptr(dxd), int(xd_stride), I, T,
+              _device.ptr(K), _device.ptr(k), _device.ptr(rstatus), _device.ptr(Hinv), _device.ptr(P),
+              _device.stream_ptr())
+    x_trj = _device.empty((I, T + 1, n))
+    u_trj = _device.empty((I, T, m))
+    cost = _device.empty((I,))
+    status = _device.empty((I,), torch.int32)
+    iters = _device.empty((I,), torch.int32)
+    d = {name: _device.to_device(np.ascontiguousarray(v, dtype=np.float64))
+         for name, v in (("dx", dx), ("du", du), ("xlo", xlo), ("xhi", xhi), ("ulo", ulo), ("uhi", uhi))}
+    prm, nprm = system._params()
+    _lib.call("irs_tvlqr_box_solve", system.system_id, prm, nprm, 1 if mpc else 0, _device.ptr(At),
+              _device.ptr(Bt), _device.ptr(ct), _device.ptr(K), _device.ptr(Hinv), _device.ptr(P),
+              _device.ptr(dQ), _device.ptr(dQd), _device.ptr(dR), _device.ptr(dxd), int(xd_stride),
+              _device.ptr(d["dx"]), _device.ptr(d["du"]), _device.ptr(d["xlo"]), _device.ptr(d["xhi"]),
+              _device.ptr(d["ulo"]), _device.ptr(d["uhi"]), _device.ptr(x0), float(alpha), float(eps),
+              int(max_iter), I, T, _device.ptr(x_trj), _device.ptr(u_trj), _device.ptr(cost),
+              _device.ptr(status), _device.ptr(iters), _device.stream_ptr())
+    return x_trj, u_trj, cost, status | rstatus, iters
+
+
+class _DimsOnlySystem:
+    """solve_tvlqr knows only (n, m): the bounded single-QP solve never evaluates the dynamics, but the
+    kernel is instantiated per built-in system; pick the one with matching dimensions."""
+    _BY_DIMS = {(2, 1): (0, [0.05]), (5, 2): (1, [0.1]), (12, 4): (2, [0.05, 0.775, 0.15, 9.81, 0.0015, 0.0025,
+                                                                      0.0035, 1.0, 0.0245]),
+                (6, 2): (3, [0.05, 0.2])}
+
+    def __init__(self, n, m):
+        if (n, m) not in self._BY_DIMS:
+            raise NotImplementedError("bounded TVLQR is instantiated for the built-in system dimensions only")
+        self.system_id, self._p = self._BY_DIMS[(n, m)]
+
+    def _params(self):
+        return _lib.params_array(self._p)
+
+
+def _constant_box(bound, rows, name):
+    """[2, >=rows, d] time-varying bounds -> (lo[d], hi[d]) if constant over the horizon."""
+    lo, hi = np.asarray(bound[0], dtype=np.float64), np.asarray(bound[1], dtype=np.float64)
+    lo, hi = np.atleast_2d(lo)[:rows], np.atleast_2d(hi)[:rows]
+    if np.any(lo != lo[0]) or np.any(hi != hi[0]):
+        raise NotImplementedError("time-varying %s with an active bound is not implemented "
+                                  "(per-coordinate boxes constant over the horizon are)" % name)
+    return lo[0], hi[0]
+
+
+def _violates(v, lo, hi, tol=BOUND_TOL):
     return bool(np.any(v < np.asarray(lo) - tol) or np.any(v > np.asarray(hi) + tol))
 
 
@@ -78,12 +161,20 @@ def solve_tvlqr(At, Bt, ct, Q, Qd, R, x0, x_trj_d, solver=None, indices_u_into_x
     us = _device.to_numpy(us[0])
     if not (np.all(np.isfinite(xs)) and np.all(np.isfinite(us))):
         raise ValueError(TVLQR_FAILED)
-    if x_bound_abs is not None and _violates(xs[1:], np.asarray(x_bound_abs[0])[1:T + 1],
-                                             np.asarray(x_bound_abs[1])[1:T + 1]):
-        raise NotImplementedError("an absolute state bound is active: box-constrained TVLQR is not "
-                                  "implemented (inactive-bound regime only)")
-    if u_bound_abs is not None and _violates(us, np.asarray(u_bound_abs[0])[:T],
-                                             np.asarray(u_bound_abs[1])[:T]):
-        raise NotImplementedError("an absolute input bound is active: box-constrained TVLQR is not "
-                                  "implemented (inactive-bound regime only)")
-    return xs, us
+    x_active = x_bound_abs is not None and _violates(xs[1:], np.asarray(x_bound_abs[0])[1:T + 1],
+                                                     np.asarray(x_bound_abs[1])[1:T + 1])
+    u_active = u_bound_abs is not None and _violates(us, np.asarray(u_bound_abs[0])[:T],
+                                                     np.asarray(u_bound_abs[1])[:T])
+    if not (x_active or u_active):
+        return xs, us
+    # an absolute bound is active: box-constrained QP (tv_lqr.py:113-118, :132-134)
+    big = 1e30
+    xlo, xhi = (_constant_box(x_bound_abs, T + 1, "x_bound_abs") if x_bound_abs is not None
+                else (-big * np.ones(n), big * np.ones(n)))
+    ulo, uhi = (_constant_box(u_bound_abs, T, "u_bound_abs") if u_bound_abs is not None
+                else (-big * np.ones(m), big * np.ones(m)))
+    xb, ub, _, bstatus, _ = box_solve_device(_DimsOnlySystem(n, m), False, dA, dB, dc, dQ, dQd, dR, Q, Qd, R,
+                                             dxd, 0, dx0, xlo, xhi, ulo, uhi)
+    if int(bstatus.item()) != 0:
+        raise ValueError(TVLQR_FAILED)
+    return _device.to_numpy(xb[0]), _device.to_numpy(ub[0])

@@ -640,3 +640,87 @@ def test_ragged_sample_counts_match_oracle(api, name, N, engine):
     assert rel_err(At, Ao) < tol
     assert rel_err(Bt, Bo) < tol
     assert float(np.max(np.abs(ct - co))) < tol * max(1.0, float(np.max(np.abs(x_trj))))
+
+
+# ------------------------------------------------------------------------------------------------
+# box-constrained TVLQR: irs_lqr/tv_lqr.py:113-118,:132-134
+# ------------------------------------------------------------------------------------------------
+def _bicycle_lin(T, u_const):
+    cfg = ec.bicycle(T=T)
+    orc = cr.BicycleOracle(cfg["h"])
+    u0 = np.tile(np.array(u_const), (T, 1))
+    x_trj = cr.rollout(orc, cfg["x0"], u0)
+    At, Bt, ct = cr.exact_tv_matrices(orc, x_trj, u0)
+    return cfg, orc, At, Bt, ct
+
+
+def test_solve_tvlqr_active_bounds_matches_admm_oracle_and_dense_qp(api):
+    """One QP with an active steer / steer-rate box: the CUDA ADMM against the numpy ADMM (1e-6) and
+    against an independent dense QP solve (scipy SLSQP, 1e-5); the plan obeys the bounds."""
+    from oracle import box_tvlqr as bq
+    T = 12
+    cfg, orc, At, Bt, ct = _bicycle_lin(T, [0.5, 0.6])
+    xlo, xhi = np.array([-1e4, -1e4, -1e4, -1e4, -0.3]), np.array([1e4, 1e4, 1e4, 1e4, 0.3])
+    ulo, uhi = np.array([-1e4, -0.4]), np.array([1e4, 0.4])
+    xb = np.stack((np.tile(xlo, (T + 1, 1)), np.tile(xhi, (T + 1, 1))))
+    ub = np.stack((np.tile(ulo, (T, 1)), np.tile(uhi, (T, 1))))
+    xs, us = api.solve_tvlqr(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"], None,
+                             x_bound_abs=xb, u_bound_abs=ub)
+    xo, uo, _ = bq.admm_box_qp(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"], xlo, xhi, ulo, uhi)
+    np.testing.assert_allclose(xs, xo, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(us, uo, rtol=0, atol=1e-6)
+    xr, ur, res = bq.dense_qp_reference(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"], xlo, xhi,
+                                        ulo, uhi)
+    assert res.success
+    np.testing.assert_allclose(us, ur, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(xs, xr, rtol=0, atol=2e-5)
+    assert np.all(xs[1:, 4] <= 0.3 + 1e-6) and np.all(np.abs(us[:, 1]) <= 0.4 + 1e-6)
+    assert np.max(np.abs(xs[:, 4])) > 0.29          # the bound really is active
+    # inactive bounds still take the exact one-pass path and agree with the unbounded call
+    wide = np.stack((np.tile(-1e4 * np.ones(5), (T + 1, 1)), np.tile(1e4 * np.ones(5), (T + 1, 1))))
+    x1, u1 = api.solve_tvlqr(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"], None,
+                             x_bound_abs=wide)
+    x2, u2 = api.solve_tvlqr(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"], None)
+    assert np.array_equal(x1, x2) and np.array_equal(u1, u2)
+
+
+def test_bicycle_descent_with_active_steer_bound_matches_oracle(api):
+    """The bicycle example's +-pi/4 steer bound (bicycle_first_order.py:23-26) is active: local_descent
+    must run the reference's loop (box QP at every timestep, first input on the true dynamics).
+    Checked against the numpy restatement of that loop; the result obeys the bound and lowers the cost."""
+    from oracle import box_tvlqr as bq
+    T = 40
+    cfg = ec.bicycle(T=T)
+    s = make_system(api, "bicycle")
+    solver = api.IrsLqrExact(s, make_params(api, cfg, T=T))
+    x_new, u_new = solver.local_descent(solver.x_trj, solver.u_trj)
+    cost = solver.evaluate_cost(x_new, u_new)
+    assert solver.bounded_admm_iterations > 0              # the bounded path ran
+    orc = cr.BicycleOracle(cfg["h"])
+    At, Bt, ct = cr.exact_tv_matrices(orc, solver.x_trj, solver.u_trj)
+    xo, uo, _ = bq.mpc_box_descent(orc, At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"],
+                                   cfg["xbound"][0], cfg["xbound"][1], cfg["ubound"][0], cfg["ubound"][1])
+    np.testing.assert_allclose(u_new, uo, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(x_new, xo, rtol=0, atol=2e-6)
+    assert np.max(np.abs(x_new[:, 4])) <= np.pi / 4 + 1e-6
+    assert np.max(np.abs(x_new[:, 4])) > np.pi / 4 - 1e-3
+    assert cost < solver.cost
+    # the whole bicycle loop now runs end to end (it raised NotImplementedError before)
+    solver.iterate(3, verbose=False)
+    assert len(solver.cost_lst) == 5 and np.all(np.isfinite(solver.cost_lst))
+    assert solver.cost_lst[-1] < solver.cost_lst[0]
+
+
+def test_plan_check_keeps_unbounded_problems_on_the_exact_path(api):
+    """Quadrotor / pendulum examples pass 'infinite' boxes (1e4, 1e5): no plan touches them, the
+    one-pass Riccati descent is used and equals the run without any bounds bit for bit."""
+    cfg = ec.pendulum(T=60)
+    s = make_system(api, "pendulum")
+    a = api.IrsLqrExact(s, make_params(api, cfg, T=60))
+    p2 = make_params(api, cfg, T=60)
+    p2.xbound, p2.ubound = None, None
+    b = api.IrsLqrExact(s, p2)
+    xa, ua = a.local_descent(a.x_trj, a.u_trj)
+    xb_, ub_ = b.local_descent(b.x_trj, b.u_trj)
+    assert np.array_equal(xa, xb_) and np.array_equal(ua, ub_)
+    assert not hasattr(a, "bounded_admm_iterations")
