@@ -148,7 +148,8 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
  *    P [I,T+1,n,n]; called with the penalty-augmented weights (Q + diag(dx)/2, Qd + diag(dx)/2,
  *    R + diag(du)) it yields the matrix part of the ADMM's equality-constrained step;
  *  - irs_tvlqr_plan_check: for every start time t0 rolls the affine model forward from the actual
- *    state x_trj[t0] under the unconstrained gains (K, k) and sets violated[i] = 1 if any planned
+ *    state x_trj[t0] under the unconstrained gains (K, k) (scratch: I*T*(n+m)*(n+1) doubles of device
+ *    workspace for the closed-loop rows) and sets violated[i] = 1 if any planned
  *    state (t0 < t <= T) or input leaves [lo - tol, hi + tol].  violated == 0 means every QP of the
  *    reference's loop had inactive bounds, i.e. the one-pass Riccati descent is its exact result;
  *  - irs_tvlqr_box_solve: ADMM on the box split.  mpc = 1: the reference's closed loop (QP over the
@@ -164,7 +165,7 @@ int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const
 int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const double* ct,
                          const double* K, const double* k, const double* x_trj,
                          const double* xlo, const double* xhi, const double* ulo, const double* uhi,
-                         double tol, int I, int T, int* violated, void* stream);
+                         double tol, int I, int T, int* violated, double* scratch, void* stream);
 int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int mpc,
                         const double* At, const double* Bt, const double* ct,
                         const double* K, const double* Hinv, const double* P,

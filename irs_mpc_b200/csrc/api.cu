@@ -597,13 +597,17 @@ int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const
 int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const double* ct,
                          const double* K, const double* k, const double* x_trj,
                          const double* xlo, const double* xhi, const double* ulo, const double* uhi,
-                         double tol, int I, int T, int* violated, void* stream) {
-    IRS_REQUIRE(At && Bt && ct && K && k && x_trj && xlo && xhi && ulo && uhi && violated, "null pointer argument");
+                         double tol, int I, int T, int* violated, double* scratch, void* stream) {
+    IRS_REQUIRE(At && Bt && ct && K && k && x_trj && xlo && xhi && ulo && uhi && violated && scratch,
+                "null pointer argument");
     IRS_REQUIRE(I >= 1 && T >= 1 && I <= 65535, "need 1 <= I <= 65535 and T >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(violated, 0, sizeof(int) * I, st) != cudaSuccess) return check_launch("cudaMemsetAsync");
-    PlanCheckArgs a{At, Bt, ct, K, k, x_trj, xlo, xhi, ulo, uhi, tol, violated, I, T};
-    IRS_DISPATCH_DIMS(n, m, (plan_check_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a)));
+    PlanCheckArgs a{At, Bt, ct, K, k, x_trj, xlo, xhi, ulo, uhi, tol, violated, scratch, I, T};
+    IRS_DISPATCH_DIMS(n, m, {
+        plan_rows_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a);
+        plan_check_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a);
+    });
     return check_launch("plan_check_kernel");
 }
 

@@ -33,44 +33,77 @@ struct PlanCheckArgs {
     const double* ulo;    // [m]
     const double* uhi;
     double tol;
-    int* violated;        // [I] set to 1 if any plan leaves the box (must be zeroed by the caller)
+    int* violated;        // [I] set to 1 if any plan leaves the box (zeroed by the entry point)
+    double* scratch;      // [I, T, n+m, n+1]: closed-loop rows [A + B K | B k + c] and [K | k]
     int I, T;
 };
 
-// grid = (T, I), one warp per (start time, instance); lanes = state / input coordinates
+// Stage 1, parallel over (t, instance): rows of the closed-loop map  x+ = (A + B K) x + (B k + c)  and
+// of the feedback  u = K x + k, packed as (n + m) rows of n + 1 doubles.
+template <int n, int m>
+__global__ void __launch_bounds__(32) plan_rows_kernel(const PlanCheckArgs a) {
+    constexpr int W = n + 1;
+    const int lane = threadIdx.x;
+    const int t = blockIdx.x, inst = blockIdx.y;
+    const long long it = (long long)inst * a.T + t;
+    double* out = a.scratch + it * (n + m) * W;
+    for (int e = lane; e < (n + m) * W; e += 32) {
+        const int r = e / W, c = e % W;
+        double v;
+        if (r < n) {
+            const double* Br = a.Bt + (it * n + r) * m;
+            if (c < n) {
+                v = a.At[(it * n + r) * n + c];
+#pragma unroll
+                for (int q = 0; q < m; ++q) v += Br[q] * a.K[(it * m + q) * n + c];
+            } else {
+                v = a.ct[it * n + r];
+#pragma unroll
+                for (int q = 0; q < m; ++q) v += Br[q] * a.k[it * m + q];
+            }
+        } else {
+            v = c < n ? a.K[(it * m + (r - n)) * n + c] : a.k[it * m + (r - n)];
+        }
+        out[e] = v;
+    }
+}
+
+// Stage 2, grid = (T, I), one warp per (start time, instance): lanes 0..n-1 carry the planned state,
+// lanes n..n+m-1 the planned input; one fused row product and one __syncwarp per step, next step's
+// row prefetched into registers.
 template <int n, int m>
 __global__ void __launch_bounds__(32) plan_check_kernel(const PlanCheckArgs a) {
-    static_assert(n <= 32 && m <= 32, "one lane per coordinate");
-    __shared__ double xs[n], us[m];
+    static_assert(n + m <= 32, "one lane per coordinate");
+    constexpr int W = n + 1;
+    __shared__ double xs[2][n];
     const int lane = threadIdx.x;
     const int t0 = blockIdx.x, inst = blockIdx.y;
-    const long long base = (long long)inst * a.T;
-    if (lane < n) xs[lane] = a.x_trj[((long long)inst * (a.T + 1) + t0) * n + lane];
+    const bool is_x = lane < n, active = lane < n + m;
+    const double lo = !active ? 0.0 : (is_x ? a.xlo[lane] : a.ulo[lane - n]);
+    const double hi = !active ? 0.0 : (is_x ? a.xhi[lane] : a.uhi[lane - n]);
+    if (is_x) xs[0][lane] = a.x_trj[((long long)inst * (a.T + 1) + t0) * n + lane];
+    const double* row = a.scratch + (((long long)inst * a.T + t0) * (n + m) + (active ? lane : 0)) * W;
+    double r[W], rn[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) r[q] = row[q];
     __syncwarp();
     bool bad = false;
+    int cur = 0;
     for (int t = t0; t < a.T; ++t) {
-        if (lane < m) {
-            const double* Kr = a.K + ((base + t) * m + lane) * n;
-            double u = a.k[(base + t) * m + lane];
+        if (t + 1 < a.T) {
 #pragma unroll
-            for (int q = 0; q < n; ++q) u += Kr[q] * xs[q];
-            us[lane] = u;
-            bad |= !(u >= a.ulo[lane] - a.tol && u <= a.uhi[lane] + a.tol);
+            for (int q = 0; q < W; ++q) rn[q] = row[(long long)(n + m) * W + q];
+            row += (long long)(n + m) * W;
         }
-        __syncwarp();
-        double xn = 0.0;
-        if (lane < n) {
-            const double* Ar = a.At + ((base + t) * n + lane) * n;
-            const double* Br = a.Bt + ((base + t) * n + lane) * m;
-            xn = a.ct[(base + t) * n + lane];
+        double acc[4] = {r[n], 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int q = 0; q < n; ++q) xn += Ar[q] * xs[q];
+        for (int q = 0; q < n; ++q) acc[q & 3] += r[q] * xs[cur][q];
+        const double v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        if (active) bad |= !(v >= lo - a.tol && v <= hi + a.tol);
+        if (is_x) xs[cur ^ 1][lane] = v;
+        cur ^= 1;
 #pragma unroll
-            for (int q = 0; q < m; ++q) xn += Br[q] * us[q];
-            bad |= !(xn >= a.xlo[lane] - a.tol && xn <= a.xhi[lane] + a.tol);
-        }
-        __syncwarp();
-        if (lane < n) xs[lane] = xn;
+        for (int q = 0; q < W; ++q) r[q] = rn[q];
         __syncwarp();
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&a.violated[inst], 1);

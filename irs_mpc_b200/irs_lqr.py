@@ -188,6 +188,7 @@ class IrsLqr:
                             if self.ubound is not None else (-big * np.ones(m), big * np.ones(m)))
                 db["box_host"] = (xlo, xhi, ulo, uhi)
                 db["box"] = tuple(_device.to_device(np.ascontiguousarray(v)) for v in (xlo, xhi, ulo, uhi))
+                db["plan_scratch"] = _device.empty((T * (n + m) * (n + 1),))
             else:
                 db["box"] = None
             db["K"] = _device.empty((1, T, m, n))
@@ -223,7 +224,7 @@ class IrsLqr:
             _lib.call("irs_tvlqr_plan_check", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
                       _device.ptr(K), _device.ptr(k), _device.ptr(db["x_new"]), _device.ptr(xlo),
                       _device.ptr(xhi), _device.ptr(ulo), _device.ptr(uhi), BOUND_TOL, 1, T,
-                      _device.ptr(db["violated"]), _device.stream_ptr())
+                      _device.ptr(db["violated"]), _device.ptr(db["plan_scratch"]), _device.stream_ptr())
         else:
             db["violated"].zero_()
         db["lin"] = (At, Bt, ct)
