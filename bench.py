@@ -354,6 +354,31 @@ def run_gpu(args, rank, local_rank, world):
                    "samples_per_s": I_total * T_STEPS * 1000 / (ms_b * 1e-3)}
         del bat
 
+    # 5c. the other BASELINE.json configs, device resident (parity-test cases; reported for orientation)
+    other = None
+    if world == 1 and not args.no_other_configs:
+        from irs_mpc_b200 import example_configs as gec
+        from irs_mpc_b200.systems import SYSTEM_CLASSES
+        other = {}
+        for label, name, order, Tn, Nn, proj in (
+                ("configs[0] pendulum zero-order T=200 N=1e3", "pendulum", smoothing.ZERO_ORDER, 200, 1000, False),
+                ("configs[1] bicycle first-order T=100 N=1e4", "bicycle", smoothing.FIRST_ORDER, 100, 10000, False),
+                ("configs[3] three_cart zero-order T=100 N=1e6, in-kernel projection", "three_cart",
+                 smoothing.ZERO_ORDER, 100, 1000000, True)):
+            c2 = gec.CONFIGS[name](T=Tn)
+            sys2 = SYSTEM_CLASSES[name](c2["h"])
+            xn2 = _device.to_device(np.zeros((Tn, sys2.dim_x)) + c2["x0"])
+            un2 = _device.to_device(c2["u_trj_initial"])
+            ws2 = smoothing.Workspace(sys2, order, Tn, Nn)
+
+            def step2(k, sys2=sys2, order=order, xn2=xn2, un2=un2, ws2=ws2, c2=c2, Nn=Nn, proj=proj):
+                smoothing.accumulate(sys2, order, xn2, un2, Nn, ws2, sigma=c2["sigma"], seed=SEED0 + k, it=1,
+                                     flags=2 if proj else 0)
+                smoothing.finalize(sys2, order, xn2, un2, ws2, Nn)
+            ms2 = timed(step2, max(5, min(args.steps, 20)), 3) / max(5, min(args.steps, 20))
+            other[label] = {"ms_per_linearization": ms2, "samples_per_s": Tn * Nn / (ms2 * 1e-3)}
+            del ws2
+
     # 6. CPU baseline on this box's host cores (rank 0, single GPU run only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,6 +408,7 @@ def run_gpu(args, rank, local_rank, world):
                        "l2": "no per-sample HBM input (noise generated in registers); seed changes every step"},
             "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,
             "batched_mpc": batched,
+            "other_configs": other,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
@@ -443,6 +469,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the 4096-instance leg (configs[4])")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the pendulum/bicycle/three_cart legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
