@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][i] + D[r][dq + i]
     __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast from lane 0 so that the compiler knows the warp index is warp-uniform: ring addresses,
+    // descriptors and barrier addresses then live in uniform registers (fewer R2UR around the UMMAs)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const long long num_items = (long long)a.P * a.C;
 
     if (tid == 0) {
@@ -230,11 +233,15 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
         const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
         load_nominal(item);
-        for (int r = 0; r < rounds; ++r, ++round) {
+        // One round = one 32-sample tile per warp.  CHECK = false is the hot path (every lane owns a
+        // sample); only the last round of a chunk whose length is not a multiple of 128 takes the
+        // CHECK = true path, where the padded lanes stage zeros and contribute nothing.
+        auto do_round = [&](auto check_tag, int r) {
+            constexpr bool CHECK = decltype(check_tag)::value;
             const int stage = round % NSTAGE;
             const long long s = s_begin + (long long)r * C::kTile + tid;
             float w[C::RS];
-            if (s < s_end) {
+            if (!CHECK || s < s_end) {
                 if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
                 draw_deltas<Sys, C::RS>(a, p, s, w);
                 // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers:
@@ -294,7 +301,11 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                 *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
             }
             issue_tile(stage, r == 0, r == rounds - 1);
-        }
+            ++round;
+        };
+        const int full_rounds = (int)((s_end - s_begin) / C::kTile);
+        for (int r = 0; r < full_rounds; ++r) do_round(std::false_type{}, r);
+        if (full_rounds < rounds) do_round(std::true_type{}, full_rounds);
         // ---- item finished: wait for this warp's UMMAs, meet the other warps, read all four
         //      accumulators back.  Row r of D lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64
         //      layout): lanes 0-15 of warp w hold rows 16 w .. 16 w + 15 of every accumulator. ----
