@@ -156,7 +156,10 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
  *    remaining horizon at every t0 from the actual state, first input applied to the TRUE dynamics of
  *    `system`); mpc = 0: one QP from x0 (solve_tvlqr), x_trj/u_trj receive the plan.  Bounds are per
  *    coordinate, constant in time (xlo/xhi [n], ulo/uhi [m]); dx [n], du [m] are the ADMM penalties;
- *    status[i] = 1 if a solve did not reach eps within max_iter (-> the reference's ValueError).
+ *    K0 [I,T,m,n], k0 [I,T,m] (optional, mpc = 1): the UNCONSTRAINED gains; a start time whose
+ *    unconstrained plan stays inside [lo - tol, hi + tol] skips its QP (its bounds are inactive, the
+ *    minimiser is K0 x + k0).  status[i] = 1 if a solve did not reach eps within max_iter (-> the
+ *    reference's ValueError).
  *    Algorithm and its check against a dense QP solve: oracle/box_tvlqr.py. */
 int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const double* ct,
                          const double* Q, const double* Qd, const double* R,
@@ -172,7 +175,8 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
                         const double* Q, const double* Qd, const double* R,
                         const double* xd, long long xd_stride, const double* dx, const double* du,
                         const double* xlo, const double* xhi, const double* ulo, const double* uhi,
-                        const double* x0, double alpha, double eps, int max_iter, int I, int T,
+                        const double* x0, const double* K0, const double* k0, double tol,
+                        double alpha, double eps, int max_iter, int I, int T,
                         double* x_trj, double* u_trj, double* cost, int* status, int* iters, void* stream);
 
 /* (x*, u*) of solve_tvlqr: rollout of the affine model under u = K x + k (tv_lqr.py:142-145).

@@ -74,8 +74,8 @@ SIGNATURES = {
     "irs_tvlqr_plan_check": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _i, _i,
                              _vp, _vp, _vp],
     "irs_tvlqr_box_solve": [_i, _c_double_p, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp,
-                            _vp, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, _i, _i, _i, _vp, _vp, _vp,
-                            _vp, _vp, _vp],
+                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                            _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "irs_tvlqr_linear_rollout": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "irs_rollout_closed_loop": [_i, _c_double_p, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i,
                                 _vp, _vp, _vp, _vp],

@@ -54,17 +54,6 @@ static int load_params(int system, const double* params_host, int nparams, SysPa
     return 0;
 }
 
-// Group size (warps sharing one sample tile) for the zero-order Gram split; quadrotor only.
-static int quadrotor_group() {
-    static int g = -1;
-    if (g < 0) {
-        const char* e = getenv("IRS_QUAD_GROUP");
-        g = e ? atoi(e) : 4;
-        if (g != 1 && g != 2 && g != 4) g = 4;
-    }
-    return g;
-}
-
 // The accumulate kernel launched last on this thread: irs_graph_end looks its node up in a captured
 // graph so that irs_graph_update_smoothing can re-parameterise it (seed, iter, sigma) per replay.
 static thread_local const void* g_last_smooth_func = nullptr;
@@ -144,11 +133,6 @@ static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
     // persistent grid: every resident block walks the (point, chunk) item list with stride gridDim.x
     const long long items = (long long)a.P * a.C;
     long long grid = (long long)num_sms() * blocks_per_sm;
-    if (grid > items) grid = items;
-    if (getenv("IRS_DEBUG"))
-        fprintf(stderr, "[irs] smooth_zero_order_tc: items=%lld grid=%lld blocks/SM=%d smem=%zu stages=%d\n", items, grid,
-                blocks_per_sm, smem, NSTAGE);
-    if (const char* g = getenv("IRS_TC_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
     if (grid > items) grid = items;
     g_last_smooth_func = (const void*)kern;
     kern<<<(unsigned)grid, C::kThreads, smem, st>>>(a);
@@ -309,12 +293,22 @@ using namespace irs;
 
 template <class Sys>
 static int launch_box_mpc(const BoxMpcArgs& a, cudaStream_t st) {
-    const size_t smem = box_mpc_smem_bytes<Sys::N, Sys::M>(a.T);
+    // stage the per-step matrices in shared memory when they fit next to the ADMM state
+    const size_t with_cache = box_mpc_smem_bytes<Sys::N, Sys::M>(a.T, true);
+    const bool cache = with_cache <= 200 * 1024;
+    const size_t smem = cache ? with_cache : box_mpc_smem_bytes<Sys::N, Sys::M>(a.T, false);
     IRS_REQUIRE(smem <= 200 * 1024, "horizon T=%d too long for the shared-memory resident ADMM state", a.T);
-    auto kern = box_mpc_kernel<Sys>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(box_mpc_kernel)");
-    kern<<<(unsigned)a.I, 32, smem, st>>>(a);
+    if (cache) {
+        auto kern = box_mpc_kernel<Sys, true>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(box_mpc_kernel)");
+        kern<<<(unsigned)a.I, 32, smem, st>>>(a);
+    } else {
+        auto kern = box_mpc_kernel<Sys, false>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(box_mpc_kernel)");
+        kern<<<(unsigned)a.I, 32, smem, st>>>(a);
+    }
     return check_launch("box_mpc_kernel");
 }
 
@@ -390,11 +384,8 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
         case kThreeCart: return launch_zero_order<ThreeCart<float>, 1>(a, st);
         case kQuadrotor:
             IRS_REQUIRE(S % 128 == 0, "quadrotor chunk size must be a multiple of 128");
-            switch (quadrotor_group()) {
-                case 1: return launch_zero_order<Quadrotor<float>, 1>(a, st);
-                case 2: return launch_zero_order<Quadrotor<float>, 2>(a, st);
-                default: return launch_zero_order<Quadrotor<float>, 4>(a, st);
-            }
+            // 16 regressors: the Gram rows are split over the 4 warps of a block sharing one sample tile
+            return launch_zero_order<Quadrotor<float>, 4>(a, st);
     }
     set_error("unknown system id %d", system);
     return 1;
@@ -617,7 +608,8 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
                         const double* Q, const double* Qd, const double* R,
                         const double* xd, long long xd_stride, const double* dx, const double* du,
                         const double* xlo, const double* xhi, const double* ulo, const double* uhi,
-                        const double* x0, double alpha, double eps, int max_iter, int I, int T,
+                        const double* x0, const double* K0, const double* k0, double tol,
+                        double alpha, double eps, int max_iter, int I, int T,
                         double* x_trj, double* u_trj, double* cost, int* status, int* iters, void* stream) {
     BoxMpcArgs a;
     if (load_params(system, params_host, nparams, &a.prm)) return 1;
@@ -627,7 +619,7 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
     IRS_REQUIRE(alpha > 0.0 && alpha < 2.0 && eps > 0.0, "need 0 < alpha < 2 and eps > 0");
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.K = K;  a.Hinv = Hinv;  a.P = P;  a.Q = Q;  a.Qd = Qd;  a.R = R;
     a.xd = xd;  a.xd_stride = xd_stride;  a.dx = dx;  a.du = du;  a.xlo = xlo;  a.xhi = xhi;  a.ulo = ulo;
-    a.uhi = uhi;  a.x0 = x0;  a.alpha = alpha;  a.eps = eps;  a.max_iter = max_iter;  a.mpc = mpc ? 1 : 0;
+    a.uhi = uhi;  a.x0 = x0;  a.K0 = K0;  a.k0 = k0;  a.tol = tol;  a.alpha = alpha;  a.eps = eps;  a.max_iter = max_iter;  a.mpc = mpc ? 1 : 0;
     a.x_trj = x_trj;  a.u_trj = u_trj;  a.cost = cost;  a.status = status;  a.iters = iters;  a.I = I;  a.T = T;
     cudaStream_t st = (cudaStream_t)stream;
     switch (system) {

@@ -278,7 +278,7 @@ __device__ __forceinline__ void zero_order_split(const Sys& sys, const SmoothArg
                                                  const float* fbar, float* tiles, float* out) {
     using C = ZeroOrderCfg<Sys, G>;
     constexpr int NP = role_pairs(C::d, C::Wp, G, 0);
-    static_assert(G == 2 || G == 4, "supported group sizes");
+    static_assert(G == 4, "supported group size");
     static_assert(role_pairs(C::d, C::Wp, G, G - 1) == NP && role_pairs(C::d, C::Wp, G, 1) == NP,
                   "row split must be balanced");
     float2 acc[NP];

@@ -128,6 +128,9 @@ struct BoxMpcArgs {
     const double* ulo;    // [m]
     const double* uhi;
     const double* x0;     // [I, n]
+    const double* K0;     // [I, T, m, n]   unconstrained gains (or nullptr): a start time whose
+    const double* k0;     // [I, T, m]      unconstrained plan stays inside the box skips its QP
+    double tol;           // bound tolerance of that test
     double alpha, eps;
     int max_iter;
     int mpc;              // 1: closed loop on the true dynamics (local_descent); 0: one QP from x0 (solve_tvlqr)
@@ -141,8 +144,10 @@ struct BoxMpcArgs {
 };
 
 // One warp per instance; lanes = coordinates.  Dynamic shared memory (doubles):
-//   zx, wx, x : (T+1) n each     zu, wu, u, kk : T m each     Pc : T n     scratch
-template <class Sys>
+//   zx, wx, x : (T+1) n each     zu, wu, u, kk : T m each     Pc : T n     qxd : (T+1) n     scratch
+//   CACHE: + the per-step matrices A_t, B_t, K_t, Hinv_t (and K0_t, k0_t), so that the sequential
+//   sweeps read shared memory instead of chasing global-memory latency twice per step.
+template <class Sys, bool CACHE>
 __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
     constexpr int n = Sys::N, m = Sys::M;
     static_assert(n <= 32 && m <= 32, "one lane per coordinate");
@@ -156,22 +161,61 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
     double* u = wu + T * m;
     double* kk = u + T * m;
     double* Pc = kk + T * m;
-    double* pv = Pc + T * n;      // [2][n] rolling p_{t+1}, p_t
+    double* qxd = Pc + T * n;     // Q xd_t (t < T), Qd xd_T
+    double* pv = qxd + (T + 1) * n;   // [2][n] rolling p_{t+1}, p_t
     double* ww = pv + 2 * n;      // [n]
     double* gv = ww + n;          // [m]
+    double* cache = gv + m;
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
     const long long base = (long long)inst * T;
     const double* xd_i = a.xd + inst * a.xd_stride;
     const Sys sys(a.prm);
     const double dxl = lane < n ? a.dx[lane] : 0.0, dul = lane < m ? a.du[lane] : 0.0;
-    // Pc_t = P_{t+1} c_t; cold start of the split variables: z = clip(target), w = 0
+    const bool can_skip = a.mpc && a.K0 != nullptr && a.k0 != nullptr;
+    // per-step matrices: global (L1/L2) or staged in shared memory
+    const double* Ap = a.At + base * n * n;
+    const double* Bp = a.Bt + base * n * m;
+    const double* Kp = a.K + base * m * n;
+    const double* Hp = a.Hinv + base * m * m;
+    const double* cp = a.ct + base * n;
+    const double* K0p = can_skip ? a.K0 + base * m * n : nullptr;
+    const double* k0p = can_skip ? a.k0 + base * m : nullptr;
+    if constexpr (CACHE) {
+        double* sA = cache;
+        double* sB = sA + T * n * n;
+        double* sK = sB + T * n * m;
+        double* sH = sK + T * m * n;
+        double* sc = sH + T * m * m;
+        double* sK0 = sc + T * n;
+        double* sk0 = sK0 + T * m * n;
+        for (int e = lane; e < T * n * n; e += 32) sA[e] = Ap[e];
+        for (int e = lane; e < T * n * m; e += 32) { sB[e] = Bp[e];  sK[e] = Kp[e]; }
+        for (int e = lane; e < T * m * m; e += 32) sH[e] = Hp[e];
+        for (int e = lane; e < T * n; e += 32) sc[e] = cp[e];
+        if (can_skip) {
+            for (int e = lane; e < T * m * n; e += 32) sK0[e] = K0p[e];
+            for (int e = lane; e < T * m; e += 32) sk0[e] = k0p[e];
+            K0p = sK0;  k0p = sk0;
+        }
+        Ap = sA;  Bp = sB;  Kp = sK;  Hp = sH;  cp = sc;
+    }
+    // Pc_t = P_{t+1} c_t, Q xd_t; cold start of the split variables: z = clip(target), w = 0
     for (int e = lane; e < T * n; e += 32) {
         const int t = e / n, i = e % n;
         const double* Pr = a.P + ((long long)inst * (T + 1) + t + 1) * n * n + i * n;
-        double acc = 0.0;
-        for (int q = 0; q < n; ++q) acc += Pr[q] * a.ct[(base + t) * n + q];
+        double acc = 0.0, accq = 0.0;
+        for (int q = 0; q < n; ++q) {
+            acc += Pr[q] * a.ct[(base + t) * n + q];
+            accq += a.Q[i * n + q] * xd_i[(long long)t * n + q];
+        }
         Pc[e] = acc;
+        qxd[e] = accq;
+    }
+    if (lane < n) {
+        double accq = 0.0;
+        for (int q = 0; q < n; ++q) accq += a.Qd[lane * n + q] * xd_i[(long long)T * n + q];
+        qxd[T * n + lane] = accq;
     }
     for (int e = lane; e < (T + 1) * n; e += 32) {
         const int i = e % n;
@@ -191,41 +235,64 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
     bool failed = false;
     const int n_starts = a.mpc ? T : 1;
     for (int t0 = 0; t0 < n_starts; ++t0) {
-        bool converged = false;
+        bool solved = false;
+        if (can_skip) {
+            // unconstrained plan from the actual x_{t0}: if it stays inside the box the QP's bounds are
+            // inactive and its first input is K0 x + k0 exactly (what the reference's solver returns)
+            bool bad = false;
+            for (int t = t0; t < T; ++t) {
+                if (lane < m) {
+                    double acc = k0p[t * m + lane];
+#pragma unroll
+                    for (int q = 0; q < n; ++q) acc += K0p[(t * m + lane) * n + q] * x[t * n + q];
+                    u[t * m + lane] = acc;
+                    bad |= !(acc >= a.ulo[lane] - a.tol && acc <= a.uhi[lane] + a.tol);
+                }
+                __syncwarp();
+                if (lane < n) {
+                    double acc = cp[t * n + lane];
+#pragma unroll
+                    for (int q = 0; q < n; ++q) acc += Ap[(t * n + lane) * n + q] * x[t * n + q];
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc += Bp[(t * n + lane) * m + q] * u[t * m + q];
+                    x[(t + 1) * n + lane] = acc;
+                    bad |= !(acc >= a.xlo[lane] - a.tol && acc <= a.xhi[lane] + a.tol);
+                }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, bad)) break;      // the ADMM recomputes the plan anyway
+            }
+            solved = !__any_sync(0xffffffffu, bad);
+        }
+        bool converged = solved;
         for (int it = 0; it < a.max_iter && !converged; ++it) {
             // ---- backward vector recursion: p_T, then kk_t, p_t for t = T-1 .. t0 ----
             int cur = 0;
-            if (lane < n) {
-                double acc = 0.5 * dxl * (zx[T * n + lane] - wx[T * n + lane]);
-                for (int q = 0; q < n; ++q) acc += a.Qd[lane * n + q] * xd_i[(long long)T * n + q];
-                pv[lane] = -acc;
-            }
+            if (lane < n) pv[lane] = -(qxd[T * n + lane] + 0.5 * dxl * (zx[T * n + lane] - wx[T * n + lane]));
             __syncwarp();
             for (int t = T - 1; t >= t0; --t) {
                 if (lane < n) ww[lane] = Pc[t * n + lane] + pv[cur * n + lane];
                 __syncwarp();
                 if (lane < m) {
                     double g = -0.5 * dul * (zu[t * m + lane] - wu[t * m + lane]);
-                    const double* Bc = a.Bt + (base + t) * n * m + lane;
+                    const double* Bc = Bp + t * n * m + lane;
 #pragma unroll
                     for (int q = 0; q < n; ++q) g += Bc[q * m] * ww[q];
                     gv[lane] = g;
                 }
                 __syncwarp();
                 if (lane < m) {
-                    const double* Hr = a.Hinv + ((base + t) * m + lane) * m;
+                    const double* Hr = Hp + (t * m + lane) * m;
                     double acc = 0.0;
 #pragma unroll
                     for (int q = 0; q < m; ++q) acc -= Hr[q] * gv[q];
                     kk[t * m + lane] = acc;
                 }
                 if (t > t0 && lane < n) {
-                    double acc = -0.5 * dxl * (zx[t * n + lane] - wx[t * n + lane]);
-                    for (int q = 0; q < n; ++q) acc -= a.Q[lane * n + q] * xd_i[(long long)t * n + q];
-                    const double* Ac = a.At + (base + t) * n * n + lane;
+                    double acc = -(qxd[t * n + lane] + 0.5 * dxl * (zx[t * n + lane] - wx[t * n + lane]));
+                    const double* Ac = Ap + t * n * n + lane;
 #pragma unroll
                     for (int q = 0; q < n; ++q) acc += Ac[q * n] * ww[q];
-                    const double* Kc = a.K + (base + t) * m * n + lane;
+                    const double* Kc = Kp + t * m * n + lane;
 #pragma unroll
                     for (int q = 0; q < m; ++q) acc += Kc[q * n] * gv[q];
                     pv[(cur ^ 1) * n + lane] = acc;
@@ -236,7 +303,7 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
             // ---- forward affine rollout from the fixed x_{t0} ----
             for (int t = t0; t < T; ++t) {
                 if (lane < m) {
-                    const double* Kr = a.K + ((base + t) * m + lane) * n;
+                    const double* Kr = Kp + (t * m + lane) * n;
                     double acc = kk[t * m + lane];
 #pragma unroll
                     for (int q = 0; q < n; ++q) acc += Kr[q] * x[t * n + q];
@@ -244,9 +311,9 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
                 }
                 __syncwarp();
                 if (lane < n) {
-                    const double* Ar = a.At + ((base + t) * n + lane) * n;
-                    const double* Br = a.Bt + ((base + t) * n + lane) * m;
-                    double acc = a.ct[(base + t) * n + lane];
+                    const double* Ar = Ap + (t * n + lane) * n;
+                    const double* Br = Bp + (t * n + lane) * m;
+                    double acc = cp[t * n + lane];
 #pragma unroll
                     for (int q = 0; q < n; ++q) acc += Ar[q] * x[t * n + q];
 #pragma unroll
@@ -290,13 +357,14 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
         }
         if (!converged) failed = true;
         if (a.mpc) {
-            // apply the first input (the feasible split variable) to the TRUE dynamics (irs_lqr.py:183-184)
+            // apply the first input (the feasible split variable; the unconstrained one if the QP was
+            // skipped) to the TRUE dynamics (irs_lqr.py:183-184)
             if (lane == 0) {
                 double xs[n], us[m], xn[n];
 #pragma unroll
                 for (int q = 0; q < n; ++q) xs[q] = x[t0 * n + q];
 #pragma unroll
-                for (int q = 0; q < m; ++q) us[q] = zu[t0 * m + q];
+                for (int q = 0; q < m; ++q) us[q] = solved ? u[t0 * m + q] : zu[t0 * m + q];
                 sys.template step<false>(xs, us, xn);
 #pragma unroll
                 for (int q = 0; q < n; ++q) x[(t0 + 1) * n + q] = xn[q];
@@ -321,8 +389,10 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
 }
 
 template <int n, int m>
-inline size_t box_mpc_smem_bytes(int T) {
-    return sizeof(double) * ((size_t)3 * (T + 1) * n + (size_t)4 * T * m + (size_t)T * n + 2 * n + n + m);
+inline size_t box_mpc_smem_bytes(int T, bool cache) {
+    size_t d = (size_t)3 * (T + 1) * n + (size_t)4 * T * m + (size_t)T * n + (size_t)(T + 1) * n + 2 * n + n + m;
+    if (cache) d += (size_t)T * (n * n + 2 * n * m + m * m + n + m * n + m);
+    return sizeof(double) * d;
 }
 
 }  // namespace irs

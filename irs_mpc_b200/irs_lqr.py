@@ -306,7 +306,7 @@ class IrsLqr:
         x0 = db["in_dev"][:n].view(1, n)
         xb, ub, cost, status, iters = box_solve_device(
             self.system, True, At.view(1, T, n, n), Bt.view(1, T, n, m), ct.view(1, T, n), self._dQ, self._dQd,
-            self._dR, self.Q, self.Qd, self.R, self._dxd, 0, x0, xlo, xhi, ulo, uhi)
+            self._dR, self.Q, self.Qd, self.R, self._dxd, 0, x0, xlo, xhi, ulo, uhi, K0=db["K"], k0=db["k"])
         if int(status.item()) != 0:
             raise ValueError(TVLQR_FAILED)
         self.bounded_admm_iterations = int(iters.item())

@@ -63,10 +63,11 @@ def box_penalties(Q, R, rho0=BOX_RHO0):
 
 
 def box_solve_device(system, mpc, At, Bt, ct, dQ, dQd, dR, Q, Qd, R, dxd, xd_stride, x0, xlo, xhi, ulo, uhi,
-                     rho0=BOX_RHO0, alpha=BOX_ALPHA, eps=BOX_EPS, max_iter=BOX_MAX_ITER):
+                     K0=None, k0=None, rho0=BOX_RHO0, alpha=BOX_ALPHA, eps=BOX_EPS, max_iter=BOX_MAX_ITER):
     """Bounded solve on the device.  At [I,T,n,n] ... CUDA float64; Q, Qd, R numpy (for the penalty
     augmentation).  mpc=True: the reference's closed loop on the true dynamics of `system`
-    (irs_lqr.py:169-184); mpc=False: one QP from x0 (tv_lqr.py:69-145).  Returns device tensors
+    (irs_lqr.py:169-184), K0/k0 = the unconstrained gains (start times whose unconstrained plan stays
+    inside the box skip their QP); mpc=False: one QP from x0 (tv_lqr.py:69-145).  Returns device tensors
     (x_trj [I,T+1,n], u_trj [I,T,m], cost [I], status [I], iters [I])."""
     I, T, n, _ = At.shape
     m = Bt.shape[3]
@@ -95,8 +96,8 @@ def box_solve_device(system, mpc, At, Bt, ct, dQ, dQd, dR, Q, Qd, R, dxd, xd_str
               _device.ptr(Bt), _device.ptr(ct), _device.ptr(K), _device.ptr(Hinv), _device.ptr(P),
               _device.ptr(dQ), _device.ptr(dQd), _device.ptr(dR), _device.ptr(dxd), int(xd_stride),
               _device.ptr(d["dx"]), _device.ptr(d["du"]), _device.ptr(d["xlo"]), _device.ptr(d["xhi"]),
-              _device.ptr(d["ulo"]), _device.ptr(d["uhi"]), _device.ptr(x0), float(alpha), float(eps),
-              int(max_iter), I, T, _device.ptr(x_trj), _device.ptr(u_trj), _device.ptr(cost),
+              _device.ptr(d["ulo"]), _device.ptr(d["uhi"]), _device.ptr(x0), _device.ptr(K0), _device.ptr(k0),
+              BOUND_TOL, float(alpha), float(eps), int(max_iter), I, T, _device.ptr(x_trj), _device.ptr(u_trj), _device.ptr(cost),
               _device.ptr(status), _device.ptr(iters), _device.stream_ptr())
     return x_trj, u_trj, cost, status | rstatus, iters
 

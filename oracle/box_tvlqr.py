@@ -117,10 +117,13 @@ def admm_box_qp(At, Bt, ct, Q, Qd, R, x0, xd, xlo, xhi, ulo, uhi, gains=None, dx
 
 
 def mpc_box_descent(system, At, Bt, ct, Q, Qd, R, x0, xd, xlo, xhi, ulo, uhi, rho0=DEFAULT_RHO0,
-                    alpha=DEFAULT_ALPHA, eps=DEFAULT_EPS, max_iter=DEFAULT_MAX_ITER):
+                    alpha=DEFAULT_ALPHA, eps=DEFAULT_EPS, max_iter=DEFAULT_MAX_ITER, gains0=None, tol=1e-9):
     """IrsLqr.local_descent's loop (irs_lqr.py:169-184) with the bounded QP: at every t0 solve over
     the remaining horizon from the ACTUAL state, apply the first input (the feasible split variable
-    z_u) to the true dynamics.  Returns (x_trj, u_trj, total ADMM iterations)."""
+    z_u) to the true dynamics.  gains0 = (K0, k0), the unconstrained Riccati gains: a start time whose
+    unconstrained plan stays inside the box has inactive bounds, its QP minimiser is K0 x + k0 and the
+    ADMM is skipped (exactly what a QP solver returns there).  Returns (x_trj, u_trj, total ADMM
+    iterations)."""
     T, n, m = At.shape[0], Q.shape[0], R.shape[0]
     dx, du = penalties(Q, R, rho0)
     gains = augmented_gains(At, Bt, ct, Q, Qd, R, dx, du)
@@ -133,6 +136,21 @@ def mpc_box_descent(system, At, Bt, ct, Q, Qd, R, x0, xd, xlo, xhi, ulo, uhi, rh
     x_trj[0] = x0
     total = 0
     for t0 in range(T):
+        if gains0 is not None:
+            K0, k0 = gains0
+            xs, ok, u_first = x_trj[t0], True, None
+            for t in range(t0, T):
+                us = K0[t].dot(xs) + k0[t]
+                if u_first is None:
+                    u_first = us
+                xs = At[t].dot(xs) + Bt[t].dot(us) + ct[t]
+                if np.any(us < ulo - tol) or np.any(us > uhi + tol) or np.any(xs < xlo - tol) or np.any(xs > xhi + tol):
+                    ok = False
+                    break
+            if ok:
+                u_trj[t0] = u_first
+                x_trj[t0 + 1] = system.dynamics(x_trj[t0], u_trj[t0])
+                continue
         _, _, it = admm_box_qp(At, Bt, ct, Q, Qd, R, x_trj[t0], xd, xlo, xhi, ulo, uhi, gains, dx, du, z, w,
                                t0=t0, alpha=alpha, eps=eps, max_iter=max_iter)
         total += it

@@ -698,8 +698,10 @@ def test_bicycle_descent_with_active_steer_bound_matches_oracle(api):
     assert solver.bounded_admm_iterations > 0              # the bounded path ran
     orc = cr.BicycleOracle(cfg["h"])
     At, Bt, ct = cr.exact_tv_matrices(orc, solver.x_trj, solver.u_trj)
+    gains0 = cr.tvlqr_riccati(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["xd_trj"])
     xo, uo, _ = bq.mpc_box_descent(orc, At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"],
-                                   cfg["xbound"][0], cfg["xbound"][1], cfg["ubound"][0], cfg["ubound"][1])
+                                   cfg["xbound"][0], cfg["xbound"][1], cfg["ubound"][0], cfg["ubound"][1],
+                                   gains0=gains0)
     np.testing.assert_allclose(u_new, uo, rtol=0, atol=2e-6)
     np.testing.assert_allclose(x_new, xo, rtol=0, atol=2e-6)
     assert np.max(np.abs(x_new[:, 4])) <= np.pi / 4 + 1e-6
