@@ -204,8 +204,8 @@ def run_gpu(args, rank, local_rank, world):
     sigma = sampler.sigma(1)
     ws = smoothing.Workspace(system, smoothing.ZERO_ORDER, T_STEPS, N_SAMPLES)
     sharded = ShardedLinearizer(system, smoothing.ZERO_ORDER) if world > 1 else None
-    # ours per step: accumulate, nominal dynamics, finalize (+ chunk reduction when sample-sharded)
-    launches_per_step = 3 if world == 1 else 4
+    # ours per step: accumulate, finalize (+ chunk reduction when sample-sharded)
+    launches_per_step = 2 if world == 1 else 3
 
     def step_device(k):
         """Inputs resident in HBM; the seed changes every step so nothing can be cached."""

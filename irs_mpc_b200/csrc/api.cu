@@ -451,13 +451,16 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
     a.R = nranks;  a.P = P;  a.C = C;  a.n_total = n_total;
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.status = status;
     cudaStream_t st = (cudaStream_t)stream;
-    // f(xbar, ubar) in fp64 (scalar dynamics, …zero_order.py:61) -> ct; the finalize kernel turns it into c
-    IRS_DISPATCH_SYSTEM(system, double, Sys,
-                        (dyn_batch_kernel<double, Sys><<<grid_for(P, 128), 128, 0, st>>>(a.prm, 0, x_nom, u_nom, ct, P)));
-    if (check_launch("nominal dynamics kernel")) return 1;
+    const bool many = P > 8 * num_sms();      // many points: one warp per point (throughput)
+    if (many || order == 1) {
+        // f(xbar, ubar) in fp64 (scalar dynamics, …zero_order.py:61) -> ct; the finalize kernel turns it into c
+        IRS_DISPATCH_SYSTEM(system, double, Sys,
+                            (dyn_batch_kernel<double, Sys><<<grid_for(P, 128), 128, 0, st>>>(a.prm, 0, x_nom, u_nom, ct, P)));
+        if (check_launch("nominal dynamics kernel")) return 1;
+    }
     const unsigned grid = (unsigned)P;      // one block per nominal point
     if (order == 0) {
-        if (P > 8 * num_sms()) {      // many points: one warp per point (throughput)
+        if (many) {
             IRS_DISPATCH_SYSTEM(system, double, Sys,
                                 (finalize_zero_order_kernel<Sys, kFinalizeThreadsMany><<<grid, kFinalizeThreadsMany, 0, st>>>(a)));
         } else {

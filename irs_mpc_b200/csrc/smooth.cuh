@@ -441,8 +441,8 @@ __device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int
 
 // Nominal point (xbar | ubar | f(xbar, ubar)) of point p in fp64 -> shared memory.  f(xbar, ubar)
 // (scalar dynamics, …zero_order.py:61) was written into ct[p] by the dynamics kernel that
-// irs_smooth_finalize launches first, which keeps the fp64 dynamics (and its ~250 registers) out of
-// this kernel.
+// irs_smooth_finalize launches first in the many-points case, which keeps the fp64 dynamics (and its
+// ~250 registers) out of the throughput variant of this kernel.
 template <class Sys, int BT>
 __device__ __forceinline__ void nominal_to_smem(const FinalizeArgs& a, int p, double* nom, int tid) {
     constexpr int n = Sys::N, m = Sys::M;
@@ -450,6 +450,26 @@ __device__ __forceinline__ void nominal_to_smem(const FinalizeArgs& a, int p, do
         nom[q] = q < n ? a.x_nom[(long long)p * n + q]
                        : (q < n + m ? a.u_nom[(long long)p * m + (q - n)] : a.ct[(long long)p * n + (q - n - m)]);
     }
+}
+
+// Latency variant: one thread evaluates f(xbar, ubar) in fp64 itself (it runs on warp 1 while warp 0
+// factors the Gram), which saves the separate dynamics launch when there are only a few points.
+template <class Sys>
+__device__ __forceinline__ void nominal_compute_to_smem(const FinalizeArgs& a, int p, double* nom) {
+    constexpr int n = Sys::N, m = Sys::M;
+    const Sys sys(a.prm);
+    double xb[n], ub[m], fb[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) xb[q] = a.x_nom[(long long)p * n + q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) ub[q] = a.u_nom[(long long)p * m + q];
+    sys.template step<false>(xb, ub, fb);      // scalar dynamics at the nominal (…zero_order.py:61)
+#pragma unroll
+    for (int q = 0; q < n; ++q) nom[q] = xb[q];
+#pragma unroll
+    for (int q = 0; q < m; ++q) nom[n + q] = ub[q];
+#pragma unroll
+    for (int q = 0; q < n; ++q) nom[n + m + q] = fb[q];
 }
 
 // At, Bt from AB ([n][d] smem) and c = f(xbar,ubar) - A xbar - B ubar (…zero_order.py:59-62).
@@ -502,9 +522,11 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 16 : 1) finalize_zero_order_ker
             Bm[i * n + (j - d)] = s;
         }
     }
-    nominal_to_smem<Sys, BT>(a, p, nom, tid);
+    if constexpr (BT == 32) nominal_to_smem<Sys, BT>(a, p, nom, tid);     // f(xbar, ubar) was written to ct
     __syncthreads();
-    if (tid < 32) {
+    if (BT > 32 && tid == 32) {
+        nominal_compute_to_smem<Sys>(a, p, nom);
+    } else if (tid < 32) {
         // 2. Cholesky G = L L^T by warp 0 (lanes = rows).  A column whose diagonal is exactly zero
         //    (sigma = 0: regressor identically zero) gets coefficient 0, which is what the min-norm
         //    lstsq of the reference returns for it.
