@@ -158,4 +158,6 @@ def check_status(status):
     if bad:
         raise np.linalg.LinAlgError(
             "smoothing fit: the sample Gram matrix [dx du]^T[dx du] is rank deficient at %d "
-            "nominal point(s) (too few samples, or NaN in the dynamics)" % bad)
+            "nominal point(s) (too few samples, NaN in the dynamics, or regressors whose offset dwarfs "
+            "their spread — three_cart's projection='absolute' quirk far from the origin: the Gram is "
+            "accumulated in fp32)" % bad)

@@ -19,7 +19,7 @@ import numpy as np
 DEFAULT_RHO0 = 1.0
 DEFAULT_ALPHA = 1.6
 DEFAULT_EPS = 1e-8
-DEFAULT_MAX_ITER = 4000
+DEFAULT_MAX_ITER = 100000
 
 
 def penalties(Q, R, rho0=DEFAULT_RHO0):
