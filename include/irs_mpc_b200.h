@@ -215,8 +215,7 @@ int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,
  * Everything submitted to `stream` between irs_graph_begin and irs_graph_end — entry points of this
  * library and cudaMemcpyAsync alike — is captured into one graph instead of being executed.
  * irs_graph_update_smoothing rewrites seed / iter / stream_id / sigma (HOST array [n+m], NULL = keep)
- * of the captured accumulate kernel before a replay; pointers and shapes are fixed at capture.
- * sigma = 0 entries at capture time stay 0 (they mark the unused regressor slots). */
+ * of the captured accumulate kernel before a replay; pointers and shapes are fixed at capture. */
 int irs_graph_begin(void* stream);
 int irs_graph_end(void* stream, void** graph_out);
 int irs_graph_update_smoothing(void* graph, const float* sigma_host, unsigned long long seed,

@@ -157,6 +157,7 @@ static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host
     IRS_REQUIRE(noise != nullptr || sigma != nullptr, "need either replayed noise or sigma");
     {
         const SystemDims dm = system_dims(system);
+        a->nreg = dm.n + dm.m;
         for (int c = 0; c < kMaxRegressors; ++c)
             a->sigma_scaled[c] = (sigma != nullptr && c < dm.n + dm.m) ? kBoxMullerScale * sigma[c] : 0.f;
     }
@@ -768,10 +769,7 @@ int irs_graph_update_smoothing(void* graph, const float* sigma_host, unsigned lo
     a.stream = stream_id;
     if (sigma_host != nullptr) {
         // sigma holds n + m entries; the remaining slots stay zero as in fill_smooth_args
-        int live = 0;
-        for (int c = 0; c < kMaxRegressors; ++c) live = a.sigma_scaled[c] != 0.f ? c + 1 : live;
-        for (int c = 0; c < kMaxRegressors; ++c)
-            if (c < live) a.sigma_scaled[c] = kBoxMullerScale * sigma_host[c];
+        for (int c = 0; c < a.nreg && c < kMaxRegressors; ++c) a.sigma_scaled[c] = kBoxMullerScale * sigma_host[c];
     }
     g->arg_ptrs[0] = &a;
     cudaKernelNodeParams kp = g->smooth_params;

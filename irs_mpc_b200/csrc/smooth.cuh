@@ -31,6 +31,7 @@ struct SmoothArgs {
     uint32_t p0;           // global index of local point 0 (Philox counter word 1)
     unsigned long long i0; // global index of local sample 0 (Philox counter word 0)
     int flags;
+    int nreg;              // n + m: live entries of sigma_scaled
     SysParams prm;
     float sigma_scaled[16];   // kBoxMullerScale * sigma[c] (Philox mode), lives in the constant bank
 };
