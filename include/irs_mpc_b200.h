@@ -88,6 +88,21 @@ int irs_smooth_first_order_accumulate(int system, const double* params_host, int
 int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P, int C,
                              double* reduced, void* stream);
 
+/* Sample-sharded exchange over peer memory (NVLink / NVSwitch), fused with the chunk reduction: the
+ * fp64 block [P,width] of this rank is written into slot (epoch & 1, rank) of EVERY rank's exchange
+ * buffer (peer_bufs_dev: device array of `world` peer-mapped base pointers, each buffer holding
+ * [2][world][slot_stride] doubles) and this rank's arrival flag is raised to `epoch` on every rank
+ * (peer_flags_dev: device array of `world` peer-mapped int[world] arrays, zero before the first step).
+ * done_counter: zero-initialised local device word.  epoch = 1, 2, 3, ... per step.
+ * irs_peer_wait blocks the stream until all `world` flags of the local array reached `epoch`
+ * (timeout_s: gives up and sets *error = 1 instead of hanging).  Afterwards irs_smooth_finalize is
+ * called with reduced = local buffer + (epoch & 1) * world * slot_stride, nranks = world,
+ * rank_stride = slot_stride.  Replaces reduce_chunks + ncclAllGather of the sample-sharded path. */
+int irs_smooth_reduce_chunks_peer(int system, int order, const float* partials, int P, int C,
+                                  const void* peer_bufs_dev, const void* peer_flags_dev, unsigned int* done_counter,
+                                  long long slot_stride, int rank, int world, int epoch, void* stream);
+int irs_peer_wait(const int* flags, int world, int epoch, double timeout_s, int* error, void* stream);
+
 /* Fit / mean + affine offset (irs_lqr_zero_order.py:27-36,:59-62; irs_lqr_first_order.py:48-53).
  * Input is EITHER `partials` (fp32 [nranks][P,C,width], other NULL) OR `reduced` (fp64
  * [nranks][P,width]); the `nranks` buffers lie `rank_stride` elements apart (peer-mapped pointers

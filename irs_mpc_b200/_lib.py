@@ -60,6 +60,8 @@ SIGNATURES = {
     "irs_smooth_first_order_accumulate": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _ll, _vp, _vp,
                                           _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
     "irs_smooth_reduce_chunks": [_i, _i, _vp, _i, _i, _vp, _vp],
+    "irs_smooth_reduce_chunks_peer": [_i, _i, _vp, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
+    "irs_peer_wait": [_vp, _i, _i, ctypes.c_double, _vp, _vp],
     "irs_smooth_finalize": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _ll,
                             ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
     "irs_exact_linearize": [_i, _c_double_p, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],

@@ -434,6 +434,29 @@ int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P
     return check_launch("reduce_chunks_kernel");
 }
 
+int irs_smooth_reduce_chunks_peer(int system, int order, const float* partials, int P, int C,
+                                  const void* peer_bufs_dev, const void* peer_flags_dev, unsigned int* done_counter,
+                                  long long slot_stride, int rank, int world, int epoch, void* stream) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    IRS_REQUIRE(partials && peer_bufs_dev && peer_flags_dev && done_counter && P >= 1 && C >= 1, "bad exchange arguments");
+    IRS_REQUIRE(world >= 1 && rank >= 0 && rank < world && epoch >= 1, "bad rank / world / epoch");
+    const int width = irs_partial_width(system, order);
+    IRS_REQUIRE(slot_stride >= (long long)P * width, "exchange slot too small");
+    PeerExchangeArgs a{partials, (double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, done_counter,
+                       slot_stride, P, C, width, rank, world, epoch};
+    // fixed grid: the arrival ticket counts blocks per launch
+    const unsigned grid = grid_for((long long)P * width, 256);
+    reduce_chunks_peer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("reduce_chunks_peer_kernel");
+}
+
+int irs_peer_wait(const int* flags, int world, int epoch, double timeout_s, int* error, void* stream) {
+    IRS_REQUIRE(flags && error && world >= 1 && world <= 32 && epoch >= 1, "bad wait arguments");
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, epoch,
+                                                       (unsigned long long)(timeout_s * 1e9), error);
+    return check_launch("peer_wait_kernel");
+}
+
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
                         const float* partials, const double* reduced, int nranks,

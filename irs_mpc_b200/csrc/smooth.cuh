@@ -658,6 +658,80 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* partial
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sample-sharded exchange over peer memory (NVLink): the chunk reduction of a rank writes its fp64
+// block [P, width] straight into slot `rank` of EVERY peer's exchange buffer and then raises this
+// rank's arrival flag on every peer — compute and all-gather are one kernel, no NCCL call, no extra
+// pass over the data.  peer_bufs[r] / peer_flags[r] are the peer-mapped base addresses of rank r's
+// buffer / flag array (torch symmetric memory).  Flags carry the step epoch, so they never need a
+// reset; the exchange buffer is double buffered by epoch parity (a rank can be at most one step
+// ahead of a peer: its next finalize waits for that peer's next flag).
+// ---------------------------------------------------------------------------------------------
+struct PeerExchangeArgs {
+    const float* partials;        // [P, C, width] local fp32 partials
+    double* const* peer_bufs;     // [world] device array: base of each rank's exchange buffer
+    int* const* peer_flags;       // [world] device array: base of each rank's flag array [world]
+    unsigned int* done_counter;   // local: blocks finished (monotone over launches)
+    long long slot_stride;        // doubles per (parity, rank) slot  (>= P * width)
+    int P, C, width;
+    int rank, world;
+    int epoch;                    // step counter, >= 1
+};
+
+__global__ void __launch_bounds__(256) reduce_chunks_peer_kernel(const PeerExchangeArgs a) {
+    const long long total = (long long)a.P * a.width;
+    const long long slot = ((long long)(a.epoch & 1) * a.world + a.rank) * a.slot_stride;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / a.width;
+        const int e = (int)(idx % a.width);
+        const float* src = a.partials + (p * a.C) * a.width + e;
+        double s = 0.0;
+        for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * a.width];
+        for (int r = 0; r < a.world; ++r) a.peer_bufs[r][slot + idx] = s;      // NVLink stores (local for r == rank)
+    }
+    // last block of the grid: everything this rank wrote is visible system-wide -> raise the flags
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(a.done_counter, 1u) + 1u;
+        last = ticket == (unsigned int)a.epoch * gridDim.x;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        for (int r = threadIdx.x; r < a.world; r += blockDim.x) {
+            int* flag = a.peer_flags[r] + a.rank;
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(a.epoch) : "memory");
+        }
+    }
+}
+
+// Waits until every rank's block of step `epoch` has arrived in the local exchange buffer (flags are
+// written by the peers).  One thread per rank polls with acquire loads; after timeout_ns the kernel
+// gives up and sets *error = 1 (a missing peer must not hang the GPU).
+__global__ void __launch_bounds__(32) peer_wait_kernel(const int* flags, int world, int epoch,
+                                                       unsigned long long timeout_ns, int* error) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (true) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if (v >= epoch) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) {
+                *error = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Exact linearization at the nominal points, all in fp64 (irs_lqr_exact.py:15-31):
 // [A|B] = jacobian_xu(xbar, ubar), c = f(xbar, ubar) - A xbar - B ubar.  One thread per point.
 // ---------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ The gather helpers are backend agnostic (NCCL on GPUs, gloo in the CPU tests).
 import torch
 import torch.distributed as dist
 
-from . import _device, smoothing
+from . import _device, _lib, smoothing
 
 
 def shard_range(total, world, rank):
@@ -69,10 +69,66 @@ def gather_ranks(local, group=None):
     return out.view((world,) + tuple(local.shape))
 
 
+class PeerExchange:
+    """Exchange buffers in peer-mapped (symmetric) memory for the sample-sharded path: every rank's
+    chunk-reduction kernel stores its fp64 block directly into all peers over NVLink and raises an
+    arrival flag (csrc/smooth.cuh: reduce_chunks_peer_kernel) — the all-gather is fused into the
+    reduction, there is no NCCL call on the data path.  torch's symmetric-memory allocator is used
+    for the address exchange only (plumbing)."""
+
+    TIMEOUT_S = 10.0
+
+    def __init__(self, nelem, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.slot_stride = (int(nelem) + 15) // 16 * 16
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty((2 * self.world * self.slot_stride,), dtype=torch.float64, device=dev)
+        self.flags = symm_mem.empty((64,), dtype=torch.int32, device=dev)
+        self.buf.zero_()
+        self.flags.zero_()
+        self._hbuf = symm_mem.rendezvous(self.buf, group)
+        self._hflags = symm_mem.rendezvous(self.flags, group)
+        self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.error = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.epoch = 0
+        torch.cuda.synchronize()
+        self._hflags.barrier()          # every rank's flags are zero before anyone raises one
+
+    def reduce_and_scatter(self, system, order, ws):
+        """Enqueue the fused chunk reduction + peer stores of this step; returns the epoch."""
+        self.epoch += 1
+        P = ws.partials.shape[0]
+        _lib.call("irs_smooth_reduce_chunks_peer", system.system_id, order, _device.ptr(ws.partials), P, ws.C,
+                  self._hbuf.buffer_ptrs_dev, self._hflags.buffer_ptrs_dev, _device.ptr(self.counter),
+                  self.slot_stride, self.rank, self.world, self.epoch, _device.stream_ptr())
+        return self.epoch
+
+    def wait(self):
+        """Block the stream until every rank's block of the current epoch has arrived locally."""
+        _lib.call("irs_peer_wait", _device.ptr(self.flags), self.world, self.epoch, self.TIMEOUT_S,
+                  _device.ptr(self.error), _device.stream_ptr())
+
+    def gathered(self):
+        """Device view [world * slot_stride] of the current epoch's blocks (rank order)."""
+        off = (self.epoch & 1) * self.world * self.slot_stride
+        return self.buf[off:off + self.world * self.slot_stride]
+
+    def check(self):
+        if int(self.error.item()) != 0:
+            raise RuntimeError("peer exchange timed out: a rank did not deliver its block within %.0f s"
+                               % self.TIMEOUT_S)
+
+
 class ShardedLinearizer:
-    def __init__(self, system, order, group=None):
+    def __init__(self, system, order, group=None, peer_memory=None):
+        """peer_memory: None = use the fused peer-memory exchange when symmetric memory can be set up
+        (NCCL all-gather otherwise), False = always NCCL, True = require it."""
         self.system, self.order, self.group = system, order, group
         self._ws = None
+        self._peer_memory = peer_memory
+        self._px = None
 
     def _workspace(self, P, N):
         key = (self.system.system_id, self.order, P, N)
@@ -100,6 +156,21 @@ class ShardedLinearizer:
         At, Bt, ct = unpack_abc(full[:, :width - 1], n, m)
         return At, Bt, ct, full[:, width - 1].to(torch.int32)
 
+    def _peer_exchange(self, nelem):
+        if self._peer_memory is False:
+            return None
+        if self._px is None or self._px.slot_stride < nelem:
+            try:
+                self._px = PeerExchange(nelem, self.group)
+            except Exception as e:      # no symmetric memory on this system: fall back to NCCL (plumbing only)
+                if self._peer_memory is True:
+                    raise
+                self._peer_memory = False
+                self._px = None
+                import warnings
+                warnings.warn("peer-memory exchange unavailable (%s); using NCCL all-gather" % e)
+        return self._px
+
     def linearize_n(self, x_nom, u_nom, N_local, **kw):
         """Sample-sharded.  Every rank draws N_local samples per point (global sample index
         rank*N_local + i); returns (At, Bt, ct, status) fitted on all W*N_local samples."""
@@ -108,6 +179,12 @@ class ShardedLinearizer:
         ws = self._workspace(T, N_local)
         smoothing.accumulate(self.system, self.order, x_nom, u_nom, N_local, ws,
                              i0=rank * N_local, **kw)
+        px = self._peer_exchange(T * ws.width)
+        if px is not None:
+            px.reduce_and_scatter(self.system, self.order, ws)
+            px.wait()
+            return smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local,
+                                      reduced=px.gathered(), nranks=world, rank_stride=px.slot_stride)
         mine = smoothing.reduce_chunks(self.system, self.order, ws)
         everyone = gather_ranks(mine, self.group)
         return smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local,

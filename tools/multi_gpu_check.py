@@ -66,6 +66,15 @@ def main():
     identical = all(torch.equal(g, gathered[0]) for g in gathered)
     report("sample sharding vs one GPU", err < 1e-5 and int(stn.sum()) == 0, "(rel err %.2e)" % err)
     report("sample sharding identical on ranks", identical)
+    used_peer = sh._px is not None
+    sh_nccl = ShardedLinearizer(s, smoothing.ZERO_ORDER, peer_memory=False)
+    Ac, Bc, cc, _ = sh_nccl.linearize_n(x, u, N, **kw)
+    same = torch.equal(Ac, An) and torch.equal(Bc, Bn) and torch.equal(cc, cn)
+    report("peer-memory exchange == NCCL path", same and used_peer, "(peer memory in use: %s)" % used_peer)
+    for k in range(20):                       # epochs / double buffering over repeated steps
+        A2, B2, c2, _ = sh.linearize_n(x, u, N, **kw)
+    sh._px.check()
+    report("peer exchange stable over 20 steps", torch.equal(A2, An) and torch.equal(c2, cn))
 
     # 3. instance sharding
     I, Tb, Nb = 4 * world, 20, 1000
