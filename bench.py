@@ -9,7 +9,8 @@ Workload (config.workload): BASELINE.json configs[2] — quadrotor 12-state, Irs
 T=100, N=1e5 samples/step per GPU.  A "step" is one full smoothing linearization
 (IrsLqrZeroOrder.get_TV_matrices: T x N perturbed dynamics evaluations + least-squares fits).
 For N GPUs the SAMPLE axis is sharded (weak scaling: every GPU draws 1e5 samples per step, the
-global fit uses N*1e5) with one all-gather of the per-step fp64 Gram blocks.
+global fit uses N*1e5); the per-step fp64 Gram blocks are exchanged by the chunk-reduction kernel
+itself through peer memory (NCCL all-gather as fallback).
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
 """
@@ -204,8 +205,9 @@ def run_gpu(args, rank, local_rank, world):
     sigma = sampler.sigma(1)
     ws = smoothing.Workspace(system, smoothing.ZERO_ORDER, T_STEPS, N_SAMPLES)
     sharded = ShardedLinearizer(system, smoothing.ZERO_ORDER) if world > 1 else None
-    # ours per step: accumulate, finalize (+ chunk reduction when sample-sharded)
-    launches_per_step = 2 if world == 1 else 3
+    # ours per step: accumulate, finalize (+ fused chunk reduction / peer exchange and the arrival wait when
+    # sample-sharded)
+    launches_per_step = 2 if world == 1 else 4
 
     def step_device(k):
         """Inputs resident in HBM; the seed changes every step so nothing can be cached."""
@@ -404,7 +406,10 @@ def run_gpu(args, rank, local_rank, world):
             "config": {"workload": "quadrotor zero-order T=100 N=1e5/step/GPU (BASELINE.json configs[2])",
                        "system": "quadrotor n=12 m=4", "mode": "zero_order", "T": T_STEPS,
                        "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-7 + Box-Muller in-kernel",
-                       "sharding": "none" if world == 1 else "sample axis, all_gather of fp64 Gram blocks",
+                       "sharding": "none" if world == 1 else (
+                           "sample axis; fp64 Gram blocks exchanged by the reduction kernel itself (peer-memory "
+                           "stores over NVLink + arrival flags)" if sharded._px is not None else
+                           "sample axis, NCCL all_gather of fp64 Gram blocks"),
                        "l2": "no per-sample HBM input (noise generated in registers); seed changes every step"},
             "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,
             "batched_mpc": batched,
