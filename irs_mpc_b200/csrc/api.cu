@@ -457,6 +457,29 @@ int irs_peer_wait(const int* flags, int world, int epoch, double timeout_s, int*
     return check_launch("peer_wait_kernel");
 }
 
+// Index tables of the finalize kernel (smooth.cuh: FinalizeTables), uploaded once per system.
+static const FinalizeTables* finalize_tables(int system, cudaStream_t st) {
+    static bool ready[kNumSystems] = {false, false, false, false};
+    FinalizeTables* base = nullptr;
+    if (cudaGetSymbolAddress((void**)&base, g_finalize_tables) != cudaSuccess) return nullptr;
+    if (!ready[system]) {
+        const SystemDims dm = system_dims(system);
+        const int d = dm.n + dm.m, W = d + dm.n;
+        static FinalizeTables host[kNumSystems];
+        FinalizeTables& t = host[system];
+        memset(&t, 0, sizeof(t));
+        int e = 0;
+        for (int i = 0; i < d; ++i)
+            for (int j = i; j < W; ++j, ++e) { t.gram_i[e] = (unsigned char)i;  t.gram_j[e] = (unsigned char)j; }
+        e = 0;
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c <= r; ++c, ++e) { t.tri_r[e] = (unsigned char)r;  t.tri_c[e] = (unsigned char)c; }
+        if (cudaMemcpyAsync(base + system, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+        ready[system] = true;
+    }
+    return base + system;
+}
+
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
                         const float* partials, const double* reduced, int nranks,
@@ -475,6 +498,8 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
     a.R = nranks;  a.P = P;  a.C = C;  a.n_total = n_total;
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.status = status;
     cudaStream_t st = (cudaStream_t)stream;
+    a.tables = finalize_tables(system, st);
+    if (a.tables == nullptr) return check_launch("finalize index tables") ? 1 : (set_error("finalize index tables"), 1);
     const bool many = P > 8 * num_sms();      // many points: one warp per point (throughput)
     if (many || order == 1) {
         // f(xbar, ubar) in fp64 (scalar dynamics, …zero_order.py:61) -> ct; the finalize kernel turns it into c

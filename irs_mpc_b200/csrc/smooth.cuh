@@ -401,6 +401,17 @@ __global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArg
 constexpr int kFinalizeThreads = 128;
 constexpr int kFinalizeThreadsMany = 32;
 
+// Index tables of the finalize kernel, built once per system on the host (api.cu) and kept in global
+// memory: packed Gram entry e -> (i, j), packed lower-triangle entry -> (row, col).  (A per-block
+// search for them costs more than the factorisation itself when a block owns a single point.)
+constexpr int kMaxGramEntries = kMaxRegressors * (kMaxRegressors + 1) / 2 + kMaxRegressors * kMaxRegressors;
+constexpr int kMaxTriEntries = kMaxRegressors * (kMaxRegressors + 1) / 2;
+struct FinalizeTables {
+    unsigned char gram_i[kMaxGramEntries], gram_j[kMaxGramEntries];
+    unsigned char tri_r[kMaxTriEntries], tri_c[kMaxTriEntries];
+};
+__device__ FinalizeTables g_finalize_tables[4];
+
 struct FinalizeArgs {
     const double* x_nom;     // [P, n]
     const double* u_nom;     // [P, m]
@@ -414,6 +425,7 @@ struct FinalizeArgs {
     double* Bt;              // [P, n, m]
     double* ct;              // [P, n]
     int* status;             // [P] 0 ok, 1 rank-deficient Gram
+    const FinalizeTables* tables;   // index tables of this system (device)
     SysParams prm;
 };
 
@@ -492,30 +504,22 @@ __device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const do
 }
 
 template <class Sys, int BT>
-__global__ void __launch_bounds__(BT, BT == 32 ? 16 : 1) finalize_zero_order_kernel(const FinalizeArgs a) {
+__global__ void __launch_bounds__(BT, BT == 32 ? 32 : 1) finalize_zero_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
-    constexpr int W = d + n;
     constexpr int NACC = gram_nacc(n, m);
     __shared__ double Gm[d * d];      // Gram (then its Cholesky factor, lower)
     __shared__ double Bm[d * n];      // right-hand sides Z^T dF, then the solution
     __shared__ double sAB[n * d];
     __shared__ double inv_diag[d];
     __shared__ double nom[d + n];
-    __shared__ unsigned char tri_r[d * (d + 1) / 2], tri_c[d * (d + 1) / 2];   // packed lower triangle -> (row, col)
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
-    for (int e = tid; e < d * (d + 1) / 2; e += BT) {
-        int r = 0;
-        while ((r + 1) * (r + 2) / 2 <= e) ++r;
-        tri_r[e] = (unsigned char)r;
-        tri_c[e] = (unsigned char)(e - r * (r + 1) / 2);
-    }
+    const unsigned char* __restrict__ tri_r = a.tables->tri_r;
+    const unsigned char* __restrict__ tri_c = a.tables->tri_c;
     // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs
     for (int e = tid; e < NACC; e += BT) {
         const double s = sum_partials(a, p, e, NACC);
-        int i = 0;
-        while (i + 1 < d && gram_row_offset(i + 1, W) <= e) ++i;
-        const int j = i + (e - gram_row_offset(i, W));
+        const int i = a.tables->gram_i[e], j = a.tables->gram_j[e];
         if (j < d) {
             Gm[i * d + j] = s;
             Gm[j * d + i] = s;
