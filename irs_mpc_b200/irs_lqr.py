@@ -76,7 +76,6 @@ class IrsLqr:
         self._db = None
         self._graphs = {}
         self._last_descent = None
-        self.timings = {}
 
         self.x_trj = self.rollout(self.x0, self.u_trj)
         self.cost = self.evaluate_cost(self.x_trj, self.u_trj)

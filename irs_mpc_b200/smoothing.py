@@ -83,17 +83,6 @@ class Workspace:
         status = h[na + nb + nc:].view(np.int32)[:P].copy()
         return At, Bt, ct, status
 
-    def upload_nominal(self, x_trj, u_trj):
-        """One pinned H2D copy; returns the (x_nom, u_nom) device views."""
-        self.stage_nominal(x_trj, u_trj)
-        self.enqueue_upload()
-        return self.x_nom, self.u_nom
-
-    def download(self):
-        """One D2H copy into pinned memory + one sync -> (At, Bt, ct, status) numpy arrays."""
-        self.enqueue_download()
-        return self.read_download()
-
     def h2d_bytes(self):
         return self._nom.numel() * 8
 

@@ -98,3 +98,29 @@ def test_argument_validation_messages(built_lib):
     assert rc != 0 and b"no Jacobian" in built_lib.irs_last_error()
     rc = built_lib.irs_tvlqr_riccati(3, 3, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, None)
     assert rc != 0 and b"unsupported TVLQR dims" in built_lib.irs_last_error()
+
+
+def test_box_penalties_and_bound_helpers(built_lib):
+    """Host logic of the bounded TVLQR (irs_mpc_b200/tv_lqr.py) — no GPU needed."""
+    from irs_mpc_b200 import tv_lqr
+    Q = np.diag([5.0, 5.0, 3.0, 0.1, 0.0])
+    R = np.diag([1.0, 0.1])
+    dx, du = tv_lqr.box_penalties(Q, R)
+    assert dx.shape == (5,) and du.shape == (2,)
+    assert np.all(dx >= np.diag(Q)) and np.all(dx >= np.diag(Q).mean() - 1e-15)      # floored at the mean curvature
+    assert np.all(du >= 0.5 * np.diag(R)) and np.all(du > 0)
+    dx2, du2 = tv_lqr.box_penalties(Q, R, rho0=10.0)
+    np.testing.assert_allclose(dx2, 10.0 * dx)
+    np.testing.assert_allclose(du2, 10.0 * du)
+    # constant-in-time boxes are accepted, time-varying ones are refused
+    lo, hi = tv_lqr._constant_box(np.stack((np.tile(-np.ones(3), (6, 1)), np.tile(np.ones(3), (6, 1)))), 6, "x")
+    assert np.array_equal(lo, -np.ones(3)) and np.array_equal(hi, np.ones(3))
+    varying = np.stack((np.tile(-np.ones(3), (6, 1)), np.tile(np.ones(3), (6, 1))))
+    varying[1, 3, 0] = 2.0
+    with pytest.raises(NotImplementedError):
+        tv_lqr._constant_box(varying, 6, "x")
+    assert tv_lqr._violates(np.array([1.1]), np.array([-1.0]), np.array([1.0]))
+    assert not tv_lqr._violates(np.array([1.0 + 1e-12]), np.array([-1.0]), np.array([1.0]))
+    with pytest.raises(NotImplementedError):
+        tv_lqr._DimsOnlySystem(3, 3)
+    assert tv_lqr._DimsOnlySystem(5, 2).system_id == 1
