@@ -500,8 +500,14 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
     cudaStream_t st = (cudaStream_t)stream;
     a.tables = finalize_tables(system, st);
     if (a.tables == nullptr) return check_launch("finalize index tables") ? 1 : (set_error("finalize index tables"), 1);
-    const bool many = P > 8 * num_sms();      // many points: one warp per point (throughput)
-    if (many || order == 1) {
+    // many points: four threads per point, else one block per point (IRS_FINALIZE_VARIANT=block|quad
+    // overrides; the variants are bit-identical, tests/test_gpu_parity.py)
+    bool quad = P > 8 * num_sms();
+    if (const char* e = getenv("IRS_FINALIZE_VARIANT")) {
+        if (!strcmp(e, "block")) quad = false;
+        else if (!strcmp(e, "quad")) quad = true;
+    }
+    if (quad || order == 1) {
         // f(xbar, ubar) in fp64 (scalar dynamics, …zero_order.py:61) -> ct; the finalize kernel turns it into c
         IRS_DISPATCH_SYSTEM(system, double, Sys,
                             (dyn_batch_kernel<double, Sys><<<grid_for(P, 128), 128, 0, st>>>(a.prm, 0, x_nom, u_nom, ct, P)));
@@ -509,9 +515,14 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
     }
     const unsigned grid = (unsigned)P;      // one block per nominal point
     if (order == 0) {
-        if (many) {
-            IRS_DISPATCH_SYSTEM(system, double, Sys,
-                                (finalize_zero_order_kernel<Sys, kFinalizeThreadsMany><<<grid, kFinalizeThreadsMany, 0, st>>>(a)));
+        if (quad) {
+            IRS_DISPATCH_SYSTEM(system, double, Sys, {
+                using QC = FinalizeQuadCfg<Sys>;
+                auto kern = finalize_zero_order_quad_kernel<Sys>;
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QC::kSmemBytes) != cudaSuccess)
+                    return check_launch("cudaFuncSetAttribute(finalize_zero_order_quad_kernel)");
+                kern<<<(unsigned)((P + QC::PPB - 1) / QC::PPB), kFinalizeQuadThreads, QC::kSmemBytes, st>>>(a);
+            });
         } else {
             IRS_DISPATCH_SYSTEM(system, double, Sys,
                                 (finalize_zero_order_kernel<Sys, kFinalizeThreads><<<grid, kFinalizeThreads, 0, st>>>(a)));

@@ -393,13 +393,11 @@ __global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArg
 }
 
 // ---------------------------------------------------------------------------------------------
-// Finalize (fp64, one block of BT threads per nominal point).  BT = 128 when there are few points
-// (latency: the sum over chunks and the nominal dynamics run beside the warp that factors the
-// Gram); BT = 32 when there are many (throughput: the factorisation is a one-warp job, idle warps
-// would only hold registers).
+// Finalize (fp64).  Few points: one block of 128 threads per nominal point (latency: the sum over
+// chunks and the nominal dynamics run beside the warp that factors the Gram).  Many points: four
+// threads per point (finalize_zero_order_quad_kernel below).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinalizeThreads = 128;
-constexpr int kFinalizeThreadsMany = 32;
 
 // Index tables of the finalize kernel, built once per system on the host (api.cu) and kept in global
 // memory: packed Gram entry e -> (i, j), packed lower-triangle entry -> (row, col).  (A per-block
@@ -504,7 +502,7 @@ __device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const do
 }
 
 template <class Sys, int BT>
-__global__ void __launch_bounds__(BT, BT == 32 ? 32 : 1) finalize_zero_order_kernel(const FinalizeArgs a) {
+__global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int NACC = gram_nacc(n, m);
     __shared__ double Gm[d * d];      // Gram (then its Cholesky factor, lower)
@@ -527,9 +525,8 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 32 : 1) finalize_zero_order_ker
             Bm[i * n + (j - d)] = s;
         }
     }
-    if constexpr (BT == 32) nominal_to_smem<Sys, BT>(a, p, nom, tid);     // f(xbar, ubar) was written to ct
     __syncthreads();
-    if (BT > 32 && tid == 32) {
+    if (tid == 32) {
         nominal_compute_to_smem<Sys>(a, p, nom);
     } else if (tid < 32) {
         // 2. Cholesky G = L L^T by warp 0 (lanes = rows).  A column whose diagonal is exactly zero
@@ -566,52 +563,26 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 32 : 1) finalize_zero_order_ker
         // 3. solve L L^T X = B, one right-hand side per lane (reciprocal diagonal: no divisions)
         if (lane < n) {
             const int q = lane;
-            if constexpr (BT > 32) {
-                // latency variant: fully unrolled, solution in registers, the L loads pipeline
-                double y[d];
+            // fully unrolled, solution in registers, the L loads pipeline
+            double y[d];
 #pragma unroll
-                for (int r = 0; r < d; ++r) {
-                    double s0 = Bm[r * n + q];
+            for (int r = 0; r < d; ++r) {
+                double s0 = Bm[r * n + q];
 #pragma unroll
-                    for (int k = 0; k < r; ++k) s0 -= Gm[r * d + k] * y[k];
-                    y[r] = s0 * inv_diag[r];
-                }
+                for (int k = 0; k < r; ++k) s0 -= Gm[r * d + k] * y[k];
+                y[r] = s0 * inv_diag[r];
+            }
 #pragma unroll
-                for (int r = d - 1; r >= 0; --r) {
-                    double s0 = y[r];
+            for (int r = d - 1; r >= 0; --r) {
+                double s0 = y[r];
 #pragma unroll
-                    for (int k = r + 1; k < d; ++k) s0 -= Gm[k * d + r] * y[k];
-                    y[r] = s0 * inv_diag[r];
-                }
+                for (int k = r + 1; k < d; ++k) s0 -= Gm[k * d + r] * y[k];
+                y[r] = s0 * inv_diag[r];
+            }
 #pragma unroll
-                for (int r = 0; r < d; ++r) {
-                    if (!(y[r] == y[r]) || fabs(y[r]) > 1e300) bad = true;
-                    sAB[q * d + r] = y[r];      // [A|B] = X^T
-                }
-            } else {
-                // throughput variant: compact loops, solution in shared memory (56 registers); the
-                // SAME operations in the same order as the latency variant, so that a point's result
-                // does not depend on how many points the launch holds (sharding reproducibility)
-#pragma unroll 1
-                for (int r = 0; r < d; ++r) {
-                    double s0 = Bm[r * n + q];
-#pragma unroll 4
-                    for (int k = 0; k < r; ++k) s0 -= Gm[r * d + k] * Bm[k * n + q];
-                    Bm[r * n + q] = s0 * inv_diag[r];
-                }
-#pragma unroll 1
-                for (int r = d - 1; r >= 0; --r) {
-                    double s0 = Bm[r * n + q];
-#pragma unroll 4
-                    for (int k = r + 1; k < d; ++k) s0 -= Gm[k * d + r] * Bm[k * n + q];
-                    Bm[r * n + q] = s0 * inv_diag[r];
-                }
-#pragma unroll 1
-                for (int r = 0; r < d; ++r) {
-                    const double v = Bm[r * n + q];
-                    if (!(v == v) || fabs(v) > 1e300) bad = true;
-                    sAB[q * d + r] = v;      // [A|B] = X^T
-                }
+            for (int r = 0; r < d; ++r) {
+                if (!(y[r] == y[r]) || fabs(y[r]) > 1e300) bad = true;
+                sAB[q * d + r] = y[r];      // [A|B] = X^T
             }
         }
         bad = __any_sync(0xffffffffu, bad);
@@ -619,6 +590,234 @@ __global__ void __launch_bounds__(BT, BT == 32 ? 32 : 1) finalize_zero_order_ker
     }
     __syncthreads();
     write_abc<Sys, BT>(a, p, sAB, nom, tid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalize for many points (batched MPC: 4096 instances x T points): FOUR threads ("quad") per
+// nominal point, 32 points per block.  The warp-per-point variant above spends a whole warp
+// instruction on every scalar step of a 16 x 16 factorisation (136 useful lanes out of 16 x 5 x 32
+// in the trailing update, 12 of 32 in the solves); here a warp carries eight points:
+//   * the packed lower triangle of a point's Gram lives in shared memory as L[entry][point]
+//     (1 KB per point, so a dozen warps per SM stay resident and hide the fp64 latencies);
+//   * Cholesky, left-looking: for column k every quad thread recomputes the pivot (same operands,
+//     same order: identical bits) and takes every fourth row below it; one __syncwarp per column;
+//   * solves: each thread owns ceil(n / 4) right-hand sides, loaded straight from global memory
+//     into registers and solved in place, L read from shared memory (quad-uniform broadcast);
+// The floating-point operations and their order are those of finalize_zero_order_kernel, entry by
+// entry (left-looking here, right-looking there: each entry still receives its updates in ascending
+// column order), so a point's result does not depend on which variant a launch picks — checked
+// bit for bit by tests/test_gpu_parity.py::test_finalize_variants_are_bit_identical.
+// ---------------------------------------------------------------------------------------------
+// Compile-time loop: f(std::integral_constant<int, I>) for I = I0 .. I1 - 1 (the triangular loop
+// nests must be unrolled at compile time so that the solution stays in registers).
+template <int I0, int I1, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I0 < I1) {
+        f(std::integral_constant<int, I0>{});
+        static_for<I0 + 1, I1>(f);
+    }
+}
+
+constexpr int kFinalizeQuadThreads = 128;
+constexpr int kQuad = 4;
+
+template <class Sys>
+struct FinalizeQuadCfg {
+    static constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    static constexpr int W = d + n;
+    static constexpr int NACC = gram_nacc(n, m);
+    static constexpr int TRI = d * (d + 1) / 2;
+    static constexpr int PPB = kFinalizeQuadThreads / kQuad;     // points per block
+    static constexpr int QT = (n + kQuad - 1) / kQuad;           // right-hand sides per thread
+    static constexpr int LDP = PPB + 1;                          // padded point stride (doubles)
+    // Gram load slots: packed row i holds d - i Gram entries, ceil((d - i) / 4) per quad thread
+    __host__ __device__ static constexpr int row_slots(int i) { return (d - i + kQuad - 1) / kQuad; }
+    __host__ __device__ static constexpr int slot_offset(int i) {
+        int o = 0;
+        for (int r = 0; r < i; ++r) o += row_slots(r);
+        return o;
+    }
+    static constexpr int GSLOTS = slot_offset(d);
+    static constexpr size_t kSmemBytes = (size_t)(TRI + d) * LDP * sizeof(double);
+};
+
+// Fixed-order sums (ranks, then chunks: the order of sum_partials) of U entries of one point at once;
+// the loads of the U entries are independent, so they are in flight together.
+// pbase = offset of the point inside a rank buffer (chunk 0), rel[u] = entry index, < 0 = none (sum 0).
+template <int U>
+__device__ __forceinline__ void sum_partials_multi(const FinalizeArgs& a, long long pbase, const int (&rel)[U],
+                                                   int width, double (&s)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = 0.0;
+    for (int r = 0; r < a.R; ++r) {
+        if (a.reduced != nullptr) {
+            const double* src = a.reduced + r * a.rank_stride + pbase;
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] += v[u];
+        } else {
+            const float* src = a.partials + r * a.rank_stride + pbase;
+            for (int c = 0; c < a.C; ++c, src += width) {
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) s[u] += (double)v[u];
+            }
+        }
+    }
+}
+
+template <class Sys>
+__global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_quad_kernel(const FinalizeArgs a) {
+    using C = FinalizeQuadCfg<Sys>;
+    constexpr int n = C::n, m = C::m, d = C::d, QT = C::QT, PPB = C::PPB, NACC = C::NACC;
+    constexpr int LDP = C::LDP;
+    extern __shared__ double fin_L[];            // [TRI][LDP]  packed lower triangle, (r, c) -> r (r + 1) / 2 + c
+    double* fin_inv = fin_L + C::TRI * LDP;      // [d][LDP]    reciprocal pivots
+    const int tid = threadIdx.x, g = tid & (kQuad - 1), pt = tid / kQuad;
+    const long long p_raw = (long long)blockIdx.x * PPB + pt;
+    const bool active = p_raw < a.P;
+    // the quads past the last point redo the last point and write nothing (every lane then takes part
+    // in the warp synchronisations and no lane factors garbage)
+    const long long p = active ? p_raw : (long long)a.P - 1;
+    // entries of one point inside a rank buffer: [C][width] fp32 partials or [width] fp64 reduced
+    const long long pbase = p * (a.reduced != nullptr ? (long long)NACC : (long long)a.C * NACC);
+#define IRS_L(r, c) fin_L[((r) * ((r) + 1) / 2 + (c)) * LDP + pt]
+
+    // 1. Gram entries of the point -> shared memory: packed row i holds G[i][i..d-1] contiguously, the
+    //    quad reads four consecutive entries at a time (fixed-order sum over ranks and chunks)
+    {
+        int rel[C::GSLOTS];
+        static_for<0, d>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+#pragma unroll
+            for (int t = 0; t < C::row_slots(i); ++t) {
+                const int j = i + g + kQuad * t;
+                rel[C::slot_offset(i) + t] = j < d ? gram_row_offset(i, C::W) + (j - i) : -1;
+            }
+        });
+        double s[C::GSLOTS];
+        sum_partials_multi<C::GSLOTS>(a, pbase, rel, NACC, s);
+        static_for<0, d>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+#pragma unroll
+            for (int t = 0; t < C::row_slots(i); ++t) {
+                const int j = i + g + kQuad * t;
+                if (j < d) fin_L[(j * (j + 1) / 2 + i) * LDP + pt] = s[C::slot_offset(i) + t];
+            }
+        });
+    }
+    __syncwarp();
+
+    // 2. Cholesky G = L L^T.  A column whose diagonal is exactly zero (sigma = 0: regressor identically
+    //    zero) gets coefficient 0, which is what the min-norm lstsq of the reference returns for it.
+    bool bad = false;
+    unsigned zero_mask = 0;
+    static_for<0, d>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        double lk[k > 0 ? k : 1];            // row k of the factor (entries j < k)
+        static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  lk[j] = IRS_L(k, j); });
+        const double d0 = IRS_L(k, k);       // the original diagonal entry G_kk (never overwritten)
+        double dk = d0;
+        static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  dk -= lk[j] * lk[j]; });
+        bool zero_col = false;
+        // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones
+        if (d0 == 0.0) { zero_col = true; dk = 1.0; }
+        else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
+        const double ikk = rsqrt(dk);
+        if (g == 0) fin_inv[k * LDP + pt] = ikk;      // the solves only ever need the reciprocal pivot
+#pragma unroll
+        for (int t = 0; t < (d - 1 - k + kQuad - 1) / kQuad; ++t) {
+            const int r = k + 1 + g + kQuad * t;
+            if (r < d) {
+                double* row = fin_L + (r * (r + 1) / 2) * LDP + pt;
+                double s = row[k * LDP];
+                static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  s -= row[j * LDP] * lk[j]; });
+                row[k * LDP] = zero_col ? 0.0 : s * ikk;
+            }
+        }
+        if (zero_col) zero_mask |= 1u << k;
+        __syncwarp();
+    });
+
+    // 3. right-hand sides of this thread (columns q = QT g .. QT g + QT - 1 of Z^T dF) -> registers,
+    //    solved in place: L L^T X = B
+    double y[d][QT];
+    {
+        constexpr int RH = (d + 1) / 2;          // two batches of rows: fewer loads (registers) in flight
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int rel[RH * QT];
+#pragma unroll
+            for (int rr = 0; rr < RH; ++rr)
+#pragma unroll
+                for (int qq = 0; qq < QT; ++qq) {
+                    const int r = h * RH + rr, q = QT * g + qq;
+                    rel[rr * QT + qq] = (r < d && q < n && !((zero_mask >> r) & 1u))
+                                            ? gram_row_offset(r, C::W) + (d - r) + q : -1;
+                }
+            double s[RH * QT];
+            sum_partials_multi<RH * QT>(a, pbase, rel, NACC, s);
+#pragma unroll
+            for (int rr = 0; rr < RH; ++rr)
+#pragma unroll
+                for (int qq = 0; qq < QT; ++qq)
+                    if (h * RH + rr < d) y[h * RH + rr][qq] = s[rr * QT + qq];
+        }
+    }
+    static_for<0, d>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        static_for<0, r>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const double l = IRS_L(r, k);
+#pragma unroll
+            for (int qq = 0; qq < QT; ++qq) y[r][qq] -= l * y[k][qq];
+        });
+        const double inv = fin_inv[r * LDP + pt];
+#pragma unroll
+        for (int qq = 0; qq < QT; ++qq) y[r][qq] *= inv;
+    });
+    // (compiler fence: without it the factor entries loaded by the forward pass are kept for the
+    //  backward pass — 136 doubles — and spill)
+    __syncwarp();
+    static_for<0, d>([&](auto rc) {
+        constexpr int r = d - 1 - decltype(rc)::value;
+        static_for<r + 1, d>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const double l = IRS_L(k, r);
+#pragma unroll
+            for (int qq = 0; qq < QT; ++qq) y[r][qq] -= l * y[k][qq];
+        });
+        const double inv = fin_inv[r * LDP + pt];
+#pragma unroll
+        for (int qq = 0; qq < QT; ++qq) y[r][qq] *= inv;
+    });
+    // 4. [A|B] = X^T and c = f(xbar, ubar) - A xbar - B ubar (f(xbar, ubar) was written to ct)
+#pragma unroll
+    for (int qq = 0; qq < QT; ++qq) {
+        const int q = QT * g + qq;
+        if (q < n) {
+            double acc = a.ct[p * n + q];
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                const double v = y[r][qq];
+                if (!(v == v) || fabs(v) > 1e300) bad = true;
+                if (active) {
+                    if (r < n) a.At[(p * n + q) * n + r] = v;
+                    else a.Bt[(p * n + q) * m + (r - n)] = v;
+                }
+                acc -= v * (r < n ? a.x_nom[p * n + r] : a.u_nom[p * m + (r - n)]);
+            }
+            if (active) a.ct[p * n + q] = acc;
+        }
+    }
+    // a point is flagged if any of its quad threads saw a bad pivot or a non-finite coefficient
+    bad = __any_sync(0xfu << (4 * ((tid & 31) / 4)), bad);
+    if (active && g == 0) a.status[p] = bad ? 1 : 0;
+#undef IRS_L
 }
 
 template <class Sys>

@@ -283,7 +283,9 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
-                    split_bf16x2(c0 < d ? w[c0] : 0.f, c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
+                    // padding rows are zero at compile time (inline asm is not constant-folded)
+                    if (c0 < d) split_bf16x2(w[c0], c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
+                    else p1[q] = p2[q] = 0u;
                 }
                 *reinterpret_cast<uint4*>(sm + (C::grp_z1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
                 *reinterpret_cast<uint4*>(sm + (C::grp_z2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
@@ -295,7 +297,8 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int c0 = 8 * g + 2 * q, c1 = c0 + 1;
-                    split_bf16x2(c0 < n ? w[d + c0] : 0.f, c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
+                    if (c0 < n) split_bf16x2(w[d + c0], c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
+                    else p1[q] = p2[q] = 0u;
                 }
                 *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
                 *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);

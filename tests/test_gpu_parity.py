@@ -486,6 +486,51 @@ def test_full_size_properties(api, name, N):
         assert rel_err(_device.to_numpy(B4), Be) < 2e-3
 
 
+@pytest.mark.parametrize("name,N", [("pendulum", 700), ("bicycle", 700), ("three_cart", 5000), ("quadrotor", 5000)])
+def test_finalize_variants_are_bit_identical(api, name, N, monkeypatch):
+    """The two finalize kernels (one block per point for few points, four threads per point for many)
+    perform the same fp64 operations in the same order: a point's (A, B, c) must not depend on how
+    many points a launch holds (instance / timestep sharding relies on it).  One regressor is given
+    sigma = 0 to take the zero-column branch, the point count is ragged against the 32-point blocks,
+    and N spans two chunks for the larger systems."""
+    import torch
+    from irs_mpc_b200 import _device, smoothing
+    P = 1300                                   # > 8 * 148: the launch would pick the quad variant
+    cfg = ec.CONFIGS[name](T=4)
+    s = make_system(api, name)
+    n, m = s.dim_x, s.dim_u
+    rng = np.random.default_rng(77)
+    x_nom = _device.to_device(cfg["x0"] + 0.1 * rng.standard_normal((P, n)))
+    u_nom = _device.to_device(cfg["u_trj_initial"][0] + 0.1 * rng.standard_normal((P, m)))
+    sigma = np.array(cfg["sigma"], dtype=np.float64).copy()
+    sigma[1] = 0.0
+    ws = smoothing.Workspace(s, smoothing.ZERO_ORDER, P, N)
+    smoothing.accumulate(s, smoothing.ZERO_ORDER, x_nom, u_nom, N, ws, sigma=sigma, seed=5, it=1)
+    out = {}
+    for variant in ("block", "quad"):
+        monkeypatch.setenv("IRS_FINALIZE_VARIANT", variant)
+        At, Bt, ct, status = smoothing.finalize(s, smoothing.ZERO_ORDER, x_nom, u_nom, ws, N)
+        assert int(status.sum().item()) == 0
+        out[variant] = (At.clone(), Bt.clone(), ct.clone())
+    for a, b in zip(out["block"], out["quad"]):
+        assert torch.equal(a, b)
+    assert float(out["quad"][0].abs().max()) > 0 and bool(torch.isfinite(out["quad"][0]).all())
+    assert float(out["quad"][0][:, :, 1].abs().max()) == 0.0        # zero regressor -> zero coefficient
+    monkeypatch.delenv("IRS_FINALIZE_VARIANT")
+    few = 100                                  # few points: the launch picks the block variant itself
+    At, Bt, ct, status = smoothing.finalize(s, smoothing.ZERO_ORDER, x_nom[:few].contiguous(),
+                                            u_nom[:few].contiguous(), ws, N, partials=ws.partials[:few])
+    for a, b in zip((At, Bt, ct), out["quad"]):
+        assert torch.equal(a[:few], b[:few])
+    # a point whose Gram block is not finite is flagged (status 1) by both variants, and only that point
+    ws.partials[7].fill_(float("nan"))
+    for variant in ("block", "quad"):
+        monkeypatch.setenv("IRS_FINALIZE_VARIANT", variant)
+        status = smoothing.finalize(s, smoothing.ZERO_ORDER, x_nom, u_nom, ws, N)[3]
+        st = _device.to_numpy(status)
+        assert st[7] == 1 and st.sum() == 1
+
+
 # ------------------------------------------------------------------------------------------------
 # batched MPC instances (BASELINE.json configs[4])
 # ------------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ for b in blocks[1:]:
         if "--hist" in sys.argv:
             ops = collections.Counter()
             for line in b.split("\n"):
-                m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P[0-9T]+\s+)?([A-Z0-9_]+)", line)
+                m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P[0-9T]+\s+)?([A-Z0-9_]+)", line)
                 if m:
                     ops[m.group(1)] += 1
             print(name, sum(ops.values()))
