@@ -128,6 +128,8 @@ static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
         int occ = by_regs < by_smem ? by_regs : by_smem;
         if (by_tmem < occ) occ = by_tmem;
         if (occ > 32) occ = 32;
+        if (const char* e = getenv("IRS_TC_BLOCKS_PER_SM"))      // tuning: cap the resident blocks
+            if (atoi(e) >= 1 && atoi(e) < occ) occ = atoi(e);
         blocks_per_sm = occ < 1 ? 1 : occ;
     }
     // persistent grid: every resident block walks the (point, chunk) item list with stride gridDim.x
@@ -611,8 +613,16 @@ static int tvlqr_riccati_impl(int n, int m, const double* At, const double* Bt, 
     IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
     TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T, Hinv_out, P_out};
     cudaStream_t st = (cudaStream_t)stream;
-    // few instances: one block per instance (latency); many: one warp per instance (throughput)
-    const bool per_block = I <= 2 * num_sms();
+    // few instances: one block per instance (latency); many: one warp per instance (throughput) —
+    // except where the register-tiled block kernel applies (even n, m): it moves half the shared-memory
+    // bytes per DFMA and is the faster one at every instance count (4096 quadrotor instances: 1.30 ms
+    // against 1.63 ms), so those dimensions always take it and a problem's result does not depend on I
+    const bool tiled_dims = n % 2 == 0 && m % 2 == 0 && Hinv_out == nullptr && P_out == nullptr;
+    bool per_block = I <= 2 * num_sms() || tiled_dims;
+    if (const char* e = getenv("IRS_TVLQR_VARIANT")) {      // tuning / tests: block | warp
+        if (!strcmp(e, "block")) per_block = true;
+        else if (!strcmp(e, "warp")) per_block = false;
+    }
     const bool extra = Hinv_out != nullptr || P_out != nullptr;     // only the generic kernel writes them
     static const bool no_tiles = getenv("IRS_TVLQR_NO_TILES") != nullptr;
     IRS_DISPATCH_DIMS(n, m, {

@@ -25,6 +25,9 @@
 #pragma once
 #include "smooth.cuh"
 
+#ifndef IRS_TC_NOM_BATCH
+#define IRS_TC_NOM_BATCH 64
+#endif
 #ifndef IRS_TC_MIN_BLOCKS
 #define IRS_TC_MIN_BLOCKS 4
 #endif
@@ -81,6 +84,10 @@ struct TcCfg {
     static constexpr int kTmemCols = kWarps * kN < 32 ? 32 : kWarps * kN;   // one accumulator per warp
     static constexpr int NACC = gram_nacc(n, m);
     static constexpr int RS = (W + 1) / 2 * 2;
+    // Nominal points prepared per batch (one thread each).  64 for the quadrotor: batched MPC runs one
+    // short item (8 rounds) per nominal point, and a per-item preparation stalls the block for ~1,400
+    // cycles; 1 (per item, as measured faster) for the small systems, whose items are long.
+    static constexpr int kNomBatch = d > 8 ? IRS_TC_NOM_BATCH : 1;
     static_assert(kRows <= kM, "operand rows must fit one M = 64 UMMA");
     static_assert(kN % 8 == 0 && kN >= 8 && kN <= 256, "invalid UMMA N");
     static_assert(kN % 16 == 0, "accumulator read-back uses 16-column TMEM loads");
@@ -125,12 +132,16 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     constexpr int kXU = (n + m + 3) / 4 * 4;             // xbar | ubar, padded to float4
     constexpr int kNom = kXU + (n + 3) / 4 * 4;          // ... | fbar, padded to float4
     constexpr int kScr = C::dq + 1;                      // padded scratch row (bank-conflict free)
+    constexpr int kNomBatch = C::kNomBatch;              // nominal points prepared per batch
     extern __shared__ __align__(128) unsigned char stage_mem[];   // [warp][stage][kStageBytes]
     __shared__ uint64_t mbar_empty[C::kWarps][NSTAGE];   // UMMA commit -> owning warp: tile drained
     __shared__ uint64_t mbar_done[C::kWarps];            // UMMA commit -> owning warp: accumulator complete
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float nom_s[kNom];          // nominal point of the current item (fp32)
-    __shared__ double pos64_s[4];                        // its leading coordinates in fp64 (projection)
+    // nominal points (xbar | ubar | f(xbar, ubar), fp32) of this block's next kNomBatch items, prepared
+    // kNomBatch at a time by one thread each: the loads and the scalar dynamics at the nominal then
+    // cost one latency per batch instead of one per item
+    __shared__ __align__(16) float nom_tab[kNomBatch][kNom];
+    __shared__ double pos64_tab[kNomBatch][4];           // leading coordinates in fp64 (projection)
     __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][i] + D[r][dq + i]
     __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
 
@@ -160,13 +171,43 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const Sys sys(a.prm);
-    // nominal point of an item -> nom_s (two block barriers inside; all threads call it)
+    // nominal points of the items first, first + gridDim.x, ... -> nom_tab (all threads call it; the
+    // caller's barriers order it against the readers)
+    auto prepare_nominals = [&](long long first) {
+        if (tid < kNomBatch) {
+            const long long it2 = first + (long long)tid * gridDim.x;
+            if (it2 < num_items) {
+                const int p = (int)(it2 / a.C);
+                float xb[n], ub[m], fb[n];
+#pragma unroll
+                for (int q = 0; q < n; ++q) {
+                    const double v = a.x_nom[(long long)p * n + q];
+                    xb[q] = (float)v;
+                    if (q < 4) pos64_tab[tid][q] = v;
+                }
+#pragma unroll
+                for (int q = 0; q < m; ++q) ub[q] = (float)a.u_nom[(long long)p * m + q];
+                sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
+                float* row = nom_tab[tid];
+#pragma unroll
+                for (int q = 0; q < n; ++q) row[q] = xb[q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) row[n + q] = ub[q];
+#pragma unroll
+                for (int q = n + m; q < kXU; ++q) row[q] = 0.f;
+#pragma unroll
+                for (int q = 0; q < n; ++q) row[kXU + q] = fb[q];
+            }
+        }
+    };
+    // kNomBatch == 1: the nominal point of one item, cooperatively (two block barriers inside)
     auto load_nominal = [&](long long item) {
         const int p = (int)(item / a.C);
+        float* nom_s = nom_tab[0];
         if (tid < n) {
             const double v = a.x_nom[(long long)p * n + tid];
             nom_s[tid] = (float)v;
-            if (tid < 4) pos64_s[tid] = v;
+            if (tid < 4) pos64_tab[0][tid] = v;
         } else if (tid < n + m) {
             nom_s[tid] = (float)a.u_nom[(long long)p * m + (tid - n)];
         }
@@ -194,7 +235,6 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     unsigned char* my_ring = stage_mem + (size_t)warp * NSTAGE * C::kStageBytes;
     const uint32_t ring_u32 = smem_u32(my_ring);
     const uint32_t my_off = (uint32_t)(lane >> 3) * C::kLBO + (uint32_t)(lane & 7) * 16;
-    const float4* nom4 = reinterpret_cast<const float4*>(nom_s);
 
     // Issue the UMMAs of a staged tile (all lanes call it; one lane issues).
     auto issue_tile = [&](int stage, bool first, bool last) {
@@ -232,7 +272,18 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         const long long s_begin = (long long)c * a.S;
         const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
         const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
-        load_nominal(item);
+        const int slot = kNomBatch == 1 ? 0 : it % kNomBatch;
+        if constexpr (kNomBatch == 1) {
+            load_nominal(item);
+        } else {
+            if (slot == 0) {
+                if (it > 0) __syncthreads();      // every warp is done with the previous batch of nominal points
+                prepare_nominals(item);
+                __syncthreads();
+            }
+        }
+        const float4* nom4 = reinterpret_cast<const float4*>(nom_tab[slot]);
+        const double* pos64_s = pos64_tab[slot];
         // One round = one 32-sample tile per warp.  CHECK = false is the hot path (every lane owns a
         // sample); only the last round of a chunk whose length is not a multiple of 128 takes the
         // CHECK = true path, where the padded lanes stage zeros and contribute nothing.
@@ -354,7 +405,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             const int i = ij >> 8, j = ij & 0xff;
             out[e] = scratch[C::row_1(j) * kScr + i] - scratch[C::row_2(j) * kScr + i];
         }
-        // (the two barriers of the next load_nominal order these scratch reads before its next writes)
+        // (the next item's barriers order these scratch reads before its scratch writes)
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();

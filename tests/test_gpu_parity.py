@@ -522,6 +522,27 @@ def test_finalize_variants_are_bit_identical(api, name, N, monkeypatch):
                                             u_nom[:few].contiguous(), ws, N, partials=ws.partials[:few])
     for a, b in zip((At, Bt, ct), out["quad"]):
         assert torch.equal(a[:few], b[:few])
+    # the multi-rank inputs of the sample-sharded path: two fp32 partial buffers (summed in rank
+    # order), and two fp64 chunk-reduced blocks (what the ranks exchange)
+    both = _device.empty((2,) + tuple(ws.partials.shape), torch.float32)
+    red = _device.empty((2, P, ws.width))
+    both[0].copy_(ws.partials)
+    smoothing.reduce_chunks(s, smoothing.ZERO_ORDER, ws, out=red[0])
+    smoothing.accumulate(s, smoothing.ZERO_ORDER, x_nom, u_nom, N, ws, sigma=sigma, seed=5, it=1, i0=N)
+    both[1].copy_(ws.partials)
+    smoothing.reduce_chunks(s, smoothing.ZERO_ORDER, ws, out=red[1])
+    for kw in (dict(partials=both, nranks=2, rank_stride=ws.partials.numel()),
+               dict(reduced=red, nranks=2, rank_stride=red[0].numel())):
+        res = {}
+        for variant in ("block", "quad"):
+            monkeypatch.setenv("IRS_FINALIZE_VARIANT", variant)
+            At, Bt, ct, status = smoothing.finalize(s, smoothing.ZERO_ORDER, x_nom, u_nom, ws, 2 * N, **kw)
+            assert int(status.sum().item()) == 0
+            res[variant] = (At.clone(), Bt.clone(), ct.clone())
+        for a, b in zip(res["block"], res["quad"]):
+            assert torch.equal(a, b)
+        assert bool(torch.isfinite(res["quad"][0]).all()) and float(res["quad"][0].abs().max()) > 0
+    ws.partials.copy_(both[0])
     # a point whose Gram block is not finite is flagged (status 1) by both variants, and only that point
     ws.partials[7].fill_(float("nan"))
     for variant in ("block", "quad"):
