@@ -48,6 +48,14 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// One lane of the (converged) warp: elect.sync tells ptxas that the guarded region runs in a single
+// thread, so the tcgen05 operands move to uniform registers without a vote loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     auto issue_tile = [&](int stage, bool first, bool last) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
             const uint64_t desc0 = umma_smem_desc(ring_u32 + stage * C::kStageBytes, C::kLBO, C::kSBO);
 #pragma unroll
             for (int kb = 0; kb < C::kWarpTile / 16; ++kb) {   // one UMMA = K 16 = two k-groups of 8 samples
