@@ -89,15 +89,6 @@ static bool use_tensor_cores(int system) {
     if (e == -1) return system == kQuadrotor || system == kThreeCart;   // measured: see DESIGN.md
     return e == 1;
 }
-static int tc_stages() {
-    static int g = -1;
-    if (g < 0) {
-        const char* e = getenv("IRS_TC_STAGES");
-        g = (e && atoi(e) == 2) ? 2 : 1;      // measured: one tile per warp is fastest
-    }
-    return g;
-}
-
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -108,11 +99,12 @@ static int num_sms() {
     return n;
 }
 
-template <class Sys, int NSTAGE>
-static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
+template <class Sys, bool REPLAY>
+static int launch_zero_order_tc_mode(const SmoothArgs& a, cudaStream_t st) {
     using C = TcCfg<Sys>;
+    constexpr int NSTAGE = 1;      // measured: one tile per warp is fastest
     const size_t smem = (size_t)NSTAGE * C::kWarps * C::kStageBytes;
-    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE>;
+    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE, REPLAY>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -143,7 +135,8 @@ static int launch_zero_order_tc_stages(const SmoothArgs& a, cudaStream_t st) {
 
 template <class Sys>
 static int launch_zero_order_tc(const SmoothArgs& a, cudaStream_t st) {
-    return tc_stages() == 2 ? launch_zero_order_tc_stages<Sys, 2>(a, st) : launch_zero_order_tc_stages<Sys, 1>(a, st);
+    // the noise source is a compile-time mode of the kernel (replayed deltas or the Philox stream)
+    return a.noise != nullptr ? launch_zero_order_tc_mode<Sys, true>(a, st) : launch_zero_order_tc_mode<Sys, false>(a, st);
 }
 
 static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host, int nparams,

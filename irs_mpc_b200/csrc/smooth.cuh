@@ -47,10 +47,12 @@ __host__ __device__ constexpr int gram_row_offset(int i, int W) { return i * W -
 // One sample: regressors w[0..D) = (dx | du), responses w[D..D+N) = f(xbar+dx, ubar+du) - fbar.
 // ---------------------------------------------------------------------------------------------
 // Deltas of sample i of nominal point p: replayed from a.noise or drawn from the Philox stream.
-template <class Sys, int RS>
+// MODE: -1 = decided at run time, 0 = Philox, 1 = replay (a compile-time mode keeps the test and the
+// other path's code out of the hot loop).
+template <class Sys, int RS, int MODE = -1>
 __device__ __forceinline__ void draw_deltas(const SmoothArgs& a, int p, long long i, float (&w)[RS]) {
     constexpr int d = Sys::D;
-    if (a.noise != nullptr) {
+    if (MODE == 1 || (MODE == -1 && a.noise != nullptr)) {
         const float* src = a.noise + ((long long)p * a.N + i) * d;
         if constexpr (d % 4 == 0) {
 #pragma unroll

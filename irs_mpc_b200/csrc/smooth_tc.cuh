@@ -133,7 +133,7 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& p1, u
 // block barrier.  (tcgen05.mma from different threads are not ordered against each other, hence one
 // accumulator per issuing warp.)  At the end of an item the block meets once: every warp reads its
 // TMEM lane quarter of all four accumulators, adds them and the packed Gram block is written.
-template <class Sys, int NSTAGE>
+template <class Sys, int NSTAGE, bool REPLAY>
 __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_kernel(const SmoothArgs a) {
     using C = TcCfg<Sys>;
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             float w[C::RS];
             if (!CHECK || s < s_end) {
                 if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
-                draw_deltas<Sys, C::RS>(a, p, s, w);
+                draw_deltas<Sys, C::RS, REPLAY ? 1 : 0>(a, p, s, w);
                 // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers:
                 // measured faster than the register copy)
                 float xu[kXU], f[n];
