@@ -33,7 +33,7 @@ N_SAMPLES = 100000
 FLOPS_PER_SAMPLE = 838        # quadrotor zero-order, algorithmic, FMA = 2
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 SEED0 = 0x1255 + 3
-DRAM_BYTES_PER_LAUNCH = 38656   # ncu capture of the dominant kernel, see roofline.traffic_source
+DRAM_BYTES_PER_LAUNCH = 47100   # ncu capture of the dominant kernel, see roofline.traffic_source
 
 
 def log(*a):
@@ -417,7 +417,7 @@ def run_gpu(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1>",
+            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1,false>",
                          "achieved": achieved_tflops, "peak": best, "unit": "TFLOP/s",
                          "frac": achieved_tflops / best if best > 0 else None,
                          "peak_source": "measured on this box: dependent-chain FFMA microbenchmark (irs_fp32_fma_peak); "
@@ -432,7 +432,7 @@ def run_gpu(args, rank, local_rank, world):
                                        "issue, not by HBM or the tensor pipe (DESIGN.md 3.1)",
                          "hbm_gbs_measured_peak": peaks.get("hbm_gbs")},
             "roofline_replay_mode": None if world > 1 else {
-                "bound": "hbm", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1> (noise replayed from HBM)",
+                "bound": "hbm", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1,true> (noise replayed from HBM)",
                 "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)", "bytes_per_sample": 64,
