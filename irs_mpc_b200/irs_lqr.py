@@ -395,9 +395,8 @@ class _SampledIrsLqr(IrsLqr):
 
     def _graph_update(self, graph):
         s = self.sampling
-        sig = np.ascontiguousarray(s.sigma(self.iter), dtype=np.float32)
-        _lib.call("irs_graph_update_smoothing", graph, sig.ctypes.data_as(ctypes.c_void_p), int(s.seed),
-                  int(self.iter), int(s.stream_id))
+        _, sig_ptr = s.sigma32(self.iter)
+        _lib.call("irs_graph_update_smoothing", graph, sig_ptr, s.seed, int(self.iter), s.stream_id)
 
     def _enqueue_linearize(self, ws):
         s = self.sampling

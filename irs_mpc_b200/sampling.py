@@ -5,7 +5,7 @@ from numpy's global RNG (irs_lqr/irs_lqr_zero_order.py:12-22; e.g.
 examples/pendulum/pendulum_zero_order.py:38-43).  Any such callable is still honoured (it is
 called T times and the result replayed through the kernels).  `GaussianSampling` describes the
 same distribution declaratively so that the noise can be generated inside the kernel with
-Philox4x32-10 and never touches HBM:
+Philox4x32-7 and never touches HBM:
 
     sigma_iter = sigma0 / iter**power          (variance stepping of the example scripts)
     delta[i, c] = sigma_iter[c] * normal(seed; sample i, point t, iter, stream)
@@ -43,6 +43,16 @@ class GaussianSampling:
 
     def sigma(self, it):
         return self.sigma0 / (float(it) ** self.power)
+
+    def sigma32(self, it):
+        """sigma(it) as the contiguous float32 array (and its pointer) the kernels take; the last
+        iteration's array is kept (the schedule is a pure function of `it`)."""
+        c = getattr(self, "_sigma32_cache", None)
+        if c is None or c[0] != it:
+            arr = np.ascontiguousarray(self.sigma(it), dtype=np.float32)
+            c = (it, arr, arr.ctypes.data_as(ctypes.c_void_p))
+            self._sigma32_cache = c
+        return c[1], c[2]
 
     def flags(self):
         return {None: 0, "absolute": 2, "delta": 4}[self.projection]

@@ -54,12 +54,14 @@ class Workspace:
         if self._nom_host is None:
             self._nom_host = torch.empty(self._nom.shape, dtype=torch.float64).pin_memory()
             self._out_host = torch.empty(self._out.shape, dtype=torch.float64).pin_memory()
+            self._nom_host_np = self._nom_host.numpy()      # numpy views of the pinned mirrors
+            self._out_host_np = self._out_host.numpy()
 
     def stage_nominal(self, x_trj, u_trj):
         """numpy [>=P, n], [>=P, m] -> the pinned host mirror of [x_nom | u_nom] (no device work)."""
         P, n, m = self.P, self.n, self.m
         self._host_buffers()
-        h = self._nom_host.numpy()
+        h = self._nom_host_np
         h[:P * n] = np.asarray(x_trj, dtype=np.float64)[:P].reshape(-1)
         h[P * n:] = np.asarray(u_trj, dtype=np.float64)[:P].reshape(-1)
 
@@ -75,12 +77,12 @@ class Workspace:
         """Synchronise and unpack the pinned mirror -> (At, Bt, ct, status) numpy arrays."""
         P, n, m = self.P, self.n, self.m
         torch.cuda.current_stream().synchronize()
-        h = self._out_host.numpy()
+        h = self._out_host_np.copy()      # ONE copy out of the pinned mirror; the results are views of it
         na, nb, nc = P * n * n, P * n * m, P * n
-        At = h[:na].reshape(P, n, n).copy()
-        Bt = h[na:na + nb].reshape(P, n, m).copy()
-        ct = h[na + nb:na + nb + nc].reshape(P, n).copy()
-        status = h[na + nb + nc:].view(np.int32)[:P].copy()
+        At = h[:na].reshape(P, n, n)
+        Bt = h[na:na + nb].reshape(P, n, m)
+        ct = h[na + nb:na + nb + nc].reshape(P, n)
+        status = h[na + nb + nc:].view(np.int32)[:P]
         return At, Bt, ct, status
 
     def h2d_bytes(self):
@@ -143,7 +145,10 @@ def linearize(system, order, x_nom, u_nom, N, ws=None, **kw):
 
 
 def check_status(status):
-    bad = int(status.sum().item()) if isinstance(status, torch.Tensor) else int(np.sum(status))
+    if isinstance(status, torch.Tensor):
+        bad = int(status.sum().item())
+    else:
+        bad = int(np.count_nonzero(status)) if status.any() else 0
     if bad:
         raise np.linalg.LinAlgError(
             "smoothing fit: the sample Gram matrix [dx du]^T[dx du] is rank deficient at %d "
