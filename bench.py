@@ -316,7 +316,7 @@ def run_gpu(args, rank, local_rank, world):
         xn, un = solver.local_descent(x_host, u_host)
         return solver.evaluate_cost(xn, un)
     it_steps = max(3, min(args.steps, 20))
-    ms_iter = timed(one_iteration, it_steps, 2)
+    ms_iter = timed(one_iteration, it_steps, 4)      # the call sequence is captured into a CUDA graph on its 3rd call
     iters_per_s = it_steps / (ms_iter * 1e-3)
 
     # 5b. BASELINE.json configs[4]: 4096 independent quadrotor MPC instances (T=100, N=1e3 samples/step as

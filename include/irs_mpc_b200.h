@@ -157,6 +157,17 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
                       const double* xd, long long xd_stride, int I, int T,
                       double* K, double* k, int* status, void* stream);
 
+/* The same recursion restricted to the steps t_hi-1 .. t_lo (even n, m only).  A segment that does
+ * not start at T reads (P, p) of step t_hi from carry [I, n*n + n]; one that does not end at 0 writes
+ * (P, p) of step t_lo there.  Chaining the segments [t1,T), [t2,t1), ..., [0,tk) on one stream
+ * reproduces irs_tvlqr_riccati bit for bit; IrsLqr.local_descent uses it to solve the late timesteps
+ * while the early ones are still being linearized on another stream.  status: the segment from T
+ * sets it, later segments can only raise it. */
+int irs_tvlqr_riccati_segment(int n, int m, const double* At, const double* Bt, const double* ct,
+                              const double* Q, const double* Qd, const double* R,
+                              const double* xd, long long xd_stride, int I, int T, int t_lo, int t_hi,
+                              double* carry, double* K, double* k, int* status, void* stream);
+
 /* Box-constrained solve_tvlqr / local_descent (irs_lqr/tv_lqr.py:113-118,:132-134 absolute bounds;
  * irs_lqr/irs_lqr.py:160-184 re-solve at every timestep).  Three pieces:
  *  - irs_tvlqr_riccati_ex: irs_tvlqr_riccati that also returns Hinv [I,T,m,m] = (R/2 + B'PB)^-1 and

@@ -72,6 +72,7 @@ SIGNATURES = {
     "irs_jacobian_xu_batch_f64": [_i, _c_double_p, _i, _vp, _vp, _vp, _ll, _vp],
     "irs_project_batch_f64": [_i, _c_double_p, _i, _vp, _ll, _vp],
     "irs_tvlqr_riccati": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp],
+    "irs_tvlqr_riccati_segment": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "irs_tvlqr_riccati_ex": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "irs_tvlqr_plan_check": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _i, _i,
                              _vp, _vp, _vp],

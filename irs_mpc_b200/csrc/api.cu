@@ -601,10 +601,17 @@ int irs_project_batch_f64(int system, const double* params_host, int nparams, do
 static int tvlqr_riccati_impl(int n, int m, const double* At, const double* Bt, const double* ct,
                               const double* Q, const double* Qd, const double* R,
                               const double* xd, long long xd_stride, int I, int T,
-                              double* K, double* k, int* status, double* Hinv_out, double* P_out, void* stream) {
+                              double* K, double* k, int* status, double* Hinv_out, double* P_out, void* stream,
+                              int t_lo = 0, int t_hi = 0, double* carry = nullptr) {
     IRS_REQUIRE(At && Bt && ct && Q && Qd && R && xd && K && k && status, "null pointer argument");
     IRS_REQUIRE(I >= 1 && T >= 1, "need I >= 1 and T >= 1");
-    TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T, Hinv_out, P_out};
+    TvlqrArgs a{At, Bt, ct, Q, Qd, R, xd, xd_stride, K, k, status, I, T, Hinv_out, P_out, t_lo, t_hi, carry};
+    if (t_hi > 0) {      // a segment of the recursion: register-tiled kernel only
+        IRS_REQUIRE(0 <= t_lo && t_lo < t_hi && t_hi <= T, "bad segment [%d, %d) of T=%d", t_lo, t_hi, T);
+        IRS_REQUIRE(n % 2 == 0 && m % 2 == 0 && Hinv_out == nullptr && P_out == nullptr,
+                    "segmented Riccati needs even n, m (n=%d, m=%d)", n, m);
+        IRS_REQUIRE((t_lo == 0 && t_hi == T) || carry != nullptr, "a partial segment needs the carry buffer");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     // few instances: one block per instance (latency); many: one warp per instance (throughput) —
     // except where the register-tiled block kernel applies (even n, m): it moves half the shared-memory
@@ -616,12 +623,13 @@ static int tvlqr_riccati_impl(int n, int m, const double* At, const double* Bt, 
         if (!strcmp(e, "block")) per_block = true;
         else if (!strcmp(e, "warp")) per_block = false;
     }
+    if (t_hi > 0) per_block = true;                                 // segments exist in the tiled kernel only
     const bool extra = Hinv_out != nullptr || P_out != nullptr;     // only the generic kernel writes them
     static const bool no_tiles = getenv("IRS_TVLQR_NO_TILES") != nullptr;
     IRS_DISPATCH_DIMS(n, m, {
         if (per_block) {
             if constexpr (N_ % 2 == 0 && M_ % 2 == 0) {
-                if (!no_tiles && !extra) {
+                if ((!no_tiles || t_hi > 0) && !extra) {
                     tvlqr_riccati_tiled_kernel<N_, M_>
                         <<<(unsigned)I, kTvlqrTiledThreads, sizeof(TvlqrTiledSmem<N_, M_>), st>>>(a);
                     return check_launch("tvlqr_riccati_tiled_kernel");
@@ -642,6 +650,15 @@ int irs_tvlqr_riccati(int n, int m, const double* At, const double* Bt, const do
                       const double* xd, long long xd_stride, int I, int T,
                       double* K, double* k, int* status, void* stream) {
     return tvlqr_riccati_impl(n, m, At, Bt, ct, Q, Qd, R, xd, xd_stride, I, T, K, k, status, nullptr, nullptr, stream);
+}
+
+int irs_tvlqr_riccati_segment(int n, int m, const double* At, const double* Bt, const double* ct,
+                              const double* Q, const double* Qd, const double* R,
+                              const double* xd, long long xd_stride, int I, int T, int t_lo, int t_hi,
+                              double* carry, double* K, double* k, int* status, void* stream) {
+    IRS_REQUIRE(t_hi >= 1, "need t_hi >= 1");
+    return tvlqr_riccati_impl(n, m, At, Bt, ct, Q, Qd, R, xd, xd_stride, I, T, K, k, status, nullptr, nullptr, stream,
+                              t_lo, t_hi, carry);
 }
 
 int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const double* ct,
@@ -767,13 +784,14 @@ int irs_evaluate_cost(int n, int m, const double* x_trj, const double* u_trj,
 // graph; irs_graph_update_smoothing rewrites the arguments of the captured accumulate kernel
 // (seed, iteration, sigma change between replays; pointers and shapes must not).
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxSmoothNodes = 16;      // accumulate launches per captured sequence (timestep segments)
 struct IrsGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t smooth_node = nullptr;
-    cudaKernelNodeParams smooth_params{};
-    SmoothArgs args{};
-    void* arg_ptrs[1] = {nullptr};
+    int num_smooth = 0;
+    cudaGraphNode_t smooth_node[kMaxSmoothNodes] = {};
+    cudaKernelNodeParams smooth_params[kMaxSmoothNodes] = {};
+    SmoothArgs args[kMaxSmoothNodes] = {};
 };
 
 int irs_graph_begin(void* stream) {
@@ -800,10 +818,11 @@ int irs_graph_end(void* stream, void** graph_out) {
         if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
-        if (kp.func == g_last_smooth_func) {
-            g->smooth_node = nodes[i];
-            g->smooth_params = kp;
-            g->args = *reinterpret_cast<const SmoothArgs*>(kp.kernelParams[0]);
+        if (kp.func == g_last_smooth_func && g->num_smooth < kMaxSmoothNodes) {
+            const int q = g->num_smooth++;
+            g->smooth_node[q] = nodes[i];
+            g->smooth_params[q] = kp;
+            g->args[q] = *reinterpret_cast<const SmoothArgs*>(kp.kernelParams[0]);
         }
     }
     delete[] nodes;
@@ -822,23 +841,25 @@ int irs_graph_update_smoothing(void* graph, const float* sigma_host, unsigned lo
                                unsigned stream_id) {
     IrsGraph* g = reinterpret_cast<IrsGraph*>(graph);
     IRS_REQUIRE(g != nullptr && g->exec != nullptr, "invalid graph handle");
-    IRS_REQUIRE(g->smooth_node != nullptr, "the captured sequence contains no smoothing accumulate kernel");
+    IRS_REQUIRE(g->num_smooth > 0, "the captured sequence contains no smoothing accumulate kernel");
     IRS_REQUIRE(iter < (1u << 24), "iter out of range");
-    SmoothArgs& a = g->args;
-    a.seed_lo = (uint32_t)(seed & 0xffffffffull);
-    a.seed_hi = (uint32_t)(seed >> 32);
-    a.iter = iter;
-    a.stream = stream_id;
-    if (sigma_host != nullptr) {
-        // sigma holds n + m entries; the remaining slots stay zero as in fill_smooth_args
-        for (int c = 0; c < a.nreg && c < kMaxRegressors; ++c) a.sigma_scaled[c] = kBoxMullerScale * sigma_host[c];
+    for (int q = 0; q < g->num_smooth; ++q) {      // every accumulate launch of the sequence (timestep segments)
+        SmoothArgs& a = g->args[q];
+        a.seed_lo = (uint32_t)(seed & 0xffffffffull);
+        a.seed_hi = (uint32_t)(seed >> 32);
+        a.iter = iter;
+        a.stream = stream_id;
+        if (sigma_host != nullptr) {
+            // sigma holds n + m entries; the remaining slots stay zero as in fill_smooth_args
+            for (int c = 0; c < a.nreg && c < kMaxRegressors; ++c) a.sigma_scaled[c] = kBoxMullerScale * sigma_host[c];
+        }
+        void* arg_ptrs[1] = {&a};
+        cudaKernelNodeParams kp = g->smooth_params[q];
+        kp.kernelParams = arg_ptrs;
+        kp.extra = nullptr;
+        if (cudaGraphExecKernelNodeSetParams(g->exec, g->smooth_node[q], &kp) != cudaSuccess)
+            return check_launch("cudaGraphExecKernelNodeSetParams");
     }
-    g->arg_ptrs[0] = &a;
-    cudaKernelNodeParams kp = g->smooth_params;
-    kp.kernelParams = g->arg_ptrs;
-    kp.extra = nullptr;
-    if (cudaGraphExecKernelNodeSetParams(g->exec, g->smooth_node, &kp) != cudaSuccess)
-        return check_launch("cudaGraphExecKernelNodeSetParams");
     return 0;
 }
 

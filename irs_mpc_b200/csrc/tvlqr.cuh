@@ -28,6 +28,12 @@ struct TvlqrArgs {
     int I, T;
     double* Hinv;        // optional [I, T, m, m]: (R/2 + B'PB)^-1 of every step (bounded solve)
     double* Pout;        // optional [I, T+1, n, n]: value-function Hessians P_t
+    // Segment of the recursion (tiled kernel only): steps t_hi-1 .. t_lo.  t_hi == 0 means the whole
+    // horizon.  A segment that does not start at T reads (P, p) of step t_hi from carry [I, n*n + n];
+    // one that does not end at 0 writes (P, p) of step t_lo there.  Splitting the pass this way lets
+    // the late timesteps be solved while the early ones are still being linearized.
+    int t_lo, t_hi;
+    double* carry;
 };
 
 // Reciprocal in fp64 from the hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps — a
@@ -342,6 +348,7 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
     const int gt = threadIdx.x, warp = gt >> 5, lane = gt & 31;
     const int inst = blockIdx.x;
     const double* xd_i = a.xd + inst * a.xd_stride;
+    const int t_hi = a.t_hi > 0 ? a.t_hi : a.T, t_lo = a.t_hi > 0 ? a.t_lo : 0;
     bool ok = true;
     // Work is assigned to warps by ROLE (one code path per warp and phase: no intra-warp divergence
     // between the tile kinds); tile origins are loop invariants.
@@ -351,12 +358,12 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
     const int h_r0 = 2 * (lane / hm), h_c0 = 2 * (lane % hm);          // m x m tiles: warp 1
     // running global pointers of step t (stepped back once per iteration: no 64-bit index math inside)
     constexpr int kRA = (n * n + G - 1) / G;
-    const double* pA = a.At + ((long long)inst * a.T + (a.T - 1)) * n * n + gt;
-    const double* pB = a.Bt + ((long long)inst * a.T + (a.T - 1)) * n * m + gt;
-    const double* pc = a.ct + ((long long)inst * a.T + (a.T - 1)) * n + gt;
-    const double* pxd = xd_i + (long long)(a.T - 1) * n + gt;
-    double* pK = a.K + ((long long)inst * a.T + (a.T - 1)) * m * n;
-    double* pk = a.k + ((long long)inst * a.T + (a.T - 1)) * m;
+    const double* pA = a.At + ((long long)inst * a.T + (t_hi - 1)) * n * n + gt;
+    const double* pB = a.Bt + ((long long)inst * a.T + (t_hi - 1)) * n * m + gt;
+    const double* pc = a.ct + ((long long)inst * a.T + (t_hi - 1)) * n + gt;
+    const double* pxd = xd_i + (long long)(t_hi - 1) * n + gt;
+    double* pK = a.K + ((long long)inst * a.T + (t_hi - 1)) * m * n;
+    double* pk = a.k + ((long long)inst * a.T + (t_hi - 1)) * m;
     static_assert(n * m <= G && n <= G, "one prefetch slot per thread for B, c, xd");
     double rA[kRA], rB = 0.0, rc = 0.0, rxd = 0.0;
     auto prefetch = [&] {
@@ -373,18 +380,24 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
         if (gt < n) { s.c[gt] = rc;  s.xd[gt] = rxd; }
     };
     prefetch();
-    // terminal condition: P_T = Qd, p_T = -Qd xd_T; constants into shared memory
-    for (int e = gt; e < n * n; e += G) { s.P[e] = a.Qd[e];  s.Q[e] = a.Q[e]; }
+    // terminal condition: P_T = Qd, p_T = -Qd xd_T (or the carried (P, p) of a later segment);
+    // constants into shared memory
+    double* carry_i = a.carry != nullptr ? a.carry + (long long)inst * (n * n + n) : nullptr;
+    for (int e = gt; e < n * n; e += G) { s.P[e] = t_hi == a.T ? a.Qd[e] : carry_i[e];  s.Q[e] = a.Q[e]; }
     for (int e = gt; e < m * m; e += G) s.Rh[e] = 0.5 * a.R[e];
     for (int i = gt; i < n; i += G) {
-        double acc = 0.0;
-        for (int q = 0; q < n; ++q) acc -= a.Qd[i * n + q] * xd_i[(long long)a.T * n + q];
-        s.p[i] = acc;
+        if (t_hi == a.T) {
+            double acc = 0.0;
+            for (int q = 0; q < n; ++q) acc -= a.Qd[i * n + q] * xd_i[(long long)a.T * n + q];
+            s.p[i] = acc;
+        } else {
+            s.p[i] = carry_i[n * n + i];
+        }
     }
     publish();
     __syncthreads();
-    for (int t = a.T - 1; t >= 0; --t) {
-        if (t > 0) prefetch();
+    for (int t = t_hi - 1; t >= t_lo; --t) {
+        if (t > t_lo) prefetch();
         // ---- phase 1: PA = P A (warps 0-1), PB = P B (warp 2), w = P c + p (warp 3) ----
         if (gt < hn * hn) {
             double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -480,14 +493,19 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
             s.P[e] = 0.5 * (s.Pn[i * n + j] + s.Pn[j * n + i]);
         }
         if (warp == 2 && lane < n) s.p[lane] = pnew;
-        if (t > 0) publish();
+        if (t > t_lo) publish();
         __syncthreads();
     }
     // NaN guard on the final value function
     for (int e = gt; e < n * n; e += G)
         if (!(s.P[e] == s.P[e])) ok = false;
     ok = __syncthreads_and(ok);
-    if (gt == 0) a.status[inst] = ok ? 0 : 1;
+    // the first segment (from T) sets the status, later ones can only raise it
+    if (gt == 0) a.status[inst] = (ok ? 0 : 1) | (t_hi == a.T ? 0 : a.status[inst]);
+    if (t_lo > 0) {      // hand (P, p) of step t_lo to the next segment
+        for (int e = gt; e < n * n; e += G) carry_i[e] = s.P[e];
+        for (int i = gt; i < n; i += G) carry_i[n * n + i] = s.p[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -29,6 +29,9 @@ from .tv_lqr import BOUND_TOL, TVLQR_FAILED, box_solve_device, get_solver, ricca
 
 # CUDA-graph replay of the per-iteration call sequence (IRS_CUDA_GRAPH=0 forces eager launches)
 _USE_GRAPHS = os.environ.get("IRS_CUDA_GRAPH", "1") != "0"
+_USE_PIPELINE = os.environ.get("IRS_PIPELINE", "1") != "0"     # see _SampledIrsLqr._pipeline_segments
+_PIPELINE_MIN_STEPS = 8                                        # timesteps per segment below which it does not pay
+_PIPELINE_SEGMENTS = int(os.environ.get("IRS_PIPELINE_SEGMENTS", "0"))      # 0 = sized from the work per launch
 
 
 class IrsLqrParameters:
@@ -205,13 +208,9 @@ class IrsLqr:
         x_all = db["in_dev"][:nx].view(T + 1, n)
         u_nom = db["in_dev"][nx:].view(T, m)
         x_nom = x_all[:T]
-        At, Bt, ct, status = self._tv_matrices_device(x_nom, u_nom)
-        db["sstatus"].copy_(status)
         K, k = db["K"], db["k"]
-        _lib.call("irs_tvlqr_riccati", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
-                  _device.ptr(self._dQ), _device.ptr(self._dQd), _device.ptr(self._dR),
-                  _device.ptr(self._dxd), 0, 1, T, _device.ptr(K), _device.ptr(k),
-                  _device.ptr(db["rstatus"]), _device.stream_ptr())
+        At, Bt, ct, status = self._linearize_and_riccati(db, x_nom, u_nom)
+        db["sstatus"].copy_(status)
         prm, nprm = self.system._params()
         _lib.call("irs_rollout_closed_loop", self.system.system_id, prm, nprm, _device.ptr(K),
                   _device.ptr(k), _device.ptr(x_all), _device.ptr(self._dxd), 0,
@@ -228,6 +227,16 @@ class IrsLqr:
             db["violated"].zero_()
         db["lin"] = (At, Bt, ct)
         db["out_host"].copy_(db["out_dev"], non_blocking=True)
+
+    def _linearize_and_riccati(self, db, x_nom, u_nom):
+        """Linearization along the nominal trajectory, then the backward pass -> db["K"], db["k"]."""
+        T, n, m = self.T, self.dim_x, self.dim_u
+        At, Bt, ct, status = self._tv_matrices_device(x_nom, u_nom)
+        _lib.call("irs_tvlqr_riccati", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                  _device.ptr(self._dQ), _device.ptr(self._dQd), _device.ptr(self._dR),
+                  _device.ptr(self._dxd), 0, 1, T, _device.ptr(db["K"]), _device.ptr(db["k"]),
+                  _device.ptr(db["rstatus"]), _device.stream_ptr())
+        return At, Bt, ct, status
 
     def _graph_key(self):
         """None when this call sequence cannot be replayed from a CUDA graph (see _SampledIrsLqr)."""
@@ -386,6 +395,67 @@ class _SampledIrsLqr(IrsLqr):
                 self.system, self.order, x_nom, u_nom, noise.shape[1], self._ws, noise=noise)
         return At, Bt, ct, status
 
+
+    def _pipeline_segments(self):
+        """Timestep segments [(lo, hi), ...], late timesteps first, or None for the one-pass sequence.
+        The backward Riccati pass needs the late timesteps first, so the horizon is linearized in a
+        few launches from the back and each segment's fit and Riccati steps run on a second stream
+        while the next segment is still sampling: the sequential pass hides behind the smoothing
+        kernel instead of following it.  A segment is sized to about one resident grid of the
+        smoothing kernel (592 blocks on a B200; measured on the quadrotor, T=100, N=1e5: five segments
+        of 500 work items 470 us per descent, three 495, four — 625 items, a second wave of 33 —
+        504, ten 600, one pass 515).  Results are bit-identical to the one-pass sequence (global
+        point index in the Philox counter, carried (P, p) between segments)."""
+        n, m, T = self.dim_x, self.dim_u, self.T
+        if not _USE_PIPELINE or not isinstance(self.sampling, GaussianSampling) or n % 2 or m % 2:
+            return None
+        if _PIPELINE_SEGMENTS > 0:
+            k = _PIPELINE_SEGMENTS
+        else:
+            C, _ = smoothing.plan(self.system.system_id, self.order, T, self.sampling.num_samples)
+            if T * C < 2 * 592:
+                return None       # less than two resident grids of sampling work: nothing to hide behind
+            k = min(8, -(-(T * C) // 592))
+        while k > 1 and T // k < _PIPELINE_MIN_STEPS:
+            k -= 1
+        if k < 2:
+            return None
+        cuts = [(i * T) // k for i in range(k + 1)]
+        return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
+
+    def _linearize_and_riccati(self, db, x_nom, u_nom):
+        segs = self._pipeline_segments()
+        if segs is None:
+            return super()._linearize_and_riccati(db, x_nom, u_nom)
+        s = self.sampling
+        T, n, m = self.T, self.dim_x, self.dim_u
+        key = (self.system.system_id, self.order, T, s.num_samples)
+        if self._ws is None or self._ws.key != key:
+            self._ws = smoothing.Workspace(self.system, self.order, T, s.num_samples)
+        ws = self._ws
+        if "carry" not in db:
+            db["carry"] = _device.empty((n * n + n,))
+            db["side"] = torch.cuda.Stream(priority=-1)
+        main, side = torch.cuda.current_stream(), db["side"]
+        sig = s.sigma(self.iter)
+        for lo, hi in segs:
+            smoothing.accumulate(self.system, self.order, x_nom, u_nom, s.num_samples, ws, sigma=sig,
+                                 seed=s.seed, it=self.iter, stream_id=s.stream_id, flags=s.flags(),
+                                 point_range=(lo, hi))
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, s.num_samples, point_range=(lo, hi))
+                _lib.call("irs_tvlqr_riccati_segment", n, m, _device.ptr(ws.At), _device.ptr(ws.Bt),
+                          _device.ptr(ws.ct), _device.ptr(self._dQ), _device.ptr(self._dQd),
+                          _device.ptr(self._dR), _device.ptr(self._dxd), 0, 1, T, lo, hi,
+                          _device.ptr(db["carry"]), _device.ptr(db["K"]), _device.ptr(db["k"]),
+                          _device.ptr(db["rstatus"]), _device.stream_ptr())
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+        return ws.At, ws.Bt, ws.ct, ws.status
 
     def _graph_key(self):
         s = self.sampling

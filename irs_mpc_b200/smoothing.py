@@ -93,8 +93,16 @@ class Workspace:
 
 
 def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=0, it=1,
-               stream_id=0, p0=0, i0=0, flags=0):
-    """Launch the accumulation kernel: partial Gram blocks (order 0) or Jacobian sums (order 1)."""
+               stream_id=0, p0=0, i0=0, flags=0, point_range=None):
+    """Launch the accumulation kernel: partial Gram blocks (order 0) or Jacobian sums (order 1).
+    point_range = (lo, hi): only the nominal points lo..hi-1 of (x_nom, u_nom, ws) — the Philox
+    counters carry the global point index, so the ranges of a split launch reproduce the full one."""
+    partials = ws.partials
+    if point_range is not None:
+        lo, hi = point_range
+        x_nom, u_nom, partials = x_nom[lo:hi], u_nom[lo:hi], partials[lo:hi]
+        noise = None if noise is None else noise[lo:hi]
+        p0 += lo
     P = x_nom.shape[0]
     prm, nprm = system._params()
     if system.batch_differs_from_scalar and order == ZERO_ORDER:
@@ -109,7 +117,7 @@ def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=
           else "irs_smooth_first_order_accumulate")
     _lib.call(fn, system.system_id, prm, nprm, flags, _device.ptr(x_nom), _device.ptr(u_nom), P,
               int(N), sig, _device.ptr(noise), int(seed), int(it), int(stream_id),
-              int(p0), int(i0), ws.C, ws.S, _device.ptr(ws.partials), _device.stream_ptr())
+              int(p0), int(i0), ws.C, ws.S, _device.ptr(partials), _device.stream_ptr())
 
 
 def reduce_chunks(system, order, ws, out=None):
@@ -123,15 +131,22 @@ def reduce_chunks(system, order, ws, out=None):
 
 
 def finalize(system, order, x_nom, u_nom, ws, n_total, partials=None, reduced=None, nranks=1,
-             rank_stride=0):
-    """Fit from fp32 per-chunk partials (default: ws.partials) or from fp64 reduced blocks."""
-    P = x_nom.shape[0]
+             rank_stride=0, point_range=None):
+    """Fit from fp32 per-chunk partials (default: ws.partials) or from fp64 reduced blocks.
+    point_range = (lo, hi): only the nominal points lo..hi-1 (single-rank partials only)."""
     prm, nprm = system._params()
     part = None if reduced is not None else (ws.partials if partials is None else partials)
+    At, Bt, ct, status = ws.At, ws.Bt, ws.ct, ws.status
+    if point_range is not None:
+        lo, hi = point_range
+        assert reduced is None and nranks == 1
+        x_nom, u_nom, part = x_nom[lo:hi], u_nom[lo:hi], part[lo:hi]
+        At, Bt, ct, status = At[lo:hi], Bt[lo:hi], ct[lo:hi], status[lo:hi]
+    P = x_nom.shape[0]
     _lib.call("irs_smooth_finalize", system.system_id, prm, nprm, order, _device.ptr(x_nom),
               _device.ptr(u_nom), P, ws.C, _device.ptr(part), _device.ptr(reduced), nranks,
-              int(rank_stride), float(n_total), _device.ptr(ws.At), _device.ptr(ws.Bt),
-              _device.ptr(ws.ct), _device.ptr(ws.status), _device.stream_ptr())
+              int(rank_stride), float(n_total), _device.ptr(At), _device.ptr(Bt),
+              _device.ptr(ct), _device.ptr(status), _device.stream_ptr())
     return ws.At, ws.Bt, ws.ct, ws.status
 
 

@@ -642,6 +642,68 @@ def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
         assert np.array_equal(A1, A2) and np.array_equal(B1, B2) and np.array_equal(c1, c2)
 
 
+@pytest.mark.parametrize("n,m", [(12, 4), (6, 2)])
+def test_riccati_segments_chain_to_the_full_pass(api, n, m):
+    """irs_tvlqr_riccati_segment over [t1,T), [t2,t1), [0,t2) with the carried (P, p) reproduces the
+    one-launch backward pass bit for bit (what the pipelined descent relies on)."""
+    import torch
+    from irs_mpc_b200 import _device, _lib, tv_lqr
+    I, T = 3, 37
+    rng = np.random.default_rng(3)
+    At = _device.to_device(np.eye(n) + 0.05 * rng.standard_normal((I, T, n, n)))
+    Bt = _device.to_device(0.1 * rng.standard_normal((I, T, n, m)))
+    ct = _device.to_device(0.01 * rng.standard_normal((I, T, n)))
+    Q, Qd, R = (_device.to_device(v) for v in (np.eye(n), 10 * np.eye(n), 0.1 * np.eye(m)))
+    xd = _device.to_device(rng.standard_normal((I, T + 1, n)))
+    K0, k0, st0 = tv_lqr.riccati_device(At, Bt, ct, Q, Qd, R, xd, (T + 1) * n)
+    K = torch.full_like(K0, float("nan"))
+    k = torch.full_like(k0, float("nan"))
+    st = _device.empty((I,), torch.int32)
+    carry = _device.empty((I, n * n + n))
+    for lo, hi in ((25, 37), (11, 25), (0, 11)):
+        _lib.call("irs_tvlqr_riccati_segment", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                  _device.ptr(Q), _device.ptr(Qd), _device.ptr(R), _device.ptr(xd), (T + 1) * n, I, T, lo, hi,
+                  _device.ptr(carry), _device.ptr(K), _device.ptr(k), _device.ptr(st), _device.stream_ptr())
+    assert torch.equal(K, K0) and torch.equal(k, k0) and int(st.sum().item()) == 0 == int(st0.sum().item())
+    # a partial segment without the carry buffer is refused
+    with pytest.raises(_lib.IrsCudaError, match="carry"):
+        _lib.call("irs_tvlqr_riccati_segment", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                  _device.ptr(Q), _device.ptr(Qd), _device.ptr(R), _device.ptr(xd), (T + 1) * n, I, T, 5, T,
+                  None, _device.ptr(K), _device.ptr(k), _device.ptr(st), _device.stream_ptr())
+
+
+@pytest.mark.parametrize("name,T,N,graphs", [("quadrotor", 30, 2000, True), ("quadrotor", 30, 2000, False),
+                                             ("three_cart", 40, 3000, True)])
+def test_pipelined_descent_is_bit_identical_to_one_pass(api, name, T, N, graphs):
+    """local_descent linearizes the horizon in three launches from the back and runs each segment's
+    fit + Riccati steps on a second stream (irs_lqr._SampledIrsLqr._pipeline_segments); the iterates
+    must equal those of the one-pass sequence bit for bit, eagerly and replayed from a CUDA graph."""
+    from irs_mpc_b200 import irs_lqr as mod
+    cfg = ec.CONFIGS[name](T=T)
+    n = cfg["x0"].shape[0]
+
+    def run(pipeline):
+        old = mod._USE_PIPELINE, mod._USE_GRAPHS, mod._PIPELINE_SEGMENTS
+        mod._USE_PIPELINE, mod._USE_GRAPHS, mod._PIPELINE_SEGMENTS = pipeline, graphs, 3    # forced: the test problem is small
+        try:
+            s = make_system(api, name)
+            sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=23,
+                                           projection="delta" if name == "three_cart" else None)
+            solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=T), sampler)
+            assert (solver._pipeline_segments() is not None) == pipeline
+            solver.iterate(4, verbose=False)
+            return solver
+        finally:
+            mod._USE_PIPELINE, mod._USE_GRAPHS, mod._PIPELINE_SEGMENTS = old
+
+    one, pipe = run(False), run(True)
+    assert one.cost_lst == pipe.cost_lst
+    for a, b in zip(one.x_trj_lst, pipe.x_trj_lst):
+        assert np.array_equal(a, b)
+    for a, b in zip(one.u_trj_lst, pipe.u_trj_lst):
+        assert np.array_equal(a, b)
+
+
 # ------------------------------------------------------------------------------------------------
 # CEM baseline (irs_lqr/cem.py) — SURVEY.md section 8f row 2
 # ------------------------------------------------------------------------------------------------
