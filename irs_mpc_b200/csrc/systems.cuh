@@ -36,6 +36,7 @@ struct Pendulum {
     template <typename S> using Rebind = Pendulum<S>;
     static constexpr int N = 2, M = 1, D = 3, NJ = 1;
     static constexpr bool kHasJacobian = true;
+    static constexpr int kTrigAhead = 0;
     static constexpr bool kHasProjection = false;
     R h;
     __device__ explicit Pendulum(const SysParams& p) : h(prm<R>(p, 0)) {}
@@ -69,6 +70,7 @@ struct Bicycle {
     template <typename S> using Rebind = Bicycle<S>;
     static constexpr int N = 5, M = 2, D = 7, NJ = 6;
     static constexpr bool kHasJacobian = true;
+    static constexpr int kTrigAhead = 0;
     static constexpr bool kHasProjection = false;
     R h;
     __device__ explicit Bicycle(const SysParams& p) : h(prm<R>(p, 0)) {}
@@ -142,12 +144,24 @@ struct Quadrotor {
         }
     }
 
+    // The Euler angles of the NEXT state, x[3+j] + h x[9+j], do not depend on the input: their sines
+    // and cosines can be evaluated one step ahead, off the sequential path of a rollout
+    // (tvlqr.cuh: rollout_trig_kernel).  sc = {sin r, cos r, sin p, cos p, sin y, cos y}.
+    static constexpr int kTrigAhead = 3;
+    __device__ __forceinline__ R next_angle(R angle, R rate) const { return angle + h * rate; }
+    static __device__ __forceinline__ void trig(R angle, R& s, R& c) { Math<R>::sincos(angle, s, c); }
+
     template <bool BATCH>
     __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
-        R sr, cr, sp, cp, sy, cy;
-        Math<R>::sincos(x[3], sr, cr);
-        Math<R>::sincos(x[4], sp, cp);
-        Math<R>::sincos(x[5], sy, cy);
+        R sc[6];
+        Math<R>::sincos(x[3], sc[0], sc[1]);
+        Math<R>::sincos(x[4], sc[2], sc[3]);
+        Math<R>::sincos(x[5], sc[4], sc[5]);
+        step_trig<BATCH>(x, u, sc, o);
+    }
+    template <bool BATCH>
+    __device__ __forceinline__ void step_trig(const R* x, const R* u, const R* sc, R* o) const {
+        const R sr = sc[0], cr = sc[1], sp = sc[2], cp = sc[3], sy = sc[4], cy = sc[5];
         const R icp = Math<R>::rcp(cp);
         const R rd0 = x[9], rd1 = x[10], rd2 = x[11];
         // thrust and moments (:43-49)
@@ -182,7 +196,9 @@ struct Quadrotor {
         o[11] = x[11] + h * (icp * srqd_crrd + rd0 * (icp * crq_srr) + rd1 * (tp * icp * srq_crr));
         // kinematics (:70)
 #pragma unroll
-        for (int i = 0; i < 6; ++i) o[i] = x[i] + h * x[6 + i];
+        for (int i = 0; i < 3; ++i) o[i] = x[i] + h * x[6 + i];
+#pragma unroll
+        for (int i = 3; i < 6; ++i) o[i] = next_angle(x[i], x[6 + i]);
     }
     __device__ __forceinline__ void jac_var(const R* x, const R* u, R* v) const {
         R sr, cr, sp, cp, sy, cy;
@@ -223,6 +239,7 @@ struct ThreeCart {
     template <typename S> using Rebind = ThreeCart<S>;
     static constexpr int N = 6, M = 2, D = 8, NJ = 0;
     static constexpr bool kHasJacobian = false;   // three_cart_dynamics.py:20
+    static constexpr int kTrigAhead = 0;
     static constexpr bool kHasProjection = true;
     static constexpr int kProjDims = 3;           // project() touches the cart positions only
     R h, d;

@@ -652,6 +652,118 @@ __global__ void __launch_bounds__(32 * kRolloutWarps) rollout_kernel(const Rollo
     if (lane == 0) a.cost[inst] = c;
 }
 
+// Rollout for systems whose next Euler angles do not depend on the input (Sys::kTrigAhead, the
+// quadrotor): the three fp64 sincos evaluations are two thirds of a step on the sequential path, and
+// the angles of step t+1 are known at the START of step t.  One block of two warps per instance:
+// warp 0 carries the recursion exactly as rollout_kernel does (lane 0 computes, the other lanes
+// prefetch the gains), warp 1 evaluates sin / cos of the next angles meanwhile (one lane per angle)
+// and hands them over through a double-buffered shared slot; one block barrier per step.  Same
+// operations on the same values as rollout_kernel (bit-identical, tests).
+template <class Sys, bool CLOSED>
+__global__ void __launch_bounds__(64) rollout_trig_kernel(const RolloutArgs a) {
+    constexpr int n = Sys::N, m = Sys::M, kA = Sys::kTrigAhead;
+    static_assert(kA > 0, "system has no input-independent angles");
+    constexpr int kSlot = CLOSED ? m * n + m : m;        // K_t | k_t   or   u_t
+    constexpr int kPer = (kSlot + 31) / 32;
+    __shared__ double slot[2][kSlot];
+    __shared__ double trig_s[2][2 * kA];                 // {sin, cos} of the angles of step t (buffer t & 1)
+    __shared__ double angr_s[2][2 * kA];                 // angles | rates of the state x_t (buffer t & 1)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int inst = blockIdx.x;
+    const Sys sys(a.prm);
+    const double* xd_i = a.xd + inst * a.xd_stride;
+    double pre[kPer];
+    auto fetch = [&](int t) {
+        const long long it = (long long)inst * a.T + t;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int e = lane + 32 * k;
+            if (e < kSlot) {
+                if (CLOSED) pre[k] = e < m * n ? a.K[it * m * n + e] : a.k[it * m + (e - m * n)];
+                else pre[k] = a.u_in[it * m + e];
+            }
+        }
+    };
+    auto publish = [&](int b) {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int e = lane + 32 * k;
+            if (e < kSlot) slot[b][e] = pre[k];
+        }
+    };
+    double x[n], u[m], xn[n];
+    if (warp == 0) {
+        fetch(0);
+        publish(0);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < n; ++q) {
+                x[q] = a.x0[(long long)inst * n + q];
+                a.x_trj[((long long)inst * (a.T + 1)) * n + q] = x[q];
+            }
+#pragma unroll
+            for (int j = 0; j < kA; ++j) { angr_s[0][j] = x[3 + j];  angr_s[0][kA + j] = x[9 + j]; }
+        }
+    } else if (lane < kA) {
+        double sv, cv;
+        Sys::trig(a.x0[(long long)inst * n + 3 + lane], sv, cv);
+        trig_s[0][2 * lane] = sv;  trig_s[0][2 * lane + 1] = cv;
+    }
+    __syncthreads();
+    for (int t = 0; t < a.T; ++t) {
+        if (warp == 0) {
+            const long long it = (long long)inst * a.T + t;
+            const double* sl = slot[t & 1];
+            if (t + 1 < a.T) fetch(t + 1);                 // in flight while lane 0 computes
+            if (lane == 0) {
+                if (CLOSED) {
+#pragma unroll
+                    for (int i = 0; i < m; ++i) {
+                        double acc = sl[m * n + i];
+#pragma unroll
+                        for (int q = 0; q < n; ++q) acc += sl[i * n + q] * x[q];
+                        u[i] = acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < m; ++i) u[i] = sl[i];
+                }
+                double sc[2 * kA];
+#pragma unroll
+                for (int j = 0; j < 2 * kA; ++j) sc[j] = trig_s[t & 1][j];
+                sys.template step_trig<false>(x, u, sc, xn);
+                if (CLOSED) {
+#pragma unroll
+                    for (int i = 0; i < m; ++i) a.u_trj[it * m + i] = u[i];
+                }
+#pragma unroll
+                for (int q = 0; q < n; ++q) {
+                    x[q] = xn[q];
+                    a.x_trj[((long long)inst * (a.T + 1) + t + 1) * n + q] = x[q];
+                }
+#pragma unroll
+                for (int j = 0; j < kA; ++j) { angr_s[(t + 1) & 1][j] = x[3 + j];  angr_s[(t + 1) & 1][kA + j] = x[9 + j]; }
+            }
+            if (t + 1 < a.T) publish((t + 1) & 1);
+        } else if (lane < kA && t + 1 < a.T) {
+            // the angles of step t+1 from the state of step t (the expression of Sys::step itself)
+            double sv, cv;
+            Sys::trig(sys.next_angle(angr_s[t & 1][lane], angr_s[t & 1][kA + lane]), sv, cv);
+            trig_s[(t + 1) & 1][2 * lane] = sv;  trig_s[(t + 1) & 1][2 * lane + 1] = cv;
+        }
+        __syncthreads();
+    }
+    // cost of the finished trajectory, parallel over t (off the sequential path)
+    __threadfence_block();
+    __syncthreads();
+    if (warp == 0) {
+        const double* u_used = CLOSED ? a.u_trj + (long long)inst * a.T * m : a.u_in + (long long)inst * a.T * m;
+        const double c = warp_trajectory_cost<n, m>(a.x_trj + (long long)inst * (a.T + 1) * n, u_used, xd_i,
+                                                    a.Q, a.R, a.T, lane);
+        if (lane == 0) a.cost[inst] = c;
+    }
+}
+
 // evaluate_cost for given trajectories (irs_lqr.py:121-137); one warp per instance, lanes over t.
 template <int n, int m>
 __global__ void __launch_bounds__(128) evaluate_cost_kernel(const double* x_trj, const double* u_trj,

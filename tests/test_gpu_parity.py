@@ -642,6 +642,41 @@ def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
         assert np.array_equal(A1, A2) and np.array_equal(B1, B2) and np.array_equal(c1, c2)
 
 
+@pytest.mark.parametrize("I", [1, 37])
+def test_quadrotor_rollout_with_trig_ahead_is_bit_identical(api, I, monkeypatch):
+    """The quadrotor rollouts evaluate sin / cos of the next Euler angles one step ahead on a second
+    warp (rollout_trig_kernel); trajectories, inputs and costs must equal the one-warp kernel's."""
+    import torch
+    from irs_mpc_b200 import _device, _lib
+    cfg = ec.CONFIGS["quadrotor"](T=60)
+    s = make_system(api, "quadrotor")
+    n, m, T = 12, 4, 60
+    rng = np.random.default_rng(9)
+    K = _device.to_device(1e-3 * rng.standard_normal((I, T, m, n)))      # weak feedback: the flight stays tame
+    k = _device.to_device(cfg["u_trj_initial"][None, :T] + 0.02 * rng.standard_normal((I, T, m)))
+    x0 = _device.to_device(cfg["x0"] + 0.05 * rng.standard_normal((I, n)))
+    xd = _device.to_device(cfg["xd_trj"][:T + 1])
+    Q, R = _device.to_device(cfg["Q"]), _device.to_device(cfg["R"])
+    prm, nprm = s._params()
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("IRS_ROLLOUT_TRIG", flag)
+        xs, us, cost = _device.empty((I, T + 1, n)), _device.empty((I, T, m)), _device.empty((I,))
+        _lib.call("irs_rollout_closed_loop", s.system_id, prm, nprm, _device.ptr(K), _device.ptr(k), _device.ptr(x0),
+                  _device.ptr(xd), 0, _device.ptr(Q), _device.ptr(R), I, T, _device.ptr(xs), _device.ptr(us),
+                  _device.ptr(cost), _device.stream_ptr())
+        xo, co = _device.empty((I, T + 1, n)), _device.empty((I,))
+        _lib.call("irs_rollout_open_loop", s.system_id, prm, nprm, _device.ptr(us), _device.ptr(x0),
+                  _device.ptr(xd), 0, _device.ptr(Q), _device.ptr(R), I, T, _device.ptr(xo), _device.ptr(co),
+                  _device.stream_ptr())
+        out[flag] = (xs, us, cost, xo, co)
+    assert all(bool(torch.isfinite(v).all()) for v in out["0"])
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a, b)
+    assert torch.equal(out["1"][0], out["1"][3])      # the open-loop rollout of the applied inputs replays the closed loop
+    assert float((out["1"][0][:, -1, 3:6]).abs().max()) > 1e-3            # the attitude really moved
+
+
 @pytest.mark.parametrize("n,m", [(12, 4), (6, 2)])
 def test_riccati_segments_chain_to_the_full_pass(api, n, m):
     """irs_tvlqr_riccati_segment over [t1,T), [t2,t1), [0,t2) with the carried (P, p) reproduces the
