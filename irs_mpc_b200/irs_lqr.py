@@ -365,6 +365,28 @@ class IrsLqrExact(IrsLqr):
         return At, Bt, ct, status
 
 
+RESIDENT_BLOCKS = 592      # resident grid of the quadrotor smoothing kernel on a B200 (148 SMs x 4)
+
+
+def pipeline_segments(T, chunks_per_step, forced=0, min_steps=_PIPELINE_MIN_STEPS):
+    """Timestep segments [(lo, hi), ...] of a pipelined descent, LATE timesteps first, or None when one
+    pass is better.  A segment is sized to about one resident grid of work items (timesteps x chunks);
+    `forced` > 0 fixes the number of segments (tests, tuning)."""
+    if forced > 0:
+        k = forced
+    else:
+        items = T * chunks_per_step
+        if items < 2 * RESIDENT_BLOCKS:
+            return None       # less than two resident grids of sampling work: nothing to hide behind
+        k = min(8, -(-items // RESIDENT_BLOCKS))
+    while k > 1 and T // k < min_steps:
+        k -= 1
+    if k < 2:
+        return None
+    cuts = [(i * T) // k for i in range(k + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
+
+
 class _SampledIrsLqr(IrsLqr):
     order = None
 
@@ -409,19 +431,8 @@ class _SampledIrsLqr(IrsLqr):
         n, m, T = self.dim_x, self.dim_u, self.T
         if not _USE_PIPELINE or not isinstance(self.sampling, GaussianSampling) or n % 2 or m % 2:
             return None
-        if _PIPELINE_SEGMENTS > 0:
-            k = _PIPELINE_SEGMENTS
-        else:
-            C, _ = smoothing.plan(self.system.system_id, self.order, T, self.sampling.num_samples)
-            if T * C < 2 * 592:
-                return None       # less than two resident grids of sampling work: nothing to hide behind
-            k = min(8, -(-(T * C) // 592))
-        while k > 1 and T // k < _PIPELINE_MIN_STEPS:
-            k -= 1
-        if k < 2:
-            return None
-        cuts = [(i * T) // k for i in range(k + 1)]
-        return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
+        C, _ = smoothing.plan(self.system.system_id, self.order, T, self.sampling.num_samples)
+        return pipeline_segments(T, C, _PIPELINE_SEGMENTS)
 
     def _linearize_and_riccati(self, db, x_nom, u_nom):
         segs = self._pipeline_segments()
