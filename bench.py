@@ -296,18 +296,16 @@ def run_gpu(args, rank, local_rank, world):
             return solver.get_TV_matrices(x_host, u_host)
     else:
         def step_e2e(k):
-            xn = _device.to_device(x_host[:T_STEPS])
-            un = _device.to_device(u_host)
-            At, Bt, ct, st = sharded.linearize_n(xn, un, N_SAMPLES, sigma=sigma, seed=SEED0 + 5000 + k, it=1)
-            return _device.to_numpy(At), _device.to_numpy(Bt), _device.to_numpy(ct), _device.to_numpy(st)
+            # numpy in, numpy out through the sharded public call: one pinned H2D, one D2H per step
+            return sharded.linearize_n_numpy(x_host[:T_STEPS], u_host, N_SAMPLES, sigma=sigma,
+                                             seed=SEED0 + 5000 + k, it=1)
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 3))
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
     n, m = 12, 4
     if world == 1:
         h2d, d2h = solver._io_bytes()            # counted from the buffers the API copies
     else:
-        h2d = T_STEPS * (n + m) * 8
-        d2h = T_STEPS * (n * n + n * m + n) * 8 + T_STEPS * 4
+        h2d, d2h = sharded._ws.h2d_bytes(), sharded._ws.d2h_bytes()
 
     # 5. iRS-LQR iterations/s: local_descent (smoothing + Riccati + closed-loop rollout) + evaluate_cost,
     #    teacher-forced from the initial trajectory, through the public numpy API (replicated per rank)

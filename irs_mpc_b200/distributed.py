@@ -15,6 +15,7 @@ The sequential Riccati pass is never split (replicated on every rank).
 
 The gather helpers are backend agnostic (NCCL on GPUs, gloo in the CPU tests).
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -170,6 +171,19 @@ class ShardedLinearizer:
                 import warnings
                 warnings.warn("peer-memory exchange unavailable (%s); using NCCL all-gather" % e)
         return self._px
+
+    def linearize_n_numpy(self, x_trj, u_trj, N_local, **kw):
+        """linearize_n with numpy in / numpy out — the sample-sharded counterpart of
+        IrsLqrZeroOrder.get_TV_matrices: one pinned host->device copy of [x_nom | u_nom], the kernels
+        and the exchange, one device->host copy of [At | Bt | ct | status]; returns
+        (At, Bt, ct, status) fitted on all W * N_local samples, identical on every rank."""
+        T = min(np.asarray(u_trj).shape[0], np.asarray(x_trj).shape[0])
+        ws = self._workspace(T, N_local)
+        ws.stage_nominal(x_trj, u_trj)
+        ws.enqueue_upload()
+        self.linearize_n(ws.x_nom, ws.u_nom, N_local, **kw)      # the fit lands in ws.At / Bt / ct / status
+        ws.enqueue_download()
+        return ws.read_download()
 
     def linearize_n(self, x_nom, u_nom, N_local, **kw):
         """Sample-sharded.  Every rank draws N_local samples per point (global sample index

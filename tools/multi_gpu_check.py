@@ -66,6 +66,11 @@ def main():
     identical = all(torch.equal(g, gathered[0]) for g in gathered)
     report("sample sharding vs one GPU", err < 1e-5 and int(stn.sum()) == 0, "(rel err %.2e)" % err)
     report("sample sharding identical on ranks", identical)
+    # numpy in / numpy out variant (pinned staging, one copy each way): same bits
+    Ah, Bh, ch, sth = sh.linearize_n_numpy(x.cpu().numpy(), u.cpu().numpy(), N, **kw)
+    report("linearize_n_numpy == linearize_n", bool((torch.from_numpy(Ah).to(An.device) == An).all())
+           and bool((torch.from_numpy(Bh).to(An.device) == Bn).all())
+           and bool((torch.from_numpy(ch).to(An.device) == cn).all()) and int(sth.sum()) == 0)
     used_peer = sh._px is not None
     sh_nccl = ShardedLinearizer(s, smoothing.ZERO_ORDER, peer_memory=False)
     Ac, Bc, cc, _ = sh_nccl.linearize_n(x, u, N, **kw)
