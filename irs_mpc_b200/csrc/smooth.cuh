@@ -452,6 +452,45 @@ __device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int
     return s;
 }
 
+// Compile-time loop: f(std::integral_constant<int, I>) for I = I0 .. I1 - 1 (the triangular loop
+// nests must be unrolled at compile time so that the solution stays in registers).
+template <int I0, int I1, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I0 < I1) {
+        f(std::integral_constant<int, I0>{});
+        static_for<I0 + 1, I1>(f);
+    }
+}
+
+// Fixed-order sums (ranks, then chunks: the order of sum_partials) of U entries of one point at once;
+// the loads of the U entries are independent, so they are in flight together.
+// pbase = offset of the point inside a rank buffer (chunk 0), rel[u] = entry index, < 0 = none (sum 0).
+template <int U>
+__device__ __forceinline__ void sum_partials_multi(const FinalizeArgs& a, long long pbase, const int (&rel)[U],
+                                                   int width, double (&s)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = 0.0;
+    for (int r = 0; r < a.R; ++r) {
+        if (a.reduced != nullptr) {
+            const double* src = a.reduced + r * a.rank_stride + pbase;
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] += v[u];
+        } else {
+            const float* src = a.partials + r * a.rank_stride + pbase;
+            for (int c = 0; c < a.C; ++c, src += width) {
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) s[u] += (double)v[u];
+            }
+        }
+    }
+}
+
 // Nominal point (xbar | ubar | f(xbar, ubar)) of point p in fp64 -> shared memory.  f(xbar, ubar)
 // (scalar dynamics, …zero_order.py:61) was written into ct[p] by the dynamics kernel that
 // irs_smooth_finalize launches first in the many-points case, which keeps the fp64 dynamics (and its
@@ -498,7 +537,7 @@ __device__ __forceinline__ void write_abc(const FinalizeArgs& a, int p, const do
     if (tid < n) {
         double acc = nom[d + tid];
 #pragma unroll
-        for (int q = 0; q < d; ++q) acc -= AB[tid * d + q] * nom[q];
+        for (int q = 0; q < d; ++q) acc = fma(-AB[tid * d + q], nom[q], acc);
         a.ct[(long long)p * n + tid] = acc;
     }
 }
@@ -514,54 +553,68 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
     __shared__ double nom[d + n];
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
-    const unsigned char* __restrict__ tri_r = a.tables->tri_r;
-    const unsigned char* __restrict__ tri_c = a.tables->tri_c;
-    // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs
-    for (int e = tid; e < NACC; e += BT) {
-        const double s = sum_partials(a, p, e, NACC);
-        const int i = a.tables->gram_i[e], j = a.tables->gram_j[e];
-        if (j < d) {
-            Gm[i * d + j] = s;
-            Gm[j * d + i] = s;
-        } else {
-            Bm[i * n + (j - d)] = s;
+    // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs; a thread's
+    //    entries are summed together so that all their loads are in flight at once
+    {
+        constexpr int NE = (NACC + BT - 1) / BT;
+        int rel[NE];
+#pragma unroll
+        for (int q = 0; q < NE; ++q) rel[q] = tid + q * BT < NACC ? tid + q * BT : -1;
+        double sums[NE];
+        const long long pbase = (long long)p * (a.reduced != nullptr ? (long long)NACC : (long long)a.C * NACC);
+        sum_partials_multi<NE>(a, pbase, rel, NACC, sums);
+#pragma unroll
+        for (int q = 0; q < NE; ++q) {
+            if (rel[q] >= 0) {
+                const int i = a.tables->gram_i[rel[q]], j = a.tables->gram_j[rel[q]];
+                if (j < d) {
+                    Gm[i * d + j] = sums[q];
+                    Gm[j * d + i] = sums[q];
+                } else {
+                    Bm[i * n + (j - d)] = sums[q];
+                }
+            }
         }
     }
     __syncthreads();
     if (tid == 32) {
         nominal_compute_to_smem<Sys>(a, p, nom);
     } else if (tid < 32) {
-        // 2. Cholesky G = L L^T by warp 0 (lanes = rows).  A column whose diagonal is exactly zero
-        //    (sigma = 0: regressor identically zero) gets coefficient 0, which is what the min-norm
-        //    lstsq of the reference returns for it.
+        // 2. Cholesky G = L L^T by warp 0, left-looking, lane = row with the row of the factor in
+        //    REGISTERS: row k reaches the other lanes by shuffles, every lane recomputes the pivot (same
+        //    operands, same order: identical bits), no shared-memory round trip inside the
+        //    factorisation.  A column whose diagonal is exactly zero (sigma = 0: regressor identically
+        //    zero) gets coefficient 0, which is what the min-norm lstsq of the reference returns for it.
         bool bad = false;
-        double diag0 = 0.0;      // lane k keeps the original diagonal entry G_kk
-        if (lane < d) diag0 = Gm[lane * d + lane];
-#pragma unroll 1
-        for (int k = 0; k < d; ++k) {
-            double dk = Gm[k * d + k];
-            const double d0 = __shfl_sync(0xffffffffu, diag0, k);
-            __syncwarp();
+        double row[d];
+#pragma unroll
+        for (int j = 0; j < d; ++j) row[j] = (lane < d && j <= lane) ? Gm[lane * d + j] : 0.0;
+        static_for<0, d>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            double lk[k > 0 ? k : 1];            // row k of the factor (entries j < k)
+            static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  lk[j] = __shfl_sync(0xffffffffu, row[j], k); });
+            const double d0 = __shfl_sync(0xffffffffu, row[k], k);      // the original diagonal entry G_kk
+            double dk = d0;
+            static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  dk = fma(-lk[j], lk[j], dk); });
             bool zero_col = false;
             // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones; the
             // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency
             if (d0 == 0.0) { zero_col = true; dk = 1.0; }
             else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
             const double ikk = rsqrt(dk);           // one special function on the critical path, not two
-            if (lane == 0) { Gm[k * d + k] = dk * ikk;  inv_diag[k] = ikk; }
-            for (int r = k + 1 + lane; r < d; r += 32) Gm[r * d + k] = zero_col ? 0.0 : Gm[r * d + k] * ikk;
+            double sk = row[k];
+            static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  sk = fma(-row[j], lk[j], sk); });
+            if (lane > k) row[k] = zero_col ? 0.0 : sk * ikk;
+            if (lane == k) { row[k] = dk * ikk;  inv_diag[k] = ikk; }
             if (zero_col)
                 for (int q = lane; q < n; q += 32) Bm[k * n + q] = 0.0;
-            __syncwarp();
-            // trailing update of the lower triangle: the packed entries (r, cc), cc <= r, are dealt
-            // round-robin to the lanes (table built once per block), entries outside the trailing
-            // block are skipped — at most 5 short steps per column instead of a 15-long row loop
-            for (int e = lane; e < d * (d + 1) / 2; e += 32) {
-                const int r = tri_r[e], cc = tri_c[e];
-                if (cc > k) Gm[r * d + cc] -= Gm[r * d + k] * Gm[cc * d + k];
-            }
-            __syncwarp();
+        });
+        if (lane < d) {
+#pragma unroll
+            for (int j = 0; j < d; ++j)
+                if (j <= lane) Gm[lane * d + j] = row[j];      // the solves read the factor from shared memory
         }
+        __syncwarp();
         // 3. solve L L^T X = B, one right-hand side per lane (reciprocal diagonal: no divisions)
         if (lane < n) {
             const int q = lane;
@@ -571,14 +624,14 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
             for (int r = 0; r < d; ++r) {
                 double s0 = Bm[r * n + q];
 #pragma unroll
-                for (int k = 0; k < r; ++k) s0 -= Gm[r * d + k] * y[k];
+                for (int k = 0; k < r; ++k) s0 = fma(-Gm[r * d + k], y[k], s0);
                 y[r] = s0 * inv_diag[r];
             }
 #pragma unroll
             for (int r = d - 1; r >= 0; --r) {
                 double s0 = y[r];
 #pragma unroll
-                for (int k = r + 1; k < d; ++k) s0 -= Gm[k * d + r] * y[k];
+                for (int k = r + 1; k < d; ++k) s0 = fma(-Gm[k * d + r], y[k], s0);
                 y[r] = s0 * inv_diag[r];
             }
 #pragma unroll
@@ -605,21 +658,13 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
 //     same order: identical bits) and takes every fourth row below it; one __syncwarp per column;
 //   * solves: each thread owns ceil(n / 4) right-hand sides, loaded straight from global memory
 //     into registers and solved in place, L read from shared memory (quad-uniform broadcast);
+// (Every multiply-add of the factorisation, the solves and c_t is an explicit fma() in both kernels:
+// whether the compiler contracts a - b * c is its own choice, and one uncontracted update is one ulp.)
 // The floating-point operations and their order are those of finalize_zero_order_kernel, entry by
 // entry (left-looking here, right-looking there: each entry still receives its updates in ascending
 // column order), so a point's result does not depend on which variant a launch picks — checked
 // bit for bit by tests/test_gpu_parity.py::test_finalize_variants_are_bit_identical.
 // ---------------------------------------------------------------------------------------------
-// Compile-time loop: f(std::integral_constant<int, I>) for I = I0 .. I1 - 1 (the triangular loop
-// nests must be unrolled at compile time so that the solution stays in registers).
-template <int I0, int I1, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I0 < I1) {
-        f(std::integral_constant<int, I0>{});
-        static_for<I0 + 1, I1>(f);
-    }
-}
-
 constexpr int kFinalizeQuadThreads = 128;
 constexpr int kQuad = 4;
 
@@ -642,35 +687,6 @@ struct FinalizeQuadCfg {
     static constexpr int GSLOTS = slot_offset(d);
     static constexpr size_t kSmemBytes = (size_t)(TRI + d) * LDP * sizeof(double);
 };
-
-// Fixed-order sums (ranks, then chunks: the order of sum_partials) of U entries of one point at once;
-// the loads of the U entries are independent, so they are in flight together.
-// pbase = offset of the point inside a rank buffer (chunk 0), rel[u] = entry index, < 0 = none (sum 0).
-template <int U>
-__device__ __forceinline__ void sum_partials_multi(const FinalizeArgs& a, long long pbase, const int (&rel)[U],
-                                                   int width, double (&s)[U]) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) s[u] = 0.0;
-    for (int r = 0; r < a.R; ++r) {
-        if (a.reduced != nullptr) {
-            const double* src = a.reduced + r * a.rank_stride + pbase;
-            double v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) s[u] += v[u];
-        } else {
-            const float* src = a.partials + r * a.rank_stride + pbase;
-            for (int c = 0; c < a.C; ++c, src += width) {
-                float v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.f;
-#pragma unroll
-                for (int u = 0; u < U; ++u) s[u] += (double)v[u];
-            }
-        }
-    }
-}
 
 template <class Sys>
 __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_quad_kernel(const FinalizeArgs a) {
@@ -724,7 +740,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
         static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  lk[j] = IRS_L(k, j); });
         const double d0 = IRS_L(k, k);       // the original diagonal entry G_kk (never overwritten)
         double dk = d0;
-        static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  dk -= lk[j] * lk[j]; });
+        static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  dk = fma(-lk[j], lk[j], dk); });
         bool zero_col = false;
         // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones
         if (d0 == 0.0) { zero_col = true; dk = 1.0; }
@@ -737,7 +753,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
             if (r < d) {
                 double* row = fin_L + (r * (r + 1) / 2) * LDP + pt;
                 double s = row[k * LDP];
-                static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  s -= row[j * LDP] * lk[j]; });
+                static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  s = fma(-row[j * LDP], lk[j], s); });
                 row[k * LDP] = zero_col ? 0.0 : s * ikk;
             }
         }
@@ -776,7 +792,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
             constexpr int k = decltype(kc)::value;
             const double l = IRS_L(r, k);
 #pragma unroll
-            for (int qq = 0; qq < QT; ++qq) y[r][qq] -= l * y[k][qq];
+            for (int qq = 0; qq < QT; ++qq) y[r][qq] = fma(-l, y[k][qq], y[r][qq]);
         });
         const double inv = fin_inv[r * LDP + pt];
 #pragma unroll
@@ -791,7 +807,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
             constexpr int k = decltype(kc)::value;
             const double l = IRS_L(k, r);
 #pragma unroll
-            for (int qq = 0; qq < QT; ++qq) y[r][qq] -= l * y[k][qq];
+            for (int qq = 0; qq < QT; ++qq) y[r][qq] = fma(-l, y[k][qq], y[r][qq]);
         });
         const double inv = fin_inv[r * LDP + pt];
 #pragma unroll
@@ -811,7 +827,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
                     if (r < n) a.At[(p * n + q) * n + r] = v;
                     else a.Bt[(p * n + q) * m + (r - n)] = v;
                 }
-                acc -= v * (r < n ? a.x_nom[p * n + r] : a.u_nom[p * m + (r - n)]);
+                acc = fma(-v, r < n ? a.x_nom[p * n + r] : a.u_nom[p * m + (r - n)], acc);
             }
             if (active) a.ct[p * n + q] = acc;
         }

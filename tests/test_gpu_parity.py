@@ -486,13 +486,16 @@ def test_full_size_properties(api, name, N):
         assert rel_err(_device.to_numpy(B4), Be) < 2e-3
 
 
+@pytest.mark.parametrize("zero_sigma", [True, False])
 @pytest.mark.parametrize("name,N", [("pendulum", 700), ("bicycle", 700), ("three_cart", 5000), ("quadrotor", 5000)])
-def test_finalize_variants_are_bit_identical(api, name, N, monkeypatch):
+def test_finalize_variants_are_bit_identical(api, name, N, zero_sigma, monkeypatch):
     """The two finalize kernels (one block per point for few points, four threads per point for many)
     perform the same fp64 operations in the same order: a point's (A, B, c) must not depend on how
-    many points a launch holds (instance / timestep sharding relies on it).  One regressor is given
-    sigma = 0 to take the zero-column branch, the point count is ragged against the 32-point blocks,
-    and N spans two chunks for the larger systems."""
+    many points a launch holds (instance / timestep sharding relies on it).  With zero_sigma one
+    regressor is given sigma = 0 to take the zero-column branch (which also makes every update with
+    that column exact — the all-nonzero case is the one that catches a multiply-add the compiler did
+    not contract); the point count is ragged against the 32-point blocks, and N spans two chunks for
+    the larger systems."""
     import torch
     from irs_mpc_b200 import _device, smoothing
     P = 1300                                   # > 8 * 148: the launch would pick the quad variant
@@ -503,7 +506,8 @@ def test_finalize_variants_are_bit_identical(api, name, N, monkeypatch):
     x_nom = _device.to_device(cfg["x0"] + 0.1 * rng.standard_normal((P, n)))
     u_nom = _device.to_device(cfg["u_trj_initial"][0] + 0.1 * rng.standard_normal((P, m)))
     sigma = np.array(cfg["sigma"], dtype=np.float64).copy()
-    sigma[1] = 0.0
+    if zero_sigma:
+        sigma[1] = 0.0
     ws = smoothing.Workspace(s, smoothing.ZERO_ORDER, P, N)
     smoothing.accumulate(s, smoothing.ZERO_ORDER, x_nom, u_nom, N, ws, sigma=sigma, seed=5, it=1)
     out = {}
@@ -515,7 +519,8 @@ def test_finalize_variants_are_bit_identical(api, name, N, monkeypatch):
     for a, b in zip(out["block"], out["quad"]):
         assert torch.equal(a, b)
     assert float(out["quad"][0].abs().max()) > 0 and bool(torch.isfinite(out["quad"][0]).all())
-    assert float(out["quad"][0][:, :, 1].abs().max()) == 0.0        # zero regressor -> zero coefficient
+    if zero_sigma:
+        assert float(out["quad"][0][:, :, 1].abs().max()) == 0.0    # zero regressor -> zero coefficient
     monkeypatch.delenv("IRS_FINALIZE_VARIANT")
     few = 100                                  # few points: the launch picks the block variant itself
     At, Bt, ct, status = smoothing.finalize(s, smoothing.ZERO_ORDER, x_nom[:few].contiguous(),
