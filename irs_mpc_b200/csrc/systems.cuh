@@ -148,7 +148,9 @@ struct Quadrotor {
     // and cosines can be evaluated one step ahead, off the sequential path of a rollout
     // (tvlqr.cuh: rollout_trig_kernel).  sc = {sin r, cos r, sin p, cos p, sin y, cos y}.
     static constexpr int kTrigAhead = 3;
-    __device__ __forceinline__ R next_angle(R angle, R rate) const { return angle + h * rate; }
+    // (explicit fma: the rollout's helper warp and its recursion evaluate this in different contexts and
+    //  must round identically)
+    __device__ __forceinline__ R next_angle(R angle, R rate) const { return fma(h, rate, angle); }
     static __device__ __forceinline__ void trig(R angle, R& s, R& c) { Math<R>::sincos(angle, s, c); }
 
     template <bool BATCH>
