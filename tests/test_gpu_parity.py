@@ -712,9 +712,9 @@ def test_riccati_segments_chain_to_the_full_pass(api, n, m):
                   None, _device.ptr(K), _device.ptr(k), _device.ptr(st), _device.stream_ptr())
 
 
-@pytest.mark.parametrize("name,T,N,graphs", [("quadrotor", 30, 2000, True), ("quadrotor", 30, 2000, False),
-                                             ("three_cart", 40, 3000, True)])
-def test_pipelined_descent_is_bit_identical_to_one_pass(api, name, T, N, graphs):
+@pytest.mark.parametrize("name,T,N,graphs,order", [("quadrotor", 30, 2000, True, 0), ("quadrotor", 30, 2000, False, 0),
+                                                   ("three_cart", 40, 3000, True, 0), ("quadrotor", 30, 500, True, 1)])
+def test_pipelined_descent_is_bit_identical_to_one_pass(api, name, T, N, graphs, order):
     """local_descent linearizes the horizon in three launches from the back and runs each segment's
     fit + Riccati steps on a second stream (irs_lqr._SampledIrsLqr._pipeline_segments); the iterates
     must equal those of the one-pass sequence bit for bit, eagerly and replayed from a CUDA graph."""
@@ -729,7 +729,8 @@ def test_pipelined_descent_is_bit_identical_to_one_pass(api, name, T, N, graphs)
             s = make_system(api, name)
             sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=23,
                                            projection="delta" if name == "three_cart" else None)
-            solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=T), sampler)
+            cls = api.IrsLqrZeroOrder if order == 0 else api.IrsLqrFirstOrder
+            solver = cls(s, make_params(api, cfg, T=T), sampler)
             assert (solver._pipeline_segments() is not None) == pipeline
             solver.iterate(4, verbose=False)
             return solver
