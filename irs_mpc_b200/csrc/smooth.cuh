@@ -862,6 +862,21 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
     write_abc<Sys, kFinalizeThreads>(a, p, sAB, nom, tid);
 }
 
+// sum_{c < C} src[c * width] in chunk order, eight loads in flight (the adds keep their order).
+__device__ __forceinline__ double sum_chunks_in_order(const float* src, int C, int width) {
+    double s = 0.0;
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = src[(long long)(c + k) * width];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (double)v[k];
+    }
+    for (; c < C; ++c) s += (double)src[(long long)c * width];
+    return s;
+}
+
 // Chunk reduction [P, C, width] fp32 -> [P, width] fp64 in fixed chunk order: the block a rank
 // contributes to the sample-sharded exchange (all-gather of per-point Gram blocks).
 __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* partials, int P, int C,
@@ -871,10 +886,7 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* partial
          idx += (long long)gridDim.x * blockDim.x) {
         const long long p = idx / width;
         const int e = (int)(idx % width);
-        const float* src = partials + (p * C) * width + e;
-        double s = 0.0;
-        for (int c = 0; c < C; ++c) s += (double)src[(long long)c * width];
-        reduced[idx] = s;
+        reduced[idx] = sum_chunks_in_order(partials + (p * C) * width + e, C, width);
     }
 }
 
@@ -905,9 +917,7 @@ __global__ void __launch_bounds__(256) reduce_chunks_peer_kernel(const PeerExcha
          idx += (long long)gridDim.x * blockDim.x) {
         const long long p = idx / a.width;
         const int e = (int)(idx % a.width);
-        const float* src = a.partials + (p * a.C) * a.width + e;
-        double s = 0.0;
-        for (int c = 0; c < a.C; ++c) s += (double)src[(long long)c * a.width];
+        const double s = sum_chunks_in_order(a.partials + (p * a.C) * a.width + e, a.C, a.width);
         for (int r = 0; r < a.world; ++r) a.peer_bufs[r][slot + idx] = s;      // NVLink stores (local for r == rank)
     }
     // last block of the grid: everything this rank wrote is visible system-wide -> raise the flags
