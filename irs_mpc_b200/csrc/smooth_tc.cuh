@@ -28,6 +28,9 @@
 #ifndef IRS_TC_NOM_BATCH
 #define IRS_TC_NOM_BATCH 64
 #endif
+#ifndef IRS_TC_PACK_TMEM
+#define IRS_TC_PACK_TMEM 1
+#endif
 #ifndef IRS_TC_MIN_BLOCKS
 #define IRS_TC_MIN_BLOCKS 4
 #endif
@@ -89,7 +92,14 @@ struct TcCfg {
     static constexpr int kSBO = (kWarpTile / 8) * kLBO;  // bytes between 8-feature groups (512)
     static constexpr int kGroups = kM / 8;
     static constexpr int kStageBytes = kGroups * kSBO;   // 4,096 per warp tile
-    static constexpr int kTmemCols = kWarps * kN < 32 ? 32 : kWarps * kN;   // one accumulator per warp
+#if IRS_TC_PACK_TMEM
+    // An M = 64 accumulator occupies lanes 0-15 of every 32-lane quarter of its TMEM columns; a second
+    // one at lane offset 16 shares the columns: two warps per column range.
+    static constexpr int kAccRanges = kWarps / 2;
+#else
+    static constexpr int kAccRanges = kWarps;                // one column range per warp
+#endif
+    static constexpr int kTmemCols = kAccRanges * kN < 32 ? 32 : kAccRanges * kN;
     static constexpr int NACC = gram_nacc(n, m);
     static constexpr int RS = (W + 1) / 2 * 2;
     // Nominal points prepared per batch (one thread each).  64 for the quadrotor: batched MPC runs one
@@ -236,7 +246,11 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = tmem_base_s;
+#if IRS_TC_PACK_TMEM
+    const uint32_t tmem_acc = tmem_base + ((uint32_t)(16 * (warp & 1)) << 16) + (uint32_t)((warp >> 1) * C::kN);
+#else
     const uint32_t tmem_acc = tmem_base + (uint32_t)(warp * C::kN);      // this warp's accumulator
+#endif
 
     [[maybe_unused]] const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
     // this warp's tile ring; byte offset of this lane's sample inside a tile (feature group 0)
@@ -381,7 +395,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             for (int q = 0; q < C::kN; ++q) sum[q] = 0.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
 #pragma unroll
-            for (int wa = 0; wa < C::kWarps; ++wa) {
+            for (int wa = 0; wa < C::kAccRanges; ++wa) {
                 uint32_t v[C::kN];
 #pragma unroll
                 for (int c0 = 0; c0 < C::kN; c0 += 16) {
@@ -397,6 +411,11 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 #pragma unroll
                 for (int q = 0; q < C::kN; ++q) sum[q] += __uint_as_float(v[q]);    // fixed warp order
             }
+#if IRS_TC_PACK_TMEM
+            // lanes 16-31 of the quarter hold the same rows of the accumulators at lane offset 16
+#pragma unroll
+            for (int q = 0; q < C::kN; ++q) sum[q] += __shfl_down_sync(0xffffffffu, sum[q], 16);
+#endif
             const int row = 16 * warp + lane;
             if (lane < 16 && row < C::kRows) {
 #pragma unroll

@@ -365,7 +365,7 @@ class IrsLqrExact(IrsLqr):
         return At, Bt, ct, status
 
 
-RESIDENT_BLOCKS = 592      # resident grid of the quadrotor smoothing kernel on a B200 (148 SMs x 4)
+RESIDENT_BLOCKS = 740      # resident grid of the quadrotor smoothing kernel on a B200 (148 SMs x 5)
 
 
 def pipeline_segments(T, chunks_per_step, forced=0, min_steps=_PIPELINE_MIN_STEPS):
@@ -424,10 +424,12 @@ class _SampledIrsLqr(IrsLqr):
         few launches from the back and each segment's fit and Riccati steps run on a second stream
         while the next segment is still sampling: the sequential pass hides behind the smoothing
         kernel instead of following it.  A segment is sized to about one resident grid of the
-        smoothing kernel (592 blocks on a B200; measured on the quadrotor, T=100, N=1e5: five segments
-        of 500 work items 470 us per descent, three 495, four — 625 items, a second wave of 33 —
-        504, ten 600, one pass 515).  Results are bit-identical to the one-pass sequence (global
-        point index in the Philox counter, carried (P, p) between segments)."""
+        smoothing kernel (740 blocks on a B200; a launch of fewer work items than resident blocks
+        takes one item-time whatever its size, one with a few more takes two: measured on the
+        quadrotor, T=100, N=1e5 with 592 resident blocks, five segments of 500 items 470 us per descent,
+        three 495, four — 625 items, a second wave of 33 — 504, ten 600, one pass 515).  Results are
+        bit-identical to the one-pass sequence (global point index in the Philox counter, carried
+        (P, p) between segments)."""
         n, m, T = self.dim_x, self.dim_u, self.T
         if not _USE_PIPELINE or not isinstance(self.sampling, GaussianSampling) or n % 2 or m % 2:
             return None
