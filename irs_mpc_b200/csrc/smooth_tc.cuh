@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         if (full_rounds < rounds) do_round(std::true_type{}, full_rounds);
         // ---- item finished: wait for this warp's UMMAs, meet the other warps, read all four
         //      accumulators back.  Row r of D lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64
-        //      layout): lanes 0-15 of warp w hold rows 16 w .. 16 w + 15 of every accumulator. ----
+        //      layout): lanes 0-15 of warp w hold rows 16 w .. 16 w + 15 of every accumulator (and
+        //      lanes 16-31 the same rows of the accumulators packed at lane offset 16). ----
         mbar_wait(&mbar_done[warp], (uint32_t)(it & 1));
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
