@@ -68,6 +68,13 @@ def test_get_solver_and_sampling_schedule(built_lib):
     s = GaussianSampling([2.0, 4.0], [1.0], 100, power=0.5)
     np.testing.assert_allclose(s.sigma(4), [1.0, 2.0, 0.5])
     assert s.flags() == 0
+    # the float32 array handed to the kernels is cached per iteration and follows the schedule
+    a4, p4 = s.sigma32(4)
+    assert a4.dtype == np.float32 and a4.flags["C_CONTIGUOUS"] and s.sigma32(4)[0] is a4
+    np.testing.assert_allclose(a4, [1.0, 2.0, 0.5])
+    a9, _ = s.sigma32(9)
+    assert a9 is not a4
+    np.testing.assert_allclose(a9, np.array([2.0, 4.0, 1.0]) / 3.0, rtol=1e-6)
     assert GaussianSampling([1.0], [1.0], 1, projection="absolute").flags() == 2
     with pytest.raises(ValueError):
         GaussianSampling([1.0], [1.0], 1, projection="bogus")
