@@ -205,9 +205,10 @@ def run_gpu(args, rank, local_rank, world):
     sigma = sampler.sigma(1)
     ws = smoothing.Workspace(system, smoothing.ZERO_ORDER, T_STEPS, N_SAMPLES)
     sharded = ShardedLinearizer(system, smoothing.ZERO_ORDER) if world > 1 else None
-    # ours per step: accumulate, finalize (+ fused chunk reduction / peer exchange and the arrival wait when
-    # sample-sharded)
-    launches_per_step = 2 if world == 1 else 4
+    # ours per step: accumulate + finalize; when sample-sharded the finalize kernel itself reduces, exchanges
+    # (peer-memory stores over NVLink + per-point arrival flags) and fits, so the count does not change
+    # (NCCL fallback: + chunk reduction, and the all-gather is NCCL's)
+    launches_per_step = 2
 
     def step_device(k):
         """Inputs resident in HBM; the seed changes every step so nothing can be cached."""
@@ -325,18 +326,10 @@ def run_gpu(args, rank, local_rank, world):
         from irs_mpc_b200.all import BatchedIrsLqrZeroOrder
         I_total = 4096
         lo, hi = rank * I_total // world, (rank + 1) * I_total // world
-        ph = 2.0 * np.pi * np.arange(lo, hi) / I_total
-        tt = np.arange(T_STEPS + 1, dtype=np.float64)
-        xdb = np.zeros((hi - lo, T_STEPS + 1, 12))
-        xdb[:, :, 0] = 1.5 * np.cos(0.05 * tt[None, :] + ph[:, None])
-        xdb[:, :, 1] = 1.5 * np.sin(0.05 * tt[None, :] + ph[:, None])
-        xdb[:, :, 2] = 0.02 * tt[None, :]
-        # instance b starts on its own helix (phase 2 pi b / 4096) plus N(0, diag(X0_SCALE^2)) from
-        # default_rng(5000 + b): 0.1 on positions / velocities, 0.01 on angles / angular rates (larger tilt
-        # noise makes the uncontrolled initial rollout tumble, which is not a meaningful MPC start)
-        X0_SCALE = np.array([0.1] * 3 + [0.01] * 3 + [0.1] * 3 + [0.01] * 3)
-        x0b = xdb[:, 0, :] + np.stack([X0_SCALE * np.random.default_rng(5000 + b).standard_normal(12)
-                                       for b in range(lo, hi)])
+        # instance b tracks the example's helix with phase 2 pi b / 4096 and starts on it plus noise from
+        # default_rng(5000 + b) (example_configs.quadrotor_batch; tests/test_full_size_parity.py uses the same)
+        from irs_mpc_b200 import example_configs as gec5
+        x0b, xdb = gec5.quadrotor_batch(lo, hi, T=T_STEPS, total=I_total)
         smp = GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], 1000, power=cfg["power"], seed=SEED0 + 77)
         bat = BatchedIrsLqrZeroOrder(system, cfg["Q"], cfg["Qd"], cfg["R"], x0b, xdb, cfg["u_trj_initial"], smp,
                                      instance_offset=lo)
@@ -405,8 +398,8 @@ def run_gpu(args, rank, local_rank, world):
                        "system": "quadrotor n=12 m=4", "mode": "zero_order", "T": T_STEPS,
                        "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-7 + Box-Muller in-kernel",
                        "sharding": "none" if world == 1 else (
-                           "sample axis; fp64 Gram blocks exchanged by the reduction kernel itself (peer-memory "
-                           "stores over NVLink + arrival flags)" if sharded._px is not None else
+                           "sample axis; fp64 Gram blocks exchanged inside the finalize kernel (peer-memory "
+                           "stores over NVLink + per-point arrival flags), no NCCL on the data path" if sharded._px is not None else
                            "sample axis, NCCL all_gather of fp64 Gram blocks"),
                        "l2": "no per-sample HBM input (noise generated in registers); seed changes every step"},
             "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,

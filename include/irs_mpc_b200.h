@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define IRS_ABI_VERSION 1
+#define IRS_ABI_VERSION 2
 
 /* system ids — the reference's four analytic DynamicalSystem subclasses
  * (examples/pendulum/pendulum_dynamics.py:8, examples/bicycle/bicycle_dynamics.py:8,
@@ -88,32 +88,40 @@ int irs_smooth_first_order_accumulate(int system, const double* params_host, int
 int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P, int C,
                              double* reduced, void* stream);
 
-/* Sample-sharded exchange over peer memory (NVLink / NVSwitch), fused with the chunk reduction: the
- * fp64 block [P,width] of this rank is written into slot (epoch & 1, rank) of EVERY rank's exchange
- * buffer (peer_bufs_dev: device array of `world` peer-mapped base pointers, each buffer holding
- * [2][world][slot_stride] doubles) and this rank's arrival flag is raised to `epoch` on every rank
- * (peer_flags_dev: device array of `world` peer-mapped int[world] arrays, zero before the first step).
- * done_counter: zero-initialised local device word.  epoch = 1, 2, 3, ... per step.
- * irs_peer_wait blocks the stream until all `world` flags of the local array reached `epoch`
- * (timeout_s: gives up and sets *error = 1 instead of hanging).  Afterwards irs_smooth_finalize is
- * called with reduced = local buffer + (epoch & 1) * world * slot_stride, nranks = world,
- * rank_stride = slot_stride.  Replaces reduce_chunks + ncclAllGather of the sample-sharded path. */
-int irs_smooth_reduce_chunks_peer(int system, int order, const float* partials, int P, int C,
-                                  const void* peer_bufs_dev, const void* peer_flags_dev, unsigned int* done_counter,
-                                  long long slot_stride, int rank, int world, int epoch, void* stream);
-int irs_peer_wait(const int* flags, int world, int epoch, double timeout_s, int* error, void* stream);
-
 /* Fit / mean + affine offset (irs_lqr_zero_order.py:27-36,:59-62; irs_lqr_first_order.py:48-53).
  * Input is EITHER `partials` (fp32 [nranks][P,C,width], other NULL) OR `reduced` (fp64
  * [nranks][P,width]); the `nranks` buffers lie `rank_stride` elements apart (peer-mapped pointers
  * are fine) and are summed in rank order, then chunk order — deterministic.  Solves the normal
  * equations (order 0; identical to lstsq for full column rank) or divides by n_total (order 1),
- * writes At [P,n,n], Bt [P,n,m], ct [P,n] (f64) and status [P] (0 ok, 1 rank deficient). */
+ * writes At [P,n,n], Bt [P,n,m], ct [P,n] (f64) and status [P] (0 ok, 1 rank deficient, 2 peer
+ * exchange timed out — irs_smooth_finalize_peer only). */
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
                         const float* partials, const double* reduced, int nranks,
                         long long rank_stride, double n_total,
                         double* At, double* Bt, double* ct, int* status, void* stream);
+
+/* irs_smooth_finalize for a SAMPLE-SHARDED run (one process per GPU), with the exchange of the per-point
+ * fp64 blocks fused into the kernel over peer memory (NVLink / NVSwitch) — replaces reduce_chunks +
+ * ncclAllGather + finalize of that path (the reference's only distributed reduction is the ZeroMQ
+ * task farm of irs_lqr/irs_lqr_quasistatic.py:228-273).  The block of point p reduces this rank's
+ * partials [P,C,width] of p in chunk order, stores the fp64 values into slot (epoch & 1, rank) of EVERY
+ * rank's exchange buffer (peer_bufs_dev: device array of `world` peer-mapped base pointers, each
+ * buffer [2][world][slot_stride] doubles), raises flag (rank, p) on every rank to `epoch`
+ * (peer_flags_dev: device array of `world` peer-mapped int[world][flag_stride] arrays, zero before the
+ * first call), waits for the `world` flags of p, sums the blocks in rank order and fits.  The epoch
+ * lives in *epoch_dev (zero-initialised local device word, advanced by the kernel itself, so the call
+ * is CUDA-graph replayable); done_counter: zero-initialised local device word.  A peer that does
+ * not deliver within timeout_s sets status[p] = 2 instead of hanging the GPU.  Every rank must
+ * issue the same sequence of calls on the same exchange; P may change from call to call.  All P
+ * blocks must be co-resident: P <= irs_smooth_finalize_peer_capacity (error otherwise). */
+int irs_smooth_finalize_peer(int system, const double* params_host, int nparams, int order,
+                             const double* x_nom, const double* u_nom, int P, int C, const float* partials,
+                             const void* peer_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
+                             unsigned int* done_counter, long long slot_stride, int flag_stride,
+                             int rank, int world, double timeout_s, double n_total,
+                             double* At, double* Bt, double* ct, int* status, void* stream);
+int irs_smooth_finalize_peer_capacity(int system, int order, int* max_points);
 
 /* IrsLqrExact.get_TV_matrices (irs_lqr/irs_lqr_exact.py:15-31), all fp64: [A|B] = jacobian_xu at
  * the nominal points, c = f(xbar,ubar) - A xbar - B ubar.  x_nom [P,n], u_nom [P,m]. */
@@ -181,7 +189,10 @@ int irs_tvlqr_riccati_segment(int n, int m, const double* At, const double* Bt, 
  *  - irs_tvlqr_box_solve: ADMM on the box split.  mpc = 1: the reference's closed loop (QP over the
  *    remaining horizon at every t0 from the actual state, first input applied to the TRUE dynamics of
  *    `system`); mpc = 0: one QP from x0 (solve_tvlqr), x_trj/u_trj receive the plan.  Bounds are per
- *    coordinate, constant in time (xlo/xhi [n], ulo/uhi [m]); dx [n], du [m] are the ADMM penalties;
+ *    coordinate: constant in time (xlo/xhi [n], ulo/uhi [m], strides 0) or one box per timestep
+ *    (xlo/xhi [T+1,n] with xbox_stride = n, ulo/uhi [T,m] with ubox_stride = m; tv_lqr.py:113-116,
+ *    :132-134 index their bounds by t; the box of x_0 is not used — x_0 is fixed); dx [n], du [m]
+ *    are the ADMM penalties;
  *    K0 [I,T,m,n], k0 [I,T,m] (optional, mpc = 1): the UNCONSTRAINED gains; a start time whose
  *    unconstrained plan stays inside [lo - tol, hi + tol] skips its QP (its bounds are inactive, the
  *    minimiser is K0 x + k0).  status[i] = 1 if a solve did not reach eps within max_iter (-> the
@@ -201,6 +212,7 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
                         const double* Q, const double* Qd, const double* R,
                         const double* xd, long long xd_stride, const double* dx, const double* du,
                         const double* xlo, const double* xhi, const double* ulo, const double* uhi,
+                        long long xbox_stride, long long ubox_stride,
                         const double* x0, const double* K0, const double* k0, double tol,
                         double alpha, double eps, int max_iter, int I, int T,
                         double* x_trj, double* u_trj, double* cost, int* status, int* iters, void* stream);

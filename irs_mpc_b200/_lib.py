@@ -12,6 +12,8 @@ LIB_PATH = os.environ.get("IRS_MPC_B200_LIB", os.path.join(_HERE, "libirs_mpc_b2
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
+ABI_VERSION = 2      # IRS_ABI_VERSION of include/irs_mpc_b200.h this binding was written against
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -60,8 +62,9 @@ SIGNATURES = {
     "irs_smooth_first_order_accumulate": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _ll, _vp, _vp,
                                           _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
     "irs_smooth_reduce_chunks": [_i, _i, _vp, _i, _i, _vp, _vp],
-    "irs_smooth_reduce_chunks_peer": [_i, _i, _vp, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
-    "irs_peer_wait": [_vp, _i, _i, ctypes.c_double, _vp, _vp],
+    "irs_smooth_finalize_peer": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i,
+                                 _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
+    "irs_smooth_finalize_peer_capacity": [_i, _i, ctypes.POINTER(_i)],
     "irs_smooth_finalize": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _ll,
                             ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
     "irs_exact_linearize": [_i, _c_double_p, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
@@ -77,7 +80,7 @@ SIGNATURES = {
     "irs_tvlqr_plan_check": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _i, _i,
                              _vp, _vp, _vp],
     "irs_tvlqr_box_solve": [_i, _c_double_p, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp,
-                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                            _vp, _vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                             _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "irs_tvlqr_linear_rollout": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "irs_rollout_closed_loop": [_i, _c_double_p, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i,
@@ -114,7 +117,7 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if handle.irs_abi_version() != 1:
+        if handle.irs_abi_version() != ABI_VERSION:
             raise ImportError("irs_mpc_b200: ABI version mismatch in %s" % LIB_PATH)
         _lib = handle
     return _lib

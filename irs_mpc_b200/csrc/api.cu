@@ -446,57 +446,40 @@ int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P
     return check_launch("reduce_chunks_kernel");
 }
 
-int irs_smooth_reduce_chunks_peer(int system, int order, const float* partials, int P, int C,
-                                  const void* peer_bufs_dev, const void* peer_flags_dev, unsigned int* done_counter,
-                                  long long slot_stride, int rank, int world, int epoch, void* stream) {
-    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
-    IRS_REQUIRE(partials && peer_bufs_dev && peer_flags_dev && done_counter && P >= 1 && C >= 1, "bad exchange arguments");
-    IRS_REQUIRE(world >= 1 && rank >= 0 && rank < world && epoch >= 1, "bad rank / world / epoch");
-    const int width = irs_partial_width(system, order);
-    IRS_REQUIRE(slot_stride >= (long long)P * width, "exchange slot too small");
-    PeerExchangeArgs a{partials, (double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, done_counter,
-                       slot_stride, P, C, width, rank, world, epoch};
-    // fixed grid: the arrival ticket counts blocks per launch
-    const unsigned grid = grid_for((long long)P * width, 256);
-    reduce_chunks_peer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    return check_launch("reduce_chunks_peer_kernel");
-}
-
-int irs_peer_wait(const int* flags, int world, int epoch, double timeout_s, int* error, void* stream) {
-    IRS_REQUIRE(flags && error && world >= 1 && world <= 32 && epoch >= 1, "bad wait arguments");
-    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, epoch,
-                                                       (unsigned long long)(timeout_s * 1e9), error);
-    return check_launch("peer_wait_kernel");
-}
-
-// Index tables of the finalize kernel (smooth.cuh: FinalizeTables), uploaded once per system.
-static const FinalizeTables* finalize_tables(int system, cudaStream_t st) {
-    static bool ready[kNumSystems] = {false, false, false, false};
-    FinalizeTables* base = nullptr;
+// Index tables of the finalize kernel (smooth.cuh: constant-initialised __device__ data, per device).
+static const FinalizeTables* finalize_tables(int system) {
+    const FinalizeTables* base = nullptr;
     if (cudaGetSymbolAddress((void**)&base, g_finalize_tables) != cudaSuccess) return nullptr;
-    if (!ready[system]) {
-        const SystemDims dm = system_dims(system);
-        const int d = dm.n + dm.m, W = d + dm.n;
-        static FinalizeTables host[kNumSystems];
-        FinalizeTables& t = host[system];
-        memset(&t, 0, sizeof(t));
-        int e = 0;
-        for (int i = 0; i < d; ++i)
-            for (int j = i; j < W; ++j, ++e) { t.gram_i[e] = (unsigned char)i;  t.gram_j[e] = (unsigned char)j; }
-        e = 0;
-        for (int r = 0; r < d; ++r)
-            for (int c = 0; c <= r; ++c, ++e) { t.tri_r[e] = (unsigned char)r;  t.tri_c[e] = (unsigned char)c; }
-        if (cudaMemcpyAsync(base + system, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
-        ready[system] = true;
-    }
     return base + system;
 }
 
-int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
-                        const double* x_nom, const double* u_nom, int P, int C,
-                        const float* partials, const double* reduced, int nranks,
-                        long long rank_stride, double n_total,
-                        double* At, double* Bt, double* ct, int* status, void* stream) {
+// Blocks of the one-block-per-point finalize kernels that can be resident together on this device.
+static int finalize_resident_blocks(int system, int order, int* out) {
+    int per_sm = 0;
+    cudaError_t e = cudaSuccess;
+    if (order == 0) {
+        IRS_DISPATCH_SYSTEM(system, double, Sys,
+                            (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                 &per_sm, finalize_zero_order_kernel<Sys, kFinalizeThreads>, kFinalizeThreads, 0)));
+    } else {
+        switch (system) {
+            case kPendulum: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Pendulum<double>>, kFinalizeThreads, 0); break;
+            case kBicycle: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Bicycle<double>>, kFinalizeThreads, 0); break;
+            case kQuadrotor: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Quadrotor<double>>, kFinalizeThreads, 0); break;
+            default: set_error("system %d has no first-order path", system); return 1;
+        }
+    }
+    if (e != cudaSuccess) return check_launch("cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    *out = per_sm * num_sms();
+    return 0;
+}
+
+static int smooth_finalize_impl(int system, const double* params_host, int nparams, int order,
+                                const double* x_nom, const double* u_nom, int P, int C,
+                                const float* partials, const double* reduced, int nranks,
+                                long long rank_stride, double n_total,
+                                double* At, double* Bt, double* ct, int* status, const PeerFusedArgs* peer,
+                                void* stream) {
     FinalizeArgs a;
     if (load_params(system, params_host, nparams, &a.prm)) return 1;
     IRS_REQUIRE(order == 0 || order == 1, "order must be 0 or 1");
@@ -509,8 +492,10 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
     a.x_nom = x_nom;  a.u_nom = u_nom;  a.partials = partials;  a.rank_stride = rank_stride;
     a.R = nranks;  a.P = P;  a.C = C;  a.n_total = n_total;
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.status = status;
+    memset(&a.peer, 0, sizeof(a.peer));
+    if (peer != nullptr) a.peer = *peer;
     cudaStream_t st = (cudaStream_t)stream;
-    a.tables = finalize_tables(system, st);
+    a.tables = finalize_tables(system);
     if (a.tables == nullptr) return check_launch("finalize index tables") ? 1 : (set_error("finalize index tables"), 1);
     // many points: four threads per point, else one block per point (IRS_FINALIZE_VARIANT=block|quad
     // overrides; the variants are bit-identical, tests/test_gpu_parity.py)
@@ -519,8 +504,9 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
         if (!strcmp(e, "block")) quad = false;
         else if (!strcmp(e, "quad")) quad = true;
     }
+    if (peer != nullptr) quad = false;      // the fused exchange lives in the one-block-per-point kernels
     if (quad || order == 1) {
-        // f(xbar, ubar) in fp64 (scalar dynamics, …zero_order.py:61) -> ct; the finalize kernel turns it into c
+        // f(xbar, ubar) in fp64 (scalar dynamics, ...zero_order.py:61) -> ct; the finalize kernel turns it into c
         IRS_DISPATCH_SYSTEM(system, double, Sys,
                             (dyn_batch_kernel<double, Sys><<<grid_for(P, 128), 128, 0, st>>>(a.prm, 0, x_nom, u_nom, ct, P)));
         if (check_launch("nominal dynamics kernel")) return 1;
@@ -548,6 +534,41 @@ int irs_smooth_finalize(int system, const double* params_host, int nparams, int 
         }
     }
     return check_launch("finalize_kernel");
+}
+
+int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
+                        const double* x_nom, const double* u_nom, int P, int C,
+                        const float* partials, const double* reduced, int nranks,
+                        long long rank_stride, double n_total,
+                        double* At, double* Bt, double* ct, int* status, void* stream) {
+    return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, reduced, nranks,
+                                rank_stride, n_total, At, Bt, ct, status, nullptr, stream);
+}
+
+int irs_smooth_finalize_peer_capacity(int system, int order, int* max_points) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems && (order == 0 || order == 1) && max_points, "bad arguments");
+    return finalize_resident_blocks(system, order, max_points);
+}
+
+int irs_smooth_finalize_peer(int system, const double* params_host, int nparams, int order,
+                             const double* x_nom, const double* u_nom, int P, int C, const float* partials,
+                             const void* peer_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
+                             unsigned int* done_counter, long long slot_stride, int flag_stride,
+                             int rank, int world, double timeout_s, double n_total,
+                             double* At, double* Bt, double* ct, int* status, void* stream) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    IRS_REQUIRE(partials && peer_bufs_dev && peer_flags_dev && epoch_dev && done_counter, "null pointer argument");
+    IRS_REQUIRE(world >= 1 && world <= kFinalizeThreads && rank >= 0 && rank < world, "bad rank / world");
+    IRS_REQUIRE(timeout_s > 0.0, "timeout must be positive");
+    const int width = irs_partial_width(system, order);
+    IRS_REQUIRE(slot_stride >= (long long)P * width && flag_stride >= P, "exchange buffers too small for P=%d", P);
+    int resident = 0;
+    if (finalize_resident_blocks(system, order, &resident)) return 1;
+    IRS_REQUIRE(P <= resident, "the fused exchange needs its %d blocks co-resident (%d fit): use the all-gather path", P, resident);
+    PeerFusedArgs px{(double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, done_counter,
+                     slot_stride, flag_stride, rank, world, (unsigned long long)(timeout_s * 1e9)};
+    return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, nullptr, 1, 0,
+                                n_total, At, Bt, ct, status, &px, stream);
 }
 
 int irs_exact_linearize(int system, const double* params_host, int nparams,
@@ -708,6 +729,7 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
                         const double* Q, const double* Qd, const double* R,
                         const double* xd, long long xd_stride, const double* dx, const double* du,
                         const double* xlo, const double* xhi, const double* ulo, const double* uhi,
+                        long long xbox_stride, long long ubox_stride,
                         const double* x0, const double* K0, const double* k0, double tol,
                         double alpha, double eps, int max_iter, int I, int T,
                         double* x_trj, double* u_trj, double* cost, int* status, int* iters, void* stream) {
@@ -717,9 +739,14 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
                     x0 && x_trj && u_trj && cost && status && iters, "null pointer argument");
     IRS_REQUIRE(I >= 1 && T >= 1 && max_iter >= 1, "need I >= 1, T >= 1, max_iter >= 1");
     IRS_REQUIRE(alpha > 0.0 && alpha < 2.0 && eps > 0.0, "need 0 < alpha < 2 and eps > 0");
+    {
+        const SystemDims dm = system_dims(system);
+        IRS_REQUIRE((xbox_stride == 0 || xbox_stride == dm.n) && (ubox_stride == 0 || ubox_stride == dm.m),
+                    "box strides must be 0 (constant box) or n / m (one box per timestep)");
+    }
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.K = K;  a.Hinv = Hinv;  a.P = P;  a.Q = Q;  a.Qd = Qd;  a.R = R;
     a.xd = xd;  a.xd_stride = xd_stride;  a.dx = dx;  a.du = du;  a.xlo = xlo;  a.xhi = xhi;  a.ulo = ulo;
-    a.uhi = uhi;  a.x0 = x0;  a.K0 = K0;  a.k0 = k0;  a.tol = tol;  a.alpha = alpha;  a.eps = eps;  a.max_iter = max_iter;  a.mpc = mpc ? 1 : 0;
+    a.uhi = uhi;  a.xbox_stride = xbox_stride;  a.ubox_stride = ubox_stride;  a.x0 = x0;  a.K0 = K0;  a.k0 = k0;  a.tol = tol;  a.alpha = alpha;  a.eps = eps;  a.max_iter = max_iter;  a.mpc = mpc ? 1 : 0;
     a.x_trj = x_trj;  a.u_trj = u_trj;  a.cost = cost;  a.status = status;  a.iters = iters;  a.I = I;  a.T = T;
     cudaStream_t st = (cudaStream_t)stream;
     switch (system) {

@@ -401,16 +401,43 @@ __global__ void __launch_bounds__(128) smooth_first_order_kernel(const SmoothArg
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinalizeThreads = 128;
 
-// Index tables of the finalize kernel, built once per system on the host (api.cu) and kept in global
-// memory: packed Gram entry e -> (i, j), packed lower-triangle entry -> (row, col).  (A per-block
-// search for them costs more than the factorisation itself when a block owns a single point.)
+// Index tables of the finalize kernel, one per system, built at COMPILE time (constant-initialised
+// __device__ data: present on every device of the process without an upload, no host-side state):
+// packed Gram entry e -> (i, j), packed lower-triangle entry -> (row, col).  (A per-block search for
+// them costs more than the factorisation itself when a block owns a single point.)
 constexpr int kMaxGramEntries = kMaxRegressors * (kMaxRegressors + 1) / 2 + kMaxRegressors * kMaxRegressors;
 constexpr int kMaxTriEntries = kMaxRegressors * (kMaxRegressors + 1) / 2;
 struct FinalizeTables {
     unsigned char gram_i[kMaxGramEntries], gram_j[kMaxGramEntries];
     unsigned char tri_r[kMaxTriEntries], tri_c[kMaxTriEntries];
 };
-__device__ FinalizeTables g_finalize_tables[4];
+constexpr FinalizeTables make_finalize_tables(int n, int m) {
+    FinalizeTables t{};
+    const int d = n + m, W = d + n;
+    int e = 0;
+    for (int i = 0; i < d; ++i)
+        for (int j = i; j < W; ++j, ++e) { t.gram_i[e] = (unsigned char)i;  t.gram_j[e] = (unsigned char)j; }
+    e = 0;
+    for (int r = 0; r < d; ++r)
+        for (int c = 0; c <= r; ++c, ++e) { t.tri_r[e] = (unsigned char)r;  t.tri_c[e] = (unsigned char)c; }
+    return t;
+}
+// indexed by SystemId: pendulum, bicycle, quadrotor, three_cart
+__device__ const FinalizeTables g_finalize_tables[kNumSystems] = {
+    make_finalize_tables(2, 1), make_finalize_tables(5, 2), make_finalize_tables(12, 4), make_finalize_tables(6, 2)};
+
+// Fused sample-sharded exchange (one process per GPU, peer-mapped buffers over NVLink): see
+// peer_exchange_point below.  world == 0: not sharded.
+struct PeerFusedArgs {
+    double* const* peer_bufs;     // [world] device array: base of each rank's exchange buffer
+    int* const* peer_flags;       // [world] device array: base of each rank's flag array [world][flag_stride]
+    int* epoch;                   // local: exchanges completed so far (advanced by the last block of a launch)
+    unsigned int* done_counter;   // local: blocks of the current launch that have finished (reset by the last)
+    long long slot_stride;        // doubles per (parity, rank) slot (>= P * width)
+    int flag_stride;              // flags per rank row (>= P)
+    int rank, world;
+    unsigned long long timeout_ns;
+};
 
 struct FinalizeArgs {
     const double* x_nom;     // [P, n]
@@ -426,16 +453,29 @@ struct FinalizeArgs {
     double* ct;              // [P, n]
     int* status;             // [P] 0 ok, 1 rank-deficient Gram
     const FinalizeTables* tables;   // index tables of this system (device)
+    PeerFusedArgs peer;             // fused exchange of the sample-sharded path (world == 0: unused)
     SysParams prm;
 };
 
+// Where a finalize block reads its sums from: the launch arguments, or (fused exchange) the local
+// exchange buffer of the current epoch.
+struct PartialSource {
+    const float* partials;
+    const double* reduced;
+    long long rank_stride;
+    int R, C;
+};
+__device__ __forceinline__ PartialSource partial_source(const FinalizeArgs& a) {
+    return PartialSource{a.partials, a.reduced, a.rank_stride, a.R, a.C};
+}
+
 // Fixed-order sum over ranks, then chunks, of entry e of point p (deterministic; the chunk loop is
 // unrolled by eight so that the loads are in flight together while the adds keep their order).
-__device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int e, int width) {
+__device__ __forceinline__ double sum_partials(const PartialSource& a, int p, int e, int width) {
     double s = 0.0;
     for (int r = 0; r < a.R; ++r) {
         if (a.reduced != nullptr) {
-            s += a.reduced[r * a.rank_stride + (long long)p * width + e];
+            s += __ldcg(a.reduced + r * a.rank_stride + (long long)p * width + e);      // L2: may be peer-written
         } else {
             const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * width + e;
             int c = 0;
@@ -452,6 +492,94 @@ __device__ __forceinline__ double sum_partials(const FinalizeArgs& a, int p, int
     return s;
 }
 
+// sum_{c < C} src[c * width] in chunk order, eight loads in flight (the adds keep their order).
+__device__ __forceinline__ double sum_chunks_in_order(const float* src, int C, int width) {
+    double s = 0.0;
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = src[(long long)(c + k) * width];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (double)v[k];
+    }
+    for (; c < C; ++c) s += (double)src[(long long)c * width];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sample-sharded exchange FUSED into the finalize kernel (one process per GPU, peer-mapped exchange
+// buffers over NVLink / NVSwitch; torch symmetric memory provides the address exchange only).
+// The block that owns nominal point p
+//   1. reduces its rank's fp32 per-chunk partials of p to fp64 (fixed chunk order) and stores each
+//      value straight into slot `rank` of EVERY rank's exchange buffer (NVLink stores),
+//   2. raises this rank's arrival flag of point p on every rank (system-scope release), and
+//   3. waits (acquire loads, timeout instead of a hang) until every rank's block of p has arrived,
+// after which the ordinary finalize sums the `world` blocks in rank order from the LOCAL buffer.
+// No separate reduction / wait kernels, no NCCL call: compute, all-gather and fit are one launch,
+// and a point is fitted as soon as ITS blocks are there, not when the whole step is.
+// Flags carry the exchange epoch (never reset; the epoch lives in device memory and is advanced by
+// the last block of a launch, so the sequence is CUDA-graph replayable and a changed grid — a
+// shorter horizon — cannot desynchronise it); buffers are double buffered by epoch parity: a rank
+// can run at most one exchange ahead of a peer, because its next kernel needs that peer's next flags.
+// Blocks only ever wait for REMOTE blocks of the same point, so the launch needs all its blocks
+// co-resident on every rank (the host checks P against the occupancy and uses NCCL beyond that).
+// Returns the epoch; *timed_out = a peer did not deliver in time (the caller flags status 2).
+// ---------------------------------------------------------------------------------------------
+template <int BT>
+__device__ __forceinline__ int peer_exchange_point(const FinalizeArgs& a, int p, int width, int tid,
+                                                   PartialSource* src, bool* timed_out) {
+    const PeerFusedArgs& x = a.peer;
+    // every block reads the epoch before the LAST block of this launch advances it
+    const int epoch = *reinterpret_cast<volatile int*>(x.epoch) + 1;
+    const long long slot0 = (long long)(epoch & 1) * x.world * x.slot_stride;
+    const long long mine = slot0 + (long long)x.rank * x.slot_stride + (long long)p * width;
+    for (int e = tid; e < width; e += BT) {
+        const double s = sum_chunks_in_order(a.partials + ((long long)p * a.C) * width + e, a.C, width);
+        for (int r = 0; r < x.world; ++r) x.peer_bufs[r][mine + e] = s;      // local for r == rank
+    }
+    __threadfence_system();
+    __syncthreads();
+    int late = 0;
+    if (tid < x.world) {
+        int* remote = x.peer_flags[tid] + (long long)x.rank * x.flag_stride + p;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+        const int* local = x.peer_flags[x.rank] + (long long)tid * x.flag_stride + p;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (true) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+            if (v >= epoch) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > x.timeout_ns) { late = 1;  break; }
+            __nanosleep(100);
+        }
+    }
+    *timed_out = __syncthreads_or(late) != 0;
+    src->partials = nullptr;
+    src->reduced = x.peer_bufs[x.rank] + slot0;
+    src->rank_stride = x.slot_stride;
+    src->R = x.world;
+    src->C = 1;
+    return epoch;
+}
+
+// Last block of a fused launch: reset the block counter and publish the epoch (all other blocks have
+// finished, hence read the old epoch already).
+__device__ __forceinline__ void peer_exchange_finish(const FinalizeArgs& a, int epoch, int tid) {
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int ticket = atomicAdd(a.peer.done_counter, 1u) + 1u;
+        if (ticket == gridDim.x) {
+            *a.peer.done_counter = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile int*>(a.peer.epoch) = epoch;
+        }
+    }
+}
+
 // Compile-time loop: f(std::integral_constant<int, I>) for I = I0 .. I1 - 1 (the triangular loop
 // nests must be unrolled at compile time so that the solution stays in registers).
 template <int I0, int I1, class F>
@@ -466,7 +594,7 @@ __device__ __forceinline__ void static_for(F&& f) {
 // the loads of the U entries are independent, so they are in flight together.
 // pbase = offset of the point inside a rank buffer (chunk 0), rel[u] = entry index, < 0 = none (sum 0).
 template <int U>
-__device__ __forceinline__ void sum_partials_multi(const FinalizeArgs& a, long long pbase, const int (&rel)[U],
+__device__ __forceinline__ void sum_partials_multi(const PartialSource& a, long long pbase, const int (&rel)[U],
                                                    int width, double (&s)[U]) {
 #pragma unroll
     for (int u = 0; u < U; ++u) s[u] = 0.0;
@@ -475,7 +603,7 @@ __device__ __forceinline__ void sum_partials_multi(const FinalizeArgs& a, long l
             const double* src = a.reduced + r * a.rank_stride + pbase;
             double v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? src[rel[u]] : 0.0;
+            for (int u = 0; u < U; ++u) v[u] = rel[u] >= 0 ? __ldcg(src + rel[u]) : 0.0;      // L2: may be peer-written
 #pragma unroll
             for (int u = 0; u < U; ++u) s[u] += v[u];
         } else {
@@ -553,6 +681,11 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
     __shared__ double nom[d + n];
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
+    // 0. sample-sharded run: exchange this point's chunk-reduced block with the other ranks first
+    PartialSource src = partial_source(a);
+    bool peer_late = false;
+    int epoch = 0;
+    if (a.peer.world > 0) epoch = peer_exchange_point<BT>(a, p, NACC, tid, &src, &peer_late);
     // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs; a thread's
     //    entries are summed together so that all their loads are in flight at once
     {
@@ -561,8 +694,8 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
 #pragma unroll
         for (int q = 0; q < NE; ++q) rel[q] = tid + q * BT < NACC ? tid + q * BT : -1;
         double sums[NE];
-        const long long pbase = (long long)p * (a.reduced != nullptr ? (long long)NACC : (long long)a.C * NACC);
-        sum_partials_multi<NE>(a, pbase, rel, NACC, sums);
+        const long long pbase = (long long)p * (src.reduced != nullptr ? (long long)NACC : (long long)src.C * NACC);
+        sum_partials_multi<NE>(src, pbase, rel, NACC, sums);
 #pragma unroll
         for (int q = 0; q < NE; ++q) {
             if (rel[q] >= 0) {
@@ -641,10 +774,11 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
             }
         }
         bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) a.status[p] = bad ? 1 : 0;
+        if (lane == 0) a.status[p] = peer_late ? 2 : (bad ? 1 : 0);      // 2: a peer's block never arrived
     }
     __syncthreads();
     write_abc<Sys, BT>(a, p, sAB, nom, tid);
+    if (a.peer.world > 0) peer_exchange_finish(a, epoch, tid);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -718,7 +852,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
             }
         });
         double s[C::GSLOTS];
-        sum_partials_multi<C::GSLOTS>(a, pbase, rel, NACC, s);
+        sum_partials_multi<C::GSLOTS>(partial_source(a), pbase, rel, NACC, s);
         static_for<0, d>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
 #pragma unroll
@@ -778,7 +912,7 @@ __global__ void __launch_bounds__(kFinalizeQuadThreads, 3) finalize_zero_order_q
                                             ? gram_row_offset(r, C::W) + (d - r) + q : -1;
                 }
             double s[RH * QT];
-            sum_partials_multi<RH * QT>(a, pbase, rel, NACC, s);
+            sum_partials_multi<RH * QT>(partial_source(a), pbase, rel, NACC, s);
 #pragma unroll
             for (int rr = 0; rr < RH; ++rr)
 #pragma unroll
@@ -848,7 +982,11 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
     const int tid = threadIdx.x;
     const int p = blockIdx.x;
     const Sys sys(a.prm);
-    for (int e = tid; e < NJ; e += kFinalizeThreads) sV[e] = sum_partials(a, p, e, NJ) / a.n_total;
+    PartialSource src = partial_source(a);
+    bool peer_late = false;
+    int epoch = 0;
+    if (a.peer.world > 0) epoch = peer_exchange_point<kFinalizeThreads>(a, p, NJ, tid, &src, &peer_late);
+    for (int e = tid; e < NJ; e += kFinalizeThreads) sV[e] = sum_partials(src, p, e, NJ) / a.n_total;
     nominal_to_smem<Sys, kFinalizeThreads>(a, p, nom, tid);
     __syncthreads();
     if (tid == 0) {
@@ -856,25 +994,11 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
         for (int k = 0; k < NJ; ++k) v[k] = sV[k];
         sys.jac_assemble(v, J);
         for (int e = 0; e < n * d; ++e) sAB[e] = J[e];
-        a.status[p] = 0;
+        a.status[p] = peer_late ? 2 : 0;
     }
     __syncthreads();
     write_abc<Sys, kFinalizeThreads>(a, p, sAB, nom, tid);
-}
-
-// sum_{c < C} src[c * width] in chunk order, eight loads in flight (the adds keep their order).
-__device__ __forceinline__ double sum_chunks_in_order(const float* src, int C, int width) {
-    double s = 0.0;
-    int c = 0;
-    for (; c + 8 <= C; c += 8) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = src[(long long)(c + k) * width];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += (double)v[k];
-    }
-    for (; c < C; ++c) s += (double)src[(long long)c * width];
-    return s;
+    if (a.peer.world > 0) peer_exchange_finish(a, epoch, tid);
 }
 
 // Chunk reduction [P, C, width] fp32 -> [P, width] fp64 in fixed chunk order: the block a rank
@@ -887,78 +1011,6 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const float* partial
         const long long p = idx / width;
         const int e = (int)(idx % width);
         reduced[idx] = sum_chunks_in_order(partials + (p * C) * width + e, C, width);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Sample-sharded exchange over peer memory (NVLink): the chunk reduction of a rank writes its fp64
-// block [P, width] straight into slot `rank` of EVERY peer's exchange buffer and then raises this
-// rank's arrival flag on every peer — compute and all-gather are one kernel, no NCCL call, no extra
-// pass over the data.  peer_bufs[r] / peer_flags[r] are the peer-mapped base addresses of rank r's
-// buffer / flag array (torch symmetric memory).  Flags carry the step epoch, so they never need a
-// reset; the exchange buffer is double buffered by epoch parity (a rank can be at most one step
-// ahead of a peer: its next finalize waits for that peer's next flag).
-// ---------------------------------------------------------------------------------------------
-struct PeerExchangeArgs {
-    const float* partials;        // [P, C, width] local fp32 partials
-    double* const* peer_bufs;     // [world] device array: base of each rank's exchange buffer
-    int* const* peer_flags;       // [world] device array: base of each rank's flag array [world]
-    unsigned int* done_counter;   // local: blocks finished (monotone over launches)
-    long long slot_stride;        // doubles per (parity, rank) slot  (>= P * width)
-    int P, C, width;
-    int rank, world;
-    int epoch;                    // step counter, >= 1
-};
-
-__global__ void __launch_bounds__(256) reduce_chunks_peer_kernel(const PeerExchangeArgs a) {
-    const long long total = (long long)a.P * a.width;
-    const long long slot = ((long long)(a.epoch & 1) * a.world + a.rank) * a.slot_stride;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long p = idx / a.width;
-        const int e = (int)(idx % a.width);
-        const double s = sum_chunks_in_order(a.partials + (p * a.C) * a.width + e, a.C, a.width);
-        for (int r = 0; r < a.world; ++r) a.peer_bufs[r][slot + idx] = s;      // NVLink stores (local for r == rank)
-    }
-    // last block of the grid: everything this rank wrote is visible system-wide -> raise the flags
-    __threadfence_system();
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(a.done_counter, 1u) + 1u;
-        last = ticket == (unsigned int)a.epoch * gridDim.x;
-    }
-    __syncthreads();
-    if (last) {
-        __threadfence_system();
-        for (int r = threadIdx.x; r < a.world; r += blockDim.x) {
-            int* flag = a.peer_flags[r] + a.rank;
-            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(a.epoch) : "memory");
-        }
-    }
-}
-
-// Waits until every rank's block of step `epoch` has arrived in the local exchange buffer (flags are
-// written by the peers).  One thread per rank polls with acquire loads; after timeout_ns the kernel
-// gives up and sets *error = 1 (a missing peer must not hang the GPU).
-__global__ void __launch_bounds__(32) peer_wait_kernel(const int* flags, int world, int epoch,
-                                                       unsigned long long timeout_ns, int* error) {
-    const int r = threadIdx.x;
-    if (r < world) {
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while (true) {
-            int v;
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-            if (v >= epoch) break;
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t - t0 > timeout_ns) {
-                *error = 1;
-                break;
-            }
-            __nanosleep(200);
-        }
     }
 }
 

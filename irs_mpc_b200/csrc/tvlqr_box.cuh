@@ -123,10 +123,11 @@ struct BoxMpcArgs {
     long long xd_stride;
     const double* dx;     // [n] ADMM penalties on the states
     const double* du;     // [m] ... on the inputs
-    const double* xlo;    // [n]
+    const double* xlo;    // [n], or [T+1, n] when xbox_stride = n (time-varying box, tv_lqr.py:113-114,:132-134)
     const double* xhi;
-    const double* ulo;    // [m]
+    const double* ulo;    // [m], or [T, m] when ubox_stride = m (tv_lqr.py:115-116)
     const double* uhi;
+    long long xbox_stride, ubox_stride;      // 0: the box is constant over the horizon
     const double* x0;     // [I, n]
     const double* K0;     // [I, T, m, n]   unconstrained gains (or nullptr): a start time whose
     const double* k0;     // [I, T, m]      unconstrained plan stays inside the box skips its QP
@@ -219,13 +220,13 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
     }
     for (int e = lane; e < (T + 1) * n; e += 32) {
         const int i = e % n;
-        zx[e] = fmin(fmax(xd_i[e], a.xlo[i]), a.xhi[i]);
+        zx[e] = fmin(fmax(xd_i[e], a.xlo[(e / n) * a.xbox_stride + i]), a.xhi[(e / n) * a.xbox_stride + i]);
         wx[e] = 0.0;
         x[e] = 0.0;
     }
     for (int e = lane; e < T * m; e += 32) {
         const int j = e % m;
-        zu[e] = fmin(fmax(0.0, a.ulo[j]), a.uhi[j]);
+        zu[e] = fmin(fmax(0.0, a.ulo[(e / m) * a.ubox_stride + j]), a.uhi[(e / m) * a.ubox_stride + j]);
         wu[e] = 0.0;
         u[e] = 0.0;
     }
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
 #pragma unroll
                     for (int q = 0; q < n; ++q) acc += K0p[(t * m + lane) * n + q] * x[t * n + q];
                     u[t * m + lane] = acc;
-                    bad |= !(acc >= a.ulo[lane] - a.tol && acc <= a.uhi[lane] + a.tol);
+                    bad |= !(acc >= a.ulo[t * a.ubox_stride + lane] - a.tol && acc <= a.uhi[t * a.ubox_stride + lane] + a.tol);
                 }
                 __syncwarp();
                 if (lane < n) {
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
 #pragma unroll
                     for (int q = 0; q < m; ++q) acc += Bp[(t * n + lane) * m + q] * u[t * m + q];
                     x[(t + 1) * n + lane] = acc;
-                    bad |= !(acc >= a.xlo[lane] - a.tol && acc <= a.xhi[lane] + a.tol);
+                    bad |= !(acc >= a.xlo[(t + 1) * a.xbox_stride + lane] - a.tol && acc <= a.xhi[(t + 1) * a.xbox_stride + lane] + a.tol);
                 }
                 __syncwarp();
                 if (__any_sync(0xffffffffu, bad)) break;      // the ADMM recomputes the plan anyway
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
             for (int e = (t0 + 1) * n + lane; e < (T + 1) * n; e += 32) {
                 const int i = e % n;
                 const double xh = a.alpha * x[e] + (1.0 - a.alpha) * zx[e];
-                const double zn = fmin(fmax(xh + wx[e], a.xlo[i]), a.xhi[i]);
+                const double zn = fmin(fmax(xh + wx[e], a.xlo[(e / n) * a.xbox_stride + i]), a.xhi[(e / n) * a.xbox_stride + i]);
                 wx[e] += xh - zn;
                 r_prim = fmax(r_prim, fabs(x[e] - zn));
                 r_dual = fmax(r_dual, fabs(a.dx[i] * (zn - zx[e])));
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(32) box_mpc_kernel(const BoxMpcArgs a) {
             for (int e = t0 * m + lane; e < T * m; e += 32) {
                 const int j = e % m;
                 const double uh = a.alpha * u[e] + (1.0 - a.alpha) * zu[e];
-                const double zn = fmin(fmax(uh + wu[e], a.ulo[j]), a.uhi[j]);
+                const double zn = fmin(fmax(uh + wu[e], a.ulo[(e / m) * a.ubox_stride + j]), a.uhi[(e / m) * a.ubox_stride + j]);
                 wu[e] += uh - zn;
                 r_prim = fmax(r_prim, fabs(u[e] - zn));
                 r_dual = fmax(r_dual, fabs(a.du[j] * (zn - zu[e])));

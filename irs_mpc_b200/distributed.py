@@ -71,65 +71,74 @@ def gather_ranks(local, group=None):
 
 
 class PeerExchange:
-    """Exchange buffers in peer-mapped (symmetric) memory for the sample-sharded path: every rank's
-    chunk-reduction kernel stores its fp64 block directly into all peers over NVLink and raises an
-    arrival flag (csrc/smooth.cuh: reduce_chunks_peer_kernel) — the all-gather is fused into the
-    reduction, there is no NCCL call on the data path.  torch's symmetric-memory allocator is used
-    for the address exchange only (plumbing)."""
+    """Exchange buffers in peer-mapped (symmetric) memory for the sample-sharded path.  The finalize
+    kernel itself reduces this rank's partials of a nominal point, stores the fp64 block into every
+    peer over NVLink, raises a per-point arrival flag and waits for the peers' flags of that point
+    (csrc/smooth.cuh: peer_exchange_point) — reduction, all-gather and fit are ONE launch and there is
+    no NCCL call on the data path.  torch's symmetric-memory allocator is used for the address
+    exchange only (plumbing).
+
+    The epoch lives in device memory and is advanced by the kernel, flags are indexed by point: a
+    changed horizon (fewer or more points per call) keeps the ranks in step, and the call sequence can
+    be replayed from a CUDA graph.  A peer that does not deliver within `timeout_s` makes the points
+    concerned return status 2, which `smoothing.check_status` turns into a RuntimeError."""
 
     TIMEOUT_S = 10.0
 
-    def __init__(self, nelem, group=None):
+    def __init__(self, points, width, group=None, timeout_s=None):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.slot_stride = (int(nelem) + 15) // 16 * 16
+        self.points, self.width = int(points), int(width)
+        self.slot_stride = (self.points * self.width + 15) // 16 * 16
+        self.flag_stride = (self.points + 31) // 32 * 32
+        self.timeout_s = float(self.TIMEOUT_S if timeout_s is None else timeout_s)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.buf = symm_mem.empty((2 * self.world * self.slot_stride,), dtype=torch.float64, device=dev)
-        self.flags = symm_mem.empty((64,), dtype=torch.int32, device=dev)
+        self.flags = symm_mem.empty((self.world * self.flag_stride,), dtype=torch.int32, device=dev)
         self.buf.zero_()
         self.flags.zero_()
         self._hbuf = symm_mem.rendezvous(self.buf, group)
         self._hflags = symm_mem.rendezvous(self.flags, group)
+        self.epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.error = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.epoch = 0
         torch.cuda.synchronize()
         self._hflags.barrier()          # every rank's flags are zero before anyone raises one
 
-    def reduce_and_scatter(self, system, order, ws):
-        """Enqueue the fused chunk reduction + peer stores of this step; returns the epoch."""
-        self.epoch += 1
-        P = ws.partials.shape[0]
-        _lib.call("irs_smooth_reduce_chunks_peer", system.system_id, order, _device.ptr(ws.partials), P, ws.C,
-                  self._hbuf.buffer_ptrs_dev, self._hflags.buffer_ptrs_dev, _device.ptr(self.counter),
-                  self.slot_stride, self.rank, self.world, self.epoch, _device.stream_ptr())
-        return self.epoch
+    def fits(self, P, width):
+        return P * width <= self.slot_stride and P <= self.flag_stride and width == self.width
 
-    def wait(self):
-        """Block the stream until every rank's block of the current epoch has arrived locally."""
-        _lib.call("irs_peer_wait", _device.ptr(self.flags), self.world, self.epoch, self.TIMEOUT_S,
-                  _device.ptr(self.error), _device.stream_ptr())
+    def finalize(self, system, order, x_nom, u_nom, ws, n_total):
+        """Enqueue the fused reduce + exchange + fit of this step (all ranks, same order)."""
+        P = x_nom.shape[0]
+        prm, nprm = system._params()
+        _lib.call("irs_smooth_finalize_peer", system.system_id, prm, nprm, order, _device.ptr(x_nom),
+                  _device.ptr(u_nom), P, ws.C, _device.ptr(ws.partials), self._hbuf.buffer_ptrs_dev,
+                  self._hflags.buffer_ptrs_dev, _device.ptr(self.epoch), _device.ptr(self.counter),
+                  self.slot_stride, self.flag_stride, self.rank, self.world, self.timeout_s, float(n_total),
+                  _device.ptr(ws.At), _device.ptr(ws.Bt), _device.ptr(ws.ct), _device.ptr(ws.status),
+                  _device.stream_ptr())
+        return ws.At, ws.Bt, ws.ct, ws.status
 
-    def gathered(self):
-        """Device view [world * slot_stride] of the current epoch's blocks (rank order)."""
-        off = (self.epoch & 1) * self.world * self.slot_stride
-        return self.buf[off:off + self.world * self.slot_stride]
 
-    def check(self):
-        if int(self.error.item()) != 0:
-            raise RuntimeError("peer exchange timed out: a rank did not deliver its block within %.0f s"
-                               % self.TIMEOUT_S)
+def peer_capacity(system, order):
+    """Nominal points per call the fused exchange supports (its blocks must be co-resident)."""
+    import ctypes
+    cap = ctypes.c_int(0)
+    _lib.call("irs_smooth_finalize_peer_capacity", system.system_id, order, ctypes.byref(cap))
+    return cap.value
 
 
 class ShardedLinearizer:
-    def __init__(self, system, order, group=None, peer_memory=None):
+    def __init__(self, system, order, group=None, peer_memory=None, peer_timeout_s=None):
         """peer_memory: None = use the fused peer-memory exchange when symmetric memory can be set up
         (NCCL all-gather otherwise), False = always NCCL, True = require it."""
         self.system, self.order, self.group = system, order, group
         self._ws = None
         self._peer_memory = peer_memory
+        self._peer_timeout_s = peer_timeout_s
         self._px = None
+        self._graphs = {}
 
     def _workspace(self, P, N):
         key = (self.system.system_id, self.order, P, N)
@@ -157,12 +166,20 @@ class ShardedLinearizer:
         At, Bt, ct = unpack_abc(full[:, :width - 1], n, m)
         return At, Bt, ct, full[:, width - 1].to(torch.int32)
 
-    def _peer_exchange(self, nelem):
+    def _peer_exchange(self, P, width):
+        """The fused exchange for P points per call, or None (NCCL all-gather path).  An exchange is
+        re-created (collectively: every rank sees the same P) only when P outgrows it; a SMALLER P
+        reuses it — flags are per point and the epoch lives on the device, so nothing can go stale."""
         if self._peer_memory is False:
             return None
-        if self._px is None or self._px.slot_stride < nelem:
+        if P > peer_capacity(self.system, self.order):
+            if self._peer_memory is True:
+                raise RuntimeError("the fused peer exchange needs all %d finalize blocks co-resident" % P)
+            return None
+        if self._px is None or not self._px.fits(P, width):
             try:
-                self._px = PeerExchange(nelem, self.group)
+                self._px = PeerExchange(P, width, self.group, self._peer_timeout_s)
+                self._graphs = {}
             except Exception as e:      # no symmetric memory on this system: fall back to NCCL (plumbing only)
                 if self._peer_memory is True:
                     raise
@@ -176,29 +193,30 @@ class ShardedLinearizer:
         """linearize_n with numpy in / numpy out — the sample-sharded counterpart of
         IrsLqrZeroOrder.get_TV_matrices: one pinned host->device copy of [x_nom | u_nom], the kernels
         and the exchange, one device->host copy of [At | Bt | ct | status]; returns
-        (At, Bt, ct, status) fitted on all W * N_local samples, identical on every rank."""
+        (At, Bt, ct, status) fitted on all W * N_local samples, identical on every rank.  Raises
+        (smoothing.check_status) on a rank-deficient fit or a peer-exchange timeout."""
         T = min(np.asarray(u_trj).shape[0], np.asarray(x_trj).shape[0])
         ws = self._workspace(T, N_local)
         ws.stage_nominal(x_trj, u_trj)
         ws.enqueue_upload()
         self.linearize_n(ws.x_nom, ws.u_nom, N_local, **kw)      # the fit lands in ws.At / Bt / ct / status
         ws.enqueue_download()
-        return ws.read_download()
+        At, Bt, ct, status = ws.read_download()
+        smoothing.check_status(status)
+        return At, Bt, ct, status
 
     def linearize_n(self, x_nom, u_nom, N_local, **kw):
         """Sample-sharded.  Every rank draws N_local samples per point (global sample index
-        rank*N_local + i); returns (At, Bt, ct, status) fitted on all W*N_local samples."""
+        rank*N_local + i); returns (At, Bt, ct, status) fitted on all W*N_local samples.  No host
+        synchronisation: a failed exchange shows up as status 2 (smoothing.check_status raises)."""
         T = x_nom.shape[0]
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         ws = self._workspace(T, N_local)
         smoothing.accumulate(self.system, self.order, x_nom, u_nom, N_local, ws,
                              i0=rank * N_local, **kw)
-        px = self._peer_exchange(T * ws.width)
+        px = self._peer_exchange(T, ws.width)
         if px is not None:
-            px.reduce_and_scatter(self.system, self.order, ws)
-            px.wait()
-            return smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local,
-                                      reduced=px.gathered(), nranks=world, rank_stride=px.slot_stride)
+            return px.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local)
         mine = smoothing.reduce_chunks(self.system, self.order, ws)
         everyone = gather_ranks(mine, self.group)
         return smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local,

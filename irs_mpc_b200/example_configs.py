@@ -62,5 +62,24 @@ def three_cart(T=100):
                 projection=True)
 
 
+def quadrotor_batch(lo, hi, T=100, total=4096):
+    """BASELINE.json configs[4]: instances lo..hi-1 of `total` independent quadrotor MPC problems (the
+    reference runs one IrsLqr object per problem, irs_lqr/irs_lqr.py:34-71).  Instance b tracks the helix
+    of quadrotor/quadrotor_zero_order.py:23-27 with phase 2 pi b / total and starts on it plus
+    N(0, diag(scale^2)) from default_rng(5000 + b): 0.1 on positions / velocities, 0.01 on angles /
+    angular rates (larger tilt noise makes the uncontrolled initial rollout tumble).
+    Returns (x0 [I,12], xd_trj [I,T+1,12])."""
+    ph = 2.0 * np.pi * np.arange(lo, hi) / total
+    tt = np.arange(T + 1, dtype=np.float64)
+    xd = np.zeros((hi - lo, T + 1, 12))
+    xd[:, :, 0] = 1.5 * np.cos(0.05 * tt[None, :] + ph[:, None])
+    xd[:, :, 1] = 1.5 * np.sin(0.05 * tt[None, :] + ph[:, None])
+    xd[:, :, 2] = 0.02 * tt[None, :]
+    scale = np.array([0.1] * 3 + [0.01] * 3 + [0.1] * 3 + [0.01] * 3)
+    x0 = xd[:, 0, :] + np.stack([scale * np.random.default_rng(5000 + b).standard_normal(12)
+                                 for b in range(lo, hi)])
+    return x0, xd
+
+
 CONFIGS = {"pendulum": pendulum, "bicycle": bicycle, "quadrotor": quadrotor,
            "three_cart": three_cart}

@@ -32,6 +32,7 @@ _USE_GRAPHS = os.environ.get("IRS_CUDA_GRAPH", "1") != "0"
 _USE_PIPELINE = os.environ.get("IRS_PIPELINE", "1") != "0"     # see _SampledIrsLqr._pipeline_segments
 _PIPELINE_MIN_STEPS = 8                                        # timesteps per segment below which it does not pay
 _PIPELINE_SEGMENTS = int(os.environ.get("IRS_PIPELINE_SEGMENTS", "0"))      # 0 = sized from the work per launch
+START_BOUND_TOL = 1e-6      # tolerance of the start-state box test in local_descent
 
 
 class IrsLqrParameters:
@@ -269,11 +270,19 @@ class IrsLqr:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 _lib.call("irs_graph_begin", side.cuda_stream)
+                handle = ctypes.c_void_p()
                 try:
                     enqueue()
-                finally:
-                    handle = ctypes.c_void_p()
-                    _lib.call("irs_graph_end", side.cuda_stream, ctypes.byref(handle))
+                except BaseException:
+                    # end the capture (a stream must not stay in capture mode), drop the partial graph and
+                    # let the ORIGINAL exception propagate
+                    try:
+                        _lib.call("irs_graph_end", side.cuda_stream, ctypes.byref(handle))
+                        _lib.call("irs_graph_destroy", handle)
+                    except _lib.IrsCudaError:
+                        pass
+                    raise
+                _lib.call("irs_graph_end", side.cuda_stream, ctypes.byref(handle))
             slot[1] = handle
         self._graph_update(slot[1])
         _lib.call("irs_graph_launch", slot[1], _device.stream_ptr())
@@ -301,6 +310,16 @@ class IrsLqr:
             cost = float(o[nx + nu])
         if not (np.all(np.isfinite(x_out)) and np.all(np.isfinite(u_out))):
             raise ValueError(TVLQR_FAILED)
+        if self.xbound is not None:
+            # every QP of the reference's loop also boxes its START state xt[0] = the actual x_t
+            # (tv_lqr.py:113-114 at t = 0, called from irs_lqr.py:170-182): a closed-loop state the true
+            # dynamics pushed outside xbound makes that QP infeasible -> the reference's ValueError.
+            # START_BOUND_TOL: a state steered ONTO a bound lands on it to the accuracy of the bounded
+            # solve, which must not count as outside (OSQP itself accepts 1e-3).
+            xlo, xhi = np.asarray(self.xbound[0], dtype=np.float64), np.asarray(self.xbound[1], dtype=np.float64)
+            start = x_out[:T]
+            if np.any(start < xlo - START_BOUND_TOL) or np.any(start > xhi + START_BOUND_TOL):
+                raise ValueError(TVLQR_FAILED)
         self._last_descent_cost = cost
         self._last_descent = (x_out, u_out, x_out.copy(), u_out.copy())
         return x_out, u_out
@@ -474,7 +493,9 @@ class _SampledIrsLqr(IrsLqr):
         s = self.sampling
         if not isinstance(s, GaussianSampling):
             return None           # a Python closure is called T times per iteration: nothing to replay
-        return (self.system.system_id, self.order, self.T, s.num_samples, s.flags())
+        # the captured kernels bake the system parameters: a changed parameter re-captures
+        return (self.system.system_id, self.order, self.T, s.num_samples, s.flags(),
+                tuple(float(v) for v in self.system.device_params()))
 
     def _graph_update(self, graph):
         s = self.sampling

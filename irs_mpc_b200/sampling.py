@@ -77,6 +77,8 @@ class GaussianSampling:
     def __call__(self, xbar, ubar, it):
         """Reference closure signature.  Successive calls within one iteration walk t = 0, 1, ...
         (get_TV_matrices calls sampling once per timestep in order, irs_lqr_zero_order.py:49-50)."""
+        if it != getattr(self, "_t_iter", None):      # a new iteration starts again at t = 0
+            self._t, self._t_iter = 0, it
         z = self.deltas(1, it, t0=self._t)[0].astype(np.float64)
         self._t += 1
         return z[:, :self.dim_x], z[:, self.dim_x:]

@@ -160,13 +160,21 @@ def linearize(system, order, x_nom, u_nom, N, ws=None, **kw):
 
 
 def check_status(status):
+    """status per nominal point: 0 ok, 1 rank-deficient fit, 2 peer exchange timed out (multi-GPU)."""
     if isinstance(status, torch.Tensor):
-        bad = int(status.sum().item())
-    else:
-        bad = int(np.count_nonzero(status)) if status.any() else 0
-    if bad:
-        raise np.linalg.LinAlgError(
-            "smoothing fit: the sample Gram matrix [dx du]^T[dx du] is rank deficient at %d "
-            "nominal point(s) (too few samples, NaN in the dynamics, or regressors whose offset dwarfs "
-            "their spread — three_cart's projection='absolute' quirk far from the origin: the Gram is "
-            "accumulated in fp32)" % bad)
+        status = status.detach().cpu().numpy()
+    status = np.asarray(status)
+    if not status.any():
+        return
+    late = int(np.count_nonzero(status == 2))
+    if late:
+        raise RuntimeError(
+            "peer exchange timed out: the Gram blocks of %d nominal point(s) did not arrive from every rank "
+            "(a rank is missing, far behind, or issued a different call sequence); the fit was NOT computed"
+            % late)
+    bad = int(np.count_nonzero(status))
+    raise np.linalg.LinAlgError(
+        "smoothing fit: the sample Gram matrix [dx du]^T[dx du] is rank deficient at %d "
+        "nominal point(s) (too few samples, NaN in the dynamics, or regressors whose offset dwarfs "
+        "their spread — three_cart's projection='absolute' quirk far from the origin: the Gram is "
+        "accumulated in fp32)" % bad)

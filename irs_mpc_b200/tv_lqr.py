@@ -5,7 +5,18 @@ problem is solved by an affine Riccati recursion on the GPU (csrc/tvlqr.cuh) —
 iterative — which is the QP's minimiser whenever no box bound is active.  When an absolute bound
 IS active, the QP is solved by ADMM on the box split with Riccati-structured linear solves
 (csrc/tvlqr_box.cuh; same algorithm as oracle/box_tvlqr.py, which is checked against a dense QP
-solve).  The position-controlled / relative-bound variants are not implemented.
+solve); the boxes may vary over the horizon as in the reference (x_bound_abs[:, t], u_bound_abs[:, t]).
+
+Relative bounds: the reference bounds the auxiliary variables dxt / dut (tv_lqr.py:119-124), which it
+ties to x / u only inside `if indices_u_into_x is not None` (:100-108).  With indices_u_into_x=None —
+the analytic-dynamics hot path — they are free variables, so x_bound_rel / u_bound_rel constrain
+nothing unless a lower bound exceeds its upper bound (infeasible QP -> the reference's ValueError).
+That literal behaviour is reproduced.  The position-controlled variant (indices_u_into_x given) belongs
+to the quasistatic drivers and is not implemented.
+
+Start state: the reference also boxes xt[0] = x0 (:113-114), so an x0 outside x_bound_abs[:, 0] makes
+the QP infeasible; reproduced (ValueError).  xinit / uinit are initial guesses of an iterative solver;
+the solves here are direct (or warm-started internally) and ignore them.
 """
 import numpy as np
 import torch
@@ -64,7 +75,8 @@ def box_penalties(Q, R, rho0=BOX_RHO0):
 
 def box_solve_device(system, mpc, At, Bt, ct, dQ, dQd, dR, Q, Qd, R, dxd, xd_stride, x0, xlo, xhi, ulo, uhi,
                      K0=None, k0=None, rho0=BOX_RHO0, alpha=BOX_ALPHA, eps=BOX_EPS, max_iter=BOX_MAX_ITER):
-    """Bounded solve on the device.  At [I,T,n,n] ... CUDA float64; Q, Qd, R numpy (for the penalty
+    """Bounded solve on the device.  xlo / xhi: [n] (constant box) or [T+1, n] (one box per timestep);
+    ulo / uhi: [m] or [T, m].  At [I,T,n,n] ... CUDA float64; Q, Qd, R numpy (for the penalty
     augmentation).  mpc=True: the reference's closed loop on the true dynamics of `system`
     (irs_lqr.py:169-184), K0/k0 = the unconstrained gains (start times whose unconstrained plan stays
     inside the box skip their QP); mpc=False: one QP from x0 (tv_lqr.py:69-145).  Returns device tensors
@@ -92,11 +104,16 @@ def box_solve_device(system, mpc, At, Bt, ct, dQ, dQd, dR, Q, Qd, R, dxd, xd_str
     d = {name: _device.to_device(np.ascontiguousarray(v, dtype=np.float64))
          for name, v in (("dx", dx), ("du", du), ("xlo", xlo), ("xhi", xhi), ("ulo", ulo), ("uhi", uhi))}
     prm, nprm = system._params()
+    xbox_stride = n if np.ndim(xlo) == 2 else 0
+    ubox_stride = m if np.ndim(ulo) == 2 else 0
+    if (xbox_stride and np.shape(xlo) != (T + 1, n)) or (ubox_stride and np.shape(ulo) != (T, m)):
+        raise ValueError("time-varying boxes must be [T+1, n] (states) and [T, m] (inputs)")
     _lib.call("irs_tvlqr_box_solve", system.system_id, prm, nprm, 1 if mpc else 0, _device.ptr(At),
               _device.ptr(Bt), _device.ptr(ct), _device.ptr(K), _device.ptr(Hinv), _device.ptr(P),
               _device.ptr(dQ), _device.ptr(dQd), _device.ptr(dR), _device.ptr(dxd), int(xd_stride),
               _device.ptr(d["dx"]), _device.ptr(d["du"]), _device.ptr(d["xlo"]), _device.ptr(d["xhi"]),
-              _device.ptr(d["ulo"]), _device.ptr(d["uhi"]), _device.ptr(x0), _device.ptr(K0), _device.ptr(k0),
+              _device.ptr(d["ulo"]), _device.ptr(d["uhi"]), xbox_stride, ubox_stride, _device.ptr(x0),
+              _device.ptr(K0), _device.ptr(k0),
               BOUND_TOL, float(alpha), float(eps), int(max_iter), I, T, _device.ptr(x_trj), _device.ptr(u_trj), _device.ptr(cost),
               _device.ptr(status), _device.ptr(iters), _device.stream_ptr())
     return x_trj, u_trj, cost, status | rstatus, iters
@@ -118,14 +135,19 @@ class _DimsOnlySystem:
         return _lib.params_array(self._p)
 
 
-def _constant_box(bound, rows, name):
-    """[2, >=rows, d] time-varying bounds -> (lo[d], hi[d]) if constant over the horizon."""
+def _box_rows(bound, rows, dim, name):
+    """The reference indexes its bounds by timestep (x_bound_abs[0, t]: tv_lqr.py:113-116): accepts
+    [2, rows, dim] (or [2, dim], broadcast over the horizon) -> (lo, hi), each [dim] when the box is
+    constant over the horizon, else [rows, dim]."""
     lo, hi = np.asarray(bound[0], dtype=np.float64), np.asarray(bound[1], dtype=np.float64)
-    lo, hi = np.atleast_2d(lo)[:rows], np.atleast_2d(hi)[:rows]
-    if np.any(lo != lo[0]) or np.any(hi != hi[0]):
-        raise NotImplementedError("time-varying %s with an active bound is not implemented "
-                                  "(per-coordinate boxes constant over the horizon are)" % name)
-    return lo[0], hi[0]
+    if lo.ndim == 1:
+        lo, hi = np.tile(lo, (rows, 1)), np.tile(hi, (rows, 1))
+    if lo.shape[0] < rows or lo.shape[1] != dim or hi.shape != lo.shape:
+        raise ValueError("%s must hold %d rows of %d bounds" % (name, rows, dim))
+    lo, hi = np.ascontiguousarray(lo[:rows]), np.ascontiguousarray(hi[:rows])
+    if np.all(lo == lo[0]) and np.all(hi == hi[0]):
+        return lo[0], hi[0]
+    return lo, hi
 
 
 def _violates(v, lo, hi, tol=BOUND_TOL):
@@ -137,9 +159,14 @@ def solve_tvlqr(At, Bt, ct, Q, Qd, R, x0, x_trj_d, solver=None, indices_u_into_x
                 xinit=None, uinit=None):
     """Same arguments and return value as the reference (tv_lqr.py:30-33, :142-145):
     numpy float64 in, (x*[T+1,n], u*[T,m]) out.  ValueError(TVLQR_FAILED) on failure (:139-140)."""
-    if indices_u_into_x is not None or x_bound_rel is not None or u_bound_rel is not None:
+    if indices_u_into_x is not None:
         raise NotImplementedError(
-            "position-controlled / relative-bound TVLQR is outside the analytic-dynamics hot path")
+            "position-controlled TVLQR (indices_u_into_x) belongs to the quasistatic drivers, outside the "
+            "analytic-dynamics hot path")
+    for rel in (x_bound_rel, u_bound_rel):
+        # bounds on the free variables dxt / dut (see the module docstring): inert unless infeasible
+        if rel is not None and np.any(np.asarray(rel[0], dtype=np.float64) > np.asarray(rel[1], dtype=np.float64)):
+            raise ValueError(TVLQR_FAILED)
     At = np.asarray(At, dtype=np.float64)
     Bt = np.asarray(Bt, dtype=np.float64)
     T, n, m = At.shape[0], At.shape[1], Bt.shape[2]
@@ -162,18 +189,21 @@ def solve_tvlqr(At, Bt, ct, Q, Qd, R, x0, x_trj_d, solver=None, indices_u_into_x
     us = _device.to_numpy(us[0])
     if not (np.all(np.isfinite(xs)) and np.all(np.isfinite(us))):
         raise ValueError(TVLQR_FAILED)
-    x_active = x_bound_abs is not None and _violates(xs[1:], np.asarray(x_bound_abs[0])[1:T + 1],
-                                                     np.asarray(x_bound_abs[1])[1:T + 1])
-    u_active = u_bound_abs is not None and _violates(us, np.asarray(u_bound_abs[0])[:T],
-                                                     np.asarray(u_bound_abs[1])[:T])
+    big = 1e30
+    xlo, xhi = (_box_rows(x_bound_abs, T + 1, n, "x_bound_abs") if x_bound_abs is not None
+                else (-big * np.ones(n), big * np.ones(n)))
+    ulo, uhi = (_box_rows(u_bound_abs, T, m, "u_bound_abs") if u_bound_abs is not None
+                else (-big * np.ones(m), big * np.ones(m)))
+    if np.any(xlo > xhi) or np.any(ulo > uhi):
+        raise ValueError(TVLQR_FAILED)                      # empty box: infeasible QP
+    # xt[0] = x0 is boxed too (tv_lqr.py:113-114): a start state outside its box is an infeasible QP
+    if _violates(xs[0], xlo[0] if xlo.ndim == 2 else xlo, xhi[0] if xhi.ndim == 2 else xhi):
+        raise ValueError(TVLQR_FAILED)
+    x_active = _violates(xs[1:], xlo[1:] if xlo.ndim == 2 else xlo, xhi[1:] if xhi.ndim == 2 else xhi)
+    u_active = _violates(us, ulo, uhi)
     if not (x_active or u_active):
         return xs, us
     # an absolute bound is active: box-constrained QP (tv_lqr.py:113-118, :132-134)
-    big = 1e30
-    xlo, xhi = (_constant_box(x_bound_abs, T + 1, "x_bound_abs") if x_bound_abs is not None
-                else (-big * np.ones(n), big * np.ones(n)))
-    ulo, uhi = (_constant_box(u_bound_abs, T, "u_bound_abs") if u_bound_abs is not None
-                else (-big * np.ones(m), big * np.ones(m)))
     xb, ub, _, bstatus, _ = box_solve_device(_DimsOnlySystem(n, m), False, dA, dB, dc, dQ, dQd, dR, Q, Qd, R,
                                              dxd, 0, dx0, xlo, xhi, ulo, uhi)
     if int(bstatus.item()) != 0:

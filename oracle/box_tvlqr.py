@@ -102,8 +102,10 @@ def admm_box_qp(At, Bt, ct, Q, Qd, R, x0, xd, xlo, xhi, ulo, uhi, gains=None, dx
         # relaxed projection + dual
         xh = alpha * x[t0 + 1:] + (1.0 - alpha) * zx[t0 + 1:]
         uh = alpha * u[t0:] + (1.0 - alpha) * zu[t0:]
-        zx_new = np.clip(xh + wx[t0 + 1:], xlo, xhi)
-        zu_new = np.clip(uh + wu[t0:], ulo, uhi)
+        # boxes: [n] / [m] constant over the horizon, or one row per timestep ([T+1, n] / [T, m])
+        zx_new = np.clip(xh + wx[t0 + 1:], xlo[t0 + 1:] if np.ndim(xlo) == 2 else xlo,
+                         xhi[t0 + 1:] if np.ndim(xhi) == 2 else xhi)
+        zu_new = np.clip(uh + wu[t0:], ulo[t0:] if np.ndim(ulo) == 2 else ulo, uhi[t0:] if np.ndim(uhi) == 2 else uhi)
         wx[t0 + 1:] += xh - zx_new
         wu[t0:] += uh - zu_new
         r_prim = max(np.max(np.abs(x[t0 + 1:] - zx_new)), np.max(np.abs(u[t0:] - zu_new)))
@@ -187,11 +189,13 @@ def dense_qp_reference(At, Bt, ct, Q, Qd, R, x0, xd, xlo, xhi, ulo, uhi):
         e = s0 + Su.dot(uv) - xdv
         return 2.0 * Su.T.dot(Qbig.dot(e)) + 2.0 * Rbig.dot(uv)
 
-    lo = np.tile(xlo, T)
-    hi = np.tile(xhi, T)
+    # boxes: [n] / [m] constant over the horizon, or one row per timestep ([T+1, n] / [T, m])
+    lo = np.asarray(xlo)[1:T + 1].reshape(-1) if np.ndim(xlo) == 2 else np.tile(xlo, T)
+    hi = np.asarray(xhi)[1:T + 1].reshape(-1) if np.ndim(xhi) == 2 else np.tile(xhi, T)
     cons = [{"type": "ineq", "fun": lambda uv: (s0 + Su.dot(uv))[n:] - lo, "jac": lambda uv: Su[n:]},
             {"type": "ineq", "fun": lambda uv: hi - (s0 + Su.dot(uv))[n:], "jac": lambda uv: -Su[n:]}]
-    bounds = list(zip(np.tile(ulo, T), np.tile(uhi, T)))
+    bounds = list(zip(np.asarray(ulo)[:T].reshape(-1) if np.ndim(ulo) == 2 else np.tile(ulo, T),
+                      np.asarray(uhi)[:T].reshape(-1) if np.ndim(uhi) == 2 else np.tile(uhi, T)))
     res = minimize(cost, np.zeros(T * m), jac=grad, bounds=bounds, constraints=cons, method="SLSQP",
                    options={"maxiter": 500, "ftol": 1e-14})
     uv = res.x

@@ -1,12 +1,16 @@
-"""Multi-GPU equivalence checks on real GPUs (run under torchrun, one rank per GPU):
+"""Multi-GPU equivalence checks on real GPUs, one rank per GPU.  Run by tests/test_multi_gpu.py (which
+skips on a single-GPU box) or by hand:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29520 tools/multi_gpu_check.py
+        --master-port 29520 tests/multi_gpu_worker.py
 
  1. timestep sharding (ShardedLinearizer.linearize_t) reproduces the single-GPU linearization bit for bit;
  2. sample sharding (linearize_n, W ranks x N samples) equals ONE GPU drawing the same W*N samples per
     point up to fp32 summation order (1e-5), and is bit-identical on every rank;
- 3. instance sharding (BatchedIrsLqrZeroOrder with instance_offset) reproduces the unsharded batch bit
+ 3. the fused peer-memory exchange equals the NCCL all-gather path bit for bit, survives a horizon that
+    shrinks and grows again on a live linearizer, and a rank that does not deliver in time raises
+    RuntimeError on its peers (never a silent fit on stale blocks);
+ 4. instance sharding (BatchedIrsLqrZeroOrder with instance_offset) reproduces the unsharded batch bit
     for bit.
 Rank 0 prints one line per check.
 """
@@ -77,11 +81,52 @@ def main():
     same = torch.equal(Ac, An) and torch.equal(Bc, Bn) and torch.equal(cc, cn)
     report("peer-memory exchange == NCCL path", same and used_peer, "(peer memory in use: %s)" % used_peer)
     for k in range(20):                       # epochs / double buffering over repeated steps
-        A2, B2, c2, _ = sh.linearize_n(x, u, N, **kw)
-    sh._px.check()
+        A2, B2, c2, st2 = sh.linearize_n(x, u, N, **kw)
+    smoothing.check_status(st2)
     report("peer exchange stable over 20 steps", torch.equal(A2, An) and torch.equal(c2, cn))
 
-    # 3. instance sharding
+    # 2b. a horizon that shrinks and grows again on a LIVE linearizer (shrinking-horizon MPC): the
+    #     exchange is reused, the ranks stay in step, and every size still equals the NCCL path
+    ok_shape = True
+    px_before = sh._px
+    for Ts in (11, 5, 23, T):
+        As, Bs, cs, sts = sh.linearize_n(x[:Ts].contiguous(), u[:Ts].contiguous(), N, **kw)
+        As, Bs, cs = As.clone(), Bs.clone(), cs.clone()
+        smoothing.check_status(sts)
+        Ar, Br, cr_, _ = sh_nccl.linearize_n(x[:Ts].contiguous(), u[:Ts].contiguous(), N, **kw)
+        ok_shape = ok_shape and torch.equal(As, Ar) and torch.equal(Bs, Br) and torch.equal(cs, cr_)
+    flags = torch.tensor([1.0 if (ok_shape and sh._px is px_before) else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    report("horizon change on a live exchange", bool(flags.item() == 1.0), "(T = 11, 5, 23, %d; same exchange object)" % T)
+
+    # 2c. a late rank: the others must raise, not fit on stale blocks; the late rank itself still finds
+    #     everybody's blocks, and the next step is in step again
+    import time
+    sh_short = ShardedLinearizer(s, smoothing.ZERO_ORDER, peer_memory=True, peer_timeout_s=0.5)
+    sh_short.linearize_n(x, u, N, **kw)       # warm: buffers, rendezvous
+    torch.cuda.synchronize()
+    dist.barrier()
+    raised = False
+    if rank == world - 1:
+        time.sleep(2.5)
+    try:
+        Al, Bl, cl, stl = sh_short.linearize_n(x, u, N, **kw)
+        smoothing.check_status(stl)
+    except RuntimeError as e:
+        raised = "peer exchange timed out" in str(e)
+    expect = rank != world - 1
+    flags = torch.tensor([1.0 if raised == expect else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    report("late rank raises on its peers", bool(flags.item() == 1.0))
+    torch.cuda.synchronize()
+    dist.barrier()
+    Al, Bl, cl, stl = sh_short.linearize_n(x, u, N, **kw)
+    smoothing.check_status(stl)
+    flags = torch.tensor([1.0 if (torch.equal(Al, An) and torch.equal(cl, cn)) else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    report("exchange recovers after a timeout", bool(flags.item() == 1.0))
+
+    # 4. instance sharding
     I, Tb, Nb = 4 * world, 20, 1000
     cfgb = ec.quadrotor(T=Tb)
     x0 = 0.02 * np.random.default_rng(7).standard_normal((I, 12))

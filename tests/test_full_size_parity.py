@@ -1,0 +1,232 @@
+"""Full-size parity against the float64 oracle, one test per BASELINE.json config (SURVEY.md
+section 8(d) recipe): the noise `default_rng(1000 + cfg).standard_normal((T, N_par, d))` with
+N_par = min(N, 1e4) is replayed into BOTH sides — the CUDA path through an ordinary `sampling`
+closure (the reference's own plug-in point, irs_lqr_zero_order.py:12-22) and the oracle
+(oracle/cpu_restatement.py, pinned on the reference's outputs) — at the horizon and sample count the
+config names, from the example's initial rollout.
+
+Bar (BASELINE.json north_star): fitted (A_t, B_t, c_t) within 1e-4 relative (max-abs error over
+max-abs value per array) and the teacher-forced descent (trajectory, cost) within 1e-4.
+
+Reference lines: irs_lqr/irs_lqr_zero_order.py:38-63, irs_lqr/irs_lqr_first_order.py:28-54,
+irs_lqr/irs_lqr.py:148-186.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cpu_restatement as cr          # noqa: E402
+from oracle import example_configs as ec          # noqa: E402
+
+RTOL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available()
+    import irs_mpc_b200.all as m
+    return m
+
+
+SYSTEM_CLASS = {"pendulum": "PendulumDynamics", "bicycle": "BicycleDynamics",
+                "quadrotor": "QuadrotorDynamics", "three_cart": "ThreeCartDynamics"}
+
+
+def make_solver(api, name, cls, cfg, sampling, wide_bounds=False):
+    system = getattr(api, SYSTEM_CLASS[name])(cfg["h"])
+    p = api.IrsLqrParameters()
+    T = cfg["T"]
+    p.Q, p.Qd, p.R, p.x0 = cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"]
+    p.xd_trj, p.u_trj_initial = cfg["xd_trj"][:T + 1], cfg["u_trj_initial"][:T]
+    p.xbound, p.ubound = cfg["xbound"], cfg["ubound"]
+    if wide_bounds:
+        n, m = system.dim_x, system.dim_u
+        p.xbound = [-1e4 * np.ones(n), 1e4 * np.ones(n)]
+        p.ubound = np.array([-1e4 * np.ones(m), 1e4 * np.ones(m)])
+    return system, getattr(api, cls)(system, p, sampling)
+
+
+def replayed_noise(cfg_index, T, N, sigma):
+    """[T, N, d] float64 deltas whose values are float32 numbers (what the kernel reads), SURVEY 8(d)."""
+    eps = np.random.default_rng(1000 + cfg_index).standard_normal((T, N, sigma.shape[0])).astype(np.float32)
+    return (eps * sigma.astype(np.float32)).astype(np.float64)
+
+
+class ReplayClosure:
+    """`sampling(xbar, ubar, iter) -> (dx, du)`: walks t = 0..T-1 on every pass over the horizon."""
+
+    def __init__(self, deltas, n, post=None):
+        self.deltas, self.n, self.post, self.calls = deltas, n, post, 0
+
+    def __call__(self, xbar, ubar, it):
+        t = self.calls % self.deltas.shape[0]
+        self.calls += 1
+        dx, du = self.deltas[t][:, :self.n], self.deltas[t][:, self.n:]
+        if self.post is not None:
+            return self.post(xbar, dx, ubar, du)
+        return dx, du
+
+
+def oracle_descent(orc, cfg, At, Bt, ct, x0):
+    K, k = cr.tvlqr_riccati(At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["xd_trj"])
+    x_o, u_o = cr.closed_loop_descent(orc, K, k, x0)
+    return x_o, u_o, cr.evaluate_cost(x_o, u_o, cfg["xd_trj"], cfg["Q"], cfg["R"])
+
+
+def check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o, u_factor=5.0):
+    At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    assert At.shape == At_o.shape and Bt.shape == Bt_o.shape and ct.shape == ct_o.shape
+    assert rel_err(At, At_o) < RTOL, ("A", rel_err(At, At_o))
+    assert rel_err(Bt, Bt_o) < RTOL, ("B", rel_err(Bt, Bt_o))
+    scale = max(1.0, float(np.max(np.abs(solver.x_trj))))
+    assert float(np.max(np.abs(ct - ct_o))) < RTOL * scale, ("c", float(np.max(np.abs(ct - ct_o))))
+    x_new, u_new = solver.local_descent(solver.x_trj, solver.u_trj)
+    cost = solver.evaluate_cost(x_new, u_new)
+    x_o, u_o, cost_o = oracle_descent(orc, cfg, At_o, Bt_o, ct_o, solver.x_trj[0])
+    assert rel_err(x_new, x_o) < RTOL, ("x", rel_err(x_new, x_o))
+    assert rel_err(u_new, u_o) < u_factor * RTOL, ("u", rel_err(u_new, u_o))
+    assert abs(cost - cost_o) / abs(cost_o) < RTOL, ("cost", cost, cost_o)
+
+
+def test_cfg1_pendulum_zero_order_T200_N1e3(api):
+    cfg = ec.pendulum(T=200)
+    deltas = replayed_noise(1, 200, 1000, cfg["sigma"])
+    system, solver = make_solver(api, "pendulum", "IrsLqrZeroOrder", cfg, ReplayClosure(deltas, 2))
+    orc = cr.PendulumOracle(cfg["h"])
+    At_o, Bt_o, ct_o = cr.zero_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o)
+
+
+def test_cfg2_bicycle_first_order_T100_N1e4(api):
+    """The descent is compared with the steer bound widened: with the example's +-pi/4 bound the
+    reference's QPs have active constraints, a comparison the box-QP tests cover separately
+    (test_gpu_parity.py::test_bicycle_descent_with_active_steer_bound_matches_oracle)."""
+    cfg = ec.bicycle(T=100)
+    deltas = replayed_noise(2, 100, 10000, cfg["sigma"])
+    system, solver = make_solver(api, "bicycle", "IrsLqrFirstOrder", cfg, ReplayClosure(deltas, 5),
+                                 wide_bounds=True)
+    orc = cr.BicycleOracle(cfg["h"])
+    At_o, Bt_o, ct_o = cr.first_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o)
+
+
+def test_cfg3_quadrotor_zero_order_T100_replay_N1e4(api):
+    cfg = ec.quadrotor(T=100)
+    deltas = replayed_noise(3, 100, 10000, cfg["sigma"])
+    system, solver = make_solver(api, "quadrotor", "IrsLqrZeroOrder", cfg, ReplayClosure(deltas, 12))
+    orc = cr.QuadrotorOracle(cfg["h"])
+    At_o, Bt_o, ct_o = cr.zero_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o)
+
+
+def test_cfg3_quadrotor_zero_order_T100_philox_N1e5(api):
+    """The configuration bench.py times (25 chunks of the accumulate plan per timestep, in-kernel
+    Philox noise), against the oracle on the very deltas the kernel drew (`sampler.deltas`)."""
+    cfg = ec.quadrotor(T=100)
+    T, N = 100, 100000
+    sampler = api.GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], N, power=cfg["power"], seed=0x1255 + 3)
+    system, solver = make_solver(api, "quadrotor", "IrsLqrZeroOrder", cfg, sampler)
+    orc = cr.QuadrotorOracle(cfg["h"])
+    At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    x_new, u_new = solver.local_descent(solver.x_trj, solver.u_trj)
+    cost = solver.evaluate_cost(x_new, u_new)
+    At_o, Bt_o, ct_o = np.zeros_like(At), np.zeros_like(Bt), np.zeros_like(ct)
+    step = 10                      # timesteps per oracle batch (64 MB of deltas at a time)
+    for t0 in range(0, T, step):
+        d = sampler.deltas(step, solver.iter, t0=t0).astype(np.float64)
+        a, b, c = cr.zero_order_tv_matrices(orc, solver.x_trj[t0:t0 + step + 1], solver.u_trj[t0:t0 + step], d)
+        At_o[t0:t0 + step], Bt_o[t0:t0 + step], ct_o[t0:t0 + step] = a, b, c
+    assert rel_err(At, At_o) < RTOL and rel_err(Bt, Bt_o) < RTOL
+    assert float(np.max(np.abs(ct - ct_o))) < RTOL * max(1.0, float(np.max(np.abs(solver.x_trj))))
+    x_o, u_o, cost_o = oracle_descent(orc, cfg, At_o, Bt_o, ct_o, solver.x_trj[0])
+    assert rel_err(x_new, x_o) < RTOL and rel_err(u_new, u_o) < 5 * RTOL
+    assert abs(cost - cost_o) / abs(cost_o) < RTOL
+
+
+@pytest.mark.parametrize("projection", ["absolute", "delta"])
+def test_cfg4_three_cart_zero_order_T100_N1e4(api, projection):
+    """three_cart_zero_order.py:38-43: the sampling closure returns projection(...) — ABSOLUTE points
+    (SURVEY Appendix A-5), reproduced literally; "delta" is the corrected variant (projected point minus
+    the nominal).  The closure here calls the ORACLE's projection, i.e. the CUDA side only sees numbers."""
+    cfg = ec.three_cart(T=100)
+    orc = cr.ThreeCartOracle(cfg["h"])
+    raw = replayed_noise(4, 100, 10000, cfg["sigma"])
+
+    def post(xbar, dx, ubar, du):
+        xp, up = orc.projection(xbar, dx, ubar, du)
+        if projection == "absolute":
+            return xp.astype(np.float32).astype(np.float64), up.astype(np.float32).astype(np.float64)
+        return (xp - xbar).astype(np.float32).astype(np.float64), du
+
+    closure = ReplayClosure(raw, 6, post)
+    system, solver = make_solver(api, "three_cart", "IrsLqrZeroOrder", cfg, closure)
+    deltas = np.stack([np.hstack(post(solver.x_trj[t], raw[t][:, :6], solver.u_trj[t], raw[t][:, 6:]))
+                       for t in range(100)])
+    At_o, Bt_o, ct_o = cr.zero_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
+    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o)
+
+
+def test_cfg4_three_cart_inkernel_projection_philox_N1e6_sample(api):
+    """cfg4 at its full sample count runs the projection INSIDE the kernel on Philox noise; the oracle
+    follows on the first 8 timesteps (8e6 samples), both projection modes."""
+    cfg = ec.three_cart(T=100)
+    orc = cr.ThreeCartOracle(cfg["h"])
+    T, N, Tc = 100, 1000000, 8
+    for projection in ("absolute", "delta"):
+        sampler = api.GaussianSampling(cfg["sigma"][:6], cfg["sigma"][6:], N, power=cfg["power"], seed=0x1255 + 4,
+                                       projection=projection)
+        system, solver = make_solver(api, "three_cart", "IrsLqrZeroOrder", cfg, sampler)
+        At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+        for t in range(Tc):
+            d = sampler.deltas(1, solver.iter, t0=t)[0].astype(np.float64)
+            xp, up = orc.projection(solver.x_trj[t], d[:, :6], solver.u_trj[t], d[:, 6:])
+            if projection == "absolute":
+                d = np.hstack((xp, up))
+            else:
+                d[:, :6] = xp - solver.x_trj[t]
+            a, b, c = cr.zero_order_tv_matrices(orc, solver.x_trj[t:t + 2], solver.u_trj[t:t + 1], d[None])
+            assert rel_err(At[t], a[0]) < RTOL, (projection, t, rel_err(At[t], a[0]))
+            assert rel_err(Bt[t], b[0]) < RTOL, (projection, t, rel_err(Bt[t], b[0]))
+            assert float(np.max(np.abs(ct[t] - c[0]))) < RTOL * max(1.0, float(np.max(np.abs(solver.x_trj))))
+
+
+def test_cfg5_batched_4096_quadrotor_instances(api):
+    """All 4096 instances step together (T=100, N=1000 in-kernel samples per nominal point); eight of them
+    are followed by the oracle on the deltas their nominal points drew (point index b*T + t)."""
+    I, T, N = 4096, 100, 1000
+    cfg = ec.quadrotor(T=T)
+    x0, xd = ec.quadrotor_batch(0, I, T=T, total=I)
+    system = api.QuadrotorDynamics(cfg["h"])
+    sampler = api.GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], N, power=cfg["power"], seed=0x1255 + 77)
+    bat = api.BatchedIrsLqrZeroOrder(system, cfg["Q"], cfg["Qd"], cfg["R"], x0, xd, cfg["u_trj_initial"], sampler)
+    from irs_mpc_b200 import _device
+    At, Bt, ct, status = bat.linearize()
+    assert int(status.sum().item()) == 0
+    picks = [0, 1, 511, 512, 2047, 2048, 4094, 4095]
+    At_h = {b: _device.to_numpy(At[b]) for b in picks}
+    Bt_h = {b: _device.to_numpy(Bt[b]) for b in picks}
+    ct_h = {b: _device.to_numpy(ct[b]) for b in picks}
+    x_nom = _device.to_numpy(bat.x_trj)
+    u_nom = _device.to_numpy(bat.u_trj)
+    x_new, u_new, cost_new = bat.local_descent()
+    bat.check()
+    x_new, u_new, cost_new = _device.to_numpy(x_new), _device.to_numpy(u_new), _device.to_numpy(cost_new)
+    orc = cr.QuadrotorOracle(cfg["h"])
+    for b in picks:
+        d = sampler.deltas(T, bat.iter, t0=b * T).astype(np.float64)
+        a, bb, c = cr.zero_order_tv_matrices(orc, x_nom[b], u_nom[b], d)
+        assert rel_err(At_h[b], a) < RTOL and rel_err(Bt_h[b], bb) < RTOL, b
+        assert float(np.max(np.abs(ct_h[b] - c))) < RTOL * max(1.0, float(np.max(np.abs(x_nom[b])))), b
+        K, k = cr.tvlqr_riccati(a, bb, c, cfg["Q"], cfg["Qd"], cfg["R"], xd[b])
+        x_o, u_o = cr.closed_loop_descent(orc, K, k, x_nom[b][0])
+        cost_o = cr.evaluate_cost(x_o, u_o, xd[b], cfg["Q"], cfg["R"])
+        assert rel_err(x_new[b], x_o) < RTOL and rel_err(u_new[b], u_o) < 5 * RTOL, b
+        assert abs(cost_new[b] - cost_o) / abs(cost_o) < RTOL, b

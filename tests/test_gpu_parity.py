@@ -853,6 +853,50 @@ def test_solve_tvlqr_active_bounds_matches_admm_oracle_and_dense_qp(api):
     assert np.array_equal(x1, x2) and np.array_equal(u1, u2)
 
 
+def test_solve_tvlqr_time_varying_and_relative_bounds(api):
+    """tv_lqr.py:113-124: the reference indexes its boxes by timestep.  A steer box that tightens over
+    the horizon and a steer-rate box that opens up, against the numpy ADMM and the dense QP solve; the
+    start-state box (an x0 outside it is an infeasible QP) and the relative bounds (free variables when
+    indices_u_into_x is None: inert unless empty)."""
+    from oracle import box_tvlqr as bq
+    T = 12
+    cfg, orc, At, Bt, ct = _bicycle_lin(T, [0.5, 0.6])
+    steer = np.linspace(0.45, 0.2, T + 1)
+    rate = np.linspace(0.25, 0.6, T)
+    xhi = np.tile(np.array([1e4, 1e4, 1e4, 1e4, 0.0]), (T + 1, 1))
+    xhi[:, 4] = steer
+    xlo = -xhi
+    uhi = np.tile(np.array([1e4, 0.0]), (T, 1))
+    uhi[:, 1] = rate
+    ulo = -uhi
+    args = (At, Bt, ct, cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"])
+    xs, us = api.solve_tvlqr(*args, None, x_bound_abs=np.stack((xlo, xhi)), u_bound_abs=np.stack((ulo, uhi)))
+    xo, uo, _ = bq.admm_box_qp(*args, xlo, xhi, ulo, uhi)
+    np.testing.assert_allclose(xs, xo, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(us, uo, rtol=0, atol=1e-6)
+    xr, ur, res = bq.dense_qp_reference(*args, xlo, xhi, ulo, uhi)
+    assert res.success
+    np.testing.assert_allclose(us, ur, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(xs, xr, rtol=0, atol=2e-5)
+    assert np.all(np.abs(xs[1:, 4]) <= steer[1:] + 1e-6) and np.all(np.abs(us[:, 1]) <= rate + 1e-6)
+    assert np.sum(np.abs(xs[1:, 4]) > steer[1:] - 1e-4) >= 2      # active at more than one timestep
+    # relative bounds with indices_u_into_x=None bound free variables: no effect ...
+    rel_x = np.stack((-1e-3 * np.ones((T, 5)), 1e-3 * np.ones((T, 5))))
+    rel_u = np.stack((-1e-3 * np.ones((T, 2)), 1e-3 * np.ones((T, 2))))
+    x1, u1 = api.solve_tvlqr(*args, None, x_bound_rel=rel_x, u_bound_rel=rel_u)
+    x2, u2 = api.solve_tvlqr(*args, None)
+    assert np.array_equal(x1, x2) and np.array_equal(u1, u2)
+    # ... unless they are empty (infeasible program)
+    with pytest.raises(ValueError, match="TV_LQR failed"):
+        api.solve_tvlqr(*args, None, x_bound_rel=np.stack((1e-3 * np.ones((T, 5)), -1e-3 * np.ones((T, 5)))))
+    # x_0 is boxed as well (tv_lqr.py:113-114 at t = 0)
+    tight = np.stack((np.tile(cfg["x0"] + 0.5, (T + 1, 1)), np.tile(cfg["x0"] + 1e4, (T + 1, 1))))
+    with pytest.raises(ValueError, match="TV_LQR failed"):
+        api.solve_tvlqr(*args, None, x_bound_abs=tight)
+    with pytest.raises(NotImplementedError):
+        api.solve_tvlqr(*args, None, indices_u_into_x=np.array([0, 1]))
+
+
 def test_bicycle_descent_with_active_steer_bound_matches_oracle(api):
     """The bicycle example's +-pi/4 steer bound (bicycle_first_order.py:23-26) is active: local_descent
     must run the reference's loop (box QP at every timestep, first input on the true dynamics).

@@ -25,7 +25,7 @@ def test_header_symbols_exported_and_bound(built_lib):
         assert hasattr(built_lib, name), "library does not export %s" % name
         assert name in _lib.SIGNATURES, "no ctypes signature for %s" % name
     assert sorted(_lib.SIGNATURES) == names
-    assert built_lib.irs_abi_version() == 1
+    assert built_lib.irs_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_system_dims_and_partial_width(built_lib):
@@ -119,13 +119,20 @@ def test_box_penalties_and_bound_helpers(built_lib):
     dx2, du2 = tv_lqr.box_penalties(Q, R, rho0=10.0)
     np.testing.assert_allclose(dx2, 10.0 * dx)
     np.testing.assert_allclose(du2, 10.0 * du)
-    # constant-in-time boxes are accepted, time-varying ones are refused
-    lo, hi = tv_lqr._constant_box(np.stack((np.tile(-np.ones(3), (6, 1)), np.tile(np.ones(3), (6, 1)))), 6, "x")
+    # boxes indexed by timestep as in the reference (tv_lqr.py:113-116): a box that is constant over the
+    # horizon collapses to one row, a time-varying one keeps a row per timestep, [2, dim] broadcasts
+    lo, hi = tv_lqr._box_rows(np.stack((np.tile(-np.ones(3), (6, 1)), np.tile(np.ones(3), (6, 1)))), 6, 3, "x")
     assert np.array_equal(lo, -np.ones(3)) and np.array_equal(hi, np.ones(3))
     varying = np.stack((np.tile(-np.ones(3), (6, 1)), np.tile(np.ones(3), (6, 1))))
     varying[1, 3, 0] = 2.0
-    with pytest.raises(NotImplementedError):
-        tv_lqr._constant_box(varying, 6, "x")
+    lo, hi = tv_lqr._box_rows(varying, 6, 3, "x")
+    assert lo.shape == (6, 3) and hi.shape == (6, 3) and hi[3, 0] == 2.0 and hi[2, 0] == 1.0
+    lo, hi = tv_lqr._box_rows(varying, 3, 3, "x")          # the varying row lies beyond the horizon asked for
+    assert lo.shape == (3,)
+    lo, hi = tv_lqr._box_rows(np.stack((-np.ones(3), np.ones(3))), 4, 3, "x")
+    assert lo.shape == (3,)
+    with pytest.raises(ValueError):
+        tv_lqr._box_rows(varying, 7, 3, "x")               # fewer rows than the horizon
     assert tv_lqr._violates(np.array([1.1]), np.array([-1.0]), np.array([1.0]))
     assert not tv_lqr._violates(np.array([1.0 + 1e-12]), np.array([-1.0]), np.array([1.0]))
     with pytest.raises(NotImplementedError):
