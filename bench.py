@@ -214,9 +214,9 @@ def run_gpu(args, rank, local_rank, world):
         """Inputs resident in HBM; the seed changes every step so nothing can be cached."""
         if world == 1:
             smoothing.accumulate(system, smoothing.ZERO_ORDER, x_nom, u_nom, N_SAMPLES, ws, sigma=sigma,
-                                 seed=SEED0 + k, it=1)
+                                 seed=SEED0 + k, it=1, flags=sampler.flags())
             return smoothing.finalize(system, smoothing.ZERO_ORDER, x_nom, u_nom, ws, N_SAMPLES)
-        return sharded.linearize_n(x_nom, u_nom, N_SAMPLES, sigma=sigma, seed=SEED0 + k, it=1)
+        return sharded.linearize_n(x_nom, u_nom, N_SAMPLES, sigma=sigma, seed=SEED0 + k, it=1, flags=sampler.flags())
 
     def barrier():
         if world > 1:
@@ -247,7 +247,7 @@ def run_gpu(args, rank, local_rank, world):
     # 2. dominant kernel alone (accumulate), CUDA events on the launching stream
     def only_accumulate(k):
         smoothing.accumulate(system, smoothing.ZERO_ORDER, x_nom, u_nom, N_SAMPLES, ws, sigma=sigma,
-                             seed=SEED0 + 1000 + k, it=1)
+                             seed=SEED0 + 1000 + k, it=1, flags=sampler.flags())
     ms_kernel = timed(only_accumulate, args.steps, 1) / args.steps
     clocks.window(t_w0, time.time())
     # sustained repeat of the same step so that the 50 ms sampler sees the clocks under this load
@@ -299,7 +299,7 @@ def run_gpu(args, rank, local_rank, world):
         def step_e2e(k):
             # numpy in, numpy out through the sharded public call: one pinned H2D, one D2H per step
             return sharded.linearize_n_numpy(x_host[:T_STEPS], u_host, N_SAMPLES, sigma=sigma,
-                                             seed=SEED0 + 5000 + k, it=1)
+                                             seed=SEED0 + 5000 + k, it=1, flags=sampler.flags())
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 3))
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
     n, m = 12, 4
@@ -366,7 +366,7 @@ def run_gpu(args, rank, local_rank, world):
 
             def step2(k, sys2=sys2, order=order, xn2=xn2, un2=un2, ws2=ws2, c2=c2, Nn=Nn, proj=proj):
                 smoothing.accumulate(sys2, order, xn2, un2, Nn, ws2, sigma=c2["sigma"], seed=SEED0 + k, it=1,
-                                     flags=2 if proj else 0)
+                                     flags=(2 if proj else 0) | sampler.flags())
                 smoothing.finalize(sys2, order, xn2, un2, ws2, Nn)
             ms2 = timed(step2, max(5, min(args.steps, 20)), 3) / max(5, min(args.steps, 20))
             other[label] = {"ms_per_linearization": ms2, "samples_per_s": Tn * Nn / (ms2 * 1e-3)}
@@ -396,7 +396,8 @@ def run_gpu(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "quadrotor zero-order T=100 N=1e5/step/GPU (BASELINE.json configs[2])",
                        "system": "quadrotor n=12 m=4", "mode": "zero_order", "T": T_STEPS,
-                       "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-7 + Box-Muller in-kernel",
+                       "samples_per_step_per_gpu": N_SAMPLES, "noise": "Philox4x32-7 + Box-Muller in-kernel, antithetic pairs x +- z "
+                                                                     "(GaussianSampling default; one draw per pair)",
                        "sharding": "none" if world == 1 else (
                            "sample axis; fp64 Gram blocks exchanged inside the finalize kernel (peer-memory "
                            "stores over NVLink + per-point arrival flags), no NCCL on the data path" if sharded._px is not None else

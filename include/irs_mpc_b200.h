@@ -35,7 +35,13 @@ enum {
                                     only three_cart distinguishes (three_cart_dynamics.py:109-194) */
   IRS_PROJECT_ABSOLUTE = 2,      /* three_cart_zero_order.py:43: sampling returns projection(...) =
                                     absolute points (three_cart_dynamics.py:196-264), reproduced literally */
-  IRS_PROJECT_DELTA = 4          /* corrected variant: projected point minus nominal */
+  IRS_PROJECT_DELTA = 4,         /* corrected variant: projected point minus nominal */
+  IRS_ANTITHETIC = 8             /* in-kernel Philox noise in antithetic pairs: sample 2q is xbar + z_q, sample
+                                    2q+1 is xbar - z_q, one counter (and one Box-Muller draw) per pair.  The
+                                    reference draws independent normals (e.g. pendulum_zero_order.py:38-43);
+                                    each sample keeps the same marginal N(0, sigma^2), the even-order terms of
+                                    f cancel in Z^T dF, and the fused kernel needs one operand row per pair.
+                                    Ignored when deltas are replayed.  i0 must be even. */
 };
 
 int irs_abi_version(void);
@@ -130,9 +136,10 @@ int irs_exact_linearize(int system, const double* params_host, int nparams,
                         double* At, double* Bt, double* ct, void* stream);
 
 /* The Philox words / deltas exactly as the fused kernels draw them (bookkeeping tests).
- * words [P,N,ceil(d/4),4] u32 or NULL; deltas [P,N,d] f32 or NULL; sigma_host: HOST array [d]. */
+ * words [P,N,ceil(d/4),4] u32 or NULL; deltas [P,N,d] f32 or NULL; sigma_host: HOST array [d];
+ * antithetic != 0: the IRS_ANTITHETIC stream (samples 2q, 2q+1 share the words of counter q). */
 int irs_philox_dump(int P, long long N, int d, const float* sigma_host, unsigned long long seed,
-                    unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
+                    unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0, int antithetic,
                     unsigned* words, float* deltas, void* stream);
 
 /* DynamicalSystem.dynamics_batch (irs_lqr/dynamical_system.py:24-37). batch_variant != 0 selects

@@ -68,7 +68,7 @@ SIGNATURES = {
     "irs_smooth_finalize": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _ll,
                             ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
     "irs_exact_linearize": [_i, _c_double_p, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
-    "irs_philox_dump": [_i, _ll, _i, _vp, _ull, _u, _u, _u, _ull, _vp, _vp, _vp],
+    "irs_philox_dump": [_i, _ll, _i, _vp, _ull, _u, _u, _u, _ull, _i, _vp, _vp, _vp],
     "irs_dynamics_batch_f32": [_i, _c_double_p, _i, _i, _vp, _vp, _vp, _ll, _vp],
     "irs_dynamics_batch_f64": [_i, _c_double_p, _i, _i, _vp, _vp, _vp, _ll, _vp],
     "irs_jacobian_xu_batch_f32": [_i, _c_double_p, _i, _vp, _vp, _vp, _ll, _vp],

@@ -99,12 +99,12 @@ static int num_sms() {
     return n;
 }
 
-template <class Sys, bool REPLAY>
+template <class Sys, int MODE>
 static int launch_zero_order_tc_mode(const SmoothArgs& a, cudaStream_t st) {
     using C = TcCfg<Sys>;
     constexpr int NSTAGE = 1;      // measured: one tile per warp is fastest
     const size_t smem = (size_t)NSTAGE * C::kWarps * C::kStageBytes;
-    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE, REPLAY>;
+    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE, MODE>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -135,8 +135,11 @@ static int launch_zero_order_tc_mode(const SmoothArgs& a, cudaStream_t st) {
 
 template <class Sys>
 static int launch_zero_order_tc(const SmoothArgs& a, cudaStream_t st) {
-    // the noise source is a compile-time mode of the kernel (replayed deltas or the Philox stream)
-    return a.noise != nullptr ? launch_zero_order_tc_mode<Sys, true>(a, st) : launch_zero_order_tc_mode<Sys, false>(a, st);
+    // the noise source is a compile-time mode of the kernel: replayed deltas, the Philox stream with one
+    // draw per sample, or the Philox stream in antithetic pairs (one draw and one operand row per pair)
+    if (a.noise != nullptr) return launch_zero_order_tc_mode<Sys, kTcReplay>(a, st);
+    if (a.flags & kFlagAntithetic) return launch_zero_order_tc_mode<Sys, kTcPaired>(a, st);
+    return launch_zero_order_tc_mode<Sys, kTcPhilox>(a, st);
 }
 
 static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host, int nparams,
@@ -161,6 +164,9 @@ static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host
                 "projection flags are only defined for three_cart");
     IRS_REQUIRE(!((flags & IRS_PROJECT_ABSOLUTE) && (flags & IRS_PROJECT_DELTA)),
                 "IRS_PROJECT_ABSOLUTE and IRS_PROJECT_DELTA are exclusive");
+    IRS_REQUIRE(!((flags & IRS_ANTITHETIC) && noise == nullptr && (i0 & 1ull)),
+                "antithetic pairs: the global index of the first local sample (i0) must be even");
+    if (noise != nullptr) flags &= ~IRS_ANTITHETIC;      // replayed deltas are whatever the caller drew
     a->x_nom = x_nom;  a->u_nom = u_nom;  a->noise = noise;
     a->partials = partials;  a->N = N;  a->S = S;  a->P = P;  a->C = C;
     a->seed_lo = (uint32_t)(seed & 0xffffffffull);
@@ -591,14 +597,15 @@ int irs_exact_linearize(int system, const double* params_host, int nparams,
 }
 
 int irs_philox_dump(int P, long long N, int d, const float* sigma_host, unsigned long long seed,
-                    unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
+                    unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0, int antithetic,
                     unsigned* words, float* deltas, void* stream) {
     IRS_REQUIRE(P >= 1 && N >= 1 && d >= 1 && d <= kMaxRegressors, "bad dump arguments");
     IRS_REQUIRE(deltas == nullptr || sigma_host != nullptr, "deltas need sigma");
     PhiloxDumpArgs a;
     a.P = P;  a.d = d;  a.N = N;
     a.seed_lo = (uint32_t)(seed & 0xffffffffull);  a.seed_hi = (uint32_t)(seed >> 32);
-    a.iter = iter;  a.stream = stream_id;  a.p0 = p0;  a.i0 = i0;  a.words = words;  a.deltas = deltas;
+    a.iter = iter;  a.stream = stream_id;  a.p0 = p0;  a.i0 = i0;  a.antithetic = antithetic ? 1 : 0;
+    a.words = words;  a.deltas = deltas;
     for (int c = 0; c < kMaxRegressors; ++c)
         a.sigma_scaled[c] = (sigma_host != nullptr && c < d) ? kBoxMullerScale * sigma_host[c] : 0.f;
     const long long total = (long long)P * N * ((d + 3) / 4);

@@ -17,6 +17,7 @@ enum SmoothFlags {
     kFlagSamplesBatchVariant = 1,   // samples use dynamics_batch semantics (irs_lqr_zero_order.py:51)
     kFlagProjectAbsolute = 2,       // three_cart_zero_order.py:43 quirk: sampling returns absolute points
     kFlagProjectDelta = 4,          // corrected variant: projected point minus nominal
+    kFlagAntithetic = 8,            // Philox stream in antithetic pairs: sample 2q = +z_q, sample 2q+1 = -z_q
 };
 
 struct SmoothArgs {
@@ -46,6 +47,26 @@ __host__ __device__ constexpr int gram_row_offset(int i, int W) { return i * W -
 // ---------------------------------------------------------------------------------------------
 // One sample: regressors w[0..D) = (dx | du), responses w[D..D+N) = f(xbar+dx, ubar+du) - fbar.
 // ---------------------------------------------------------------------------------------------
+// w[c] = sigma[c] * normal_c of Philox counter (ctr0, point p, iteration, stream): ceil(d / 4) counter
+// blocks, Box-Muller on word pairs (spec: oracle/philox_ref.py).
+template <class Sys, int RS>
+__device__ __forceinline__ void philox_normals(const SmoothArgs& a, int p, unsigned long long ctr0, float (&w)[RS]) {
+    constexpr int d = Sys::D;
+    constexpr int nblk = (d + 3) / 4;
+#pragma unroll
+    for (int j = 0; j < nblk; ++j) {
+        uint32_t r[4];
+        philox4x32((uint32_t)ctr0, a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j, a.stream,
+                   a.seed_lo, a.seed_hi, r);
+        float e[4];
+        box_muller_raw(r[0], r[1], e[0], e[1]);
+        box_muller_raw(r[2], r[3], e[2], e[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * j + q < d) w[4 * j + q] = a.sigma_scaled[4 * j + q] * e[q];
+    }
+}
+
 // Deltas of sample i of nominal point p: replayed from a.noise or drawn from the Philox stream.
 // MODE: -1 = decided at run time, 0 = Philox, 1 = replay (a compile-time mode keeps the test and the
 // other path's code out of the hot loop).
@@ -65,19 +86,17 @@ __device__ __forceinline__ void draw_deltas(const SmoothArgs& a, int p, long lon
             for (int c = 0; c < d; ++c) w[c] = __ldg(src + c);
         }
     } else {
-        constexpr int nblk = (d + 3) / 4;
-        const unsigned long long gi = a.i0 + (unsigned long long)i;
+        unsigned long long gi = a.i0 + (unsigned long long)i;
+        if (a.flags & kFlagAntithetic) {
+            // antithetic pairs: samples 2q and 2q + 1 are +z_q and -z_q, one Philox draw per PAIR
+            const bool minus = (gi & 1ull) != 0;
+            philox_normals<Sys, RS>(a, p, gi >> 1, w);
+            if (minus) {
 #pragma unroll
-        for (int j = 0; j < nblk; ++j) {
-            uint32_t r[4];
-            philox4x32((uint32_t)gi, a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j, a.stream,
-                       a.seed_lo, a.seed_hi, r);
-            float e[4];
-            box_muller_raw(r[0], r[1], e[0], e[1]);
-            box_muller_raw(r[2], r[3], e[2], e[3]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * j + q < d) w[4 * j + q] = a.sigma_scaled[4 * j + q] * e[q];
+                for (int c = 0; c < d; ++c) w[c] = -w[c];
+            }
+        } else {
+            philox_normals<Sys, RS>(a, p, gi, w);
         }
     }
 }
@@ -1061,6 +1080,7 @@ struct PhiloxDumpArgs {
     long long N;
     uint32_t seed_lo, seed_hi, iter, stream, p0;
     unsigned long long i0;
+    int antithetic;          // samples 2q, 2q + 1 = +z_q, -z_q (one counter per pair)
     uint32_t* words;
     float* deltas;
     float sigma_scaled[16];
@@ -1075,8 +1095,13 @@ __global__ void philox_dump_kernel(const PhiloxDumpArgs a) {
         const long long i = (idx / nblk) % a.N;
         const int p = (int)(idx / nblk / a.N);
         uint32_t r[4];
-        philox4x32((uint32_t)(a.i0 + (unsigned long long)i), a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j,
-                   a.stream, a.seed_lo, a.seed_hi, r);
+        unsigned long long gi = a.i0 + (unsigned long long)i;
+        float sg = 1.f;
+        if (a.antithetic) {
+            sg = (gi & 1ull) ? -1.f : 1.f;
+            gi >>= 1;
+        }
+        philox4x32((uint32_t)gi, a.p0 + (uint32_t)p, (a.iter << 8) | (uint32_t)j, a.stream, a.seed_lo, a.seed_hi, r);
         if (a.words != nullptr)
             for (int q = 0; q < 4; ++q) a.words[idx * 4 + q] = r[q];
         if (a.deltas != nullptr) {
@@ -1085,7 +1110,7 @@ __global__ void philox_dump_kernel(const PhiloxDumpArgs a) {
             box_muller_raw(r[2], r[3], e[2], e[3]);
             for (int q = 0; q < 4; ++q)
                 if (4 * j + q < a.d)
-                    a.deltas[((long long)p * a.N + i) * a.d + 4 * j + q] = a.sigma_scaled[4 * j + q] * e[q];
+                    a.deltas[((long long)p * a.N + i) * a.d + 4 * j + q] = sg * (a.sigma_scaled[4 * j + q] * e[q]);
         }
     }
 }

@@ -143,7 +143,24 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& p1, u
 // block barrier.  (tcgen05.mma from different threads are not ordered against each other, hence one
 // accumulator per issuing warp.)  At the end of an item the block meets once: every warp reads its
 // TMEM lane quarter of all four accumulators, adds them and the packed Gram block is written.
-template <class Sys, int NSTAGE, bool REPLAY>
+//
+// MODE selects the noise source at compile time (the other paths stay out of the hot loop):
+//   kTcPhilox   one Philox draw per sample (independent samples), lane = sample;
+//   kTcReplay   deltas read from a.noise ([P, N, d] fp32, coalesced LDG.128), lane = sample;
+//   kTcPaired   antithetic pairs (kFlagAntithetic): samples 2q and 2q + 1 are x +- z_q, lane = PAIR.
+//               One Philox + Box-Muller draw serves two dynamics evaluations, and because the
+//               regressors of a pair are exact negatives of each other its Gram contribution
+//               collapses to ONE operand row:
+//                   z z^T + (-z)(-z)^T = 2 z z^T,     z dF+^T + (-z) dF-^T = z (f(x+z) - f(x-z))^T
+//               so a pair stages the row [z | f+ - f-] once (the nominal response cancels), the
+//               tensor core does half the work per sample, and the regressor block is doubled when
+//               the accumulator is read back (exact).  A chunk of odd length ends in a lone + member,
+//               staged as [z / sqrt 2 | sqrt 2 (f+ - fbar)].  With an in-kernel projection
+//               (three_cart) the projected regressors of a pair are no longer negatives: the pair
+//               then shares only the noise draw and stages two rows.
+enum TcMode { kTcPhilox = 0, kTcReplay = 1, kTcPaired = 2 };
+
+template <class Sys, int NSTAGE, int MODE>
 __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_kernel(const SmoothArgs a) {
     using C = TcCfg<Sys>;
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
@@ -293,7 +310,6 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         const int c = (int)(item % a.C);
         const long long s_begin = (long long)c * a.S;
         const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
-        const int rounds = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
         const int slot = kNomBatch == 1 ? 0 : it % kNomBatch;
         if constexpr (kNomBatch == 1) {
             load_nominal(item);
@@ -306,46 +322,37 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         }
         const float4* nom4 = reinterpret_cast<const float4*>(nom_tab[slot]);
         const double* pos64_s = pos64_tab[slot];
-        // One round = one 32-sample tile per warp.  CHECK = false is the hot path (every lane owns a
-        // sample); only the last round of a chunk whose length is not a multiple of 128 takes the
-        // CHECK = true path, where the padded lanes stage zeros and contribute nothing.
-        auto do_round = [&](auto check_tag, int r) {
-            constexpr bool CHECK = decltype(check_tag)::value;
-            const int stage = round % NSTAGE;
-            const long long s = s_begin + (long long)r * C::kTile + tid;
-            float w[C::RS];
-            if (!CHECK || s < s_end) {
-                if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
-                draw_deltas<Sys, C::RS, REPLAY ? 1 : 0>(a, p, s, w);
-                // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers:
-                // measured faster than the register copy)
-                float xu[kXU], f[n];
+        // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers: measured
+        // faster than the register copy)
+        auto load_xu = [&](float (&xu)[kXU]) {
 #pragma unroll
-                for (int q = 0; q < kXU / 4; ++q) {
-                    const float4 v = nom4[q];
-                    xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
-                }
-                project_deltas<Sys, C::RS>(a, p, xu, xu + n, pos64_s, w);
-#pragma unroll
-                for (int q = 0; q < d; ++q) xu[q] += w[q];
-                if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar
-                    if (batch) sys.template step<true>(xu, xu + n, f);
-                    else sys.template step<false>(xu, xu + n, f);
-                } else {
-                    sys.template step<false>(xu, xu + n, f);
-                }
-#pragma unroll
-                for (int q = 0; q < (n + 3) / 4; ++q) {
-                    const float4 v = nom4[kXU / 4 + q];
-                    const float fb[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (4 * q + k < n) w[d + 4 * q + k] = f[4 * q + k] - fb[k];
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
+            for (int q = 0; q < kXU / 4; ++q) {
+                const float4 v = nom4[q];
+                xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
             }
+        };
+        auto dynamics = [&](const float (&xu)[kXU], float (&f)[n]) {
+            if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar
+                if (batch) sys.template step<true>(xu, xu + n, f);
+                else sys.template step<false>(xu, xu + n, f);
+            } else {
+                sys.template step<false>(xu, xu + n, f);
+            }
+        };
+        // w[d ..] = f - fbar
+        auto minus_nominal_response = [&](const float (&f)[n], float (&w)[C::RS], float scale) {
+#pragma unroll
+            for (int q = 0; q < (n + 3) / 4; ++q) {
+                const float4 v = nom4[kXU / 4 + q];
+                const float fb[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * q + k < n) w[d + 4 * q + k] = scale * (f[4 * q + k] - fb[k]);
+            }
+        };
+        // One operand row per lane -> this warp's tile (bf16x2 split, MN-major), then the tile's UMMAs.
+        auto stage_and_issue = [&](const float (&w)[C::RS], bool first, bool last) {
+            const int stage = round % NSTAGE;
             // the tile must have been drained by the UMMAs that last read it
             if (round >= NSTAGE) mbar_wait(&mbar_empty[warp][stage], (uint32_t)((round / NSTAGE - 1) & 1));
             unsigned char* sm = my_ring + stage * C::kStageBytes + my_off;
@@ -376,10 +383,104 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                 *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
                 *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
             }
-            issue_tile(stage, r == 0, r == rounds - 1);
+            issue_tile(stage, first, last);
             ++round;
         };
-        const int full_rounds = (int)((s_end - s_begin) / C::kTile);
+        auto zero_row = [&](float (&w)[C::RS]) {
+#pragma unroll
+            for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
+        };
+        const long long len = s_end - s_begin;                // samples of this chunk
+        // pairs share a noise draw only (two operand rows per pair) when the regressors are projected
+        [[maybe_unused]] const bool pair_rows =
+            Sys::kHasProjection && (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) != 0;
+        const long long units = MODE == kTcPaired ? (len + 1) / 2 : len;      // lanes of work: pairs or samples
+        const int rounds = (int)((units + C::kTile - 1) / C::kTile);
+        // One round = one lane-unit per thread (a sample, or an antithetic pair).  CHECK = false is the
+        // hot path (every lane owns a full unit); only the last round of a chunk whose length is not a
+        // multiple of the tile takes the CHECK = true path, where missing samples stage zeros.
+        auto do_round = [&](auto check_tag, int r) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+            const long long lu = (long long)r * C::kTile + tid;       // this lane's unit inside the chunk
+            float w[C::RS];
+            if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
+            if constexpr (MODE != kTcPaired) {
+                if (!CHECK || lu < len) {
+                    draw_deltas<Sys, C::RS, MODE == kTcReplay ? 1 : 0>(a, p, s_begin + lu, w);
+                    float xu[kXU], f[n];
+                    load_xu(xu);
+                    project_deltas<Sys, C::RS>(a, p, xu, xu + n, pos64_s, w);
+#pragma unroll
+                    for (int q = 0; q < d; ++q) xu[q] += w[q];
+                    dynamics(xu, f);
+                    minus_nominal_response(f, w, 1.f);
+                } else {
+                    zero_row(w);
+                }
+                stage_and_issue(w, r == 0, r == rounds - 1);
+            } else {
+                const bool have_plus = !CHECK || 2 * lu < len;
+                const bool have_minus = !CHECK || 2 * lu + 1 < len;
+                // the pair's draw: counter word 0 = global pair index (a.i0 and s_begin are even)
+                const unsigned long long pair = ((a.i0 + (unsigned long long)s_begin) >> 1) + (unsigned long long)lu;
+                bool two_rows = false;
+                if constexpr (Sys::kHasProjection) two_rows = pair_rows;
+                if (!two_rows) {
+                    if (have_plus) {
+                        philox_normals<Sys, C::RS>(a, p, pair, w);
+                        float xu[kXU], fp[n];
+                        load_xu(xu);
+#pragma unroll
+                        for (int q = 0; q < d; ++q) xu[q] += w[q];
+                        dynamics(xu, fp);
+                        if (have_minus) {
+                            float fm[n];
+                            load_xu(xu);
+#pragma unroll
+                            for (int q = 0; q < d; ++q) xu[q] -= w[q];
+                            dynamics(xu, fm);
+#pragma unroll
+                            for (int q = 0; q < n; ++q) w[d + q] = fp[q] - fm[q];
+                        } else {
+                            // lone + member at the end of an odd chunk: [z / sqrt 2 | sqrt 2 (f+ - fbar)]
+                            minus_nominal_response(fp, w, 1.41421356237309505f);
+#pragma unroll
+                            for (int q = 0; q < d; ++q) w[q] *= 0.70710678118654752f;
+                        }
+                    } else {
+                        zero_row(w);
+                    }
+                    stage_and_issue(w, r == 0, r == rounds - 1);
+                } else {
+                    if constexpr (Sys::kHasProjection) {
+                        float z[d];
+                        if (have_plus) {
+                            philox_normals<Sys, C::RS>(a, p, pair, w);
+#pragma unroll
+                            for (int q = 0; q < d; ++q) z[q] = w[q];
+                        }
+#pragma unroll 1
+                        for (int half = 0; half < 2; ++half) {
+                            if (half == 0 ? have_plus : have_minus) {
+#pragma unroll
+                                for (int q = 0; q < d; ++q) w[q] = half == 0 ? z[q] : -z[q];
+                                float xu[kXU], f[n];
+                                load_xu(xu);
+                                project_deltas<Sys, C::RS>(a, p, xu, xu + n, pos64_s, w);
+#pragma unroll
+                                for (int q = 0; q < d; ++q) xu[q] += w[q];
+                                dynamics(xu, f);
+                                minus_nominal_response(f, w, 1.f);
+                            } else {
+                                zero_row(w);
+                            }
+                            stage_and_issue(w, r == 0 && half == 0, r == rounds - 1 && half == 1);
+                        }
+                    }
+                }
+            }
+        };
+        const int full_rounds = (int)((MODE == kTcPaired ? len / 2 : len) / C::kTile);
         for (int r = 0; r < full_rounds; ++r) do_round(std::false_type{}, r);
         if (full_rounds < rounds) do_round(std::true_type{}, full_rounds);
         // ---- item finished: wait for this warp's UMMAs, meet the other warps, read all four
@@ -428,10 +529,13 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         asm volatile("tcgen05.fence::after_thread_sync;");
         // G[i][j] = sum_k z_i w_j = sum over the two pieces of w_j of s_row[i] (second-piece rows negated)
         float* out = a.partials + item * C::NACC;
+        // paired rows: the regressor block of a pair is 2 z z^T (exact doubling)
+        const float zz_scale = (MODE == kTcPaired && !pair_rows) ? 2.f : 1.f;
         for (int e = tid; e < C::NACC; e += C::kThreads) {
             const int ij = idx_s[e];
             const int i = ij >> 8, j = ij & 0xff;
-            out[e] = scratch[C::row_1(j) * kScr + i] - scratch[C::row_2(j) * kScr + i];
+            const float v = scratch[C::row_1(j) * kScr + i] - scratch[C::row_2(j) * kScr + i];
+            out[e] = j < d ? zz_scale * v : v;
         }
         // (the next item's barriers order these scratch reads before its scratch writes)
     }

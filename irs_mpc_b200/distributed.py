@@ -211,6 +211,8 @@ class ShardedLinearizer:
         synchronisation: a failed exchange shows up as status 2 (smoothing.check_status raises)."""
         T = x_nom.shape[0]
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if kw.get("flags", 0) & 8 and kw.get("noise") is None and N_local % 2 and world > 1:
+            raise ValueError("antithetic pairs must not straddle ranks: N_local must be even (got %d)" % N_local)
         ws = self._workspace(T, N_local)
         smoothing.accumulate(self.system, self.order, x_nom, u_nom, N_local, ws,
                              i0=rank * N_local, **kw)

@@ -25,9 +25,13 @@ PROJECTION_MODES = (None, "absolute", "delta")
 
 class GaussianSampling:
     def __init__(self, sigma_x, sigma_u, num_samples, power=0.5, seed=0x1255, projection=None,
-                 stream_id=0):
+                 stream_id=0, antithetic=True):
         """projection: None | "absolute" (reference quirk, three_cart_zero_order.py:43 returns
-        projection(...) = absolute points) | "delta" (corrected: projected point minus nominal)."""
+        projection(...) = absolute points) | "delta" (corrected: projected point minus nominal).
+        antithetic: draw the samples in pairs x +- z (sample 2q = +z_q, 2q+1 = -z_q).  Every sample
+        keeps the marginal N(0, sigma^2) of the reference's closure; the even-order terms of the dynamics
+        cancel exactly in the fit, and the fused kernel draws one Philox / Box-Muller block and stages
+        one Gram row per pair.  False: independent samples as in the reference's `np.random.normal`."""
         if projection not in PROJECTION_MODES:
             raise ValueError("projection must be one of %s" % (PROJECTION_MODES,))
         self.sigma0 = np.concatenate((np.atleast_1d(np.asarray(sigma_x, dtype=np.float64)),
@@ -39,6 +43,7 @@ class GaussianSampling:
         self.seed = int(seed)
         self.projection = projection
         self.stream_id = int(stream_id)
+        self.antithetic = bool(antithetic)
         self._t = 0   # timestep counter used when called through the reference closure signature
 
     def sigma(self, it):
@@ -55,7 +60,7 @@ class GaussianSampling:
         return c[1], c[2]
 
     def flags(self):
-        return {None: 0, "absolute": 2, "delta": 4}[self.projection]
+        return {None: 0, "absolute": 2, "delta": 4}[self.projection] | (8 if self.antithetic else 0)
 
     def deltas(self, T, it, t0=0, i0=0, num_samples=None, return_words=False):
         """Deltas [T, N, d] (numpy float32) exactly as the fused kernels draw them."""
@@ -65,7 +70,8 @@ class GaussianSampling:
         out = _device.empty((T, N, d), torch.float32)
         words = _device.empty((T, N, (d + 3) // 4, 4), torch.int32) if return_words else None
         _lib.call("irs_philox_dump", T, N, d, sig.ctypes.data_as(ctypes.c_void_p), self.seed, int(it), self.stream_id,
-                  int(t0), int(i0), _device.ptr(words), _device.ptr(out), _device.stream_ptr())
+                  int(t0), int(i0), 1 if self.antithetic else 0, _device.ptr(words), _device.ptr(out),
+                  _device.stream_ptr())
         z = _device.to_numpy(out)
         if return_words:
             return z, _device.to_numpy(words).view(np.uint32)

@@ -15,6 +15,10 @@ bookkeeping is checked bit-for-bit against this file:
       theta = 2 pi (f(wb) - 1.5)                                      in [-pi, pi)
       e_a, e_b = r cos(theta), r sin(theta)
   delta z[i, c] = sigma[c] * e[c]   for c < d  (dx in the first n columns, du in the last m)
+
+Antithetic stream (GaussianSampling(antithetic=True), kernel flag IRS_ANTITHETIC): samples come in
+pairs that share one counter — sample index i uses counter word 0 = i >> 1 and
+  delta z[i, c] = (+1 if i even else -1) * sigma[c] * e[c].
 """
 import numpy as np
 
@@ -42,10 +46,12 @@ def philox4x32(counter, key, rounds=10):
     return np.stack(c, axis=-1).astype(np.uint32)
 
 
-def words_for(T, N, d, seed, it, instance=0, t0=0, i0=0):
+def words_for(T, N, d, seed, it, instance=0, t0=0, i0=0, antithetic=False):
     """uint32 words [T, N, ceil(d/4), 4] exactly as the kernel draws them."""
     nblk = (d + 3) // 4
     i = (np.arange(N, dtype=np.uint64) + np.uint64(i0))[None, :, None]
+    if antithetic:
+        i = i >> np.uint64(1)
     t = (np.arange(T, dtype=np.uint64) + np.uint64(t0))[:, None, None]
     j = np.arange(nblk, dtype=np.uint64)[None, None, :]
     ctr = np.zeros((T, N, nblk, 4), dtype=np.uint32)
@@ -71,15 +77,18 @@ def box_muller(wa, wb):
     return r * np.cos(th), r * np.sin(th)
 
 
-def standard_normals(T, N, d, seed, it, instance=0, t0=0, i0=0):
+def standard_normals(T, N, d, seed, it, instance=0, t0=0, i0=0, antithetic=False):
     """float64 normals [T, N, d] (the kernel computes the same values in float32)."""
-    w = words_for(T, N, d, seed, it, instance, t0, i0)
+    w = words_for(T, N, d, seed, it, instance, t0, i0, antithetic)
     e0, e1 = box_muller(w[..., 0], w[..., 1])
     e2, e3 = box_muller(w[..., 2], w[..., 3])
     e = np.stack((e0, e1, e2, e3), axis=-1).reshape(T, N, -1)
+    if antithetic:
+        sign = np.where((np.arange(N, dtype=np.uint64) + np.uint64(i0)) & np.uint64(1), -1.0, 1.0)
+        e = e * sign[None, :, None]
     return e[..., :d]
 
 
-def deltas(T, N, sigma, seed, it, instance=0, t0=0, i0=0):
+def deltas(T, N, sigma, seed, it, instance=0, t0=0, i0=0, antithetic=False):
     sigma = np.asarray(sigma, dtype=np.float32).astype(np.float64)
-    return standard_normals(T, N, sigma.shape[0], seed, it, instance, t0, i0) * sigma
+    return standard_normals(T, N, sigma.shape[0], seed, it, instance, t0, i0, antithetic) * sigma

@@ -144,16 +144,25 @@ def test_three_cart_has_no_jacobian(api):
 # ------------------------------------------------------------------------------------------------
 # Philox bookkeeping
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("antithetic", [False, True])
 @pytest.mark.parametrize("d", [3, 7, 8, 16])
-def test_philox_words_bit_exact_and_normals(api, d):
+def test_philox_words_bit_exact_and_normals(api, d, antithetic):
     sig = np.linspace(0.5, 2.0, d)
-    s = api.GaussianSampling(sig[:d - 1], sig[d - 1:], 777, power=0.5, seed=0x1234ABCD5678, stream_id=5)
+    s = api.GaussianSampling(sig[:d - 1], sig[d - 1:], 777, power=0.5, seed=0x1234ABCD5678, stream_id=5,
+                             antithetic=antithetic)
     T, it, t0, i0 = 3, 4, 11, 1000
     z, words = s.deltas(T, it, t0=t0, i0=i0, return_words=True)
-    ref_words = philox_ref.words_for(T, 777, d, s.seed, it, instance=5, t0=t0, i0=i0)
+    ref_words = philox_ref.words_for(T, 777, d, s.seed, it, instance=5, t0=t0, i0=i0, antithetic=antithetic)
     np.testing.assert_array_equal(words, ref_words)
-    ref_z = philox_ref.deltas(T, 777, s.sigma(it), s.seed, it, instance=5, t0=t0, i0=i0)
+    ref_z = philox_ref.deltas(T, 777, s.sigma(it), s.seed, it, instance=5, t0=t0, i0=i0, antithetic=antithetic)
     np.testing.assert_allclose(z, ref_z, rtol=0, atol=2e-5 * float(np.max(s.sigma(it))))
+    if antithetic:
+        # index bookkeeping of the pairs is exact: sample 2q+1 is the bitwise negation of sample 2q
+        # (i0 even), and an odd i0 starts on a - member
+        np.testing.assert_array_equal(z[:, 1:777:2], -z[:, 0:776:2])
+        np.testing.assert_array_equal(words[:, 1:777:2], words[:, 0:776:2])
+        z_odd = s.deltas(T, it, t0=t0, i0=i0 + 1)
+        np.testing.assert_array_equal(z_odd[:, :776], z[:, 1:])
     # the closure form walks timesteps in call order
     s.reset_timestep()
     dx0, du0 = s(None, None, it)
@@ -780,24 +789,28 @@ def test_cem_matches_numpy_restatement(api, name, T, B):
 # ------------------------------------------------------------------------------------------------
 # ragged / edge sample counts through both Gram engines
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("antithetic", [False, True])
 @pytest.mark.parametrize("engine", [0, 1])
 @pytest.mark.parametrize("name,N", [("quadrotor", 17), ("quadrotor", 127), ("quadrotor", 128), ("quadrotor", 129),
-                                    ("quadrotor", 4097), ("pendulum", 4), ("pendulum", 33), ("bicycle", 300),
-                                    ("three_cart", 257)])
-def test_ragged_sample_counts_match_oracle(api, name, N, engine):
-    """Sample counts that do not fill a 32-sample warp tile, a 128-sample block round or a 4096-sample
-    chunk: the padded lanes must contribute nothing (fit vs the fp64 oracle on the same deltas)."""
+                                    ("quadrotor", 255), ("quadrotor", 256), ("quadrotor", 257),
+                                    ("quadrotor", 4097), ("quadrotor", 8191), ("pendulum", 4), ("pendulum", 33),
+                                    ("bicycle", 300), ("three_cart", 257)])
+def test_ragged_sample_counts_match_oracle(api, name, N, engine, antithetic):
+    """Sample counts that do not fill a 32-sample warp tile, a 128-sample block round (256 samples when a
+    lane owns an antithetic pair) or a 4096-sample chunk: the padded lanes must contribute nothing, and
+    an odd count ends in a lone + member (fit vs the fp64 oracle on the same deltas)."""
     from irs_mpc_b200 import _device, _lib, smoothing
     T = 3
     cfg, s, u_trj = _nominal(api, name, T)
     n = s.dim_x
     x_trj = cr.rollout(cr.SYSTEMS[name](s.h), cfg["x0"], u_trj)
-    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=5)
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=5,
+                                   antithetic=antithetic)
     _lib.call("irs_set_gram_engine", engine)
     try:
         At, Bt, ct, status, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, _device.to_device(x_trj[:T]),
                                                     _device.to_device(u_trj), N, sigma=sampler.sigma(1),
-                                                    seed=sampler.seed, it=1)
+                                                    seed=sampler.seed, it=1, flags=sampler.flags())
         assert int(status.sum().item()) == 0
         At, Bt, ct = _device.to_numpy(At), _device.to_numpy(Bt), _device.to_numpy(ct)
     finally:
@@ -809,6 +822,44 @@ def test_ragged_sample_counts_match_oracle(api, name, N, engine):
     assert rel_err(At, Ao) < tol
     assert rel_err(Bt, Bo) < tol
     assert float(np.max(np.abs(ct - co))) < tol * max(1.0, float(np.max(np.abs(x_trj))))
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("name,projection,N", [("quadrotor", None, 9001), ("quadrotor", None, 12288),
+                                               ("three_cart", None, 5001), ("three_cart", "absolute", 5001),
+                                               ("three_cart", "delta", 8192), ("pendulum", None, 777),
+                                               ("bicycle", None, 1001)])
+def test_antithetic_pairs_equal_the_replay_of_their_own_deltas(api, name, projection, N, engine):
+    """The paired kernel (one Philox draw and — without projection — ONE operand row per pair, regressor
+    block doubled at read-back, lone + member scaled by sqrt 2) against the ordinary one-row-per-sample
+    kernel fed, through the replay path, with the deltas of the same antithetic stream: both are fp32
+    accumulations of the same sums, so they agree far inside the 1e-4 budget; the index bookkeeping of
+    the pairs (which counter, which sign, which samples exist) would show up as O(1) differences."""
+    import torch
+    from irs_mpc_b200 import _device, _lib, smoothing
+    T = 3
+    cfg, s, u_trj = _nominal(api, name, T)
+    n = s.dim_x
+    x_trj = cr.rollout(cr.SYSTEMS[name](s.h), cfg["x0"], u_trj)
+    x_nom, u_nom = _device.to_device(x_trj[:T]), _device.to_device(u_trj)
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=31,
+                                   projection=projection, antithetic=True)
+    noise = _device.to_device(sampler.deltas(T, 2), torch.float32)
+    proj_flags = sampler.flags() & 6
+    _lib.call("irs_set_gram_engine", engine)
+    try:
+        Ap, Bp, cp, st, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, x_nom, u_nom, N, sigma=sampler.sigma(2),
+                                                seed=sampler.seed, it=2, flags=sampler.flags())
+        assert int(st.sum().item()) == 0
+        Ap, Bp, cp = _device.to_numpy(Ap), _device.to_numpy(Bp), _device.to_numpy(cp)
+        Ar, Br, cr_, st, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, x_nom, u_nom, N, noise=noise,
+                                                 flags=proj_flags)
+        assert int(st.sum().item()) == 0
+        Ar, Br, cr_ = _device.to_numpy(Ar), _device.to_numpy(Br), _device.to_numpy(cr_)
+    finally:
+        _lib.call("irs_set_gram_engine", -1)
+    assert rel_err(Ap, Ar) < 2e-5 and rel_err(Bp, Br) < 2e-5
+    assert float(np.max(np.abs(cp - cr_))) < 2e-5 * max(1.0, float(np.max(np.abs(x_trj))))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -67,7 +67,8 @@ def test_get_solver_and_sampling_schedule(built_lib):
         get_solver("nope")
     s = GaussianSampling([2.0, 4.0], [1.0], 100, power=0.5)
     np.testing.assert_allclose(s.sigma(4), [1.0, 2.0, 0.5])
-    assert s.flags() == 0
+    assert s.flags() == 8 and s.antithetic                     # antithetic pairs are the default stream
+    assert GaussianSampling([2.0, 4.0], [1.0], 100, antithetic=False).flags() == 0
     # the float32 array handed to the kernels is cached per iteration and follows the schedule
     a4, p4 = s.sigma32(4)
     assert a4.dtype == np.float32 and a4.flags["C_CONTIGUOUS"] and s.sigma32(4)[0] is a4
@@ -75,7 +76,8 @@ def test_get_solver_and_sampling_schedule(built_lib):
     a9, _ = s.sigma32(9)
     assert a9 is not a4
     np.testing.assert_allclose(a9, np.array([2.0, 4.0, 1.0]) / 3.0, rtol=1e-6)
-    assert GaussianSampling([1.0], [1.0], 1, projection="absolute").flags() == 2
+    assert GaussianSampling([1.0], [1.0], 1, projection="absolute").flags() == 2 | 8
+    assert GaussianSampling([1.0], [1.0], 1, projection="delta", antithetic=False).flags() == 4
     with pytest.raises(ValueError):
         GaussianSampling([1.0], [1.0], 1, projection="bogus")
 

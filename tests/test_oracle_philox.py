@@ -28,3 +28,18 @@ def test_stream_statistics():
     # global indexing: an offset range equals the tail of the full range
     full = philox_ref.words_for(2, 10, 7, 9, 3)
     np.testing.assert_array_equal(full[1:, 4:], philox_ref.words_for(1, 6, 7, 9, 3, t0=1, i0=4))
+
+
+def test_antithetic_stream_bookkeeping():
+    """Antithetic stream: samples 2q and 2q + 1 share counter q and differ by the sign; any window [i0, i0+N)
+    of the stream is the same numbers (sharding over ranks by i0)."""
+    w = philox_ref.words_for(2, 11, 7, 9, 3, antithetic=True)
+    np.testing.assert_array_equal(w[:, 0:10:2], w[:, 1:11:2])
+    np.testing.assert_array_equal(w[:, 0:10:2], philox_ref.words_for(2, 5, 7, 9, 3))
+    z = philox_ref.deltas(2, 11, np.ones(7), 9, 3, antithetic=True)
+    np.testing.assert_array_equal(z[:, 0:10:2], -z[:, 1:11:2])
+    np.testing.assert_array_equal(z[:, 0:10:2], philox_ref.deltas(2, 5, np.ones(7), 9, 3))
+    np.testing.assert_array_equal(z[:, 3:], philox_ref.deltas(2, 8, np.ones(7), 9, 3, i0=3, antithetic=True))
+    e = philox_ref.standard_normals(1, 200000, 8, 0x1255, 1, antithetic=True)[0]
+    assert abs(e.mean()) < 1e-12                        # exactly symmetric
+    assert abs(e.std() - 1.0) < 5e-3

@@ -27,7 +27,8 @@ def run(name, order=0, reps=10):
     x_nom = _device.to_device(x)
     u_nom = _device.to_device(cfg["u_trj_initial"])
     ws = smoothing.Workspace(system, order, T, N)
-    flags = 2 if cfg["projection"] else 0
+    # QB_FLAGS: extra smoothing flags (8 = antithetic pairs, the GaussianSampling default)
+    flags = (2 if cfg["projection"] else 0) | int(os.environ.get("QB_FLAGS", "8"))
     times = []
     inner = 10          # launches per timed batch: host launch latency overlaps with the previous kernel
     for k in range(reps + 2):
