@@ -101,13 +101,13 @@ def test_reference_script_body_runs_unchanged(script_env, costs, key, system, it
 
 
 def test_exact_script_reproduces_stored_curve_and_result_files_load(script_env, costs, tmp_path):
-    """pendulum_exact.py end to end (10 iterations) against examples/pendulum/analysis/pendulum_exact.csv,
+    """pendulum_exact.py end to end (7 iterations, the length of the stored curve) against examples/pendulum/analysis/pendulum_exact.csv,
     then the result-file round trip: the reference scripts write `cost_lst` with np.savetxt(...,
     delimiter=",") (quadrotor_cem.py:60, bicycle_cem_easy.py:49) or np.save (pendulum_cem.py:54) and
     examples/plot_iterations.py:14-17,33-42 reads them back with np.load / np.loadtxt(delimiter=",")."""
-    ns = run_script("pendulum_exact", 10)
-    solver = ns["solver"]
     gold = np.array(costs["stored_cost_curves"]["pendulum_exact"]["values"])
+    ns = run_script("pendulum_exact", len(gold) - 2)      # the stored curve has k + 2 = 9 entries (k = 7)
+    solver = ns["solver"]
     assert len(solver.cost_lst) == len(gold)
     np.testing.assert_allclose(np.array(solver.cost_lst), gold, rtol=1e-10)
     csv = str(tmp_path / "pendulum_exact.csv")

@@ -81,7 +81,13 @@ def oracle_descent(orc, cfg, At, Bt, ct, x0):
     return x_o, u_o, cr.evaluate_cost(x_o, u_o, cfg["xd_trj"], cfg["Q"], cfg["R"])
 
 
-def check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o, u_factor=5.0):
+def check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o, u_factor=5.0, descent="oracle_fit", bounded=False):
+    """(A, B, c) of the CUDA path against the oracle's, then one teacher-forced `local_descent`.
+    descent = "oracle_fit": against Riccati + closed loop of the ORACLE's (A, B, c) — the end-to-end
+    statement of the north star; "device_fit": against Riccati + closed loop (oracle, float64) of the
+    DEVICE's (A, B, c) — for problems whose closed loop amplifies the 1e-5 fit difference by orders of
+    magnitude (see the callers), which isolates the solve + rollout.
+    bounded: the box bounds are active, the oracle runs the reference's loop with a box QP per timestep."""
     At, Bt, ct = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
     assert At.shape == At_o.shape and Bt.shape == Bt_o.shape and ct.shape == ct_o.shape
     assert rel_err(At, At_o) < RTOL, ("A", rel_err(At, At_o))
@@ -90,7 +96,16 @@ def check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o, u_factor=5.0):
     assert float(np.max(np.abs(ct - ct_o))) < RTOL * scale, ("c", float(np.max(np.abs(ct - ct_o))))
     x_new, u_new = solver.local_descent(solver.x_trj, solver.u_trj)
     cost = solver.evaluate_cost(x_new, u_new)
-    x_o, u_o, cost_o = oracle_descent(orc, cfg, At_o, Bt_o, ct_o, solver.x_trj[0])
+    fit = (At_o, Bt_o, ct_o) if descent == "oracle_fit" else (At, Bt, ct)
+    if bounded:
+        from oracle import box_tvlqr as bq
+        gains0 = cr.tvlqr_riccati(*fit, cfg["Q"], cfg["Qd"], cfg["R"], cfg["xd_trj"])
+        x_o, u_o, _ = bq.mpc_box_descent(orc, *fit, cfg["Q"], cfg["Qd"], cfg["R"], solver.x_trj[0], cfg["xd_trj"],
+                                         cfg["xbound"][0], cfg["xbound"][1], cfg["ubound"][0], cfg["ubound"][1],
+                                         gains0=gains0)
+        cost_o = cr.evaluate_cost(x_o, u_o, cfg["xd_trj"], cfg["Q"], cfg["R"])
+    else:
+        x_o, u_o, cost_o = oracle_descent(orc, cfg, *fit, solver.x_trj[0])
     assert rel_err(x_new, x_o) < RTOL, ("x", rel_err(x_new, x_o))
     assert rel_err(u_new, u_o) < u_factor * RTOL, ("u", rel_err(u_new, u_o))
     assert abs(cost - cost_o) / abs(cost_o) < RTOL, ("cost", cost, cost_o)
@@ -106,16 +121,17 @@ def test_cfg1_pendulum_zero_order_T200_N1e3(api):
 
 
 def test_cfg2_bicycle_first_order_T100_N1e4(api):
-    """The descent is compared with the steer bound widened: with the example's +-pi/4 bound the
-    reference's QPs have active constraints, a comparison the box-QP tests cover separately
-    (test_gpu_parity.py::test_bicycle_descent_with_active_steer_bound_matches_oracle)."""
+    """The example's +-pi/4 steer bound is ACTIVE on this descent (without it the smoothed model steers to
+    |delta| = 254 rad and the rollout is chaotic), so `local_descent` runs the reference's loop — a box QP
+    over the remaining horizon at every timestep (irs_lqr.py:169-184) — and the oracle does the same in
+    numpy (oracle/box_tvlqr.py, ~10 s)."""
     cfg = ec.bicycle(T=100)
     deltas = replayed_noise(2, 100, 10000, cfg["sigma"])
-    system, solver = make_solver(api, "bicycle", "IrsLqrFirstOrder", cfg, ReplayClosure(deltas, 5),
-                                 wide_bounds=True)
+    system, solver = make_solver(api, "bicycle", "IrsLqrFirstOrder", cfg, ReplayClosure(deltas, 5))
     orc = cr.BicycleOracle(cfg["h"])
     At_o, Bt_o, ct_o = cr.first_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
-    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o)
+    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o, bounded=True)
+    assert solver.bounded_admm_iterations > 0          # the bounded loop really ran
 
 
 def test_cfg3_quadrotor_zero_order_T100_replay_N1e4(api):
@@ -171,7 +187,11 @@ def test_cfg4_three_cart_zero_order_T100_N1e4(api, projection):
     deltas = np.stack([np.hstack(post(solver.x_trj[t], raw[t][:, :6], solver.u_trj[t], raw[t][:, 6:]))
                        for t in range(100)])
     At_o, Bt_o, ct_o = cr.zero_order_tv_matrices(orc, solver.x_trj, solver.u_trj, deltas)
-    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o)
+    # "absolute": the literal quirk regresses on absolute points, a linearization without meaning; its gains
+    # make the closed loop diverge (|x_T| ~ 1e4 from |x_0| ~ 1), which amplifies the 1e-5 fit difference to
+    # O(1): the descent is then checked on the device's own fit (solve + rollout in isolation)
+    check_fit_and_descent(solver, orc, cfg, At_o, Bt_o, ct_o,
+                          descent="device_fit" if projection == "absolute" else "oracle_fit")
 
 
 def test_cfg4_three_cart_inkernel_projection_philox_N1e6_sample(api):

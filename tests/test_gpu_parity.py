@@ -569,7 +569,7 @@ def test_finalize_variants_are_bit_identical(api, name, N, zero_sigma, monkeypat
 # ------------------------------------------------------------------------------------------------
 # batched MPC instances (BASELINE.json configs[4])
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,I,T,N", [("quadrotor", 5, 24, 1500), ("pendulum", 300, 30, 600)])
+@pytest.mark.parametrize("name,I,T,N", [("quadrotor", 5, 24, 3000), ("pendulum", 300, 30, 600)])
 def test_batched_instances_match_oracle_and_shard(api, name, I, T, N):
     """Every instance of a batch equals the single-problem oracle pipeline on the deltas the kernel
     drew for it (1e-4), and a shard of the batch (instance_offset) is bit-identical to the same
@@ -793,8 +793,8 @@ def test_cem_matches_numpy_restatement(api, name, T, B):
 @pytest.mark.parametrize("engine", [0, 1])
 @pytest.mark.parametrize("name,N", [("quadrotor", 17), ("quadrotor", 127), ("quadrotor", 128), ("quadrotor", 129),
                                     ("quadrotor", 255), ("quadrotor", 256), ("quadrotor", 257),
-                                    ("quadrotor", 4097), ("quadrotor", 8191), ("pendulum", 4), ("pendulum", 33),
-                                    ("bicycle", 300), ("three_cart", 257)])
+                                    ("quadrotor", 4097), ("quadrotor", 8191), ("quadrotor", 35), ("pendulum", 4),
+                                    ("pendulum", 9), ("pendulum", 33), ("bicycle", 300), ("three_cart", 257)])
 def test_ragged_sample_counts_match_oracle(api, name, N, engine, antithetic):
     """Sample counts that do not fill a 32-sample warp tile, a 128-sample block round (256 samples when a
     lane owns an antithetic pair) or a 4096-sample chunk: the padded lanes must contribute nothing, and
@@ -803,6 +803,8 @@ def test_ragged_sample_counts_match_oracle(api, name, N, engine, antithetic):
     T = 3
     cfg, s, u_trj = _nominal(api, name, T)
     n = s.dim_x
+    if antithetic and N < 2 * (n + s.dim_u) + 2:
+        pytest.skip("N antithetic samples span only ceil(N/2) directions: the fit needs N >= 2 (n + m)")
     x_trj = cr.rollout(cr.SYSTEMS[name](s.h), cfg["x0"], u_trj)
     sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=5,
                                    antithetic=antithetic)
@@ -858,8 +860,12 @@ def test_antithetic_pairs_equal_the_replay_of_their_own_deltas(api, name, projec
         Ar, Br, cr_ = _device.to_numpy(Ar), _device.to_numpy(Br), _device.to_numpy(cr_)
     finally:
         _lib.call("irs_set_gram_engine", -1)
-    assert rel_err(Ap, Ar) < 2e-5 and rel_err(Bp, Br) < 2e-5
-    assert float(np.max(np.abs(cp - cr_))) < 2e-5 * max(1.0, float(np.max(np.abs(x_trj))))
+    # bicycle on the tensor-core engine (not its default): its steer regressor has sigma 0.01 next to
+    # sigma 2 columns, and the 2^-17 product noise of the bf16x2 split on the cross terms is then ~1e-4 of
+    # that column's own Gram entry — both kernels carry it, independently
+    tol = 3e-4 if (name == "bicycle" and engine == 1) else 2e-5
+    assert rel_err(Ap, Ar) < tol and rel_err(Bp, Br) < tol
+    assert float(np.max(np.abs(cp - cr_))) < tol * max(1.0, float(np.max(np.abs(x_trj))))
 
 
 # ------------------------------------------------------------------------------------------------
