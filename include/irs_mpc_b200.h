@@ -36,12 +36,19 @@ enum {
   IRS_PROJECT_ABSOLUTE = 2,      /* three_cart_zero_order.py:43: sampling returns projection(...) =
                                     absolute points (three_cart_dynamics.py:196-264), reproduced literally */
   IRS_PROJECT_DELTA = 4,         /* corrected variant: projected point minus nominal */
-  IRS_ANTITHETIC = 8             /* in-kernel Philox noise in antithetic pairs: sample 2q is xbar + z_q, sample
+  IRS_ANTITHETIC = 8,            /* in-kernel Philox noise in antithetic pairs: sample 2q is xbar + z_q, sample
                                     2q+1 is xbar - z_q, one counter (and one Box-Muller draw) per pair.  The
                                     reference draws independent normals (e.g. pendulum_zero_order.py:38-43);
                                     each sample keeps the same marginal N(0, sigma^2), the even-order terms of
                                     f cancel in Z^T dF, and the fused kernel needs one operand row per pair.
                                     Ignored when deltas are replayed.  i0 must be even. */
+  IRS_CENTERED = 16              /* three_cart: the regressors handed to the fit are ABSOLUTE points near the
+                                    nominal (replayed output of the reference's projecting closure,
+                                    three_cart_zero_order.py:43).  They are accumulated relative to (xbar, ubar)
+                                    together with their first moments and shifted back in fp64 by
+                                    irs_smooth_finalize(centered = 1); an fp32 Gram of the absolute points loses
+                                    the sample spread once |xbar| >> sigma.  IRS_PROJECT_ABSOLUTE (in-kernel
+                                    projection of in-kernel noise) implies it. */
 };
 
 int irs_abi_version(void);
@@ -98,13 +105,16 @@ int irs_smooth_reduce_chunks(int system, int order, const float* partials, int P
  * Input is EITHER `partials` (fp32 [nranks][P,C,width], other NULL) OR `reduced` (fp64
  * [nranks][P,width]); the `nranks` buffers lie `rank_stride` elements apart (peer-mapped pointers
  * are fine) and are summed in rank order, then chunk order — deterministic.  Solves the normal
- * equations (order 0; identical to lstsq for full column rank) or divides by n_total (order 1),
+ * equations (order 0; identical to lstsq for full column rank) or divides by n_total (order 1);
+ * centered != 0 (three_cart, accumulate flags IRS_PROJECT_ABSOLUTE / IRS_CENTERED): the blocks hold the
+ * Gram of regressors relative to the nominal point plus their first moments, and the shift
+ * Z^T Z = Z'^T Z' + s m'^T + m' s^T + N s s^T, Z^T dF = Z'^T dF + s g^T (s = (xbar, ubar)) is undone in fp64;
  * writes At [P,n,n], Bt [P,n,m], ct [P,n] (f64) and status [P] (0 ok, 1 rank deficient, 2 peer
  * exchange timed out — irs_smooth_finalize_peer only). */
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
                         const float* partials, const double* reduced, int nranks,
-                        long long rank_stride, double n_total,
+                        long long rank_stride, double n_total, int centered,
                         double* At, double* Bt, double* ct, int* status, void* stream);
 
 /* irs_smooth_finalize for a SAMPLE-SHARDED run (one process per GPU), with the exchange of the per-point
@@ -125,7 +135,7 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
                              const double* x_nom, const double* u_nom, int P, int C, const float* partials,
                              const void* peer_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
                              unsigned int* done_counter, long long slot_stride, int flag_stride,
-                             int rank, int world, double timeout_s, double n_total,
+                             int rank, int world, double timeout_s, double n_total, int centered,
                              double* At, double* Bt, double* ct, int* status, void* stream);
 int irs_smooth_finalize_peer_capacity(int system, int order, int* max_points);
 

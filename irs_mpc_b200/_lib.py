@@ -63,10 +63,10 @@ SIGNATURES = {
                                           _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
     "irs_smooth_reduce_chunks": [_i, _i, _vp, _i, _i, _vp, _vp],
     "irs_smooth_finalize_peer": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i,
-                                 _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
+                                 _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _vp, _vp, _vp],
     "irs_smooth_finalize_peer_capacity": [_i, _i, ctypes.POINTER(_i)],
     "irs_smooth_finalize": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _ll,
-                            ctypes.c_double, _vp, _vp, _vp, _vp, _vp],
+                            ctypes.c_double, _i, _vp, _vp, _vp, _vp, _vp],
     "irs_exact_linearize": [_i, _c_double_p, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "irs_philox_dump": [_i, _ll, _i, _vp, _ull, _u, _u, _u, _ull, _i, _vp, _vp, _vp],
     "irs_dynamics_batch_f32": [_i, _c_double_p, _i, _i, _vp, _vp, _vp, _ll, _vp],

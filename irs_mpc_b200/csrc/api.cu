@@ -61,7 +61,7 @@ static thread_local const void* g_last_smooth_func = nullptr;
 template <class Sys, int G>
 static int launch_zero_order(const SmoothArgs& a, cudaStream_t st) {
     using C = ZeroOrderCfg<Sys, G>;
-    const size_t smem = G == 1 ? sizeof(float) * (C::kThreads / 32) * C::NACC
+    const size_t smem = G == 1 ? sizeof(float) * (C::kThreads / 32) * gram_width_of<Sys>()
                                : sizeof(float) * 2 * C::kTile * C::RS;      // double-buffered tile
     auto kern = smooth_zero_order_kernel<Sys, G>;
     if (smem > 48 * 1024) {
@@ -99,12 +99,12 @@ static int num_sms() {
     return n;
 }
 
-template <class Sys, int MODE>
+template <class Sys, int MODE, bool CENTERED>
 static int launch_zero_order_tc_mode(const SmoothArgs& a, cudaStream_t st) {
-    using C = TcCfg<Sys>;
+    using C = TcCfg<Sys, MODE == kTcPaired && Sys::kHasProjection>;
     constexpr int NSTAGE = 1;      // measured: one tile per warp is fastest
     const size_t smem = (size_t)NSTAGE * C::kWarps * C::kStageBytes;
-    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE, MODE>;
+    auto kern = smooth_zero_order_tc_kernel<Sys, NSTAGE, MODE, CENTERED>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -133,13 +133,21 @@ static int launch_zero_order_tc_mode(const SmoothArgs& a, cudaStream_t st) {
     return check_launch("smooth_zero_order_tc_kernel");
 }
 
-template <class Sys>
-static int launch_zero_order_tc(const SmoothArgs& a, cudaStream_t st) {
+template <class Sys, bool CENTERED>
+static int launch_zero_order_tc_centered(const SmoothArgs& a, cudaStream_t st) {
     // the noise source is a compile-time mode of the kernel: replayed deltas, the Philox stream with one
     // draw per sample, or the Philox stream in antithetic pairs (one draw and one operand row per pair)
-    if (a.noise != nullptr) return launch_zero_order_tc_mode<Sys, kTcReplay>(a, st);
-    if (a.flags & kFlagAntithetic) return launch_zero_order_tc_mode<Sys, kTcPaired>(a, st);
-    return launch_zero_order_tc_mode<Sys, kTcPhilox>(a, st);
+    if (a.noise != nullptr) return launch_zero_order_tc_mode<Sys, kTcReplay, CENTERED>(a, st);
+    if (a.flags & kFlagAntithetic) return launch_zero_order_tc_mode<Sys, kTcPaired, CENTERED>(a, st);
+    return launch_zero_order_tc_mode<Sys, kTcPhilox, CENTERED>(a, st);
+}
+
+template <class Sys>
+static int launch_zero_order_tc(const SmoothArgs& a, cudaStream_t st) {
+    if constexpr (Sys::kHasProjection) {      // centred-capable: absolute regressors accumulate relative to the nominal
+        if (a.flags & (kFlagProjectAbsolute | kFlagCentered)) return launch_zero_order_tc_centered<Sys, true>(a, st);
+    }
+    return launch_zero_order_tc_centered<Sys, false>(a, st);
 }
 
 static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host, int nparams,
@@ -167,6 +175,9 @@ static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host
     IRS_REQUIRE(!((flags & IRS_ANTITHETIC) && noise == nullptr && (i0 & 1ull)),
                 "antithetic pairs: the global index of the first local sample (i0) must be even");
     if (noise != nullptr) flags &= ~IRS_ANTITHETIC;      // replayed deltas are whatever the caller drew
+    IRS_REQUIRE(!(flags & IRS_CENTERED) || system == kThreeCart,
+                "centred accumulation (IRS_CENTERED) is built for three_cart only");
+    IRS_REQUIRE(!(flags & IRS_CENTERED) || !(flags & IRS_PROJECT_DELTA), "IRS_CENTERED and IRS_PROJECT_DELTA are exclusive");
     a->x_nom = x_nom;  a->u_nom = u_nom;  a->noise = noise;
     a->partials = partials;  a->N = N;  a->S = S;  a->P = P;  a->C = C;
     a->seed_lo = (uint32_t)(seed & 0xffffffffull);
@@ -355,7 +366,8 @@ int irs_system_dims(int system, int* n, int* m, int* nj) {
 int irs_partial_width(int system, int order) {
     if (system < 0 || system >= kNumSystems) return -1;
     const SystemDims d = system_dims(system);
-    return order == 0 ? gram_nacc(d.n, d.m) : (d.nj > 0 ? d.nj : 1);
+    // three_cart blocks carry the first moments of the centred accumulation (smooth.cuh: gram_width)
+    return order == 0 ? gram_width(d.n, d.m, system == kThreeCart) : (d.nj > 0 ? d.nj : 1);
 }
 
 int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long* S) {
@@ -483,7 +495,7 @@ static int finalize_resident_blocks(int system, int order, int* out) {
 static int smooth_finalize_impl(int system, const double* params_host, int nparams, int order,
                                 const double* x_nom, const double* u_nom, int P, int C,
                                 const float* partials, const double* reduced, int nranks,
-                                long long rank_stride, double n_total,
+                                long long rank_stride, double n_total, int centered,
                                 double* At, double* Bt, double* ct, int* status, const PeerFusedArgs* peer,
                                 void* stream) {
     FinalizeArgs a;
@@ -495,6 +507,8 @@ static int smooth_finalize_impl(int system, const double* params_host, int npara
     a.reduced = reduced;
     IRS_REQUIRE(P >= 1 && C >= 1 && nranks >= 1 && n_total >= 1.0, "bad finalize arguments");
     IRS_REQUIRE(!(order == 1 && system == kThreeCart), "three_cart has no Jacobian");
+    IRS_REQUIRE(!centered || (system == kThreeCart && order == 0), "centred accumulation is built for three_cart only");
+    a.centered = centered ? 1 : 0;
     a.x_nom = x_nom;  a.u_nom = u_nom;  a.partials = partials;  a.rank_stride = rank_stride;
     a.R = nranks;  a.P = P;  a.C = C;  a.n_total = n_total;
     a.At = At;  a.Bt = Bt;  a.ct = ct;  a.status = status;
@@ -511,6 +525,7 @@ static int smooth_finalize_impl(int system, const double* params_host, int npara
         else if (!strcmp(e, "quad")) quad = true;
     }
     if (peer != nullptr) quad = false;      // the fused exchange lives in the one-block-per-point kernels
+    if (centered) quad = false;             // ... and so does the un-shift of a centred Gram
     if (quad || order == 1) {
         // f(xbar, ubar) in fp64 (scalar dynamics, ...zero_order.py:61) -> ct; the finalize kernel turns it into c
         IRS_DISPATCH_SYSTEM(system, double, Sys,
@@ -545,10 +560,10 @@ static int smooth_finalize_impl(int system, const double* params_host, int npara
 int irs_smooth_finalize(int system, const double* params_host, int nparams, int order,
                         const double* x_nom, const double* u_nom, int P, int C,
                         const float* partials, const double* reduced, int nranks,
-                        long long rank_stride, double n_total,
+                        long long rank_stride, double n_total, int centered,
                         double* At, double* Bt, double* ct, int* status, void* stream) {
     return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, reduced, nranks,
-                                rank_stride, n_total, At, Bt, ct, status, nullptr, stream);
+                                rank_stride, n_total, centered, At, Bt, ct, status, nullptr, stream);
 }
 
 int irs_smooth_finalize_peer_capacity(int system, int order, int* max_points) {
@@ -560,7 +575,7 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
                              const double* x_nom, const double* u_nom, int P, int C, const float* partials,
                              const void* peer_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
                              unsigned int* done_counter, long long slot_stride, int flag_stride,
-                             int rank, int world, double timeout_s, double n_total,
+                             int rank, int world, double timeout_s, double n_total, int centered,
                              double* At, double* Bt, double* ct, int* status, void* stream) {
     IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
     IRS_REQUIRE(partials && peer_bufs_dev && peer_flags_dev && epoch_dev && done_counter, "null pointer argument");
@@ -574,7 +589,7 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
     PeerFusedArgs px{(double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, done_counter,
                      slot_stride, flag_stride, rank, world, (unsigned long long)(timeout_s * 1e9)};
     return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, nullptr, 1, 0,
-                                n_total, At, Bt, ct, status, &px, stream);
+                                n_total, centered, At, Bt, ct, status, &px, stream);
 }
 
 int irs_exact_linearize(int system, const double* params_host, int nparams,

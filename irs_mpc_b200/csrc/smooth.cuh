@@ -18,6 +18,9 @@ enum SmoothFlags {
     kFlagProjectAbsolute = 2,       // three_cart_zero_order.py:43 quirk: sampling returns absolute points
     kFlagProjectDelta = 4,          // corrected variant: projected point minus nominal
     kFlagAntithetic = 8,            // Philox stream in antithetic pairs: sample 2q = +z_q, sample 2q+1 = -z_q
+    kFlagCentered = 16,             // regressors are accumulated RELATIVE to the nominal point (xbar, ubar) together
+                                    // with their first moments; the finalize undoes the shift in fp64 (implied by
+                                    // kFlagProjectAbsolute; replayed absolute points: set explicitly)
 };
 
 struct SmoothArgs {
@@ -41,6 +44,14 @@ constexpr int kMaxRegressors = 16;
 __host__ __device__ constexpr int gram_nacc(int n, int m) {
     return (n + m) * (n + m + 1) / 2 + (n + m) * n;
 }
+// Width of one packed partial block.  Systems whose regressors can be absolute points (three_cart's
+// projection quirk) append the first moments [sum z' (d) | sum dF (n)] of the
+// centred accumulation (kFlagCentered); the entries are zero when a launch is not centred.
+__host__ __device__ constexpr int gram_width(int n, int m, bool centered_capable) {
+    return gram_nacc(n, m) + (centered_capable ? 2 * n + m : 0);
+}
+template <class Sys>
+__host__ __device__ constexpr int gram_width_of() { return gram_width(Sys::N, Sys::M, Sys::kHasProjection); }
 // packed upper-row layout: row i holds columns j = i..W-1, W = d + n
 __host__ __device__ constexpr int gram_row_offset(int i, int W) { return i * W - i * (i - 1) / 2; }
 
@@ -109,10 +120,19 @@ __device__ __forceinline__ void draw_deltas(const SmoothArgs& a, int p, long lon
 // reference's float64 operations; only the same arithmetic on the same values reproduces those
 // decisions.  Everything that no branch depends on (velocities, inputs) stays in fp32.
 // pos64: the kProj leading nominal coordinates in fp64 (shared memory), or nullptr = read a.x_nom.
+//
+// In BOTH projection modes w leaves this function RELATIVE to the nominal point:
+//     w[c] = fl32(proj(xbar + dx)[c] - xbar[c])  for the projected coordinates, w unchanged otherwise.
+// kFlagProjectDelta: that IS the regressor and the perturbation.  kFlagProjectAbsolute — the
+// reference closure returns ABSOLUTE points, which the solver adds to the nominal AGAIN and uses
+// un-centred as regressors, reproduced literally: the state handed to the
+// dynamics is xbar + (xbar + w) (the callers add the nominal twice) and the regressors are xbar + w,
+// accumulated as w with their first moments and shifted back in fp64 by the finalize
+// (kFlagCentered).  An fp32 Gram of the absolute points themselves loses the sample spread once
+// |xbar| >> sigma, which the quirk's meaningless linearization reaches after one descent.
 template <class Sys, int RS>
-__device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, const float* xbar,
-                                               const float* ubar, const double* pos64, float (&w)[RS]) {
-    constexpr int n = Sys::N, m = Sys::M;
+__device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, const double* pos64, float (&w)[RS]) {
+    constexpr int n = Sys::N;
     if constexpr (Sys::kHasProjection) {
         constexpr int kProj = Sys::kProjDims;
         if (a.flags & (kFlagProjectAbsolute | kFlagProjectDelta)) {
@@ -127,21 +147,21 @@ __device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, const
 #pragma unroll
             for (int c = kProj; c < n; ++c) xp[c] = 0.0;      // untouched by project()
             sysd.project(xp);
-            if (a.flags & kFlagProjectAbsolute) {
-                // the reference closure returns ABSOLUTE points which the solver adds to the
-                // nominal again and uses as regressors — reproduced literally
 #pragma unroll
-                for (int c = 0; c < kProj; ++c) w[c] = (float)xp[c];
-#pragma unroll
-                for (int c = kProj; c < n; ++c) w[c] = xbar[c] + w[c];
-#pragma unroll
-                for (int c = 0; c < m; ++c) w[n + c] = ubar[c] + w[n + c];
-            } else {
-#pragma unroll
-                for (int c = 0; c < kProj; ++c) w[c] = (float)(xp[c] - xb[c]);
-            }
+            for (int c = 0; c < kProj; ++c) w[c] = (float)(xp[c] - xb[c]);
         }
     }
+}
+
+// Replayed regressors that are absolute points (kFlagCentered without an in-kernel projection):
+// w[c] <- fl32(w[c] - nominal[c]) with the fp64 nominal, AFTER the state has been formed.
+template <class Sys, int RS>
+__device__ __forceinline__ void center_replayed(const SmoothArgs& a, int p, float (&w)[RS]) {
+    constexpr int n = Sys::N, m = Sys::M;
+#pragma unroll
+    for (int c = 0; c < n; ++c) w[c] = (float)((double)w[c] - a.x_nom[(long long)p * n + c]);
+#pragma unroll
+    for (int c = 0; c < m; ++c) w[n + c] = (float)((double)w[n + c] - a.u_nom[(long long)p * m + c]);
 }
 
 template <class Sys, bool BATCH, int RS>
@@ -150,12 +170,17 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
                                             const float* fbar, float (&w)[RS], bool want_df = true) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     draw_deltas<Sys, RS>(a, p, i, w);
-    project_deltas<Sys, RS>(a, p, xbar, ubar, nullptr, w);
+    project_deltas<Sys, RS>(a, p, nullptr, w);
+    // absolute-points quirk: the state is xbar + (xbar + w), see project_deltas
+    const float twice = (Sys::kHasProjection && (a.flags & kFlagProjectAbsolute)) ? 2.f : 1.f;
     float x[n], u[m];
 #pragma unroll
-    for (int c = 0; c < n; ++c) x[c] = xbar[c] + w[c];
+    for (int c = 0; c < n; ++c) x[c] = fmaf(twice, xbar[c], w[c]);
 #pragma unroll
-    for (int c = 0; c < m; ++c) u[c] = ubar[c] + w[n + c];
+    for (int c = 0; c < m; ++c) u[c] = fmaf(twice, ubar[c], w[n + c]);
+    if constexpr (Sys::kHasProjection) {
+        if ((a.flags & kFlagCentered) && !(a.flags & kFlagProjectAbsolute)) center_replayed<Sys, RS>(a, p, w);
+    }
     if (want_df) {
         float f[n];
         sys.template step<BATCH>(x, u, f);
@@ -266,9 +291,14 @@ __device__ __forceinline__ void zero_order_registers(const Sys& sys, const Smoot
                                                      const float* fbar, float* slabs, float* out) {
     using C = ZeroOrderCfg<Sys, 1>;
     constexpr int NP = role_pairs(C::d, C::Wp, 1, 0);
+    constexpr int WIDTH = gram_width_of<Sys>();
+    constexpr int NMOM = WIDTH - C::NACC;                    // first moments (centred-capable systems)
     float2 acc[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
+    float mom[NMOM > 0 ? NMOM : 1];
+#pragma unroll
+    for (int k = 0; k < (NMOM > 0 ? NMOM : 1); ++k) mom[k] = 0.f;
     const int lane = threadIdx.x & 31;
     for (long long s = s_begin + threadIdx.x; s < s_end; s += C::kThreads) {
         float w[C::RS];
@@ -276,15 +306,26 @@ __device__ __forceinline__ void zero_order_registers(const Sys& sys, const Smoot
         for (int c = 0; c < C::RS; ++c) w[c] = 0.f;
         make_sample<Sys, BATCH, C::RS>(sys, a, p, s, xbar, ubar, fbar, w);
         gram_update<Sys, 1, 0, NP>(w, acc);
+        if constexpr (NMOM > 0) {
+#pragma unroll
+            for (int k = 0; k < NMOM; ++k) mom[k] += w[k];
+        }
     }
     // cross-warp: each warp flushes into its own smem slab, then the block sums the slabs
-    float* slab = slabs + (threadIdx.x >> 5) * C::NACC;
+    float* slab = slabs + (threadIdx.x >> 5) * WIDTH;
     gram_flush<Sys, 1, 0, NP>(acc, slab, lane);
+    if constexpr (NMOM > 0) {
+#pragma unroll
+        for (int k = 0; k < NMOM; ++k) {
+            const float v = warp_sum(mom[k]);
+            if (lane == 0) slab[C::NACC + k] = (a.flags & (kFlagCentered | kFlagProjectAbsolute)) ? v : 0.f;
+        }
+    }
     __syncthreads();
-    for (int e = threadIdx.x; e < C::NACC; e += C::kThreads) {
+    for (int e = threadIdx.x; e < WIDTH; e += C::kThreads) {
         float s = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < C::kThreads / 32; ++wq) s += slabs[wq * C::NACC + e];
+        for (int wq = 0; wq < C::kThreads / 32; ++wq) s += slabs[wq * WIDTH + e];
         out[e] = s;
     }
 }
@@ -356,7 +397,7 @@ smooth_zero_order_kernel(const SmoothArgs a) {
     for (int q = 0; q < m; ++q) ubar[q] = (float)a.u_nom[(long long)p * m + q];
     // nominal response: the reference uses the SCALAR dynamics here (irs_lqr_zero_order.py:52)
     sys.template step<false>(xbar, ubar, fbar);
-    float* out = a.partials + ((long long)p * a.C + c) * ZeroOrderCfg<Sys, G>::NACC;
+    float* out = a.partials + ((long long)p * a.C + c) * gram_width_of<Sys>();
     if constexpr (G == 1) {
         if (a.flags & kFlagSamplesBatchVariant)
             zero_order_registers<Sys, true>(sys, a, p, s_begin, s_end, xbar, ubar, fbar, tile, out);
@@ -472,6 +513,7 @@ struct FinalizeArgs {
     double* ct;              // [P, n]
     int* status;             // [P] 0 ok, 1 rank-deficient Gram
     const FinalizeTables* tables;   // index tables of this system (device)
+    int centered;                   // the Gram was accumulated relative to the nominal point: undo the shift
     PeerFusedArgs peer;             // fused exchange of the sample-sharded path (world == 0: unused)
     SysParams prm;
 };
@@ -693,31 +735,36 @@ template <class Sys, int BT>
 __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const FinalizeArgs a) {
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int NACC = gram_nacc(n, m);
+    constexpr int WIDTH = gram_width_of<Sys>();      // NACC (+ first moments for centred-capable systems)
     __shared__ double Gm[d * d];      // Gram (then its Cholesky factor, lower)
     __shared__ double Bm[d * n];      // right-hand sides Z^T dF, then the solution
     __shared__ double sAB[n * d];
     __shared__ double inv_diag[d];
     __shared__ double nom[d + n];
+    __shared__ double mom[WIDTH - NACC > 0 ? WIDTH - NACC : 1];   // [sum z' (d) | sum dF (n)]
+    __shared__ double spread[d];      // diagonal of the CENTRED Gram: scale of the rank test
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
     // 0. sample-sharded run: exchange this point's chunk-reduced block with the other ranks first
     PartialSource src = partial_source(a);
     bool peer_late = false;
     int epoch = 0;
-    if (a.peer.world > 0) epoch = peer_exchange_point<BT>(a, p, NACC, tid, &src, &peer_late);
+    if (a.peer.world > 0) epoch = peer_exchange_point<BT>(a, p, WIDTH, tid, &src, &peer_late);
     // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs; a thread's
     //    entries are summed together so that all their loads are in flight at once
     {
-        constexpr int NE = (NACC + BT - 1) / BT;
+        constexpr int NE = (WIDTH + BT - 1) / BT;
         int rel[NE];
 #pragma unroll
-        for (int q = 0; q < NE; ++q) rel[q] = tid + q * BT < NACC ? tid + q * BT : -1;
+        for (int q = 0; q < NE; ++q) rel[q] = tid + q * BT < WIDTH ? tid + q * BT : -1;
         double sums[NE];
-        const long long pbase = (long long)p * (src.reduced != nullptr ? (long long)NACC : (long long)src.C * NACC);
-        sum_partials_multi<NE>(src, pbase, rel, NACC, sums);
+        const long long pbase = (long long)p * (src.reduced != nullptr ? (long long)WIDTH : (long long)src.C * WIDTH);
+        sum_partials_multi<NE>(src, pbase, rel, WIDTH, sums);
 #pragma unroll
         for (int q = 0; q < NE; ++q) {
-            if (rel[q] >= 0) {
+            if (rel[q] >= NACC) {
+                mom[rel[q] - NACC] = sums[q];
+            } else if (rel[q] >= 0) {
                 const int i = a.tables->gram_i[rel[q]], j = a.tables->gram_j[rel[q]];
                 if (j < d) {
                     Gm[i * d + j] = sums[q];
@@ -725,6 +772,27 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
                 } else {
                     Bm[i * n + (j - d)] = sums[q];
                 }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < d) spread[tid] = Gm[tid * d + tid];
+    if constexpr (WIDTH > NACC) {
+        // 1b. centred accumulation: z = s + z' with s = (xbar, ubar) in fp64, so
+        //       Z^T Z  = Z'^T Z' + s m'^T + m' s^T + N s s^T,      Z^T dF = Z'^T dF + s g^T
+        //     (m' = sum z', g = sum dF).  The fp32 partials only ever held O(sigma) numbers.
+        if (a.centered) {
+            __syncthreads();      // spread[] read the centred diagonal
+            for (int e = tid; e < d * d; e += BT) {
+                const int i = e / d, j = e % d;
+                const double si = i < n ? a.x_nom[(long long)p * n + i] : a.u_nom[(long long)p * m + (i - n)];
+                const double sj = j < n ? a.x_nom[(long long)p * n + j] : a.u_nom[(long long)p * m + (j - n)];
+                Gm[e] = fma(a.n_total * si, sj, fma(si, mom[j], fma(mom[i], sj, Gm[e])));
+            }
+            for (int e = tid; e < d * n; e += BT) {
+                const int i = e / n, q = e % n;
+                const double si = i < n ? a.x_nom[(long long)p * n + i] : a.u_nom[(long long)p * m + (i - n)];
+                Bm[e] = fma(si, mom[d + q], Bm[e]);
             }
         }
     }
@@ -750,9 +818,12 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
             static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  dk = fma(-lk[j], lk[j], dk); });
             bool zero_col = false;
             // pivot <= 1e-6 * G_kk: the column is (numerically) a combination of earlier ones; the
-            // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency
+            // fp32 partial sums carry ~1e-7 relative noise, so anything below is rank deficiency.
+            // (Centred accumulation: the noise is relative to the SPREAD of the column, i.e. the centred
+            //  diagonal, and a pivot of the shifted Gram is never below that of the centred one.)
+            const double scale_k = (WIDTH > NACC && a.centered) ? spread[k] : d0;
             if (d0 == 0.0) { zero_col = true; dk = 1.0; }
-            else if (!(dk > 1e-6 * d0)) { bad = true; dk = 1.0; }
+            else if (!(dk > 1e-6 * scale_k)) { bad = true; dk = 1.0; }
             const double ikk = rsqrt(dk);           // one special function on the critical path, not two
             double sk = row[k];
             static_for<0, k>([&](auto jc) { constexpr int j = decltype(jc)::value;  sk = fma(-row[j], lk[j], sk); });
@@ -825,7 +896,8 @@ template <class Sys>
 struct FinalizeQuadCfg {
     static constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     static constexpr int W = d + n;
-    static constexpr int NACC = gram_nacc(n, m);
+    static constexpr int NACC = gram_width_of<Sys>();      // stride of a packed partial block (the first
+                                                           // moments of centred-capable systems are not read here)
     static constexpr int TRI = d * (d + 1) / 2;
     static constexpr int PPB = kFinalizeQuadThreads / kQuad;     // points per block
     static constexpr int QT = (n + kQuad - 1) / kQuad;           // right-hand sides per thread

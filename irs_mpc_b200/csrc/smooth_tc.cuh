@@ -75,19 +75,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <class Sys>
+// DUAL: the operand tile of a lane holds TWO sample rows ("members" 0 and 1, e.g. the + and - member of
+// an antithetic pair whose projected regressors are not negatives of each other).  Possible when two
+// rows fit the M = 64 operand (three_cart, bicycle, pendulum).  One UMMA pair then serves two samples:
+// D [64 x 4 dq] holds the two wanted diagonal blocks (member h rows x member h columns) and two cross
+// blocks that are never read.
+template <class Sys, bool DUAL = false>
 struct TcCfg {
     static constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     static constexpr int W = d + n;
     static constexpr int dq = (d + 7) / 8 * 8;           // regressor rows per piece (8-feature groups)
     static constexpr int nq = (n + 7) / 8 * 8;           // response rows per piece
-    static constexpr int kN = 2 * dq;                    // UMMA N (columns of D): [z_1 | z_2]
-    static constexpr int kRows = 2 * dq + 2 * nq;        // used rows of A (<= 64)
+    static constexpr int kMembers = DUAL ? 2 : 1;        // sample rows per lane and tile
+    static constexpr int kN = kMembers * 2 * dq;         // UMMA N (columns of D): [z_1 | z_2] per member
+    static constexpr int kRows = kMembers * (2 * dq + 2 * nq);   // used rows of A (<= 64)
     static constexpr int kM = 64;
     static constexpr int kWarps = 4;                     // self-contained warp pipelines per block
-    static constexpr int kThreads = 32 * kWarps;         // lane = sample
-    static constexpr int kTile = kThreads;               // samples per block round
-    static constexpr int kWarpTile = 32;                 // samples per warp tile (two K = 16 UMMAs)
+    static constexpr int kThreads = 32 * kWarps;         // lane = sample (or antithetic pair)
+    static constexpr int kTile = kThreads;               // lane-units per block round
+    static constexpr int kWarpTile = 32;                 // operand columns per warp tile (two K = 16 UMMAs)
     static constexpr int kLBO = 128;                     // bytes between k-groups (8 samples)
     static constexpr int kSBO = (kWarpTile / 8) * kLBO;  // bytes between 8-feature groups (512)
     static constexpr int kGroups = kM / 8;
@@ -101,6 +107,8 @@ struct TcCfg {
 #endif
     static constexpr int kTmemCols = kAccRanges * kN < 32 ? 32 : kAccRanges * kN;
     static constexpr int NACC = gram_nacc(n, m);
+    static constexpr int WIDTH = gram_width_of<Sys>();   // NACC (+ first moments, centred-capable systems)
+    static constexpr int NMOM = WIDTH - NACC;
     static constexpr int RS = (W + 1) / 2 * 2;
     // Nominal points prepared per batch (one thread each).  64 for the quadrotor: batched MPC runs one
     // short item (8 rounds) per nominal point, and a per-item preparation stalls the block for ~1,400
@@ -109,13 +117,22 @@ struct TcCfg {
     static_assert(kRows <= kM, "operand rows must fit one M = 64 UMMA");
     static_assert(kN % 8 == 0 && kN >= 8 && kN <= 256, "invalid UMMA N");
     static_assert(kN % 16 == 0, "accumulator read-back uses 16-column TMEM loads");
+    static_assert(kTmemCols == 32 || kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256, "TMEM allocation");
     // instruction descriptor: D fp32, A/B bf16, both MN-major, N >> 3, M >> 4
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-    // feature-group index (8 rows each) of the four pieces
-    static constexpr int grp_z1 = 0, grp_z2 = dq / 8, grp_f1 = 2 * dq / 8, grp_f2 = (2 * dq + nq) / 8;
-    __host__ __device__ static constexpr int row_1(int j) { return j < d ? j : 2 * dq + (j - d); }
-    __host__ __device__ static constexpr int row_2(int j) { return j < d ? dq + j : 2 * dq + nq + (j - d); }
+    // feature-group index (8 rows each) of the four pieces of member h: the regressor pieces of all members
+    // come first (they are the B operand = the first kN rows), then the response pieces
+    __host__ __device__ static constexpr int grp_z1(int h) { return h * (2 * dq / 8); }
+    __host__ __device__ static constexpr int grp_z2(int h) { return grp_z1(h) + dq / 8; }
+    __host__ __device__ static constexpr int grp_f1(int h) { return kMembers * (2 * dq / 8) + h * (2 * nq / 8); }
+    __host__ __device__ static constexpr int grp_f2(int h) { return grp_f1(h) + nq / 8; }
+    __host__ __device__ static constexpr int row_1(int h, int j) { return j < d ? 8 * grp_z1(h) + j : 8 * grp_f1(h) + (j - d); }
+    __host__ __device__ static constexpr int row_2(int h, int j) { return j < d ? 8 * grp_z2(h) + j : 8 * grp_f2(h) + (j - d); }
+    // member of operand row r
+    __host__ __device__ static constexpr int member_of_row(int r) {
+        return r < kN ? r / (2 * dq) : (r - kN) / (2 * nq);
+    }
 };
 
 // fp32 pair -> two packed bf16x2 words (low half = v0, high half = v1): first pieces p1 = bf16_rn(v)
@@ -160,14 +177,22 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& p1, u
 //               then shares only the noise draw and stages two rows.
 enum TcMode { kTcPhilox = 0, kTcReplay = 1, kTcPaired = 2 };
 
-template <class Sys, int NSTAGE, int MODE>
+// CENTERED (centred-capable systems only, gram_width_of): the regressors of the launch are relative to
+// the nominal point (kFlagProjectAbsolute, or replayed absolute points with kFlagCentered) and their
+// first moments [sum z' | sum dF] are appended to the packed block — per-lane fp32 sums of a few dozen
+// values each, reduced by shuffles, so they carry far less rounding noise than a running sum.
+template <class Sys, int NSTAGE, int MODE, bool CENTERED>
 __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_kernel(const SmoothArgs a) {
-    using C = TcCfg<Sys>;
+    // three_cart pairs whose regressors are projected stage both members in one tile
+    constexpr bool DUAL = MODE == kTcPaired && Sys::kHasProjection;
+    using C = TcCfg<Sys, DUAL>;
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     constexpr int kXU = (n + m + 3) / 4 * 4;             // xbar | ubar, padded to float4
     constexpr int kNom = kXU + (n + 3) / 4 * 4;          // ... | fbar, padded to float4
     constexpr int kScr = C::dq + 1;                      // padded scratch row (bank-conflict free)
     constexpr int kNomBatch = C::kNomBatch;              // nominal points prepared per batch
+    constexpr int kMom = C::NMOM > 0 ? C::NMOM : 1;
+    static_assert(!CENTERED || C::NMOM == d + n, "centred accumulation needs the first-moment slots");
     extern __shared__ __align__(128) unsigned char stage_mem[];   // [warp][stage][kStageBytes]
     __shared__ uint64_t mbar_empty[C::kWarps][NSTAGE];   // UMMA commit -> owning warp: tile drained
     __shared__ uint64_t mbar_done[C::kWarps];            // UMMA commit -> owning warp: accumulator complete
@@ -177,8 +202,9 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     // cost one latency per batch instead of one per item
     __shared__ __align__(16) float nom_tab[kNomBatch][kNom];
     __shared__ double pos64_tab[kNomBatch][4];           // leading coordinates in fp64 (projection)
-    __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][i] + D[r][dq + i]
+    __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][z_1 col i] - D[r][z_2 col i] of r's member
     __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
+    __shared__ float mom_s[C::kWarps][kMom];             // per-warp first moments of the item
 
     const int tid = threadIdx.x, lane = tid & 31;
     // broadcast from lane 0 so that the compiler knows the warp index is warp-uniform: ring addresses,
@@ -199,6 +225,11 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         int i = 0;
         while (i + 1 < d && gram_row_offset(i + 1, C::W) <= e) ++i;
         idx_s[e] = (uint16_t)((i << 8) | (i + (e - gram_row_offset(i, C::W))));
+    }
+    if constexpr (DUAL) {
+        // a launch that stages one row per lane (no projection) never writes the second member's rows
+        for (int e = tid; e < NSTAGE * C::kWarps * C::kStageBytes / 16; e += C::kThreads)
+            reinterpret_cast<uint4*>(stage_mem)[e] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -270,6 +301,8 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 #endif
 
     [[maybe_unused]] const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
+    // absolute-points quirk (project_deltas): the state handed to the dynamics is xbar + (xbar + w)
+    [[maybe_unused]] const float twice = (Sys::kHasProjection && (a.flags & kFlagProjectAbsolute)) ? 2.f : 1.f;
     // this warp's tile ring; byte offset of this lane's sample inside a tile (feature group 0)
     unsigned char* my_ring = stage_mem + (size_t)warp * NSTAGE * C::kStageBytes;
     const uint32_t ring_u32 = smem_u32(my_ring);
@@ -303,7 +336,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         __syncwarp();
     };
 
-    int round = 0;      // running round counter of this warp (tile ring position)
+    int round = 0;      // running tile counter of this warp (tile ring position)
     int it = 0;         // running item counter of this block
     for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int p = (int)(item / a.C);
@@ -322,6 +355,9 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         }
         const float4* nom4 = reinterpret_cast<const float4*>(nom_tab[slot]);
         const double* pos64_s = pos64_tab[slot];
+        float mom[kMom];                                      // first moments of this lane's rows (CENTERED)
+#pragma unroll
+        for (int q = 0; q < kMom; ++q) mom[q] = 0.f;
         // the nominal point stays in shared memory (broadcast LDS.128 instead of 28 registers: measured
         // faster than the register copy)
         auto load_xu = [&](float (&xu)[kXU]) {
@@ -329,6 +365,14 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             for (int q = 0; q < kXU / 4; ++q) {
                 const float4 v = nom4[q];
                 xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
+            }
+        };
+        // xu = xbar + w (the absolute-points quirk adds the nominal twice)
+        auto perturb = [&](float (&xu)[kXU], const float (&w)[C::RS]) {
+#pragma unroll
+            for (int q = 0; q < d; ++q) {
+                if constexpr (Sys::kHasProjection) xu[q] = fmaf(twice, xu[q], w[q]);
+                else xu[q] += w[q];
             }
         };
         auto dynamics = [&](const float (&xu)[kXU], float (&f)[n]) {
@@ -339,7 +383,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                 sys.template step<false>(xu, xu + n, f);
             }
         };
-        // w[d ..] = f - fbar
+        // w[d ..] = scale (f - fbar)
         auto minus_nominal_response = [&](const float (&f)[n], float (&w)[C::RS], float scale) {
 #pragma unroll
             for (int q = 0; q < (n + 3) / 4; ++q) {
@@ -350,12 +394,35 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                     if (4 * q + k < n) w[d + 4 * q + k] = scale * (f[4 * q + k] - fb[k]);
             }
         };
-        // One operand row per lane -> this warp's tile (bf16x2 split, MN-major), then the tile's UMMAs.
-        auto stage_and_issue = [&](const float (&w)[C::RS], bool first, bool last) {
+        // one ordinary sample row: deltas w[0 .. d) -> projected / perturbed / evaluated -> w = [z | dF]
+        auto finish_row = [&](float (&w)[C::RS]) {
+            float xu[kXU], f[n];
+            load_xu(xu);
+            project_deltas<Sys, C::RS>(a, p, pos64_s, w);
+            perturb(xu, w);
+            if constexpr (CENTERED && MODE == kTcReplay) {
+                if (!(a.flags & kFlagProjectAbsolute)) center_replayed<Sys, C::RS>(a, p, w);
+            }
+            dynamics(xu, f);
+            minus_nominal_response(f, w, 1.f);
+            if constexpr (CENTERED) {
+#pragma unroll
+                for (int q = 0; q < d + n; ++q) mom[q] += w[q];
+            }
+        };
+        auto zero_row = [&](float (&w)[C::RS]) {
+#pragma unroll
+            for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
+        };
+        // The tile must have been drained by the UMMAs that last read it (call before its first store).
+        auto wait_tile = [&]() {
             const int stage = round % NSTAGE;
-            // the tile must have been drained by the UMMAs that last read it
             if (round >= NSTAGE) mbar_wait(&mbar_empty[warp][stage], (uint32_t)((round / NSTAGE - 1) & 1));
-            unsigned char* sm = my_ring + stage * C::kStageBytes + my_off;
+        };
+        // One operand row of this lane -> member h of the warp's current tile (bf16x2 split, MN-major).
+        auto stage_row = [&](const float (&w)[C::RS], auto member_tag) {
+            constexpr int h = decltype(member_tag)::value;
+            unsigned char* sm = my_ring + (round % NSTAGE) * C::kStageBytes + my_off;
             // regressors: dq/8 groups of 8 features, first and second bf16 pieces
 #pragma unroll
             for (int g = 0; g < C::dq / 8; ++g) {
@@ -367,8 +434,8 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                     if (c0 < d) split_bf16x2(w[c0], c1 < d ? w[c1] : 0.f, p1[q], p2[q]);
                     else p1[q] = p2[q] = 0u;
                 }
-                *reinterpret_cast<uint4*>(sm + (C::grp_z1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                *reinterpret_cast<uint4*>(sm + (C::grp_z2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                *reinterpret_cast<uint4*>(sm + (C::grp_z1(h) + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                *reinterpret_cast<uint4*>(sm + (C::grp_z2(h) + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
             }
             // responses
 #pragma unroll
@@ -380,16 +447,16 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                     if (c0 < n) split_bf16x2(w[d + c0], c1 < n ? w[d + c1] : 0.f, p1[q], p2[q]);
                     else p1[q] = p2[q] = 0u;
                 }
-                *reinterpret_cast<uint4*>(sm + (C::grp_f1 + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                *reinterpret_cast<uint4*>(sm + (C::grp_f2 + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                *reinterpret_cast<uint4*>(sm + (C::grp_f1(h) + g) * C::kSBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                *reinterpret_cast<uint4*>(sm + (C::grp_f2(h) + g) * C::kSBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
             }
-            issue_tile(stage, first, last);
+        };
+        auto issue = [&](bool first, bool last) {
+            issue_tile(round % NSTAGE, first, last);
             ++round;
         };
-        auto zero_row = [&](float (&w)[C::RS]) {
-#pragma unroll
-            for (int q = 0; q < C::RS; ++q) w[q] = 0.f;      // ragged tail: contributes nothing
-        };
+        using Member0 = std::integral_constant<int, 0>;
+        using Member1 = std::integral_constant<int, DUAL ? 1 : 0>;
         const long long len = s_end - s_begin;                // samples of this chunk
         // pairs share a noise draw only (two operand rows per pair) when the regressors are projected
         [[maybe_unused]] const bool pair_rows =
@@ -402,29 +469,26 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         auto do_round = [&](auto check_tag, int r) {
             constexpr bool CHECK = decltype(check_tag)::value;
             const long long lu = (long long)r * C::kTile + tid;       // this lane's unit inside the chunk
+            const bool first = r == 0, last = r == rounds - 1;
             float w[C::RS];
             if constexpr (C::RS > C::W) w[C::RS - 1] = 0.f;
             if constexpr (MODE != kTcPaired) {
                 if (!CHECK || lu < len) {
                     draw_deltas<Sys, C::RS, MODE == kTcReplay ? 1 : 0>(a, p, s_begin + lu, w);
-                    float xu[kXU], f[n];
-                    load_xu(xu);
-                    project_deltas<Sys, C::RS>(a, p, xu, xu + n, pos64_s, w);
-#pragma unroll
-                    for (int q = 0; q < d; ++q) xu[q] += w[q];
-                    dynamics(xu, f);
-                    minus_nominal_response(f, w, 1.f);
+                    finish_row(w);
                 } else {
                     zero_row(w);
                 }
-                stage_and_issue(w, r == 0, r == rounds - 1);
+                wait_tile();
+                stage_row(w, Member0{});
+                issue(first, last);
             } else {
                 const bool have_plus = !CHECK || 2 * lu < len;
                 const bool have_minus = !CHECK || 2 * lu + 1 < len;
                 // the pair's draw: counter word 0 = global pair index (a.i0 and s_begin are even)
                 const unsigned long long pair = ((a.i0 + (unsigned long long)s_begin) >> 1) + (unsigned long long)lu;
                 bool two_rows = false;
-                if constexpr (Sys::kHasProjection) two_rows = pair_rows;
+                if constexpr (DUAL) two_rows = pair_rows;
                 if (!two_rows) {
                     if (have_plus) {
                         philox_normals<Sys, C::RS>(a, p, pair, w);
@@ -450,32 +514,34 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                     } else {
                         zero_row(w);
                     }
-                    stage_and_issue(w, r == 0, r == rounds - 1);
+                    wait_tile();
+                    stage_row(w, Member0{});
+                    issue(first, last);
                 } else {
-                    if constexpr (Sys::kHasProjection) {
+                    if constexpr (DUAL) {
+                        // both members of the pair in ONE tile: + member rows, then - member rows
                         float z[d];
                         if (have_plus) {
                             philox_normals<Sys, C::RS>(a, p, pair, w);
 #pragma unroll
                             for (int q = 0; q < d; ++q) z[q] = w[q];
-                        }
-#pragma unroll 1
-                        for (int half = 0; half < 2; ++half) {
-                            if (half == 0 ? have_plus : have_minus) {
+                            finish_row(w);
+                        } else {
 #pragma unroll
-                                for (int q = 0; q < d; ++q) w[q] = half == 0 ? z[q] : -z[q];
-                                float xu[kXU], f[n];
-                                load_xu(xu);
-                                project_deltas<Sys, C::RS>(a, p, xu, xu + n, pos64_s, w);
-#pragma unroll
-                                for (int q = 0; q < d; ++q) xu[q] += w[q];
-                                dynamics(xu, f);
-                                minus_nominal_response(f, w, 1.f);
-                            } else {
-                                zero_row(w);
-                            }
-                            stage_and_issue(w, r == 0 && half == 0, r == rounds - 1 && half == 1);
+                            for (int q = 0; q < d; ++q) z[q] = 0.f;
+                            zero_row(w);
                         }
+                        wait_tile();
+                        stage_row(w, Member0{});
+                        if (have_minus) {
+#pragma unroll
+                            for (int q = 0; q < d; ++q) w[q] = -z[q];
+                            finish_row(w);
+                        } else {
+                            zero_row(w);
+                        }
+                        stage_row(w, Member1{});
+                        issue(first, last);
                     }
                 }
             }
@@ -483,6 +549,14 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         const int full_rounds = (int)((MODE == kTcPaired ? len / 2 : len) / C::kTile);
         for (int r = 0; r < full_rounds; ++r) do_round(std::false_type{}, r);
         if (full_rounds < rounds) do_round(std::true_type{}, full_rounds);
+        if constexpr (CENTERED) {
+            // first moments of the item: lanes -> warp (shuffles) -> block (shared memory, fixed order below)
+#pragma unroll
+            for (int q = 0; q < d + n; ++q) {
+                const float v = warp_sum(mom[q]);
+                if (lane == 0) mom_s[warp][q] = v;
+            }
+        }
         // ---- item finished: wait for this warp's UMMAs, meet the other warps, read all four
         //      accumulators back.  Row r of D lives in TMEM lane (r % 16) + 32 * (r / 16) (M = 64
         //      layout): lanes 0-15 of warp w hold rows 16 w .. 16 w + 15 of every accumulator (and
@@ -520,24 +594,42 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 #endif
             const int row = 16 * warp + lane;
             if (lane < 16 && row < C::kRows) {
+                // columns of the row's OWN member: z_1 piece minus z_2 piece (the z_2 columns are negated)
+                const bool second = C::member_of_row(row) == 1;
 #pragma unroll
-                for (int i = 0; i < C::dq; ++i) scratch[row * kScr + i] = sum[i] - sum[C::dq + i];   // z_2 columns are negated
+                for (int i = 0; i < C::dq; ++i) {
+                    float v = sum[i] - sum[C::dq + i];
+                    if constexpr (DUAL) {
+                        const float v1 = sum[2 * C::dq + i] - sum[3 * C::dq + i];
+                        v = second ? v1 : v;
+                    }
+                    scratch[row * kScr + i] = v;
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();      // scratch complete; every accumulator read back (next item may overwrite)
         asm volatile("tcgen05.fence::after_thread_sync;");
-        // G[i][j] = sum_k z_i w_j = sum over the two pieces of w_j of s_row[i] (second-piece rows negated)
-        float* out = a.partials + item * C::NACC;
+        // G[i][j] = sum_k z_i w_j = sum over the two pieces of w_j of s_row[i] (second-piece rows negated),
+        // summed over the members of the tile
+        float* out = a.partials + item * C::WIDTH;
         // paired rows: the regressor block of a pair is 2 z z^T (exact doubling)
         const float zz_scale = (MODE == kTcPaired && !pair_rows) ? 2.f : 1.f;
         for (int e = tid; e < C::NACC; e += C::kThreads) {
             const int ij = idx_s[e];
             const int i = ij >> 8, j = ij & 0xff;
-            const float v = scratch[C::row_1(j) * kScr + i] - scratch[C::row_2(j) * kScr + i];
+            float v = scratch[C::row_1(0, j) * kScr + i] - scratch[C::row_2(0, j) * kScr + i];
+            if constexpr (DUAL) v += scratch[C::row_1(1, j) * kScr + i] - scratch[C::row_2(1, j) * kScr + i];
             out[e] = j < d ? zz_scale * v : v;
         }
-        // (the next item's barriers order these scratch reads before its scratch writes)
+        if constexpr (C::NMOM > 0) {
+            if (tid < C::NMOM) {
+                float v = 0.f;
+                if constexpr (CENTERED) v = (mom_s[0][tid] + mom_s[1][tid]) + (mom_s[2][tid] + mom_s[3][tid]);
+                out[C::NACC + tid] = v;
+            }
+        }
+        // (the next item's barriers order these scratch / mom_s reads before the next writes)
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();

@@ -253,50 +253,60 @@ struct ThreeCart {
         const bool g23 = (q3 - q2) < d;
         return g12 ? (g23 ? 1 : 2) : (g23 ? 3 : 0);
     }
+    // Branch-free (selects): the four contact cases are exclusive, every candidate value is computed and
+    // the case picks; each selected value is produced by the same operations as in the reference's
+    // branch, so the results are bit-identical to a branching version while a warp whose lanes fall into
+    // different cases does not serialise them (and the compiler can interleave independent samples).
     template <bool BATCH>
     __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
-        R v1 = x[3] + h * u[0];
-        R v2 = x[4];
-        R v3 = x[5] + h * u[1];
-        R q1 = x[0] + h * v1;
-        R q2 = x[1] + h * v2;
-        R q3 = x[2] + h * v3;
-        const int cs = contact_case(q1, q2, q3);
+        const R v1 = x[3] + h * u[0];
+        const R v2 = x[4];
+        const R v3 = x[5] + h * u[1];
+        const R q1 = x[0] + h * v1;
+        const R q2 = x[1] + h * v2;
+        const R q3 = x[2] + h * v3;
+        const R gap12 = q2 - q1, gap23 = q3 - q2;
+        const bool g12 = gap12 < d, g23 = gap23 < d;
+        const bool all3 = g12 && g23, pair12 = g12 && !g23, pair23 = !g12 && g23;      // cases 1, 2, 3 (:146-157)
         const R pf = BATCH ? R(1) : R(0.5);
-        if (cs == 1) {
-            const R mid = (q1 + q2 + q3) * R(1.0 / 3.0);
-            const R va = (v1 + v2 + v3) * R(1.0 / 3.0);
-            q1 = mid - d;  q2 = mid;  q3 = mid + d;
-            v1 = va;  v2 = va;  v3 = va;
-        } else if (cs == 2) {
-            const R depth = pf * (d - (q2 - q1));
-            const R va = R(0.5) * (v1 + v2);
-            q2 += depth;  q1 -= depth;
-            v1 = va;  v2 = va;
-        } else if (cs == 3) {
-            const R depth = pf * (d - (q3 - q2));
-            const R va = R(0.5) * (v2 + v3);
-            q3 += depth;  q2 -= depth;
-            v2 = va;  v3 = va;
-        }
-        o[0] = q1;  o[1] = q2;  o[2] = q3;  o[3] = v1;  o[4] = v2;  o[5] = v3;
+        const R mid = (q1 + q2 + q3) * R(1.0 / 3.0);
+        const R va3 = (v1 + v2 + v3) * R(1.0 / 3.0);
+        const R depth12 = pf * (d - gap12), va12 = R(0.5) * (v1 + v2);
+        const R depth23 = pf * (d - gap23), va23 = R(0.5) * (v2 + v3);
+        o[0] = all3 ? mid - d : (pair12 ? q1 - depth12 : q1);
+        o[1] = all3 ? mid : (pair12 ? q2 + depth12 : (pair23 ? q2 - depth23 : q2));
+        o[2] = all3 ? mid + d : (pair23 ? q3 + depth23 : q3);
+        o[3] = all3 ? va3 : (pair12 ? va12 : v1);
+        o[4] = all3 ? va3 : (pair12 ? va12 : (pair23 ? va23 : v2));
+        o[5] = all3 ? va3 : (pair23 ? va23 : v3);
     }
     __device__ __forceinline__ void jac_var(const R*, const R*, R*) const {}
     __device__ __forceinline__ void jac_assemble(const R*, R*) const {}
     __device__ __forceinline__ void project(R* x) const {
-        // sequential masks as in :216-261 (each re-evaluated on the partially projected point)
-        if ((x[1] - x[0]) < d && (x[2] - x[1]) < d) {
-            const R mid = (x[0] + x[1] + x[2]) * R(1.0 / 3.0);
-            x[1] = mid;  x[0] = mid - d;  x[2] = mid + d;
+        // sequential masks as in :216-261 (each re-evaluated on the partially projected point), written
+        // with selects: the operations that produce a selected value are those of the reference's branch
+        R x0 = x[0], x1 = x[1], x2 = x[2];
+        {
+            const bool c = (x1 - x0) < d && (x2 - x1) < d;
+            const R mid = (x0 + x1 + x2) * R(1.0 / 3.0);
+            const R lo = mid - d, hi = mid + d;
+            x1 = c ? mid : x1;  x0 = c ? lo : x0;  x2 = c ? hi : x2;
         }
-        if ((x[1] - x[0]) < d && !((x[2] - x[1]) < d)) {
-            const R depth = R(0.5) * (d - (x[1] - x[0]));
-            x[1] += depth;  x[0] -= depth;
+        {
+            const R gap = x1 - x0;
+            const bool c = gap < d && !((x2 - x1) < d);
+            const R depth = R(0.5) * (d - gap);
+            const R up = x1 + depth, dn = x0 - depth;
+            x1 = c ? up : x1;  x0 = c ? dn : x0;
         }
-        if (!((x[1] - x[0]) < d) && (x[2] - x[1]) < d) {
-            const R depth = R(0.5) * (d - (x[2] - x[1]));
-            x[2] += depth;  x[1] -= depth;
+        {
+            const R gap = x2 - x1;
+            const bool c = !((x1 - x0) < d) && gap < d;
+            const R depth = R(0.5) * (d - gap);
+            const R up = x2 + depth, dn = x1 - depth;
+            x2 = c ? up : x2;  x1 = c ? dn : x1;
         }
+        x[0] = x0;  x[1] = x1;  x[2] = x2;
     }
 };
 

@@ -116,7 +116,7 @@ class PeerExchange:
                   _device.ptr(u_nom), P, ws.C, _device.ptr(ws.partials), self._hbuf.buffer_ptrs_dev,
                   self._hflags.buffer_ptrs_dev, _device.ptr(self.epoch), _device.ptr(self.counter),
                   self.slot_stride, self.flag_stride, self.rank, self.world, self.timeout_s, float(n_total),
-                  _device.ptr(ws.At), _device.ptr(ws.Bt), _device.ptr(ws.ct), _device.ptr(ws.status),
+                  1 if ws.centered else 0, _device.ptr(ws.At), _device.ptr(ws.Bt), _device.ptr(ws.ct), _device.ptr(ws.status),
                   _device.stream_ptr())
         return ws.At, ws.Bt, ws.ct, ws.status
 

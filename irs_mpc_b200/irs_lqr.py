@@ -433,8 +433,22 @@ class _SampledIrsLqr(IrsLqr):
         else:
             noise = self._replay_noise(x_nom, u_nom)
             At, Bt, ct, status, self._ws = smoothing.linearize(
-                self.system, self.order, x_nom, u_nom, noise.shape[1], self._ws, noise=noise)
+                self.system, self.order, x_nom, u_nom, noise.shape[1], self._ws, noise=noise,
+                flags=self._replay_flags(noise, x_nom, u_nom))
         return At, Bt, ct, status
+
+    def _replay_flags(self, noise, x_nom, u_nom):
+        """A closure may return ABSOLUTE points instead of deltas — the reference's three_cart script does
+        (three_cart_zero_order.py:43 returns projection(...)), and the solver uses them
+        literally.  Points that lie closer to the nominal than to the origin are accumulated relative to
+        the nominal (IRS_CENTERED: the fit is the same least squares, shifted back in fp64), because an fp32
+        Gram of the absolute points loses the sample spread once |xbar| >> sigma."""
+        if self.order != smoothing.ZERO_ORDER or not getattr(self.system, "centered_capable", False):
+            return 0
+        mean = noise.to(torch.float64).mean(dim=1)
+        nominal = torch.cat((x_nom, u_nom), dim=1)
+        closer_to_nominal = float((mean - nominal).abs().sum().item()) < float(mean.abs().sum().item())
+        return smoothing.FLAG_CENTERED if closer_to_nominal else 0
 
 
     def _pipeline_segments(self):

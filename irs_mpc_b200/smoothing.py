@@ -15,6 +15,8 @@ from . import _device, _lib
 
 ZERO_ORDER = 0
 FIRST_ORDER = 1
+# smoothing flags (include/irs_mpc_b200.h)
+FLAG_PROJECT_ABSOLUTE, FLAG_PROJECT_DELTA, FLAG_ANTITHETIC, FLAG_CENTERED = 2, 4, 8, 16
 
 
 def plan(system_id, order, P, N):
@@ -49,6 +51,9 @@ class Workspace:
         self.u_nom = self._nom[P * n:].view(P, m)
         self._out_host = None
         self._nom_host = None
+        # the last accumulate into this workspace was centred (regressors relative to the nominal point +
+        # first moments: three_cart absolute points): the finalize must undo the shift
+        self.centered = False
 
     def _host_buffers(self):
         if self._nom_host is None:
@@ -107,6 +112,7 @@ def accumulate(system, order, x_nom, u_nom, N, ws, sigma=None, noise=None, seed=
     prm, nprm = system._params()
     if system.batch_differs_from_scalar and order == ZERO_ORDER:
         flags |= 1   # IRS_SAMPLES_BATCH_VARIANT: samples go through dynamics_batch (…zero_order.py:51)
+    ws.centered = order == ZERO_ORDER and bool(flags & (FLAG_PROJECT_ABSOLUTE | FLAG_CENTERED))
     sig = None
     if noise is None:
         sig = np.ascontiguousarray(np.asarray(sigma, dtype=np.float32))
@@ -145,7 +151,7 @@ def finalize(system, order, x_nom, u_nom, ws, n_total, partials=None, reduced=No
     P = x_nom.shape[0]
     _lib.call("irs_smooth_finalize", system.system_id, prm, nprm, order, _device.ptr(x_nom),
               _device.ptr(u_nom), P, ws.C, _device.ptr(part), _device.ptr(reduced), nranks,
-              int(rank_stride), float(n_total), _device.ptr(At), _device.ptr(Bt),
+              int(rank_stride), float(n_total), 1 if ws.centered else 0, _device.ptr(At), _device.ptr(Bt),
               _device.ptr(ct), _device.ptr(status), _device.stream_ptr())
     return ws.At, ws.Bt, ws.ct, ws.status
 

@@ -70,6 +70,7 @@ class ThreeCartDynamics(CudaDynamicalSystem):
     system_id = 3
     system_name = "three_cart"
     batch_differs_from_scalar = True
+    centered_capable = True          # absolute-point regressors can be accumulated relative to the nominal
 
     def __init__(self, dt):
         super().__init__()

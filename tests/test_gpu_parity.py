@@ -569,7 +569,7 @@ def test_finalize_variants_are_bit_identical(api, name, N, zero_sigma, monkeypat
 # ------------------------------------------------------------------------------------------------
 # batched MPC instances (BASELINE.json configs[4])
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,I,T,N", [("quadrotor", 5, 24, 3000), ("pendulum", 300, 30, 600)])
+@pytest.mark.parametrize("name,I,T,N", [("quadrotor", 5, 24, 8192), ("pendulum", 300, 30, 600)])
 def test_batched_instances_match_oracle_and_shard(api, name, I, T, N):
     """Every instance of a batch equals the single-problem oracle pipeline on the deltas the kernel
     drew for it (1e-4), and a shard of the batch (instance_offset) is bit-identical to the same
