@@ -372,6 +372,57 @@ def run_gpu(args, rank, local_rank, world):
             other[label] = {"ms_per_linearization": ms2, "samples_per_s": Tn * Nn / (ms2 * 1e-3)}
             del ws2
 
+    # 5d. STRONG scaling of the named configs: the TOTAL sample count of BASELINE.json configs[2] (N = 1e5 per
+    #     step) and configs[3] (three_cart, N = 1e6 per step) split over the ranks — sample axis (fused peer
+    #     exchange inside the finalize kernel) and, for configs[2], the north star's timestep axis (each rank
+    #     linearizes T / W timesteps, NCCL all-gather of the packed [A|B|c] blocks, 81.6 KB).  At world == 1 the
+    #     same calls give the single-GPU times the ratios refer to.  ms per step, max over ranks.
+    strong = None
+    if not args.no_strong:
+        from irs_mpc_b200 import example_configs as gec
+        from irs_mpc_b200.systems import SYSTEM_CLASSES
+        strong = {"note": "total work fixed, split over n_gpus ranks; ms per linearization step (device time, max "
+                          "over ranks); efficiency = t(1 GPU) / (n_gpus * t(n_gpus)) with the 1-GPU run of this bench"}
+        st_steps = max(5, min(args.steps, 20))
+
+        def strong_case(name, Tn, N_total, proj_flag, with_t_axis):
+            c2 = gec.CONFIGS[name](T=Tn)
+            sys2 = SYSTEM_CLASSES[name](c2["h"])
+            xn2 = _device.to_device(np.zeros((Tn, sys2.dim_x)) + c2["x0"]) if name != "quadrotor" else x_nom
+            un2 = _device.to_device(c2["u_trj_initial"]) if name != "quadrotor" else u_nom
+            fl = proj_flag | sampler.flags()
+            out = {"T": Tn, "N_total": N_total, "N_per_gpu": N_total // world}
+            if world == 1:
+                ws2 = smoothing.Workspace(sys2, smoothing.ZERO_ORDER, Tn, N_total)
+
+                def f1(k):
+                    smoothing.accumulate(sys2, smoothing.ZERO_ORDER, xn2, un2, N_total, ws2, sigma=c2["sigma"],
+                                         seed=SEED0 + k, it=1, flags=fl)
+                    smoothing.finalize(sys2, smoothing.ZERO_ORDER, xn2, un2, ws2, N_total)
+                t1 = timed(f1, st_steps, 3) / st_steps
+                out["sample_axis_ms"] = t1
+                if with_t_axis:
+                    out["timestep_axis_ms"] = t1
+                del ws2
+            else:
+                sh2 = ShardedLinearizer(sys2, smoothing.ZERO_ORDER)
+                n_loc = N_total // world
+
+                def fn(k):
+                    sh2.linearize_n(xn2, un2, n_loc, sigma=c2["sigma"], seed=SEED0 + k, it=1, flags=fl)
+                out["sample_axis_ms"] = timed(fn, st_steps, 4) / st_steps
+                out["sample_axis_exchange"] = "peer memory, fused into the finalize kernel" if sh2._px is not None \
+                    else "NCCL all_gather"
+                if with_t_axis:
+                    def ft(k):
+                        sh2.linearize_t(xn2, un2, N_total, sigma=c2["sigma"], seed=SEED0 + k, it=1, flags=fl)
+                    out["timestep_axis_ms"] = timed(ft, st_steps, 3) / st_steps
+            out["samples_per_s_sample_axis"] = Tn * N_total / (out["sample_axis_ms"] * 1e-3)
+            return out
+        strong["configs[2] quadrotor T=100 N=1e5 total"] = strong_case("quadrotor", T_STEPS, N_SAMPLES, 0, True)
+        strong["configs[3] three_cart T=100 N=1e6 total, in-kernel projection"] = strong_case(
+            "three_cart", 100, 1000000, 2, False)
+
     # 6. CPU baseline on this box's host cores (rank 0, single GPU run only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -406,6 +457,7 @@ def run_gpu(args, rank, local_rank, world):
             "iters_per_s": iters_per_s, "ms_per_iteration": ms_iter / it_steps,
             "batched_mpc": batched,
             "other_configs": other,
+            "strong_scaling": strong,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
@@ -467,6 +519,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the 4096-instance leg (configs[4])")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the pendulum/bicycle/three_cart legs")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

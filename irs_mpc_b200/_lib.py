@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("IRS_MPC_B200_LIB", os.path.join(_HERE, "libirs_mpc_b200.so"))   # env: tuning builds
+LIB_PATH = os.environ.get("IRS_MPC_B200_LIB") or os.path.join(_HERE, "libirs_mpc_b200.so")   # env: tuning builds
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 

@@ -126,9 +126,9 @@ __device__ __forceinline__ void draw_deltas(const SmoothArgs& a, int p, long lon
 // kFlagProjectDelta: that IS the regressor and the perturbation.  kFlagProjectAbsolute — the
 // reference closure returns ABSOLUTE points, which the solver adds to the nominal AGAIN and uses
 // un-centred as regressors, reproduced literally: the state handed to the
-// dynamics is xbar + (xbar + w) (the callers add the nominal twice) and the regressors are xbar + w,
-// accumulated as w with their first moments and shifted back in fp64 by the finalize
-// (kFlagCentered).  An fp32 Gram of the absolute points themselves loses the sample spread once
+// dynamics is xbar + (xbar + w) (the callers perturb the doubled nominal, systems.cuh: centred_frame) and
+// the regressors are xbar + w, accumulated as w with their first moments and shifted back in fp64 by
+// the finalize (kFlagCentered).  An fp32 Gram of the absolute points themselves loses the sample spread once
 // |xbar| >> sigma, which the quirk's meaningless linearization reaches after one descent.
 template <class Sys, int RS>
 __device__ __forceinline__ void project_deltas(const SmoothArgs& a, int p, const double* pos64, float (&w)[RS]) {
@@ -171,16 +171,15 @@ __device__ __forceinline__ void make_sample(const Sys& sys, const SmoothArgs& a,
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
     draw_deltas<Sys, RS>(a, p, i, w);
     project_deltas<Sys, RS>(a, p, nullptr, w);
-    // absolute-points quirk: the state is xbar + (xbar + w), see project_deltas
-    const float twice = (Sys::kHasProjection && (a.flags & kFlagProjectAbsolute)) ? 2.f : 1.f;
-    float x[n], u[m];
-#pragma unroll
-    for (int c = 0; c < n; ++c) x[c] = fmaf(twice, xbar[c], w[c]);
-#pragma unroll
-    for (int c = 0; c < m; ++c) u[c] = fmaf(twice, ubar[c], w[n + c]);
     if constexpr (Sys::kHasProjection) {
+        // replayed absolute points -> relative to the nominal (the caller's xbar is then the centred frame)
         if ((a.flags & kFlagCentered) && !(a.flags & kFlagProjectAbsolute)) center_replayed<Sys, RS>(a, p, w);
     }
+    float x[n], u[m];
+#pragma unroll
+    for (int c = 0; c < n; ++c) x[c] = xbar[c] + w[c];
+#pragma unroll
+    for (int c = 0; c < m; ++c) u[c] = ubar[c] + w[n + c];
     if (want_df) {
         float f[n];
         sys.template step<BATCH>(x, u, f);
@@ -395,8 +394,23 @@ smooth_zero_order_kernel(const SmoothArgs a) {
     for (int q = 0; q < n; ++q) xbar[q] = (float)a.x_nom[(long long)p * n + q];
 #pragma unroll
     for (int q = 0; q < m; ++q) ubar[q] = (float)a.u_nom[(long long)p * m + q];
-    // nominal response: the reference uses the SCALAR dynamics here (irs_lqr_zero_order.py:52)
-    sys.template step<false>(xbar, ubar, fbar);
+    // nominal response: the reference uses the SCALAR dynamics here (irs_lqr_zero_order.py:52); a centred
+    // accumulation measures against the sample dynamics at the doubled nominal (smooth_tc.cuh:
+    // reference_response; the finalize adds the difference back in fp64)
+    bool centred = false;
+    if constexpr (Sys::kHasProjection) centred = (a.flags & (kFlagCentered | kFlagProjectAbsolute)) != 0;
+    if (centred) {
+        double xd[n], ud[m];
+#pragma unroll
+        for (int q = 0; q < n; ++q) xd[q] = a.x_nom[(long long)p * n + q];
+#pragma unroll
+        for (int q = 0; q < m; ++q) ud[q] = a.u_nom[(long long)p * m + q];
+        centred_frame<Sys>(xd, ud, xbar, ubar);       // the samples are perturbed around the centred frame
+        if (a.flags & kFlagSamplesBatchVariant) sys.template step<true>(xbar, ubar, fbar);
+        else sys.template step<false>(xbar, ubar, fbar);
+    } else {
+        sys.template step<false>(xbar, ubar, fbar);
+    }
     float* out = a.partials + ((long long)p * a.C + c) * gram_width_of<Sys>();
     if constexpr (G == 1) {
         if (a.flags & kFlagSamplesBatchVariant)
@@ -741,8 +755,9 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
     __shared__ double sAB[n * d];
     __shared__ double inv_diag[d];
     __shared__ double nom[d + n];
-    __shared__ double mom[WIDTH - NACC > 0 ? WIDTH - NACC : 1];   // [sum z' (d) | sum dF (n)]
+    __shared__ double mom[WIDTH - NACC > 0 ? WIDTH - NACC : 1];   // [sum z' (d) | sum dF' (n)]
     __shared__ double spread[d];      // diagonal of the CENTRED Gram: scale of the rank test
+    __shared__ double rho[n];         // centred: f_batch(2 xbar, 2 ubar) - f(xbar, ubar), the response shift
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
     // 0. sample-sharded run: exchange this point's chunk-reduced block with the other ranks first
@@ -775,12 +790,29 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
             }
         }
     }
+    if constexpr (WIDTH > NACC) {
+        if (a.centered && tid == 32) {
+            // response shift of the centred accumulation, in fp64 (the samples of a centred launch go
+            // through the batch variant of the dynamics, the nominal response through the scalar one)
+            const Sys sys(a.prm);
+            double xb[n], ub[m], x2[n], u2[m], f2[n], fb[n];
+#pragma unroll
+            for (int q = 0; q < n; ++q) { xb[q] = a.x_nom[(long long)p * n + q];  x2[q] = 2.0 * xb[q]; }
+#pragma unroll
+            for (int q = 0; q < m; ++q) { ub[q] = a.u_nom[(long long)p * m + q];  u2[q] = 2.0 * ub[q]; }
+            sys.template step<true>(x2, u2, f2);
+            sys.template step<false>(xb, ub, fb);
+#pragma unroll
+            for (int q = 0; q < n; ++q) rho[q] = f2[q] - fb[q];
+        }
+    }
     __syncthreads();
     if (tid < d) spread[tid] = Gm[tid * d + tid];
     if constexpr (WIDTH > NACC) {
-        // 1b. centred accumulation: z = s + z' with s = (xbar, ubar) in fp64, so
-        //       Z^T Z  = Z'^T Z' + s m'^T + m' s^T + N s s^T,      Z^T dF = Z'^T dF + s g^T
-        //     (m' = sum z', g = sum dF).  The fp32 partials only ever held O(sigma) numbers.
+        // 1b. centred accumulation: z = s + z' with s = (xbar, ubar), dF = rho + dF', so
+        //       Z^T Z  = Z'^T Z' + s m'^T + m' s^T + N s s^T
+        //       Z^T dF = Z'^T dF' + m' rho^T + s g'^T + N s rho^T          (m' = sum z', g' = sum dF')
+        //     in fp64.  The fp32 partials only ever held O(sigma) numbers.
         if (a.centered) {
             __syncthreads();      // spread[] read the centred diagonal
             for (int e = tid; e < d * d; e += BT) {
@@ -792,7 +824,7 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
             for (int e = tid; e < d * n; e += BT) {
                 const int i = e / n, q = e % n;
                 const double si = i < n ? a.x_nom[(long long)p * n + i] : a.u_nom[(long long)p * m + (i - n)];
-                Bm[e] = fma(si, mom[d + q], Bm[e]);
+                Bm[e] = fma(a.n_total * si, rho[q], fma(si, mom[d + q], fma(mom[i], rho[q], Bm[e])));
             }
         }
     }

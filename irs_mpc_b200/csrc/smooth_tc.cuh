@@ -237,23 +237,42 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const Sys sys(a.prm);
-    // nominal points of the items first, first + gridDim.x, ... -> nom_tab (all threads call it; the
-    // caller's barriers order it against the readers)
+    // The point (xb | ub) the samples are perturbed around and the response fb every sample's f is measured
+    // against.  Ordinarily the fp32 nominal and the scalar dynamics there (…zero_order.py:52).  CENTERED
+    // (regressors are absolute points xbar + z', so the state of a sample is 2 xbar + z'): the doubled
+    // nominal in the system's centred frame (systems.cuh: centred_frame) and the SAMPLE dynamics there, so
+    // that the accumulated responses are O(sigma) like the regressors — f(2 xbar + z') - f(xbar) itself is
+    // ~ |xbar|, and a fp32 sum of it, multiplied by the shift |xbar| when the fit is un-centred, would cost
+    // |xbar|^2 in accuracy.  The finalize adds f_batch(2 xbar, 2 ubar) - f(xbar, ubar) back in fp64.
+    auto nominal_point = [&](int p, int slot, float (&xb)[n], float (&ub)[m], float (&fb)[n]) {
+        double xd[n], ud[m];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+            xd[q] = a.x_nom[(long long)p * n + q];
+            if (q < 4) pos64_tab[slot][q] = xd[q];
+        }
+#pragma unroll
+        for (int q = 0; q < m; ++q) ud[q] = a.u_nom[(long long)p * m + q];
+        if constexpr (CENTERED) {
+            centred_frame<Sys>(xd, ud, xb, ub);
+            if (a.flags & kFlagSamplesBatchVariant) sys.template step<true>(xb, ub, fb);
+            else sys.template step<false>(xb, ub, fb);
+        } else {
+#pragma unroll
+            for (int q = 0; q < n; ++q) xb[q] = (float)xd[q];
+#pragma unroll
+            for (int q = 0; q < m; ++q) ub[q] = (float)ud[q];
+            sys.template step<false>(xb, ub, fb);
+        }
+    };
+    // nominal points of the items first, first + gridDim.x, ... -> nom_tab, one thread each (all threads
+    // call it; the caller's barriers order it against the readers)
     auto prepare_nominals = [&](long long first) {
         if (tid < kNomBatch) {
             const long long it2 = first + (long long)tid * gridDim.x;
             if (it2 < num_items) {
-                const int p = (int)(it2 / a.C);
                 float xb[n], ub[m], fb[n];
-#pragma unroll
-                for (int q = 0; q < n; ++q) {
-                    const double v = a.x_nom[(long long)p * n + q];
-                    xb[q] = (float)v;
-                    if (q < 4) pos64_tab[tid][q] = v;
-                }
-#pragma unroll
-                for (int q = 0; q < m; ++q) ub[q] = (float)a.u_nom[(long long)p * m + q];
-                sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
+                nominal_point((int)(it2 / a.C), tid, xb, ub, fb);
                 float* row = nom_tab[tid];
 #pragma unroll
                 for (int q = 0; q < n; ++q) row[q] = xb[q];
@@ -266,28 +285,10 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             }
         }
     };
-    // kNomBatch == 1: the nominal point of one item, cooperatively (two block barriers inside)
+    // kNomBatch == 1: the nominal point of one item (two block barriers inside)
     auto load_nominal = [&](long long item) {
-        const int p = (int)(item / a.C);
-        float* nom_s = nom_tab[0];
-        if (tid < n) {
-            const double v = a.x_nom[(long long)p * n + tid];
-            nom_s[tid] = (float)v;
-            if (tid < 4) pos64_tab[0][tid] = v;
-        } else if (tid < n + m) {
-            nom_s[tid] = (float)a.u_nom[(long long)p * m + (tid - n)];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float xb[n], ub[m], fb[n];
-#pragma unroll
-            for (int q = 0; q < n; ++q) xb[q] = nom_s[q];
-#pragma unroll
-            for (int q = 0; q < m; ++q) ub[q] = nom_s[n + q];
-            sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
-#pragma unroll
-            for (int q = 0; q < n; ++q) nom_s[kXU + q] = fb[q];
-        }
+        __syncthreads();      // every warp is done with the previous item's nominal point
+        prepare_nominals(item);
         __syncthreads();
     };
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -301,8 +302,6 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
 #endif
 
     [[maybe_unused]] const bool batch = (a.flags & kFlagSamplesBatchVariant) != 0;
-    // absolute-points quirk (project_deltas): the state handed to the dynamics is xbar + (xbar + w)
-    [[maybe_unused]] const float twice = (Sys::kHasProjection && (a.flags & kFlagProjectAbsolute)) ? 2.f : 1.f;
     // this warp's tile ring; byte offset of this lane's sample inside a tile (feature group 0)
     unsigned char* my_ring = stage_mem + (size_t)warp * NSTAGE * C::kStageBytes;
     const uint32_t ring_u32 = smem_u32(my_ring);
@@ -367,13 +366,10 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
                 xu[4 * q] = v.x;  xu[4 * q + 1] = v.y;  xu[4 * q + 2] = v.z;  xu[4 * q + 3] = v.w;
             }
         };
-        // xu = xbar + w (the absolute-points quirk adds the nominal twice)
+        // xu = nominal point + w
         auto perturb = [&](float (&xu)[kXU], const float (&w)[C::RS]) {
 #pragma unroll
-            for (int q = 0; q < d; ++q) {
-                if constexpr (Sys::kHasProjection) xu[q] = fmaf(twice, xu[q], w[q]);
-                else xu[q] += w[q];
-            }
+            for (int q = 0; q < d; ++q) xu[q] += w[q];
         };
         auto dynamics = [&](const float (&xu)[kXU], float (&f)[n]) {
             if constexpr (Sys::kHasProjection) {    // only three_cart distinguishes batch / scalar
@@ -399,10 +395,11 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             float xu[kXU], f[n];
             load_xu(xu);
             project_deltas<Sys, C::RS>(a, p, pos64_s, w);
-            perturb(xu, w);
             if constexpr (CENTERED && MODE == kTcReplay) {
+                // replayed absolute points -> relative to the nominal (the state below is frame + w)
                 if (!(a.flags & kFlagProjectAbsolute)) center_replayed<Sys, C::RS>(a, p, w);
             }
+            perturb(xu, w);
             dynamics(xu, f);
             minus_nominal_response(f, w, 1.f);
             if constexpr (CENTERED) {

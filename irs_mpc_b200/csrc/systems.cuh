@@ -310,6 +310,34 @@ struct ThreeCart {
     }
 };
 
+// Centred accumulation (smooth.cuh: kFlagCentered): the regressors of nominal point (xbar, ubar) are the
+// absolute points xbar + z', so the state of a sample is 2 xbar + z'.  centred_frame() returns the fp32
+// point (xf, uf) such that the kernel evaluates f(xf + z'_x, uf + z'_u) - f(xf, uf): the doubled nominal,
+// expressed — where the dynamics allow it — in a frame in which fp32 still resolves what the dynamics
+// branch on.  three_cart is equivariant under a common shift of the positions and of the velocities, so
+// its frame moves with cart 1: positions and velocities relative to cart 1's (doubled) nominal.  The
+// response DIFFERENCE is the same in exact arithmetic, but the contact gaps (O(1)) are no longer computed
+// as differences of fp32 numbers of size 2 |xbar|, whose rounding flips the discontinuous velocity merge
+// for samples within ulp(2 |xbar|) of a contact threshold.
+template <class Sys>
+__device__ __forceinline__ void centred_frame(const double* xb, const double* ub, float* xf, float* uf) {
+    constexpr int n = Sys::N, m = Sys::M;
+    if constexpr (Sys::kHasProjection) {      // ThreeCart
+        static_assert(n == 6 && m == 2, "three_cart layout");
+        xf[0] = 0.f;
+        xf[1] = (float)(2.0 * (xb[1] - xb[0]));
+        xf[2] = (float)(2.0 * (xb[2] - xb[0]));
+        xf[3] = 0.f;
+        xf[4] = (float)(2.0 * (xb[4] - xb[3]));
+        xf[5] = (float)(2.0 * (xb[5] - xb[3]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < n; ++q) xf[q] = (float)(2.0 * xb[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < m; ++q) uf[q] = (float)(2.0 * ub[q]);
+}
+
 // Host-side dimension table (kept in sync with the functors by static_asserts in api.cu).
 struct SystemDims {
     int n, m, nj;

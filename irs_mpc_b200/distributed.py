@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _device, _lib, smoothing
+from ._graph import GraphRunner
 
 
 def shard_range(total, world, rank):
@@ -138,7 +139,7 @@ class ShardedLinearizer:
         self._peer_memory = peer_memory
         self._peer_timeout_s = peer_timeout_s
         self._px = None
-        self._graphs = {}
+        self._graphs = GraphRunner()
 
     def _workspace(self, P, N):
         key = (self.system.system_id, self.order, P, N)
@@ -179,7 +180,7 @@ class ShardedLinearizer:
         if self._px is None or not self._px.fits(P, width):
             try:
                 self._px = PeerExchange(P, width, self.group, self._peer_timeout_s)
-                self._graphs = {}
+                self._graphs.reset()        # captured sequences point at the old exchange
             except Exception as e:      # no symmetric memory on this system: fall back to NCCL (plumbing only)
                 if self._peer_memory is True:
                     raise
@@ -208,18 +209,38 @@ class ShardedLinearizer:
     def linearize_n(self, x_nom, u_nom, N_local, **kw):
         """Sample-sharded.  Every rank draws N_local samples per point (global sample index
         rank*N_local + i); returns (At, Bt, ct, status) fitted on all W*N_local samples.  No host
-        synchronisation: a failed exchange shows up as status 2 (smoothing.check_status raises)."""
+        synchronisation: a failed exchange shows up as status 2 (smoothing.check_status raises).
+        With in-kernel noise and the fused exchange the two launches of a step (accumulate, finalize with
+        the exchange inside) are replayed from a CUDA graph from the third call of a shape on — the epoch
+        of the exchange lives in device memory, only seed / iteration / sigma are re-parameterised."""
         T = x_nom.shape[0]
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if kw.get("flags", 0) & 8 and kw.get("noise") is None and N_local % 2 and world > 1:
             raise ValueError("antithetic pairs must not straddle ranks: N_local must be even (got %d)" % N_local)
         ws = self._workspace(T, N_local)
-        smoothing.accumulate(self.system, self.order, x_nom, u_nom, N_local, ws,
-                             i0=rank * N_local, **kw)
         px = self._peer_exchange(T, ws.width)
-        if px is not None:
-            return px.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local)
-        mine = smoothing.reduce_chunks(self.system, self.order, ws)
-        everyone = gather_ranks(mine, self.group)
-        return smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local,
-                                  reduced=everyone, nranks=world, rank_stride=mine.numel())
+
+        def enqueue():
+            smoothing.accumulate(self.system, self.order, x_nom, u_nom, N_local, ws, i0=rank * N_local, **kw)
+            if px is not None:
+                px.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local)
+            else:
+                mine = smoothing.reduce_chunks(self.system, self.order, ws)
+                everyone = gather_ranks(mine, self.group)
+                smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, world * N_local,
+                                   reduced=everyone, nranks=world, rank_stride=mine.numel())
+
+        key = None
+        if px is not None and kw.get("noise") is None and kw.get("sigma") is not None:
+            # everything a captured kernel reads besides (seed, it, sigma) must be part of the key
+            key = (self.system.system_id, self.order, T, N_local, world, rank, kw.get("flags", 0),
+                   kw.get("stream_id", 0), kw.get("p0", 0), x_nom.data_ptr(), u_nom.data_ptr(),
+                   tuple(float(v) for v in self.system.device_params()))
+
+        def update(handle):
+            sig = np.ascontiguousarray(np.asarray(kw["sigma"], dtype=np.float32))
+            _lib.call("irs_graph_update_smoothing", handle, sig.ctypes.data, int(kw.get("seed", 0)),
+                      int(kw.get("it", 1)), int(kw.get("stream_id", 0)))
+
+        self._graphs.run("linearize_n", key, enqueue, update)
+        return ws.At, ws.Bt, ws.ct, ws.status

@@ -22,13 +22,12 @@ import numpy as np
 import torch
 
 from . import _device, _lib, smoothing
+from ._graph import GraphRunner
 from .dynamical_system import CudaDynamicalSystem
 from .sampling import GaussianSampling
 from .tv_lqr import BOUND_TOL, TVLQR_FAILED, box_solve_device, get_solver, riccati_device
 
 
-# CUDA-graph replay of the per-iteration call sequence (IRS_CUDA_GRAPH=0 forces eager launches)
-_USE_GRAPHS = os.environ.get("IRS_CUDA_GRAPH", "1") != "0"
 _USE_PIPELINE = os.environ.get("IRS_PIPELINE", "1") != "0"     # see _SampledIrsLqr._pipeline_segments
 _PIPELINE_MIN_STEPS = 8                                        # timesteps per segment below which it does not pay
 _PIPELINE_SEGMENTS = int(os.environ.get("IRS_PIPELINE_SEGMENTS", "0"))      # 0 = sized from the work per launch
@@ -78,7 +77,7 @@ class IrsLqr:
         self._dxd = _device.to_device(np.asarray(self.xd_trj, dtype=np.float64)[:self.T + 1])
         self._ws = None
         self._db = None
-        self._graphs = {}
+        self._graphs = GraphRunner()
         self._last_descent = None
 
         self.x_trj = self.rollout(self.x0, self.u_trj)
@@ -249,43 +248,7 @@ class IrsLqr:
     def _run(self, name, enqueue):
         """Run `enqueue()` eagerly, or — from the third call of the same shape on — replay it from a
         CUDA graph captured through the library (one launch instead of ~8 API calls)."""
-        key = self._graph_key()
-        if key is None or not _USE_GRAPHS:
-            enqueue()
-            return
-        key = (name,) + key
-        slot = self._graphs.get(name)
-        if slot is None or slot[0] != key:
-            if slot is not None and slot[1] is not None:
-                _lib.call("irs_graph_destroy", slot[1])
-            self._graphs[name] = [key, None, 1]       # key, graph handle, eager calls so far
-            enqueue()
-            return
-        if slot[1] is None:
-            if slot[2] < 2:                           # let every workspace be allocated and warm first
-                slot[2] += 1
-                enqueue()
-                return
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                _lib.call("irs_graph_begin", side.cuda_stream)
-                handle = ctypes.c_void_p()
-                try:
-                    enqueue()
-                except BaseException:
-                    # end the capture (a stream must not stay in capture mode), drop the partial graph and
-                    # let the ORIGINAL exception propagate
-                    try:
-                        _lib.call("irs_graph_end", side.cuda_stream, ctypes.byref(handle))
-                        _lib.call("irs_graph_destroy", handle)
-                    except _lib.IrsCudaError:
-                        pass
-                    raise
-                _lib.call("irs_graph_end", side.cuda_stream, ctypes.byref(handle))
-            slot[1] = handle
-        self._graph_update(slot[1])
-        _lib.call("irs_graph_launch", slot[1], _device.stream_ptr())
+        self._graphs.run(name, self._graph_key(), enqueue, self._graph_update)
 
     def local_descent(self, x_trj, u_trj):
         T, n, m = self.T, self.dim_x, self.dim_u

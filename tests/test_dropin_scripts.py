@@ -77,11 +77,15 @@ def costs():
 # with its sigma (1 rad on the heading, 2 m/s on the speed) the averaged Jacobians give a first descent
 # ABOVE the initial cost — the float64 oracle with the bounded QP loop gives 3547 from 3302 on its own
 # samples, this path 3685 — although the reference's stored bicycle_easy_first.csv (unpinned: stochastic,
-# produced by an unknown revision of the script) shows 1867.
+# produced by an unknown revision of the script) shows 1867.  Nor for three_cart: its closure returns
+# ABSOLUTE points, the literal fit is a linearization without meaning and the first
+# descent lands at ~8e6 from 631 (the float64 oracle agrees on identical noise:
+# tests/test_full_size_parity.py::test_cfg4_three_cart_zero_order_T100_N1e4[absolute]); what the test shows
+# there is that the SECOND descent, from a trajectory of size |x| ~ 1e4 sigma, still fits (centred Gram).
 @pytest.mark.parametrize("key,system,iterations,improves", [("pendulum_zero_order", "pendulum", 1, True),
                                                             ("bicycle_first_order", "bicycle", 1, False),
                                                             ("quadrotor_zero_order", "quadrotor", 1, True),
-                                                            ("three_cart_zero_order", "three_cart", 1, True)])
+                                                            ("three_cart_zero_order", "three_cart", 2, False)])
 def test_reference_script_body_runs_unchanged(script_env, costs, key, system, iterations, improves):
     ns = run_script(key, iterations)
     solver = ns["solver"]

@@ -624,13 +624,13 @@ def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
     """From the third call on, local_descent / get_TV_matrices are replayed from a CUDA graph whose
     accumulate node is re-parameterised (iter, seed, sigma) — the results must equal the eager
     launches bit for bit, iteration after iteration."""
-    from irs_mpc_b200 import irs_lqr as mod
+    from irs_mpc_b200 import _graph as mod
     cfg = ec.CONFIGS[name](T=T)
     n = cfg["x0"].shape[0]
 
     def run(use_graphs):
-        old = mod._USE_GRAPHS
-        mod._USE_GRAPHS = use_graphs
+        old = mod.USE_GRAPHS
+        mod.USE_GRAPHS = use_graphs
         try:
             s = make_system(api, name)
             sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=11)
@@ -642,12 +642,13 @@ def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
                 tv.append(solver.get_TV_matrices(solver.x_trj, solver.u_trj))
             return solver, tv
         finally:
-            mod._USE_GRAPHS = old
+            mod.USE_GRAPHS = old
 
     eager, tv_e = run(False)
     graph, tv_g = run(True)
-    assert "descent" in graph._graphs and graph._graphs["descent"][1] is not None      # really replayed
-    assert "linearize" in graph._graphs and graph._graphs["linearize"][1] is not None
+    slots = graph._graphs._slots
+    assert "descent" in slots and slots["descent"][1] is not None      # really replayed
+    assert "linearize" in slots and slots["linearize"][1] is not None
     assert not eager._graphs
     assert eager.cost_lst == graph.cost_lst
     for a, b in zip(eager.x_trj_lst, graph.x_trj_lst):
@@ -727,13 +728,14 @@ def test_pipelined_descent_is_bit_identical_to_one_pass(api, name, T, N, graphs,
     """local_descent linearizes the horizon in three launches from the back and runs each segment's
     fit + Riccati steps on a second stream (irs_lqr._SampledIrsLqr._pipeline_segments); the iterates
     must equal those of the one-pass sequence bit for bit, eagerly and replayed from a CUDA graph."""
+    from irs_mpc_b200 import _graph as gmod
     from irs_mpc_b200 import irs_lqr as mod
     cfg = ec.CONFIGS[name](T=T)
     n = cfg["x0"].shape[0]
 
     def run(pipeline):
-        old = mod._USE_PIPELINE, mod._USE_GRAPHS, mod._PIPELINE_SEGMENTS
-        mod._USE_PIPELINE, mod._USE_GRAPHS, mod._PIPELINE_SEGMENTS = pipeline, graphs, 3    # forced: the test problem is small
+        old = mod._USE_PIPELINE, gmod.USE_GRAPHS, mod._PIPELINE_SEGMENTS
+        mod._USE_PIPELINE, gmod.USE_GRAPHS, mod._PIPELINE_SEGMENTS = pipeline, graphs, 3    # forced: the test problem is small
         try:
             s = make_system(api, name)
             sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], N, power=cfg["power"], seed=23,
@@ -744,7 +746,7 @@ def test_pipelined_descent_is_bit_identical_to_one_pass(api, name, T, N, graphs,
             solver.iterate(4, verbose=False)
             return solver
         finally:
-            mod._USE_PIPELINE, mod._USE_GRAPHS, mod._PIPELINE_SEGMENTS = old
+            mod._USE_PIPELINE, gmod.USE_GRAPHS, mod._PIPELINE_SEGMENTS = old
 
     one, pipe = run(False), run(True)
     assert one.cost_lst == pipe.cost_lst
