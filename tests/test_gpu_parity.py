@@ -649,7 +649,7 @@ def test_graph_replay_is_bit_identical_to_eager(api, name, T, N):
     slots = graph._graphs._slots
     assert "descent" in slots and slots["descent"][1] is not None      # really replayed
     assert "linearize" in slots and slots["linearize"][1] is not None
-    assert not eager._graphs
+    assert not eager._graphs._slots
     assert eager.cost_lst == graph.cost_lst
     for a, b in zip(eager.x_trj_lst, graph.x_trj_lst):
         assert np.array_equal(a, b)
