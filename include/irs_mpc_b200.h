@@ -203,6 +203,9 @@ int irs_tvlqr_riccati_segment(int n, int m, const double* At, const double* Bt, 
  *    workspace for the closed-loop rows) and sets violated[i] = 1 if any planned
  *    state (t0 < t <= T) or input leaves [lo - tol, hi + tol].  violated == 0 means every QP of the
  *    reference's loop had inactive bounds, i.e. the one-pass Riccati descent is its exact result;
+ *    irs_tvlqr_plan_rows fills `scratch` (it needs the gains only, not the trajectory: a caller can run
+ *    it on a second stream beside the closed-loop rollout) and plan_check is then called with
+ *    rows_ready = 1; rows_ready = 0 makes plan_check compute the rows itself;
  *  - irs_tvlqr_box_solve: ADMM on the box split.  mpc = 1: the reference's closed loop (QP over the
  *    remaining horizon at every t0 from the actual state, first input applied to the TRUE dynamics of
  *    `system`); mpc = 0: one QP from x0 (solve_tvlqr), x_trj/u_trj receive the plan.  Bounds are per
@@ -219,10 +222,12 @@ int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const
                          const double* Q, const double* Qd, const double* R,
                          const double* xd, long long xd_stride, int I, int T,
                          double* K, double* k, int* status, double* Hinv_out, double* P_out, void* stream);
+int irs_tvlqr_plan_rows(int n, int m, const double* At, const double* Bt, const double* ct,
+                        const double* K, const double* k, int I, int T, double* scratch, void* stream);
 int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const double* ct,
                          const double* K, const double* k, const double* x_trj,
                          const double* xlo, const double* xhi, const double* ulo, const double* uhi,
-                         double tol, int I, int T, int* violated, double* scratch, void* stream);
+                         double tol, int I, int T, int rows_ready, int* violated, double* scratch, void* stream);
 int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int mpc,
                         const double* At, const double* Bt, const double* ct,
                         const double* K, const double* Hinv, const double* P,

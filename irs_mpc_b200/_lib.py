@@ -77,7 +77,8 @@ SIGNATURES = {
     "irs_tvlqr_riccati": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp],
     "irs_tvlqr_riccati_segment": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "irs_tvlqr_riccati_ex": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
-    "irs_tvlqr_plan_check": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _i, _i,
+    "irs_tvlqr_plan_rows": [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "irs_tvlqr_plan_check": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _i, _i, _i,
                              _vp, _vp, _vp],
     "irs_tvlqr_box_solve": [_i, _c_double_p, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp,
                             _vp, _vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,

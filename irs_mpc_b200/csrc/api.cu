@@ -728,10 +728,20 @@ int irs_tvlqr_riccati_ex(int n, int m, const double* At, const double* Bt, const
     return tvlqr_riccati_impl(n, m, At, Bt, ct, Q, Qd, R, xd, xd_stride, I, T, K, k, status, Hinv_out, P_out, stream);
 }
 
+int irs_tvlqr_plan_rows(int n, int m, const double* At, const double* Bt, const double* ct,
+                        const double* K, const double* k, int I, int T, double* scratch, void* stream) {
+    IRS_REQUIRE(At && Bt && ct && K && k && scratch, "null pointer argument");
+    IRS_REQUIRE(I >= 1 && T >= 1 && I <= 65535, "need 1 <= I <= 65535 and T >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    PlanCheckArgs a{At, Bt, ct, K, k, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, nullptr, scratch, I, T};
+    IRS_DISPATCH_DIMS(n, m, { plan_rows_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a); });
+    return check_launch("plan_rows_kernel");
+}
+
 int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const double* ct,
                          const double* K, const double* k, const double* x_trj,
                          const double* xlo, const double* xhi, const double* ulo, const double* uhi,
-                         double tol, int I, int T, int* violated, double* scratch, void* stream) {
+                         double tol, int I, int T, int rows_ready, int* violated, double* scratch, void* stream) {
     IRS_REQUIRE(At && Bt && ct && K && k && x_trj && xlo && xhi && ulo && uhi && violated && scratch,
                 "null pointer argument");
     IRS_REQUIRE(I >= 1 && T >= 1 && I <= 65535, "need 1 <= I <= 65535 and T >= 1");
@@ -739,7 +749,9 @@ int irs_tvlqr_plan_check(int n, int m, const double* At, const double* Bt, const
     if (cudaMemsetAsync(violated, 0, sizeof(int) * I, st) != cudaSuccess) return check_launch("cudaMemsetAsync");
     PlanCheckArgs a{At, Bt, ct, K, k, x_trj, xlo, xhi, ulo, uhi, tol, violated, scratch, I, T};
     IRS_DISPATCH_DIMS(n, m, {
-        plan_rows_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a);
+        // rows_ready: irs_tvlqr_plan_rows has filled `scratch` already (it needs the gains only, so a caller
+        // can run it beside the closed-loop rollout)
+        if (!rows_ready) plan_rows_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a);
         plan_check_kernel<N_, M_><<<dim3((unsigned)T, (unsigned)I), 32, 0, st>>>(a);
     });
     return check_launch("plan_check_kernel");

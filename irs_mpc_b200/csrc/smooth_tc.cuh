@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
     // cost one latency per batch instead of one per item
     __shared__ __align__(16) float nom_tab[kNomBatch][kNom];
     __shared__ double pos64_tab[kNomBatch][4];           // leading coordinates in fp64 (projection)
+    __shared__ double nom64_s[n + m];                    // fp64 nominal of the current item (kNomBatch == 1)
     __shared__ float scratch[C::kRows * kScr];           // s_r[i] = D[r][z_1 col i] - D[r][z_2 col i] of r's member
     __shared__ uint16_t idx_s[C::NACC];                  // packed output e -> (i << 8) | j
     __shared__ float mom_s[C::kWarps][kMom];             // per-warp first moments of the item
@@ -285,10 +286,40 @@ __global__ void __launch_bounds__(128, IRS_TC_MIN_BLOCKS) smooth_zero_order_tc_k
             }
         }
     };
-    // kNomBatch == 1: the nominal point of one item (two block barriers inside)
+    // kNomBatch == 1: the nominal point of one item, cooperatively (the threads fetch the coordinates in
+    // parallel, thread 0 evaluates the reference response; two block barriers inside)
     auto load_nominal = [&](long long item) {
-        __syncthreads();      // every warp is done with the previous item's nominal point
-        prepare_nominals(item);
+        const int p = (int)(item / a.C);
+        float* nom_s = nom_tab[0];
+        if (tid < n) nom64_s[tid] = a.x_nom[(long long)p * n + tid];
+        else if (tid < n + m) nom64_s[tid] = a.u_nom[(long long)p * m + (tid - n)];
+        __syncthreads();
+        if (tid < 4 && tid < n) pos64_tab[0][tid] = nom64_s[tid];
+        if (tid == 0) {
+            float xb[n], ub[m], fb[n];
+            if constexpr (CENTERED) {
+                double xd[n], ud[m];
+#pragma unroll
+                for (int q = 0; q < n; ++q) xd[q] = nom64_s[q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) ud[q] = nom64_s[n + q];
+                centred_frame<Sys>(xd, ud, xb, ub);
+                if (a.flags & kFlagSamplesBatchVariant) sys.template step<true>(xb, ub, fb);
+                else sys.template step<false>(xb, ub, fb);
+            } else {
+#pragma unroll
+                for (int q = 0; q < n; ++q) xb[q] = (float)nom64_s[q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) ub[q] = (float)nom64_s[n + q];
+                sys.template step<false>(xb, ub, fb);   // scalar dynamics at the nominal (…zero_order.py:52)
+            }
+#pragma unroll
+            for (int q = 0; q < n; ++q) nom_s[q] = xb[q];
+#pragma unroll
+            for (int q = 0; q < m; ++q) nom_s[n + q] = ub[q];
+#pragma unroll
+            for (int q = 0; q < n; ++q) nom_s[kXU + q] = fb[q];
+        }
         __syncthreads();
     };
     asm volatile("tcgen05.fence::before_thread_sync;");

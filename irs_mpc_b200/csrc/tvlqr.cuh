@@ -540,6 +540,10 @@ __device__ __forceinline__ double warp_trajectory_cost(const double* x_trj, cons
                                                        const double* R, int T, int lane) {
     double acc = 0.0;
     for (int t = lane; t <= T; t += 32) {
+        // compiler barrier: without it the n*n + m*m loop-invariant weight loads below are hoisted out of
+        // the t loop into registers (quadrotor: 160 doubles -> 255 registers and a 384-byte spill frame for
+        // every kernel this routine is inlined into, the sequential rollouts among them)
+        asm volatile("" ::: "memory");
         double e[n];
 #pragma unroll
         for (int q = 0; q < n; ++q) e[q] = x_trj[(long long)t * n + q] - xd_i[(long long)t * n + q];

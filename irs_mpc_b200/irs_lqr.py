@@ -212,6 +212,22 @@ class IrsLqr:
         At, Bt, ct, status = self._linearize_and_riccati(db, x_nom, u_nom)
         db["sstatus"].copy_(status)
         prm, nprm = self.system._params()
+        rows_done = None
+        if db["box"] is not None:
+            # closed-loop rows of the plan check: they need the gains only, so they are computed on a
+            # second stream BESIDE the sequential rollout (plain event dependencies: capturable)
+            if "plan_stream" not in db:
+                db["plan_stream"] = torch.cuda.Stream()
+            main, side = torch.cuda.current_stream(), db["plan_stream"]
+            gains = torch.cuda.Event()
+            gains.record(main)
+            side.wait_event(gains)
+            with torch.cuda.stream(side):
+                _lib.call("irs_tvlqr_plan_rows", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                          _device.ptr(K), _device.ptr(k), 1, T, _device.ptr(db["plan_scratch"]),
+                          _device.stream_ptr())
+                rows_done = torch.cuda.Event()
+                rows_done.record(side)
         _lib.call("irs_rollout_closed_loop", self.system.system_id, prm, nprm, _device.ptr(K),
                   _device.ptr(k), _device.ptr(x_all), _device.ptr(self._dxd), 0,
                   _device.ptr(self._dQ), _device.ptr(self._dR), 1, T, _device.ptr(db["x_new"]),
@@ -219,9 +235,10 @@ class IrsLqr:
         if db["box"] is not None:
             # would any of the reference's T re-solved QPs (irs_lqr.py:169-182) have had an active bound?
             xlo, xhi, ulo, uhi = db["box"]
+            torch.cuda.current_stream().wait_event(rows_done)
             _lib.call("irs_tvlqr_plan_check", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
                       _device.ptr(K), _device.ptr(k), _device.ptr(db["x_new"]), _device.ptr(xlo),
-                      _device.ptr(xhi), _device.ptr(ulo), _device.ptr(uhi), BOUND_TOL, 1, T,
+                      _device.ptr(xhi), _device.ptr(ulo), _device.ptr(uhi), BOUND_TOL, 1, T, 1,
                       _device.ptr(db["violated"]), _device.ptr(db["plan_scratch"]), _device.stream_ptr())
         else:
             db["violated"].zero_()
@@ -352,21 +369,33 @@ RESIDENT_BLOCKS = 740      # resident grid of the quadrotor smoothing kernel on 
 
 def pipeline_segments(T, chunks_per_step, forced=0, min_steps=_PIPELINE_MIN_STEPS):
     """Timestep segments [(lo, hi), ...] of a pipelined descent, LATE timesteps first, or None when one
-    pass is better.  A segment is sized to about one resident grid of work items (timesteps x chunks);
-    `forced` > 0 fixes the number of segments (tests, tuning)."""
+    pass is better.  A segment holds at most one resident grid of work items (timesteps x chunks): a
+    launch of fewer items than resident blocks takes one item-time whatever its size.  The segments are
+    filled from the back of the horizon, so the LAST one (the earliest timesteps) is the short one: its
+    fit and Riccati steps are the only ones that no sampling launch hides.  `forced` > 0 fixes the
+    number of (equal) segments (tests, tuning)."""
     if forced > 0:
         k = forced
-    else:
-        items = T * chunks_per_step
-        if items < 2 * RESIDENT_BLOCKS:
-            return None       # less than two resident grids of sampling work: nothing to hide behind
-        k = min(8, -(-items // RESIDENT_BLOCKS))
-    while k > 1 and T // k < min_steps:
-        k -= 1
-    if k < 2:
-        return None
-    cuts = [(i * T) // k for i in range(k + 1)]
-    return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
+        while k > 1 and T // k < min_steps:
+            k -= 1
+        if k < 2:
+            return None
+        cuts = [(i * T) // k for i in range(k + 1)]
+        return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
+    items = T * chunks_per_step
+    if items < 2 * RESIDENT_BLOCKS:
+        return None       # less than two resident grids of sampling work: nothing to hide behind
+    per = max(min_steps, RESIDENT_BLOCKS // chunks_per_step)      # timesteps per full segment
+    k = min(8, -(-T // per))
+    per = max(per, -(-T // k))                                    # at most 8 launches
+    segs, hi = [], T
+    while hi > 0:
+        lo = max(0, hi - per)
+        if 0 < lo < min_steps:                                    # no sliver at the front: halve the rest
+            lo = hi // 2
+        segs.append((lo, hi))
+        hi = lo
+    return segs if len(segs) >= 2 else None
 
 
 class _SampledIrsLqr(IrsLqr):
