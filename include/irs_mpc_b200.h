@@ -64,11 +64,15 @@ int irs_set_gram_engine(int engine);
 int irs_system_dims(int system, int* n, int* m, int* nj);
 
 /* Number of fp32 accumulators per (nominal point, chunk): order 0 = zero-order Gram
- * d(d+1)/2 + d*n, order 1 = first-order nj. */
+ * d(d+1)/2 + d*n (three_cart: + d + n first moments of the centred accumulation, IRS_CENTERED),
+ * order 1 = first-order nj. */
 int irs_partial_width(int system, int order);
 
-/* Chunking plan for P nominal points x N samples: C chunks of S samples each. */
-int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long* S);
+/* Chunking plan for P nominal points x N samples: C chunks of S samples each (S a multiple of 256).
+ * chunk_samples = 0: default target (4096 samples); > 0: the caller's target — smaller chunks give more
+ * work items per launch (launches that would not fill the GPU otherwise) at the price of more partial
+ * blocks.  The plan depends on (N, chunk_samples) only, never on P. */
+int irs_smooth_plan(int system, int order, int P, long long N, long long chunk_samples, int* C, long long* S);
 
 /* IrsLqrZeroOrder.get_TV_matrices sampling + fit, accumulation stage
  * (irs_lqr/irs_lqr_zero_order.py:49-57): for each nominal point p and sample i

@@ -56,7 +56,7 @@ SIGNATURES = {
     "irs_set_gram_engine": [_i],
     "irs_system_dims": [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)],
     "irs_partial_width": [_i, _i],
-    "irs_smooth_plan": [_i, _i, _i, _ll, ctypes.POINTER(_i), ctypes.POINTER(_ll)],
+    "irs_smooth_plan": [_i, _i, _i, _ll, _ll, ctypes.POINTER(_i), ctypes.POINTER(_ll)],
     "irs_smooth_zero_order_accumulate": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _ll, _vp, _vp,
                                          _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
     "irs_smooth_first_order_accumulate": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _ll, _vp, _vp,

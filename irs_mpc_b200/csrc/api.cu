@@ -370,17 +370,21 @@ int irs_partial_width(int system, int order) {
     return order == 0 ? gram_width(d.n, d.m, system == kThreeCart) : (d.nj > 0 ? d.nj : 1);
 }
 
-int irs_smooth_plan(int system, int order, int P, long long N, int* C, long long* S) {
+int irs_smooth_plan(int system, int order, int P, long long N, long long chunk_samples, int* C, long long* S) {
     IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
-    IRS_REQUIRE(P >= 1 && N >= 1 && C && S, "bad plan arguments");
+    IRS_REQUIRE(P >= 1 && N >= 1 && C && S && chunk_samples >= 0, "bad plan arguments");
     // Samples per chunk: large enough to amortise the end-of-chunk reduction, small enough that
-    // P*C blocks give several waves over 148 SMs.  The plan depends on N ONLY, never on P, so
-    // that a timestep-sharded run (P split over ranks) sums in exactly the same order as the
-    // single-GPU run and reproduces it bit for bit.
-    const long long tile = 128;
+    // P*C blocks give several waves over 148 SMs.  The plan depends on N (and on the caller's
+    // chunk_samples) ONLY, never on P, so that a timestep-sharded run (P split over ranks) sums in
+    // exactly the same order as the single-GPU run and reproduces it bit for bit.
+    // chunk_samples = 0: the default target of 4096 (IRS_CHUNK_SAMPLES overrides it); callers whose
+    // launches are smaller than a resident grid (timestep-pipelined descents, strong scaling) ask for
+    // smaller chunks so that every SM still holds several work items.
+    const long long tile = 256;        // a block round: 128 lanes x (one sample | one antithetic pair)
     long long target = 4096;
     const char* e = getenv("IRS_CHUNK_SAMPLES");
     if (e && atoll(e) > 0) target = atoll(e);
+    if (chunk_samples > 0) target = chunk_samples;
     long long c = (N + target - 1) / target;
     long long s = (N + c - 1) / c;
     s = (s + tile - 1) / tile * tile;

@@ -32,6 +32,7 @@ _USE_PIPELINE = os.environ.get("IRS_PIPELINE", "1") != "0"     # see _SampledIrs
 _PIPELINE_MIN_STEPS = 8                                        # timesteps per segment below which it does not pay
 _PIPELINE_SEGMENTS = int(os.environ.get("IRS_PIPELINE_SEGMENTS", "0"))      # 0 = sized from the work per launch
 START_BOUND_TOL = 1e-6      # tolerance of the start-state box test in local_descent
+_DESCENT_CHUNK = int(os.environ.get("IRS_DESCENT_CHUNK", "0"))           # see _SampledIrsLqr._descent_chunk
 
 
 class IrsLqrParameters:
@@ -248,12 +249,16 @@ class IrsLqr:
     def _linearize_and_riccati(self, db, x_nom, u_nom):
         """Linearization along the nominal trajectory, then the backward pass -> db["K"], db["k"]."""
         T, n, m = self.T, self.dim_x, self.dim_u
-        At, Bt, ct, status = self._tv_matrices_device(x_nom, u_nom)
+        At, Bt, ct, status = self._descent_tv_matrices(x_nom, u_nom)
         _lib.call("irs_tvlqr_riccati", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
                   _device.ptr(self._dQ), _device.ptr(self._dQd), _device.ptr(self._dR),
                   _device.ptr(self._dxd), 0, 1, T, _device.ptr(db["K"]), _device.ptr(db["k"]),
                   _device.ptr(db["rstatus"]), _device.stream_ptr())
         return At, Bt, ct, status
+
+    def _descent_tv_matrices(self, x_nom, u_nom):
+        """The linearization inside local_descent (subclasses may plan it differently from get_TV_matrices)."""
+        return self._tv_matrices_device(x_nom, u_nom)
 
     def _graph_key(self):
         """None when this call sequence cannot be replayed from a CUDA graph (see _SampledIrsLqr)."""
@@ -369,33 +374,24 @@ RESIDENT_BLOCKS = 740      # resident grid of the quadrotor smoothing kernel on 
 
 def pipeline_segments(T, chunks_per_step, forced=0, min_steps=_PIPELINE_MIN_STEPS):
     """Timestep segments [(lo, hi), ...] of a pipelined descent, LATE timesteps first, or None when one
-    pass is better.  A segment holds at most one resident grid of work items (timesteps x chunks): a
-    launch of fewer items than resident blocks takes one item-time whatever its size.  The segments are
-    filled from the back of the horizon, so the LAST one (the earliest timesteps) is the short one: its
-    fit and Riccati steps are the only ones that no sampling launch hides.  `forced` > 0 fixes the
-    number of (equal) segments (tests, tuning)."""
+    pass is better.  Equal segments of at most one resident grid of work items (timesteps x chunks) each;
+    `forced` > 0 fixes the number of segments (tests, tuning).  Measured at BASELINE.json configs[2]
+    (quadrotor, T=100, N=1e5, 25 chunks per timestep, paired sampling kernel, three streams): one pass
+    420 us per descent, 3 segments 408, 4: 362, 5: 364, 6: 385; back-filled unequal segments
+    (29, 29, 29, 13 timesteps: short exposed tail) 395; 1024-sample chunks (98 per timestep) 390-400."""
     if forced > 0:
         k = forced
-        while k > 1 and T // k < min_steps:
-            k -= 1
-        if k < 2:
-            return None
-        cuts = [(i * T) // k for i in range(k + 1)]
-        return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
-    items = T * chunks_per_step
-    if items < 2 * RESIDENT_BLOCKS:
-        return None       # less than two resident grids of sampling work: nothing to hide behind
-    per = max(min_steps, RESIDENT_BLOCKS // chunks_per_step)      # timesteps per full segment
-    k = min(8, -(-T // per))
-    per = max(per, -(-T // k))                                    # at most 8 launches
-    segs, hi = [], T
-    while hi > 0:
-        lo = max(0, hi - per)
-        if 0 < lo < min_steps:                                    # no sliver at the front: halve the rest
-            lo = hi // 2
-        segs.append((lo, hi))
-        hi = lo
-    return segs if len(segs) >= 2 else None
+    else:
+        items = T * chunks_per_step
+        if items < 2 * RESIDENT_BLOCKS:
+            return None       # less than two resident grids of sampling work: nothing to hide behind
+        k = min(8, -(-items // RESIDENT_BLOCKS))
+    while k > 1 and T // k < min_steps:
+        k -= 1
+    if k < 2:
+        return None
+    cuts = [(i * T) // k for i in range(k + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in reversed(range(k))]
 
 
 class _SampledIrsLqr(IrsLqr):
@@ -404,6 +400,11 @@ class _SampledIrsLqr(IrsLqr):
     def __init__(self, system, params, sampling):
         super().__init__(system, params)
         self.sampling = sampling
+        self._ws_d = None
+        self._key_cache = None
+
+    def _descent_tv_matrices(self, x_nom, u_nom):
+        return self._tv_matrices_device(x_nom, u_nom, descent=True)
 
     def _replay_noise(self, x_nom, u_nom):
         """Call the user's closure once per timestep (as the reference does) and upload."""
@@ -415,9 +416,17 @@ class _SampledIrsLqr(IrsLqr):
             rows.append(np.hstack((np.asarray(dx), np.asarray(du))).astype(np.float32))
         return _device.to_device(np.stack(rows), torch.float32)
 
-    def _tv_matrices_device(self, x_nom, u_nom):
+    def _tv_matrices_device(self, x_nom, u_nom, descent=False):
         s = self.sampling
         if isinstance(s, GaussianSampling):
+            if descent and self._descent_chunk():
+                # the linearization inside local_descent: its own workspace with the descent's chunk plan
+                # (one-pass and pipelined descents then sum in the same order: bit-identical)
+                ws = self._descent_workspace()
+                smoothing.accumulate(self.system, self.order, x_nom, u_nom, s.num_samples, ws,
+                                     sigma=s.sigma(self.iter), seed=s.seed, it=self.iter, stream_id=s.stream_id,
+                                     flags=s.flags())
+                return smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, s.num_samples)
             At, Bt, ct, status, self._ws = smoothing.linearize(
                 self.system, self.order, x_nom, u_nom, s.num_samples, self._ws,
                 sigma=s.sigma(self.iter), seed=s.seed, it=self.iter, stream_id=s.stream_id,
@@ -443,6 +452,27 @@ class _SampledIrsLqr(IrsLqr):
         return smoothing.FLAG_CENTERED if closer_to_nominal else 0
 
 
+    def _descent_chunk(self):
+        """Samples per chunk of the linearization INSIDE local_descent (0 = library default, which is
+        also the measured optimum: a pipelined descent samples the horizon in launches of a few timesteps,
+        and smaller chunks give such a launch more work items per SM, but at configs[2] the extra partial
+        blocks and item epilogues cost more than the fuller SMs gain — 362 us per descent with 4096-sample
+        chunks against 390-400 with 1024 and 420-435 with 512).  IRS_DESCENT_CHUNK selects another plan."""
+        if not isinstance(self.sampling, GaussianSampling) or self.order != smoothing.ZERO_ORDER:
+            return 0
+        C, _ = smoothing.plan(self.system.system_id, self.order, self.T, self.sampling.num_samples)
+        if self.T * C < 2 * RESIDENT_BLOCKS:
+            return 0
+        return _DESCENT_CHUNK
+
+    def _descent_workspace(self):
+        s = self.sampling
+        chunk = self._descent_chunk()
+        key = (self.system.system_id, self.order, self.T, s.num_samples, chunk)
+        if self._ws_d is None or self._ws_d.key != key:
+            self._ws_d = smoothing.Workspace(self.system, self.order, self.T, s.num_samples, chunk)
+        return self._ws_d
+
     def _pipeline_segments(self):
         """Timestep segments [(lo, hi), ...], late timesteps first, or None for the one-pass sequence.
         The backward Riccati pass needs the late timesteps first, so the horizon is linearized in a
@@ -458,7 +488,7 @@ class _SampledIrsLqr(IrsLqr):
         n, m, T = self.dim_x, self.dim_u, self.T
         if not _USE_PIPELINE or not isinstance(self.sampling, GaussianSampling) or n % 2 or m % 2:
             return None
-        C, _ = smoothing.plan(self.system.system_id, self.order, T, self.sampling.num_samples)
+        C, _ = smoothing.plan(self.system.system_id, self.order, T, self.sampling.num_samples, self._descent_chunk())
         return pipeline_segments(T, C, _PIPELINE_SEGMENTS)
 
     def _linearize_and_riccati(self, db, x_nom, u_nom):
@@ -467,24 +497,37 @@ class _SampledIrsLqr(IrsLqr):
             return super()._linearize_and_riccati(db, x_nom, u_nom)
         s = self.sampling
         T, n, m = self.T, self.dim_x, self.dim_u
-        key = (self.system.system_id, self.order, T, s.num_samples)
-        if self._ws is None or self._ws.key != key:
-            self._ws = smoothing.Workspace(self.system, self.order, T, s.num_samples)
-        ws = self._ws
+        if self._descent_chunk():
+            ws = self._descent_workspace()
+        else:
+            key = (self.system.system_id, self.order, T, s.num_samples)
+            if self._ws is None or self._ws.key != key:
+                self._ws = smoothing.Workspace(self.system, self.order, T, s.num_samples)
+            ws = self._ws
         if "carry" not in db:
             db["carry"] = _device.empty((n * n + n,))
-            db["side"] = torch.cuda.Stream(priority=-1)
-        main, side = torch.cuda.current_stream(), db["side"]
+            db["side"] = torch.cuda.Stream(priority=-1)        # the sequential Riccati chain
+            db["fin"] = torch.cuda.Stream(priority=-1)         # the segment fits
+        main, side, fin = torch.cuda.current_stream(), db["side"], db["fin"]
         sig = s.sigma(self.iter)
+        # three streams: sampling launches back to back on the main stream; each segment's fit starts as
+        # soon as its samples are there (it does not wait for the previous segment's Riccati steps); the
+        # Riccati segments chain on their own stream, each behind its fit.  With the paired sampling kernel
+        # the backward pass (T x 1.3 us, sequential) is as long as the sampling itself, so it is the chain
+        # that must never wait for anything but its inputs.
         for lo, hi in segs:
             smoothing.accumulate(self.system, self.order, x_nom, u_nom, s.num_samples, ws, sigma=sig,
                                  seed=s.seed, it=self.iter, stream_id=s.stream_id, flags=s.flags(),
                                  point_range=(lo, hi))
-            ready = torch.cuda.Event()
-            ready.record(main)
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
+            sampled = torch.cuda.Event()
+            sampled.record(main)
+            fin.wait_event(sampled)
+            with torch.cuda.stream(fin):
                 smoothing.finalize(self.system, self.order, x_nom, u_nom, ws, s.num_samples, point_range=(lo, hi))
+                fitted = torch.cuda.Event()
+                fitted.record(fin)
+            side.wait_event(fitted)
+            with torch.cuda.stream(side):
                 _lib.call("irs_tvlqr_riccati_segment", n, m, _device.ptr(ws.At), _device.ptr(ws.Bt),
                           _device.ptr(ws.ct), _device.ptr(self._dQ), _device.ptr(self._dQd),
                           _device.ptr(self._dR), _device.ptr(self._dxd), 0, 1, T, lo, hi,
@@ -500,8 +543,13 @@ class _SampledIrsLqr(IrsLqr):
         if not isinstance(s, GaussianSampling):
             return None           # a Python closure is called T times per iteration: nothing to replay
         # the captured kernels bake the system parameters: a changed parameter re-captures
-        return (self.system.system_id, self.order, self.T, s.num_samples, s.flags(),
-                tuple(float(v) for v in self.system.device_params()))
+        prm = self.system.device_params()
+        c = self._key_cache
+        if c is None or c[0] != prm or c[1] != (s.num_samples, s.flags()):
+            c = (prm, (s.num_samples, s.flags()),
+                 (self.system.system_id, self.order, self.T, s.num_samples, s.flags(), tuple(float(v) for v in prm)))
+            self._key_cache = c
+        return c[2]
 
     def _graph_update(self, graph):
         s = self.sampling

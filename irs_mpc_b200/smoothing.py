@@ -19,10 +19,11 @@ FIRST_ORDER = 1
 FLAG_PROJECT_ABSOLUTE, FLAG_PROJECT_DELTA, FLAG_ANTITHETIC, FLAG_CENTERED = 2, 4, 8, 16
 
 
-def plan(system_id, order, P, N):
+def plan(system_id, order, P, N, chunk_samples=0):
+    """(C, S): C chunks of S samples per nominal point; chunk_samples = 0 is the library default."""
     C = ctypes.c_int(0)
     S = ctypes.c_longlong(0)
-    _lib.call("irs_smooth_plan", system_id, order, P, N, ctypes.byref(C), ctypes.byref(S))
+    _lib.call("irs_smooth_plan", system_id, order, P, N, int(chunk_samples), ctypes.byref(C), ctypes.byref(S))
     return C.value, S.value
 
 
@@ -33,9 +34,9 @@ class Workspace:
     points in one [x_nom | u_nom] buffer, each with a pinned host mirror, so that the numpy-facing
     API moves exactly one host->device and one device->host copy per linearization."""
 
-    def __init__(self, system, order, P, N):
-        self.key = (system.system_id, order, P, N)
-        self.C, self.S = plan(system.system_id, order, P, N)
+    def __init__(self, system, order, P, N, chunk_samples=0):
+        self.key = (system.system_id, order, P, N) if not chunk_samples else (system.system_id, order, P, N, chunk_samples)
+        self.C, self.S = plan(system.system_id, order, P, N, chunk_samples)
         self.width = _lib.lib().irs_partial_width(system.system_id, order)
         n, m = system.dim_x, system.dim_u
         self.P, self.n, self.m = P, n, m

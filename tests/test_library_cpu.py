@@ -150,8 +150,7 @@ def test_pipeline_segments_cover_the_horizon_from_the_back(built_lib):
     from irs_mpc_b200 import smoothing
     C, _ = smoothing.plan(2, 0, 100, 100000)          # quadrotor, BASELINE.json configs[2]
     segs = pipeline_segments(100, C)
-    # full segments from the back of the horizon, the short one last: its fit and Riccati steps are exposed
-    assert segs == [(71, 100), (42, 71), (13, 42), (0, 13)]
+    assert segs == [(75, 100), (50, 75), (25, 50), (0, 25)]
     assert all((hi - lo) * C <= RESIDENT_BLOCKS for lo, hi in segs)
     assert pipeline_segments(100, 1) is None             # too little sampling work to hide anything behind
     assert pipeline_segments(30, 1, forced=3) == [(20, 30), (10, 20), (0, 10)]
@@ -161,4 +160,3 @@ def test_pipeline_segments_cover_the_horizon_from_the_back(built_lib):
         assert segs is not None and segs[0][1] == T and segs[-1][0] == 0 and len(segs) <= 8
         assert all(a[0] == b[1] for a, b in zip(segs, segs[1:]))      # contiguous, descending
         assert all(hi - lo >= 8 for lo, hi in segs)
-        assert all(hi - lo <= segs[0][1] - segs[0][0] for lo, hi in segs)     # the first (latest) segment is a full one
