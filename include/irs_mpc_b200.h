@@ -263,6 +263,18 @@ int irs_rollout_open_loop(int system, const double* params_host, int nparams,
                           const double* xd, long long xd_stride, const double* Q, const double* R,
                           int I, int T, double* x_trj, double* cost, void* stream);
 
+/* CrossEntropyMethod.local_descent, steps 3-4 (irs_lqr/cem.py:173-182): marks the n_elite cheapest of the
+ * B candidates (elite [B] int, ties by index, NaN last) and refits mean [T,m] / std [T,m] (population
+ * standard deviation) of the candidate input trajectories u_candidates [B,T,m] over them.  cost [B] is the
+ * output of irs_rollout_open_loop. */
+int irs_cem_refit(const double* cost, const double* u_candidates, int B, int T, int m, int n_elite,
+                  int* elite, double* mean, double* std_out, void* stream);
+
+/* IrsLqrZeroOrder.compute_least_squares (irs_lqr/irs_lqr_zero_order.py:27-36) on explicit samples: the
+ * packed fp64 Gram block [Z^T Z | Z^T F] of Z = dxdu [N, n+m], F = deltaf [N, n] in the layout
+ * irs_smooth_finalize reads as `reduced` (P = 1, nranks = 1). */
+int irs_gram_block_f64(int n, int m, const double* Z, const double* F, long long N, double* out, void* stream);
+
 /* Measurement aid (no reference counterpart): dependent-chain FP32 FMA microbenchmark used by
  * bench.py as the measured FP32 roofline denominator.  out: device scratch of >= 148*8*256 floats;
  * *flops_host receives the flop count of one launch. */

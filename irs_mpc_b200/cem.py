@@ -4,14 +4,16 @@
 bookkeeping.  The data-parallel part of `local_descent` (cem.py:151-184) — rolling out and
 costing `batch_size` candidate input trajectories — is ONE launch of the batched open-loop
 rollout kernel (irs_rollout_open_loop, one warp per candidate, fp64) instead of a Python loop
-over candidates and timesteps.  Candidate sampling stays `np.random.normal` on the host, exactly
-as in the reference (cem.py:162-163: same global numpy RNG stream, so a seeded run draws the same
-candidates), and so do the elite selection (`np.argpartition`, :175) and the mean / std refit
-(:180-182), which touch batch_size*T*m numbers.
+over candidates and timesteps; the elite selection (`np.argpartition`, :175) and the mean / std
+refit (:180-182) run on the device too (csrc/cem.cuh: rank + refit kernels), followed by the rollout of
+the new mean, so one CEM step uploads the candidates once and reads back T*(n+2m) numbers.  Candidate
+sampling stays `np.random.normal` on the host, exactly as in the reference (cem.py:162-163: same
+global numpy RNG stream, so a seeded run draws the same candidates).
 """
 import time
 
 import numpy as np
+import torch
 
 from . import _device, _lib
 from .dynamical_system import CudaDynamicalSystem
@@ -126,18 +128,33 @@ class CrossEntropyMethod:
 
     # -- one CEM step (cem.py:151-184) --------------------------------------------------------------
     def local_descent(self, x_trj, u_trj):
+        B, T, n, m = self.batch_size, self.T, self.dim_x, self.dim_u
         # 1. candidates around the current mean (same numpy call as the reference: same stream)
-        u_trj_candidates = np.random.normal(u_trj, self.std_trj, (self.batch_size, self.T, self.dim_u))
+        u_trj_candidates = np.random.normal(u_trj, self.std_trj, (B, T, m))
+        ud = _device.to_device(np.ascontiguousarray(u_trj_candidates, dtype=np.float64))
+        x0d = _device.to_device(np.tile(np.asarray(self.x0, dtype=np.float64), (B, 1)))
+        x_cand = _device.empty((B, T + 1, n))
+        cost = _device.empty((B,))
+        prm, nprm = self.system._params()
         # 2. roll all of them out and cost them: one kernel launch
-        _, cost_array = self.rollout_batch(self.x0, u_trj_candidates)
-        # 3. the n_elite cheapest
-        best_idx = np.argpartition(cost_array, self.n_elite)[:self.n_elite]
-        best_trjs = u_trj_candidates[best_idx, :, :]
-        # 4. refit mean and std
-        u_trj_new = np.mean(best_trjs, axis=0)
-        self.std_trj = np.std(best_trjs, axis=0)
-        x_trj_new = self.rollout(self.x0, u_trj_new)
-        return x_trj_new, u_trj_new
+        _lib.call("irs_rollout_open_loop", self.system.system_id, prm, nprm, _device.ptr(ud),
+                  _device.ptr(x0d), _device.ptr(self._dxd), 0, _device.ptr(self._dQ),
+                  _device.ptr(self._dR), B, T, _device.ptr(x_cand), _device.ptr(cost), _device.stream_ptr())
+        # 3.-4. the n_elite cheapest, mean and std over them — on the device; out = [mean | std | x of the mean]
+        elite = _device.empty((B,), torch.int32)
+        out = _device.empty((2 * T * m + (T + 1) * n + 1,))
+        mean, std = out[:T * m].view(1, T, m), out[T * m:2 * T * m]
+        x_new = out[2 * T * m:2 * T * m + (T + 1) * n].view(1, T + 1, n)
+        _lib.call("irs_cem_refit", _device.ptr(cost), _device.ptr(ud), B, T, m, int(self.n_elite),
+                  _device.ptr(elite), _device.ptr(mean), _device.ptr(std), _device.stream_ptr())
+        # rollout of the new mean (cem.py:183)
+        _lib.call("irs_rollout_open_loop", self.system.system_id, prm, nprm, _device.ptr(mean),
+                  _device.ptr(x0d), _device.ptr(self._dxd), 0, _device.ptr(self._dQ),
+                  _device.ptr(self._dR), 1, T, _device.ptr(x_new), _device.ptr(out[-1:]), _device.stream_ptr())
+        h = _device.to_numpy(out)
+        self.std_trj = h[T * m:2 * T * m].reshape(T, m).copy()
+        self.last_elite = elite                      # device mask of the step (diagnostics / tests)
+        return h[2 * T * m:2 * T * m + (T + 1) * n].reshape(T + 1, n).copy(), h[:T * m].reshape(T, m).copy()
 
     def iterate(self, max_iterations, verbose=True):
         while True:

@@ -9,6 +9,7 @@
 #include "smooth_tc.cuh"
 #include "tvlqr.cuh"
 #include "tvlqr_box.cuh"
+#include "cem.cuh"
 
 namespace irs {
 
@@ -837,6 +838,26 @@ int irs_rollout_open_loop(int system, const double* params_host, int nparams,
     cudaStream_t st = (cudaStream_t)stream;
     IRS_DISPATCH_SYSTEM(system, double, Sys, launch_rollout<Sys, false>(a, st));
     return check_launch("rollout_kernel<open>");
+}
+
+int irs_cem_refit(const double* cost, const double* u_candidates, int B, int T, int m, int n_elite,
+                  int* elite, double* mean, double* std_out, void* stream) {
+    IRS_REQUIRE(cost && u_candidates && elite && mean && std_out, "null pointer argument");
+    IRS_REQUIRE(B >= 1 && T >= 1 && m >= 1 && n_elite >= 1 && n_elite <= B, "need 1 <= n_elite <= B and T, m >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    cem_rank_kernel<<<(B + 255) / 256, 256, 0, st>>>(cost, B, n_elite, elite);
+    if (check_launch("cem_rank_kernel")) return 1;
+    const int width = T * m;
+    cem_refit_kernel<<<(width + 127) / 128, 128, 0, st>>>(u_candidates, elite, B, width, n_elite, mean, std_out);
+    return check_launch("cem_refit_kernel");
+}
+
+int irs_gram_block_f64(int n, int m, const double* Z, const double* F, long long N, double* out, void* stream) {
+    IRS_REQUIRE(Z && F && out, "null pointer argument");
+    IRS_REQUIRE(n >= 1 && m >= 0 && n + m <= kMaxRegressors && N >= 1, "bad dimensions");
+    const int d = n + m, nacc = gram_nacc(n, m);
+    gram_block_f64_kernel<<<(nacc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(Z, F, N, n, d, out);
+    return check_launch("gram_block_f64_kernel");
 }
 
 int irs_fp32_fma_peak(int iters, float* out, long long out_len, double* flops_host, void* stream) {

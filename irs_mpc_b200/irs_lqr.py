@@ -597,18 +597,29 @@ class IrsLqrZeroOrder(_SampledIrsLqr):
     order = smoothing.ZERO_ORDER
 
     def compute_least_squares(self, dxdu, deltaf):
-        """irs_lqr_zero_order.py:27-36: (Ahat, Bhat) = lstsq(dxdu, deltaf)^T split.  Runs the same
-        Gram + Cholesky kernels as the fused path (normal equations in fp64 on fp32 partials)."""
-        dxdu = np.asarray(dxdu, dtype=np.float64)
-        deltaf = np.asarray(deltaf, dtype=np.float64)
-        n, d = self.dim_x, self.dim_x + self.dim_u
-        G = _device.to_device(dxdu)
-        F = _device.to_device(deltaf)
-        # small dense problem: Gram on device in fp64 through torch plumbing is NOT the hot path;
-        # this helper exists for API completeness only.
-        gram = (G.T @ G)
-        rhs = (G.T @ F)
-        L = torch.linalg.cholesky(gram)
-        AB = torch.cholesky_solve(rhs, L).T
-        AB = _device.to_numpy(AB)
-        return AB[:, :n], AB[:, n:d]
+        """irs_lqr_zero_order.py:27-36: (Ahat, Bhat) = lstsq(dxdu, deltaf)^T split, on explicit samples.
+        The library's own kernels: the packed fp64 Gram block (irs_gram_block_f64) and the Cholesky fit of
+        the finalize kernel (normal equations: identical to lstsq for full column rank; a rank-deficient
+        sample set raises LinAlgError instead of returning the min-norm solution)."""
+        dxdu = np.ascontiguousarray(np.asarray(dxdu, dtype=np.float64))
+        deltaf = np.ascontiguousarray(np.asarray(deltaf, dtype=np.float64))
+        n, m = self.dim_x, self.dim_u
+        d = n + m
+        if dxdu.ndim != 2 or dxdu.shape[1] != d or deltaf.shape != (dxdu.shape[0], n):
+            raise ValueError("expected dxdu [N, %d] and deltaf [N, %d]" % (d, n))
+        N = dxdu.shape[0]
+        Z, F = _device.to_device(dxdu), _device.to_device(deltaf)
+        width = _lib.lib().irs_partial_width(self.system.system_id, smoothing.ZERO_ORDER)
+        block = torch.zeros((1, width), dtype=torch.float64, device=Z.device)
+        _lib.call("irs_gram_block_f64", n, m, _device.ptr(Z), _device.ptr(F), N, _device.ptr(block),
+                  _device.stream_ptr())
+        zero_x, zero_u = torch.zeros((1, n), dtype=torch.float64, device=Z.device), \
+            torch.zeros((1, m), dtype=torch.float64, device=Z.device)
+        At, Bt, ct = _device.empty((1, n, n)), _device.empty((1, n, m)), _device.empty((1, n))
+        status = _device.empty((1,), torch.int32)
+        prm, nprm = self.system._params()
+        _lib.call("irs_smooth_finalize", self.system.system_id, prm, nprm, smoothing.ZERO_ORDER, _device.ptr(zero_x),
+                  _device.ptr(zero_u), 1, 1, None, _device.ptr(block), 1, 0, float(N), 0, _device.ptr(At),
+                  _device.ptr(Bt), _device.ptr(ct), _device.ptr(status), _device.stream_ptr())
+        smoothing.check_status(status)
+        return _device.to_numpy(At[0]), _device.to_numpy(Bt[0])

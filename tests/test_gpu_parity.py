@@ -788,6 +788,27 @@ def test_cem_matches_numpy_restatement(api, name, T, B):
     assert len(solver.cost_lst) == 4 and np.isfinite(c)
 
 
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_compute_least_squares_matches_lstsq(api, name):
+    """IrsLqrZeroOrder.compute_least_squares (irs_lqr_zero_order.py:27-36) on explicit samples: the
+    library's fp64 Gram block + Cholesky fit against np.linalg.lstsq (the reference's call)."""
+    cfg = ec.CONFIGS[name](T=6)
+    s = make_system(api, name)
+    n, m = s.dim_x, s.dim_u
+    sampler = api.GaussianSampling(cfg["sigma"][:n], cfg["sigma"][n:], 500, seed=1)
+    solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=6), sampler)
+    rng = np.random.default_rng(8)
+    dxdu = rng.standard_normal((700, n + m)) * cfg["sigma"]
+    AB_true = rng.standard_normal((n, n + m))
+    deltaf = dxdu @ AB_true.T + 1e-3 * rng.standard_normal((700, n))
+    A, B = solver.compute_least_squares(dxdu, deltaf)
+    AB = np.linalg.lstsq(dxdu, deltaf, rcond=None)[0].T
+    assert A.shape == (n, n) and B.shape == (n, m)
+    np.testing.assert_allclose(np.hstack((A, B)), AB, rtol=0, atol=1e-9 * max(1.0, float(np.max(np.abs(AB)))))
+    with pytest.raises(np.linalg.LinAlgError):
+        solver.compute_least_squares(dxdu[:n + m - 1], deltaf[:n + m - 1])      # fewer samples than regressors
+
+
 # ------------------------------------------------------------------------------------------------
 # ragged / edge sample counts through both Gram engines
 # ------------------------------------------------------------------------------------------------
