@@ -143,6 +143,24 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
                              double* At, double* Bt, double* ct, int* status, void* stream);
 int irs_smooth_finalize_peer_capacity(int system, int order, int* max_points);
 
+/* irs_smooth_finalize for a TIMESTEP-SHARDED run (one process per GPU; BASELINE north star: "the T x N
+ * sample rollouts shard along the time axis, with an all-gather of the small per-step (A_t, B_t, c_t)
+ * blocks"), with that all-gather fused into the kernel over peer memory.  This rank owns the global
+ * points p0 .. p0 + P - 1 of P_total (x_nom, u_nom, partials: its local slice; P = 0 allowed).  The block of
+ * a point writes its result into EVERY rank's output buffer (peer_out_bufs_dev: device array of `world`
+ * peer-mapped base pointers, each buffer [2 parities][At: P_total n n | Bt: P_total n m | ct: P_total n |
+ * status: P_total] doubles, out_stride doubles per parity) and raises flag [point] on every rank
+ * (peer_flags_dev: `world` peer-mapped int[P_total] arrays, zero before the first call); the last block
+ * waits for all P_total flags, so on completion the full linearization of step `epoch` lies in the local
+ * buffer at parity (epoch & 1).  epoch_dev / done_counter / timeout_s as for irs_smooth_finalize_peer (a
+ * missing point gets status 2).  ct_scratch: P*n doubles of local scratch. */
+int irs_smooth_finalize_gather(int system, const double* params_host, int nparams, int order,
+                               const double* x_nom, const double* u_nom, int P, int C, const float* partials,
+                               const void* peer_out_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
+                               unsigned int* done_counter, long long out_stride, int p0, int P_total,
+                               int rank, int world, double timeout_s, double n_total, int centered,
+                               double* ct_scratch, void* stream);
+
 /* IrsLqrExact.get_TV_matrices (irs_lqr/irs_lqr_exact.py:15-31), all fp64: [A|B] = jacobian_xu at
  * the nominal points, c = f(xbar,ubar) - A xbar - B ubar.  x_nom [P,n], u_nom [P,m]. */
 int irs_exact_linearize(int system, const double* params_host, int nparams,

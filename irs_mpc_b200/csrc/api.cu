@@ -592,9 +592,35 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
     if (finalize_resident_blocks(system, order, &resident)) return 1;
     IRS_REQUIRE(P <= resident, "the fused exchange needs its %d blocks co-resident (%d fit): use the all-gather path", P, resident);
     PeerFusedArgs px{(double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, done_counter,
-                     slot_stride, flag_stride, rank, world, (unsigned long long)(timeout_s * 1e9)};
+                     slot_stride, flag_stride, rank, world, (unsigned long long)(timeout_s * 1e9),
+                     kPeerExchange, 0, 0, 0};
     return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, nullptr, 1, 0,
                                 n_total, centered, At, Bt, ct, status, &px, stream);
+}
+
+int irs_smooth_finalize_gather(int system, const double* params_host, int nparams, int order,
+                               const double* x_nom, const double* u_nom, int P, int C, const float* partials,
+                               const void* peer_out_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
+                               unsigned int* done_counter, long long out_stride, int p0, int P_total,
+                               int rank, int world, double timeout_s, double n_total, int centered,
+                               double* ct_scratch, void* stream) {
+    IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
+    IRS_REQUIRE(peer_out_bufs_dev && peer_flags_dev && epoch_dev && done_counter, "null pointer argument");
+    IRS_REQUIRE(world >= 1 && world <= kFinalizeThreads && rank >= 0 && rank < world, "bad rank / world");
+    IRS_REQUIRE(timeout_s > 0.0 && P >= 0 && p0 >= 0 && P_total >= 1 && p0 + P <= P_total, "bad gather arguments");
+    const SystemDims dm = system_dims(system);
+    IRS_REQUIRE(out_stride >= (long long)P_total * (dm.n * (dm.n + dm.m + 1) + 1), "output buffers too small");
+    PeerFusedArgs px{(double* const*)peer_out_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, done_counter,
+                     0, 0, rank, world, (unsigned long long)(timeout_s * 1e9), kPeerGather, p0, P_total, out_stride};
+    if (P == 0) {      // this rank owns no timestep: it still takes part in the step
+        peer_gather_wait_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(px);
+        return check_launch("peer_gather_wait_kernel");
+    }
+    IRS_REQUIRE(partials && ct_scratch, "null pointer argument");
+    // the kernel writes its results into the ranks' output buffers; ct_scratch [P, n] is the local scratch
+    // the first-order finalize keeps f(xbar, ubar) in; status goes into the gathered buffer too
+    return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, nullptr, 1, 0,
+                                n_total, centered, ct_scratch, ct_scratch, ct_scratch, (int*)ct_scratch, &px, stream);
 }
 
 int irs_exact_linearize(int system, const double* params_host, int nparams,

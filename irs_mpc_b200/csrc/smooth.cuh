@@ -511,7 +511,15 @@ struct PeerFusedArgs {
     int flag_stride;              // flags per rank row (>= P)
     int rank, world;
     unsigned long long timeout_ns;
+    // mode kPeerGather (timestep-sharded run): peer_bufs are the ranks' OUTPUT buffers
+    // [2 parities][At: P_total n n | Bt: P_total n m | ct: P_total n | status: P_total] doubles
+    // (out_stride doubles per parity), peer_flags their flag arrays [P_total]; this rank owns the global
+    // points p0 .. p0 + P - 1
+    int mode;
+    int p0, P_total;
+    long long out_stride;
 };
+enum PeerMode { kPeerNone = 0, kPeerExchange = 1, kPeerGather = 2 };
 
 struct FinalizeArgs {
     const double* x_nom;     // [P, n]
@@ -655,6 +663,93 @@ __device__ __forceinline__ void peer_exchange_finish(const FinalizeArgs& a, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Timestep-sharded run: the all-gather of the per-step blocks [A_t | B_t | c_t] FUSED into the finalize
+// kernel.  The block of local point p writes its result straight into EVERY rank's output buffer at the
+// global point index (NVLink stores; 205 doubles per quadrotor step and rank) and raises that point's
+// arrival flag on every rank; the LAST block of the launch then waits until the flags of all P_total
+// points have arrived here, so when the kernel completes the full linearization is in local memory —
+// no NCCL call, no packing kernels, and nothing for a consumer to wait on.  Only the last block waits,
+// and only for remote blocks, which never wait for this rank: no co-residency requirement.  Epoch in
+// device memory, output double buffered by epoch parity (as for the sample-sharded exchange): a rank
+// can be one step ahead of a peer, never two.
+// ---------------------------------------------------------------------------------------------
+template <class Sys, int BT>
+__device__ __forceinline__ void write_abc_gather(const FinalizeArgs& a, int p, const double* AB,
+                                                 const double* nom /*[n+m+n] smem*/, int status_value,
+                                                 int epoch, int tid) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    const PeerFusedArgs& x = a.peer;
+    const long long g = (long long)x.p0 + p, Pt = x.P_total;
+    const long long slot = (long long)(epoch & 1) * x.out_stride;
+    double cval = 0.0;
+    if (tid < n) {
+        cval = nom[d + tid];
+#pragma unroll
+        for (int q = 0; q < d; ++q) cval = fma(-AB[tid * d + q], nom[q], cval);
+    }
+    for (int r = 0; r < x.world; ++r) {
+        double* At = x.peer_bufs[r] + slot;
+        double* Bt = At + Pt * n * n;
+        double* ct = Bt + Pt * n * m;
+        double* st = ct + Pt * n;
+        for (int e = tid; e < n * d; e += BT) {
+            const int row = e / d, cidx = e % d;
+            if (cidx < n) At[(g * n + row) * n + cidx] = AB[e];
+            else Bt[(g * n + row) * m + (cidx - n)] = AB[e];
+        }
+        if (tid < n) ct[g * n + tid] = cval;
+        if (tid == 0) st[g] = (double)status_value;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < x.world) {
+        int* remote = x.peer_flags[tid] + g;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    }
+}
+
+// Last block of a gather launch (or the only block of a rank without points): wait for all points.
+template <int BT>
+__device__ __forceinline__ void peer_gather_wait(const PeerFusedArgs& x, int epoch, int tid) {
+    const int* local = x.peer_flags[x.rank];
+    double* st = x.peer_bufs[x.rank] + (long long)(epoch & 1) * x.out_stride + x.out_stride - x.P_total;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int g = tid; g < x.P_total; g += BT) {
+        while (true) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local + g) : "memory");
+            if (v >= epoch) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > x.timeout_ns) { st[g] = 2.0;  break; }      // status 2: the point never arrived
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *x.done_counter = 0u;
+        __threadfence();
+        *reinterpret_cast<volatile int*>(x.epoch) = epoch;
+    }
+}
+
+template <int BT>
+__device__ __forceinline__ void peer_gather_finish(const FinalizeArgs& a, int epoch, int tid) {
+    __shared__ bool last_block;
+    __syncthreads();
+    if (tid == 0) last_block = atomicAdd(a.peer.done_counter, 1u) + 1u == gridDim.x;
+    __syncthreads();
+    if (last_block) peer_gather_wait<BT>(a.peer, epoch, tid);
+}
+
+// A rank that owns no timestep of a gather step still takes part in it (epochs stay in step).
+__global__ void __launch_bounds__(128) peer_gather_wait_kernel(const PeerFusedArgs x) {
+    const int epoch = *reinterpret_cast<volatile int*>(x.epoch) + 1;
+    peer_gather_wait<128>(x, epoch, threadIdx.x);
+}
+
 // Compile-time loop: f(std::integral_constant<int, I>) for I = I0 .. I1 - 1 (the triangular loop
 // nests must be unrolled at compile time so that the solution stays in registers).
 template <int I0, int I1, class F>
@@ -764,7 +859,9 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
     PartialSource src = partial_source(a);
     bool peer_late = false;
     int epoch = 0;
-    if (a.peer.world > 0) epoch = peer_exchange_point<BT>(a, p, WIDTH, tid, &src, &peer_late);
+    if (a.peer.mode == kPeerExchange) epoch = peer_exchange_point<BT>(a, p, WIDTH, tid, &src, &peer_late);
+    else if (a.peer.mode == kPeerGather) epoch = *reinterpret_cast<volatile int*>(a.peer.epoch) + 1;
+    __shared__ int status_s;
     // 1. fixed-order sum over ranks and chunks, unpacked into the symmetric Gram and the rhs; a thread's
     //    entries are summed together so that all their loads are in flight at once
     {
@@ -896,11 +993,17 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
             }
         }
         bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) a.status[p] = peer_late ? 2 : (bad ? 1 : 0);      // 2: a peer's block never arrived
+        if (lane == 0) status_s = peer_late ? 2 : (bad ? 1 : 0);      // 2: a peer's block never arrived
     }
     __syncthreads();
-    write_abc<Sys, BT>(a, p, sAB, nom, tid);
-    if (a.peer.world > 0) peer_exchange_finish(a, epoch, tid);
+    if (a.peer.mode == kPeerGather) {
+        write_abc_gather<Sys, BT>(a, p, sAB, nom, status_s, epoch, tid);
+        peer_gather_finish<BT>(a, epoch, tid);
+    } else {
+        if (tid == 0) a.status[p] = status_s;
+        write_abc<Sys, BT>(a, p, sAB, nom, tid);
+        if (a.peer.mode == kPeerExchange) peer_exchange_finish(a, epoch, tid);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1108,7 +1211,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
     PartialSource src = partial_source(a);
     bool peer_late = false;
     int epoch = 0;
-    if (a.peer.world > 0) epoch = peer_exchange_point<kFinalizeThreads>(a, p, NJ, tid, &src, &peer_late);
+    if (a.peer.mode == kPeerExchange) epoch = peer_exchange_point<kFinalizeThreads>(a, p, NJ, tid, &src, &peer_late);
+    else if (a.peer.mode == kPeerGather) epoch = *reinterpret_cast<volatile int*>(a.peer.epoch) + 1;
     for (int e = tid; e < NJ; e += kFinalizeThreads) sV[e] = sum_partials(src, p, e, NJ) / a.n_total;
     nominal_to_smem<Sys, kFinalizeThreads>(a, p, nom, tid);
     __syncthreads();
@@ -1117,11 +1221,16 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_first_order_kernel(
         for (int k = 0; k < NJ; ++k) v[k] = sV[k];
         sys.jac_assemble(v, J);
         for (int e = 0; e < n * d; ++e) sAB[e] = J[e];
-        a.status[p] = peer_late ? 2 : 0;
+        if (a.peer.mode != kPeerGather) a.status[p] = peer_late ? 2 : 0;
     }
     __syncthreads();
-    write_abc<Sys, kFinalizeThreads>(a, p, sAB, nom, tid);
-    if (a.peer.world > 0) peer_exchange_finish(a, epoch, tid);
+    if (a.peer.mode == kPeerGather) {
+        write_abc_gather<Sys, kFinalizeThreads>(a, p, sAB, nom, 0, epoch, tid);
+        peer_gather_finish<kFinalizeThreads>(a, epoch, tid);
+    } else {
+        write_abc<Sys, kFinalizeThreads>(a, p, sAB, nom, tid);
+        if (a.peer.mode == kPeerExchange) peer_exchange_finish(a, epoch, tid);
+    }
 }
 
 // Chunk reduction [P, C, width] fp32 -> [P, width] fp64 in fixed chunk order: the block a rank

@@ -122,6 +122,54 @@ class PeerExchange:
         return ws.At, ws.Bt, ws.ct, ws.status
 
 
+class TimestepGather:
+    """Output buffers in peer-mapped (symmetric) memory for the timestep-sharded path: the finalize kernel
+    of every rank writes the [A_t | B_t | c_t | status] blocks of ITS timesteps straight into every rank's
+    buffer and the last block of each launch waits for all T arrival flags (csrc/smooth.cuh:
+    write_abc_gather) — the all-gather is part of the fit kernel, two launches per step, no NCCL."""
+
+    TIMEOUT_S = 10.0
+
+    def __init__(self, system, T, group=None, timeout_s=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n, m = system.dim_x, system.dim_u
+        self.T, self.n, self.m = int(T), n, m
+        self.out_stride = (self.T * (n * (n + m + 1) + 1) + 15) // 16 * 16
+        self.timeout_s = float(self.TIMEOUT_S if timeout_s is None else timeout_s)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.out = symm_mem.empty((2 * self.out_stride,), dtype=torch.float64, device=dev)
+        self.flags = symm_mem.empty(((self.T + 31) // 32 * 32,), dtype=torch.int32, device=dev)
+        self.out.zero_()
+        self.flags.zero_()
+        self._hout = symm_mem.rendezvous(self.out, group)
+        self._hflags = symm_mem.rendezvous(self.flags, group)
+        self.epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.calls = 0                  # host mirror of the device epoch: which parity holds the last step
+        torch.cuda.synchronize()
+        self._hflags.barrier()
+
+    def finalize(self, system, order, x_loc, u_loc, ws, n_total, p0):
+        """Enqueue the fit of this rank's points [p0, p0 + P) with the fused gather (P may be 0); returns
+        device views (At [T,n,n], Bt [T,n,m], ct [T,n], status [T] float64) of the step's full result."""
+        P = 0 if x_loc is None else x_loc.shape[0]
+        prm, nprm = system._params()
+        _lib.call("irs_smooth_finalize_gather", system.system_id, prm, nprm, order, _device.ptr(x_loc),
+                  _device.ptr(u_loc), P, 1 if ws is None else ws.C, None if ws is None else _device.ptr(ws.partials),
+                  self._hout.buffer_ptrs_dev, self._hflags.buffer_ptrs_dev, _device.ptr(self.epoch),
+                  _device.ptr(self.counter), self.out_stride, int(p0), self.T, self.rank, self.world,
+                  self.timeout_s, float(n_total), 0 if ws is None or not ws.centered else 1,
+                  None if ws is None else _device.ptr(ws.ct), _device.stream_ptr())
+        self.calls += 1
+        T, n, m = self.T, self.n, self.m
+        o = self.out[(self.calls & 1) * self.out_stride:]
+        na, nb, nc = T * n * n, T * n * m, T * n
+        return (o[:na].view(T, n, n), o[na:na + nb].view(T, n, m), o[na + nb:na + nb + nc].view(T, n),
+                o[na + nb + nc:na + nb + nc + T])
+
+
 def peer_capacity(system, order):
     """Nominal points per call the fused exchange supports (its blocks must be co-resident)."""
     import ctypes
@@ -139,6 +187,7 @@ class ShardedLinearizer:
         self._peer_memory = peer_memory
         self._peer_timeout_s = peer_timeout_s
         self._px = None
+        self._tg = None
         self._graphs = GraphRunner()
 
     def _workspace(self, P, N):
@@ -149,11 +198,22 @@ class ShardedLinearizer:
 
     def linearize_t(self, x_nom, u_nom, N, **kw):
         """Timestep-sharded.  x_nom [T,n], u_nom [T,m] replicated on every rank; returns the full
-        (At, Bt, ct, status) on every rank."""
+        (At, Bt, ct, status) on every rank — bit-identical to the single-GPU linearization (global point
+        index in the Philox counter, per-point reduction order unchanged).  With peer memory the gather
+        of the per-step blocks is fused into the fit kernel (TimestepGather: status is then a float64
+        vector, 0 ok / 1 rank deficient / 2 a rank did not deliver); otherwise NCCL all-gather."""
         T = x_nom.shape[0]
         n, m = self.system.dim_x, self.system.dim_u
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         start, stop, _ = shard_range(T, world, rank)
+        tg = self._timestep_gather(T)
+        if tg is not None:
+            if stop > start:
+                ws = self._workspace(stop - start, N)
+                xs, us = x_nom[start:stop], u_nom[start:stop]       # contiguous row slices
+                smoothing.accumulate(self.system, self.order, xs, us, N, ws, p0=start + kw.pop("p0", 0), **kw)
+                return tg.finalize(self.system, self.order, xs, us, ws, N, start)
+            return tg.finalize(self.system, self.order, None, None, None, N, start)
         width = n * (n + m + 1) + 1
         if stop > start:
             ws = self._workspace(stop - start, N)
@@ -166,6 +226,21 @@ class ShardedLinearizer:
         full = gather_rows(local, T, self.group)
         At, Bt, ct = unpack_abc(full[:, :width - 1], n, m)
         return At, Bt, ct, full[:, width - 1].to(torch.int32)
+
+    def _timestep_gather(self, T):
+        if self._peer_memory is False:
+            return None
+        if self._tg is None or self._tg.T != T:
+            try:
+                self._tg = TimestepGather(self.system, T, self.group, self._peer_timeout_s)
+            except Exception as e:      # no symmetric memory on this system: NCCL (plumbing only)
+                if self._peer_memory is True:
+                    raise
+                self._peer_memory = False
+                self._tg = None
+                import warnings
+                warnings.warn("peer-memory gather unavailable (%s); using NCCL all-gather" % e)
+        return self._tg
 
     def _peer_exchange(self, P, width):
         """The fused exchange for P points per call, or None (NCCL all-gather path).  An exchange is

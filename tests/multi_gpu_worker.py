@@ -56,6 +56,25 @@ def main():
     flags = torch.tensor([1.0 if same else 0.0], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     report("timestep sharding bit-identical", bool(flags.item() == 1.0), "(T=%d over %d ranks)" % (T, world))
+    # the gather fused into the fit kernel (peer memory) against the NCCL all-gather path, repeated steps
+    # (output double buffering by epoch parity), and a horizon shorter than the world (ranks without points)
+    used_gather = sh._tg is not None
+    sh_nccl_t = ShardedLinearizer(s, smoothing.ZERO_ORDER, peer_memory=False)
+    ok_t = True
+    for rep in range(3):
+        Ag, Bg, cg, sg = sh.linearize_t(x, u, N, **kw)
+        Ag, Bg, cg = Ag.clone(), Bg.clone(), cg.clone()
+        Ac_, Bc_, cc_, sc_ = sh_nccl_t.linearize_t(x, u, N, **kw)
+        ok_t = ok_t and torch.equal(Ag, Ac_) and torch.equal(Bg, Bc_) and torch.equal(cg, cc_) and int(sg.sum()) == 0
+    Tshort = max(1, world - 1)
+    A1s, B1s, c1s, _, _ = smoothing.linearize(s, smoothing.ZERO_ORDER, x[:Tshort].contiguous(), u[:Tshort].contiguous(), N, **kw)
+    A1s, c1s = A1s.clone(), c1s.clone()
+    Ats, Bts, cts, sts = sh.linearize_t(x[:Tshort].contiguous(), u[:Tshort].contiguous(), N, **kw)
+    ok_t = ok_t and torch.equal(Ats, A1s) and torch.equal(cts, c1s) and int(sts.sum()) == 0
+    flags = torch.tensor([1.0 if ok_t else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    report("fused gather == NCCL gather", bool(flags.item() == 1.0) and used_gather,
+           "(peer memory in use: %s; T=%d and T=%d)" % (used_gather, T, Tshort))
 
     # 2. sample sharding
     An, Bn, cn, stn = sh.linearize_n(x, u, N, **kw)

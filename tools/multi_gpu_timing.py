@@ -57,6 +57,11 @@ def main():
     _graph.USE_GRAPHS = True
     shn = ShardedLinearizer(s, 0, peer_memory=False)
     res["NCCL all-gather path"] = timed(lambda k: shn.linearize_n(x, u, N, seed=k, **kw))
+    _graph.USE_GRAPHS = True
+    sht = ShardedLinearizer(s, 0, peer_memory=True)
+    res["timestep axis, fused gather"] = timed(lambda k: sht.linearize_t(x, u, N * world, seed=k, **kw))
+    shtn = ShardedLinearizer(s, 0, peer_memory=False)
+    res["timestep axis, NCCL gather"] = timed(lambda k: shtn.linearize_t(x, u, N * world, seed=k, **kw))
     if rank == 0:
         for k, v in res.items():
             print("%-40s %.4f ms" % (k, v), flush=True)
