@@ -33,7 +33,7 @@ N_SAMPLES = 100000
 FLOPS_PER_SAMPLE = 838        # quadrotor zero-order, algorithmic, FMA = 2
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 SEED0 = 0x1255 + 3
-DRAM_BYTES_PER_LAUNCH = 46590   # ncu capture of the dominant kernel, see roofline.traffic_source
+DRAM_BYTES_PER_LAUNCH = 50688   # ncu capture of the dominant kernel, see roofline.traffic_source
 
 
 def log(*a):
@@ -100,6 +100,15 @@ class ClockSampler:
                        "of the same step"}
 
 
+def _reference_timing_note():
+    """The committed timing of the unmodified reference (build container; it cannot travel to the GPU box)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_timing.json")))["cases"]
+        return "; ".join("%s T=%d N=%d: %.3g samples/s" % (k, v["T"], v["N"], v["samples_per_s"]) for k, v in t.items())
+    except Exception:
+        return "unavailable"
+
+
 def quadrotor_problem(for_cpu=False):
     if for_cpu:
         from oracle import example_configs as ec          # CPU baseline leg only
@@ -161,8 +170,8 @@ def run_reference(args, rank, world):
     value = total / secs
     sample = ("float64 numpy port (oracle/cpu_restatement.py) of IrsLqrZeroOrder.get_TV_matrices, quadrotor "
               "T=100, N=%d samples/step (bounded from 1e5; cost per sample is flat in N), %d host processes "
-              "sharded by timestep; the reference's own QuadrotorDynamics.dynamics_batch is a per-sample Python "
-              "loop (6.7e3 samples/s single-thread, SURVEY.md section 6)" % (n_samples, procs))
+              "sharded by timestep; the UNMODIFIED reference's get_TV_matrices timed in the build container "
+              "(tests/golden/reference_timing.json): %s" % (n_samples, procs, _reference_timing_note()))
     out = {
         "impl": "reference", "metric": "smoothed_dynamics_samples_per_s", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -431,8 +440,9 @@ def run_gpu(args, rank, local_rank, world):
         cpu = {"value": done / secs, "unit": "samples/s", "cores": 1, "kind": "port",
                "sample": "float64 numpy port (oracle) of IrsLqrZeroOrder.get_TV_matrices, quadrotor T=100 N=1e5 "
                          "(one full step, %.1f s, single process; numpy elementwise is single-threaded, only "
-                         "lstsq may use BLAS threads); reference's own quadrotor dynamics_batch is a Python "
-                         "per-sample loop (6.7e3 samples/s, SURVEY.md section 6)" % secs}
+                         "lstsq may use BLAS threads).  The UNMODIFIED reference's get_TV_matrices, timed in the "
+                         "build container (tests/golden/reference_timing.json, oracle/make_script_fixtures.py): "
+                         "%s" % (secs, _reference_timing_note())}
 
     if rank == 0:
         peaks = {}
@@ -461,7 +471,7 @@ def run_gpu(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1,false>",
+            "roofline": {"bound": "fp32", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1,kTcPaired,false>",
                          "achieved": achieved_tflops, "peak": best, "unit": "TFLOP/s",
                          "frac": achieved_tflops / best if best > 0 else None,
                          "peak_source": "measured on this box: dependent-chain FFMA microbenchmark (irs_fp32_fma_peak); "
@@ -470,13 +480,19 @@ def run_gpu(args, rank, local_rank, world):
                          "flops_per_sample": FLOPS_PER_SAMPLE, "kernel_ms": ms_kernel,
                          "traffic": DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                           "(profiles/r1_smooth_tc_full.txt): the kernel reads the nominal points and "
+                                           "(profiles/r2_smooth_tc_paired_full.txt): the kernel reads the nominal points and "
                                            "writes 3.3 MB of packed Gram blocks that stay in L2",
                          "bound_note": "Philox mode has no per-sample HBM stream, so the kernel is bounded by FP32 "
                                        "issue, not by HBM or the tensor pipe (DESIGN.md 3.1)",
+                         "achieved_note": "ALGORITHMIC flops (SURVEY.md 8(d): 838 per fitted sample, of which 656 are the "
+                                          "Gram update) over the measured kernel time.  The kernel executes fewer: the "
+                                          "Gram runs on the tensor cores, and an antithetic pair x +- z contributes ONE "
+                                          "rank-1 update (2 z z^T, z (f+ - f-)^T) for two fitted samples; what the "
+                                          "CUDA cores issue is 296 instructions per sample (ncu, "
+                                          "profiles/r2_smooth_tc_paired_full.txt: issue slots 70 % busy)",
                          "hbm_gbs_measured_peak": peaks.get("hbm_gbs")},
             "roofline_replay_mode": None if world > 1 else {
-                "bound": "hbm", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1,true> (noise replayed from HBM)",
+                "bound": "hbm", "kernel": "smooth_zero_order_tc_kernel<Quadrotor<float>,1,kTcReplay,false> (noise replayed from HBM)",
                 "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)", "bytes_per_sample": 64,
