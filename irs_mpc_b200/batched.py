@@ -27,8 +27,16 @@ from .tv_lqr import TVLQR_FAILED
 class BatchedIrsLqrZeroOrder:
     order = smoothing.ZERO_ORDER
 
-    def __init__(self, system, Q, Qd, R, x0, xd_trj, u_trj_initial, sampling, instance_offset=0):
-        """x0 [I,n]; xd_trj [I,T+1,n] or [T+1,n] (shared); u_trj_initial [I,T,m] or [T,m]."""
+    def __init__(self, system, Q, Qd, R, x0, xd_trj, u_trj_initial, sampling, instance_offset=0,
+                 xbound=None, ubound=None):
+        """x0 [I,n]; xd_trj [I,T+1,n] or [T+1,n] (shared); u_trj_initial [I,T,m] or [T,m].
+        xbound [2,n] / ubound [2,m]: the reference's IrsLqrParameters.xbound / ubound (irs_lqr.py:160-167), the
+        same box for every instance.  The batched path runs the one-pass Riccati descent, which is the
+        reference's result while no planned trajectory touches a bound; with bounds given, every descent is
+        followed by the plan check of all instances x start times (irs_tvlqr_plan_check) and `check()` raises
+        the reference's ValueError for instances whose QPs would have had an active bound (e.g. a quadrotor
+        plan through the +-pi/2 pitch bound that guards the 1/cos(pitch) singularity) — run those through
+        IrsLqrZeroOrder, which solves the bounded QPs."""
         if not isinstance(system, CudaDynamicalSystem):
             raise RuntimeError("the system must derive from CudaDynamicalSystem (no CPU fallback)")
         if not isinstance(sampling, GaussianSampling):
@@ -64,6 +72,18 @@ class BatchedIrsLqrZeroOrder:
         self._k = _device.empty((I, T, m))
         self._rstatus = _device.empty((I,), torch.int32)
         self._ws = smoothing.Workspace(system, self.order, I * T, sampling.num_samples)
+        self._box = None
+        if xbound is not None or ubound is not None:
+            if I > 65535:
+                raise RuntimeError("the plan check supports at most 65535 instances per object")
+            big = 1e30
+            xlo, xhi = ((np.asarray(xbound[0], dtype=np.float64), np.asarray(xbound[1], dtype=np.float64))
+                        if xbound is not None else (-big * np.ones(n), big * np.ones(n)))
+            ulo, uhi = ((np.asarray(ubound[0], dtype=np.float64), np.asarray(ubound[1], dtype=np.float64))
+                        if ubound is not None else (-big * np.ones(m), big * np.ones(m)))
+            self._box = tuple(_device.to_device(np.ascontiguousarray(v)) for v in (xlo, xhi, ulo, uhi))
+            self._plan_scratch = _device.empty((I * T * (n + m) * (n + 1),))
+            self._violated = _device.empty((I,), torch.int32)
         self._rollout_open(self._x0, self.u_trj, self.x_trj, self.cost)
         self.iter = 1
         self.cost_lst = [_device.to_numpy(self.cost)]
@@ -105,6 +125,13 @@ class BatchedIrsLqrZeroOrder:
                   _device.ptr(self._dxd), self._xd_stride, _device.ptr(self._dQ), _device.ptr(self._dR),
                   I, T, _device.ptr(self._x_new), _device.ptr(self._u_new), _device.ptr(self._cost_new),
                   _device.stream_ptr())
+        if self._box is not None:
+            from .tv_lqr import BOUND_TOL
+            xlo, xhi, ulo, uhi = self._box
+            _lib.call("irs_tvlqr_plan_check", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                      _device.ptr(self._K), _device.ptr(self._k), _device.ptr(self._x_new), _device.ptr(xlo),
+                      _device.ptr(xhi), _device.ptr(ulo), _device.ptr(uhi), BOUND_TOL, I, T, 0,
+                      _device.ptr(self._violated), _device.ptr(self._plan_scratch), _device.stream_ptr())
         return self._x_new, self._u_new, self._cost_new
 
     def check(self):
@@ -113,6 +140,11 @@ class BatchedIrsLqrZeroOrder:
         bad = int(self._rstatus.sum().item())
         if bad or not bool(torch.isfinite(self._cost_new).all().item()):
             raise ValueError(TVLQR_FAILED)
+        if self._box is not None and int(self._violated.sum().item()):
+            hit = torch.nonzero(self._violated).flatten().tolist()
+            raise ValueError(TVLQR_FAILED + " A planned trajectory of %d instance(s) touches xbound / ubound "
+                             "(first: %s, offsets into this object): the batched path does not solve bounded QPs; "
+                             "run these instances through IrsLqrZeroOrder." % (len(hit), hit[:8]))
 
     def iterate(self, max_iterations, verbose=False):
         """irs_lqr.py:188-218 for every instance: max_iterations + 1 descents, the state keeps the

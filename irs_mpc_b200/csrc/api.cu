@@ -91,13 +91,16 @@ static bool use_tensor_cores(int system) {
     return e == 1;
 }
 static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static int cached[64] = {0};      // per device (one process may drive several GPUs)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
     }
-    return n;
+    return cached[dev];
 }
 
 template <class Sys, int MODE, bool CENTERED>

@@ -809,6 +809,32 @@ def test_compute_least_squares_matches_lstsq(api, name):
         solver.compute_least_squares(dxdu[:n + m - 1], deltaf[:n + m - 1])      # fewer samples than regressors
 
 
+def test_batched_instances_bounds_are_checked(api):
+    """BatchedIrsLqrZeroOrder with the reference's xbound / ubound: wide boxes (the examples' 'infinite'
+    1e5) change nothing; a box that a planned trajectory touches is reported by check() as the reference's
+    ValueError, naming the instances — never a silently unconstrained result."""
+    from irs_mpc_b200 import _device
+    I, T, N = 6, 20, 2000
+    cfg = ec.quadrotor(T=T)
+    s = make_system(api, "quadrotor")
+    x0, xd = ec.quadrotor_batch(0, I, T=T, total=64)
+    mk = lambda **kw: api.BatchedIrsLqrZeroOrder(
+        s, cfg["Q"], cfg["Qd"], cfg["R"], x0, xd, cfg["u_trj_initial"],
+        api.GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], N, seed=3), **kw)
+    free = mk()
+    xf, uf, cf = free.local_descent()
+    free.check()
+    wide = mk(xbound=cfg["xbound"], ubound=cfg["ubound"])
+    xw, uw, cw = wide.local_descent()
+    wide.check()
+    assert np.array_equal(_device.to_numpy(xf), _device.to_numpy(xw)) and np.array_equal(_device.to_numpy(cf), _device.to_numpy(cw))
+    umax = float(np.max(np.abs(_device.to_numpy(uf))))
+    tight = mk(xbound=cfg["xbound"], ubound=np.array([-0.5 * umax * np.ones(4), 0.5 * umax * np.ones(4)]))
+    tight.local_descent()
+    with pytest.raises(ValueError, match="TV_LQR failed"):
+        tight.check()
+
+
 # ------------------------------------------------------------------------------------------------
 # ragged / edge sample counts through both Gram engines
 # ------------------------------------------------------------------------------------------------

@@ -43,3 +43,41 @@ def test_antithetic_stream_bookkeeping():
     e = philox_ref.standard_normals(1, 200000, 8, 0x1255, 1, antithetic=True)[0]
     assert abs(e.mean()) < 1e-12                        # exactly symmetric
     assert abs(e.std() - 1.0) < 5e-3
+
+
+def test_seven_round_stream_statistics():
+    """The sample stream uses Philox4x32 with 7 rounds (the smallest count Salmon et al. report as
+    Crush-resistant; 10 is the default safety margin).  Beyond the known-answer vectors of the round
+    function: uniformity of the raw words (chi-square over 256 byte bins, every byte lane), no linear
+    correlation between neighbouring counters, samples, timesteps and word lanes, and the first four moments
+    and the tail mass of the normals built from them."""
+    T, N, d = 4, 250000, 16
+    w = philox_ref.words_for(T, N, d, 0x1255, 1)                          # [T, N, 4, 4] uint32
+    flat = w.reshape(-1)
+    for shift in (0, 8, 16, 24):
+        counts = np.bincount((flat >> np.uint32(shift)) & np.uint32(0xFF), minlength=256)
+        expect = flat.size / 256.0
+        chi2 = float(np.sum((counts - expect) ** 2 / expect))
+        assert 160.0 < chi2 < 370.0, (shift, chi2)                        # chi-square(255): mean 255, sd 22.6
+    u = (w.astype(np.float64) + 0.5) / 2.0 ** 32
+    c = u - 0.5
+
+    def corr(a, b):
+        return float(np.mean(a * b) / (1.0 / 12.0))
+    lim = 5.0 / np.sqrt(T * (N - 1) * 16)                                 # 5 sigma of a sample correlation
+    assert abs(corr(c[:, 1:], c[:, :-1])) < lim                           # neighbouring samples (counter + 1)
+    assert abs(corr(c[1:], c[:-1])) < 5.0 / np.sqrt((T - 1) * N * 16)    # neighbouring timesteps
+    assert abs(corr(c[:, :, 1:], c[:, :, :-1])) < 5.0 / np.sqrt(T * N * 12)   # neighbouring counter blocks
+    assert abs(corr(c[..., 1:], c[..., :-1])) < 5.0 / np.sqrt(T * N * 12)     # neighbouring words of a block
+    e = philox_ref.standard_normals(T, N, d, 0x1255, 1).reshape(-1)
+    n = e.size
+    assert abs(e.mean()) < 5.0 / np.sqrt(n)
+    assert abs(e.var() - 1.0) < 5.0 * np.sqrt(2.0 / n)
+    assert abs(np.mean(e ** 3)) < 5.0 * np.sqrt(15.0 / n)
+    assert abs(np.mean(e ** 4) - 3.0) < 5.0 * np.sqrt(96.0 / n)
+    tail = np.mean(np.abs(e) > 3.0)
+    assert abs(tail - 0.0026998) < 5.0 * np.sqrt(0.0027 / n)
+    # cross-coordinate independence of the normals of one sample (what the Gram fit relies on)
+    z = philox_ref.standard_normals(1, 400000, d, 0x1255, 2)[0]
+    C = (z.T @ z) / z.shape[0]
+    assert float(np.max(np.abs(C - np.eye(d)))) < 5.0 / np.sqrt(z.shape[0]) * 1.5
