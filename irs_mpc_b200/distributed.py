@@ -151,9 +151,8 @@ class TimestepGather:
         torch.cuda.synchronize()
         self._hflags.barrier()
 
-    def finalize(self, system, order, x_loc, u_loc, ws, n_total, p0):
-        """Enqueue the fit of this rank's points [p0, p0 + P) with the fused gather (P may be 0); returns
-        device views (At [T,n,n], Bt [T,n,m], ct [T,n], status [T] float64) of the step's full result."""
+    def enqueue(self, system, order, x_loc, u_loc, ws, n_total, p0):
+        """Enqueue the fit of this rank's points [p0, p0 + P) with the fused gather (P may be 0)."""
         P = 0 if x_loc is None else x_loc.shape[0]
         prm, nprm = system._params()
         _lib.call("irs_smooth_finalize_gather", system.system_id, prm, nprm, order, _device.ptr(x_loc),
@@ -162,12 +161,21 @@ class TimestepGather:
                   _device.ptr(self.counter), self.out_stride, int(p0), self.T, self.rank, self.world,
                   self.timeout_s, float(n_total), 0 if ws is None or not ws.centered else 1,
                   None if ws is None else _device.ptr(ws.ct), _device.stream_ptr())
+
+    def step_done(self):
+        """Count one executed step (eager or replayed from a graph) and return device views
+        (At [T,n,n], Bt [T,n,m], ct [T,n], status [T] float64) of its full result: the parity half of the
+        output buffer the kernels of that step wrote (valid once the stream has run them)."""
         self.calls += 1
         T, n, m = self.T, self.n, self.m
         o = self.out[(self.calls & 1) * self.out_stride:]
         na, nb, nc = T * n * n, T * n * m, T * n
         return (o[:na].view(T, n, n), o[na:na + nb].view(T, n, m), o[na + nb:na + nb + nc].view(T, n),
                 o[na + nb + nc:na + nb + nc + T])
+
+    def finalize(self, system, order, x_loc, u_loc, ws, n_total, p0):
+        self.enqueue(system, order, x_loc, u_loc, ws, n_total, p0)
+        return self.step_done()
 
 
 def peer_capacity(system, order):
@@ -190,10 +198,21 @@ class ShardedLinearizer:
         self._tg = None
         self._graphs = GraphRunner()
 
-    def _workspace(self, P, N):
-        key = (self.system.system_id, self.order, P, N)
+    def _workspace(self, P, N, fill=False):
+        """fill: pick the chunk size so that the launch holds about 1.5 resident grids of work items (a rank's
+        share of a strongly scaled step is small: with the default 4096-sample chunks 100 points x 12,500
+        samples are 400 items for 740 block slots).  Only where bit-identity with the single-GPU run is not
+        part of the contract (the sample axis: its summation order differs from one GPU's anyway)."""
+        chunk = 0
+        if fill and self.order == smoothing.ZERO_ORDER:
+            C, _ = smoothing.plan(self.system.system_id, self.order, P, N)
+            if P * C < 1100:
+                chunk = max(512, -(-(N * P // 1100) // 256) * 256)
+                if chunk >= 4096:
+                    chunk = 0
+        key = (self.system.system_id, self.order, P, N) if not chunk else (self.system.system_id, self.order, P, N, chunk)
         if self._ws is None or self._ws.key != key:
-            self._ws = smoothing.Workspace(self.system, self.order, P, N)
+            self._ws = smoothing.Workspace(self.system, self.order, P, N, chunk)
         return self._ws
 
     def linearize_t(self, x_nom, u_nom, N, **kw):
@@ -208,12 +227,29 @@ class ShardedLinearizer:
         start, stop, _ = shard_range(T, world, rank)
         tg = self._timestep_gather(T)
         if tg is not None:
-            if stop > start:
-                ws = self._workspace(stop - start, N)
-                xs, us = x_nom[start:stop], u_nom[start:stop]       # contiguous row slices
-                smoothing.accumulate(self.system, self.order, xs, us, N, ws, p0=start + kw.pop("p0", 0), **kw)
-                return tg.finalize(self.system, self.order, xs, us, ws, N, start)
-            return tg.finalize(self.system, self.order, None, None, None, N, start)
+            p_base = kw.pop("p0", 0)
+            ws = self._workspace(stop - start, N) if stop > start else None
+            xs, us = (x_nom[start:stop], u_nom[start:stop]) if stop > start else (None, None)   # contiguous row slices
+
+            def enqueue():
+                if ws is not None:
+                    smoothing.accumulate(self.system, self.order, xs, us, N, ws, p0=start + p_base, **kw)
+                tg.enqueue(self.system, self.order, xs, us, ws, N, start)
+
+            # two launches per step, replayed from a CUDA graph (the epoch of the gather lives on the device)
+            key = None
+            if kw.get("noise") is None and kw.get("sigma") is not None and ws is not None:
+                key = (self.system.system_id, self.order, T, N, world, rank, kw.get("flags", 0), kw.get("stream_id", 0),
+                       p_base, x_nom.data_ptr(), u_nom.data_ptr(), id(tg),
+                       tuple(float(v) for v in self.system.device_params()))
+
+            def update(handle):
+                sig = np.ascontiguousarray(np.asarray(kw["sigma"], dtype=np.float32))
+                _lib.call("irs_graph_update_smoothing", handle, sig.ctypes.data, int(kw.get("seed", 0)),
+                          int(kw.get("it", 1)), int(kw.get("stream_id", 0)))
+
+            self._graphs.run("linearize_t", key, enqueue, update)
+            return tg.step_done()
         width = n * (n + m + 1) + 1
         if stop > start:
             ws = self._workspace(stop - start, N)
@@ -272,7 +308,7 @@ class ShardedLinearizer:
         (At, Bt, ct, status) fitted on all W * N_local samples, identical on every rank.  Raises
         (smoothing.check_status) on a rank-deficient fit or a peer-exchange timeout."""
         T = min(np.asarray(u_trj).shape[0], np.asarray(x_trj).shape[0])
-        ws = self._workspace(T, N_local)
+        ws = self._workspace(T, N_local, fill=True)
         ws.stage_nominal(x_trj, u_trj)
         ws.enqueue_upload()
         self.linearize_n(ws.x_nom, ws.u_nom, N_local, **kw)      # the fit lands in ws.At / Bt / ct / status
@@ -292,7 +328,7 @@ class ShardedLinearizer:
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if kw.get("flags", 0) & 8 and kw.get("noise") is None and N_local % 2 and world > 1:
             raise ValueError("antithetic pairs must not straddle ranks: N_local must be even (got %d)" % N_local)
-        ws = self._workspace(T, N_local)
+        ws = self._workspace(T, N_local, fill=True)
         px = self._peer_exchange(T, ws.width)
 
         def enqueue():
@@ -309,7 +345,7 @@ class ShardedLinearizer:
         if px is not None and kw.get("noise") is None and kw.get("sigma") is not None:
             # everything a captured kernel reads besides (seed, it, sigma) must be part of the key
             key = (self.system.system_id, self.order, T, N_local, world, rank, kw.get("flags", 0),
-                   kw.get("stream_id", 0), kw.get("p0", 0), x_nom.data_ptr(), u_nom.data_ptr(),
+                   kw.get("stream_id", 0), kw.get("p0", 0), x_nom.data_ptr(), u_nom.data_ptr(), id(px), ws.S,
                    tuple(float(v) for v in self.system.device_params()))
 
         def update(handle):
