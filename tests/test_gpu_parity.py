@@ -835,6 +835,25 @@ def test_batched_instances_bounds_are_checked(api):
         tight.check()
 
 
+def test_integration_stub_runs_as_documented(api, golden_dir):
+    """INTEGRATION.md section B shows the binding a reference maintainer would add (ctypes against the C
+    ABI, nothing from this package).  The code block is read out of the document and executed as written;
+    its (At, Bt, ct) on the reference-generated deltas must equal the reference's own."""
+    import re
+    from irs_mpc_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# irs_lqr/_b200.py.*?\n(.*?)```", text, flags=re.S).group(1)
+    block = block.replace('ctypes.CDLL("libirs_mpc_b200.so")', 'ctypes.CDLL(%r)' % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(block, "INTEGRATION.md:_b200.py", "exec"), ns)
+    g = gold(golden_dir, "zero_order_quadrotor.npz")
+    params = [0.05, 0.775, 0.15, 9.81, 0.0015, 0.0025, 0.0035, 1.0, 0.0245]
+    At, Bt, ct = ns["zero_order_tv_matrices"](2, params, g["x_trj"], g["u_trj"], g["deltas"])
+    assert rel_err(At, g["At"]) < FP32_RTOL and rel_err(Bt, g["Bt"]) < FP32_RTOL
+    assert float(np.max(np.abs(ct - g["ct"]))) < FP32_RTOL * max(1.0, float(np.max(np.abs(g["x_trj"]))))
+
+
 # ------------------------------------------------------------------------------------------------
 # ragged / edge sample counts through both Gram engines
 # ------------------------------------------------------------------------------------------------
