@@ -276,24 +276,34 @@ class IrsLqr:
         T, n, m = self.T, self.dim_x, self.dim_u
         db = self._descent_buffers()
         nx, nu = db["nx"], db["nu"]
-        h = db["in_host"].numpy()
+        if "in_np" not in db:      # numpy views of the pinned mirrors, and the host copy of the box, made once
+            db["in_np"], db["out_np"] = db["in_host"].numpy(), db["out_host"].numpy()
+            db["sstat_np"] = db["out_np"][nx + nu + 3:].view(np.int32)[:T]
+            db["flags_np"] = db["out_np"][nx + nu + 1:nx + nu + 3].view(np.int32)      # [riccati status, ., violated, .]
+            if self.xbound is not None:
+                db["xbox_np"] = (np.asarray(self.xbound[0], dtype=np.float64) - START_BOUND_TOL,
+                                 np.asarray(self.xbound[1], dtype=np.float64) + START_BOUND_TOL)
+        h = db["in_np"]
         h[:nx] = np.asarray(x_trj, dtype=np.float64)[:T + 1].reshape(-1)
         h[nx:] = np.asarray(u_trj, dtype=np.float64)[:T].reshape(-1)
         self._run("descent", lambda: self._enqueue_descent(db))
         # one synchronising read-back for everything the host needs
         torch.cuda.current_stream().synchronize()
-        o = db["out_host"].numpy()
-        smoothing.check_status(o[nx + nu + 3:].view(np.int32)[:T])
-        if int(o[nx + nu + 1:nx + nu + 2].view(np.int32)[0]) != 0:
+        o = db["out_np"]
+        smoothing.check_status(db["sstat_np"])
+        if int(db["flags_np"][0]) != 0:
             raise ValueError(TVLQR_FAILED)
-        if int(o[nx + nu + 2:nx + nu + 3].view(np.int32)[0]) != 0:
+        if int(db["flags_np"][2]) != 0:
             # some planned trajectory touches a bound: the reference's loop with the bounded QP
             x_out, u_out, cost = self._bounded_descent(db)
+            finite = np.all(np.isfinite(x_out)) and np.all(np.isfinite(u_out))
         else:
             x_out = o[:nx].reshape(T + 1, n).copy()
             u_out = o[nx:nx + nu].reshape(T, m).copy()
             cost = float(o[nx + nu])
-        if not (np.all(np.isfinite(x_out)) and np.all(np.isfinite(u_out))):
+            # the device cost sums every state and input of the trajectory: it is finite iff they all are
+            finite = np.isfinite(cost)
+        if not finite:
             raise ValueError(TVLQR_FAILED)
         if self.xbound is not None:
             # every QP of the reference's loop also boxes its START state xt[0] = the actual x_t
@@ -301,9 +311,9 @@ class IrsLqr:
             # dynamics pushed outside xbound makes that QP infeasible -> the reference's ValueError.
             # START_BOUND_TOL: a state steered ONTO a bound lands on it to the accuracy of the bounded
             # solve, which must not count as outside (OSQP itself accepts 1e-3).
-            xlo, xhi = np.asarray(self.xbound[0], dtype=np.float64), np.asarray(self.xbound[1], dtype=np.float64)
+            xlo, xhi = db["xbox_np"]
             start = x_out[:T]
-            if np.any(start < xlo - START_BOUND_TOL) or np.any(start > xhi + START_BOUND_TOL):
+            if (start < xlo).any() or (start > xhi).any():
                 raise ValueError(TVLQR_FAILED)
         self._last_descent_cost = cost
         self._last_descent = (x_out, u_out, x_out.copy(), u_out.copy())
