@@ -720,6 +720,18 @@ static int tvlqr_riccati_impl(int n, int m, const double* At, const double* Bt, 
     if (t_hi > 0) per_block = true;                                 // segments exist in the tiled kernel only
     const bool extra = Hinv_out != nullptr || P_out != nullptr;     // only the generic kernel writes them
     static const bool no_tiles = getenv("IRS_TVLQR_NO_TILES") != nullptr;
+    // many instances of a 4-divisible problem (quadrotor): two instances per warp, 4 x 4 register tiles
+    // (tvlqr.cuh: tvlqr_riccati_packed_kernel).  The switch point lies above every instance count the
+    // few-instance callers use and below a rank's share of a sharded batch, so a problem's result does not
+    // depend on how a large batch is sharded.  IRS_TVLQR_VARIANT=block|warp overrides.
+    if (n == 12 && m == 4 && !extra && t_hi == 0 && I > 2 * num_sms() && getenv("IRS_TVLQR_VARIANT") == nullptr) {
+        auto kern = tvlqr_riccati_packed_kernel<12, 4>;
+        const int smem = (int)sizeof(RicPackSmem<12, 4>);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(tvlqr_riccati_packed_kernel)");
+        kern<<<(unsigned)((I + kRicPackPerBlock - 1) / kRicPackPerBlock), kRicPackThreads, smem, st>>>(a);
+        return check_launch("tvlqr_riccati_packed_kernel");
+    }
     IRS_DISPATCH_DIMS(n, m, {
         if (per_block) {
             if constexpr (N_ % 2 == 0 && M_ % 2 == 0) {

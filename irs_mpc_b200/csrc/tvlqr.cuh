@@ -509,6 +509,246 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
 }
 
 // ---------------------------------------------------------------------------------------------
+// Throughput variant for MANY instances and n, m multiples of four (quadrotor 12/4; BASELINE.json
+// configs[4]: 4096 instances).  The block kernel above is shared-memory bound there (73 % LSU, ~48 KB of
+// operand traffic per instance and step with 2 x 2 tiles, a third of its threads busy, five block barriers
+// per step).  Here TWO instances share a warp — 12 lanes each — and every matrix product is cut into 4 x 4
+// register tiles of ONE code shape, so the lanes of both instances run the same instruction stream:
+//     [PA | PB] = P [A | B]              12 x 16 -> 12 tiles, one per lane   (P symmetric: its rows are its columns)
+//     [G | H0]  = B^T [PA | PB]           4 x 16 ->  4 tiles
+//     Pn        = Q + A^T PA + G^T K     12 x 12 ->  9 tiles
+// A tile step is 4 LDS.128 for 16 DFMA (4 bytes of shared memory per DFMA against 8 with 2 x 2 tiles), a
+// DFMA warp instruction carries 24 useful lanes instead of 4-32, and the phases are separated by __syncwarp
+// only: an instance never leaves its warp.  Eight instances per block of 128 threads, 46 KB of shared
+// memory, four blocks per SM: all 4096 instances of configs[4] are resident at once.  Next step's operands
+// are prefetched into registers (18 doubles per lane) during the last product of the current step.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRicPackThreads = 128;
+constexpr int kRicPackLanes = 12;                       // lanes per instance
+constexpr int kRicPackPerWarp = 2;                      // instances per warp
+constexpr int kRicPackPerBlock = kRicPackPerWarp * kRicPackThreads / 32;
+
+template <int n, int m>
+struct RicPackInst {
+    double P[n * n];              // value-function Hessian (exactly symmetric)
+    double AB[n * (n + m)];       // [A | B] of the current step, row stride n + m
+    double PAB[n * (n + m)];      // P [A | B]
+    double GH[m * (n + m)];       // B^T [PA | PB] = [G | H - R/2]
+    double Kt[m * n];
+    double p[n], w[n], c[n], xd[n], g[m], kt[m];
+};
+template <int n, int m>
+struct RicPackSmem {
+    double Q[n * n], Rh[m * m];
+    RicPackInst<n, m> inst[kRicPackPerBlock];
+};
+
+// acc[i][j] += sum_q X[q * ldx + x0 + i] * Y[q * ldy + y0 + j]   (4 x 4 tile of X^T Y; x0, y0 multiples of 4)
+template <int len>
+__device__ __forceinline__ void tile4_atb(const double* X, int ldx, int x0, const double* Y, int ldy, int y0,
+                                          double (&acc)[4][4]) {
+#pragma unroll 4      // full unrolling hoists all 48 operand loads and spills at 128 registers
+    for (int q = 0; q < len; ++q) {
+        const double2 xa = *reinterpret_cast<const double2*>(X + q * ldx + x0);
+        const double2 xb = *reinterpret_cast<const double2*>(X + q * ldx + x0 + 2);
+        const double2 ya = *reinterpret_cast<const double2*>(Y + q * ldy + y0);
+        const double2 yb = *reinterpret_cast<const double2*>(Y + q * ldy + y0 + 2);
+        const double x[4] = {xa.x, xa.y, xb.x, xb.y}, y[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(x[i], y[j], acc[i][j]);
+    }
+}
+__device__ __forceinline__ void tile4_store(double* D, int ld, int r0, int c0, const double (&acc)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<double2*>(D + (r0 + i) * ld + c0) = make_double2(acc[i][0], acc[i][1]);
+        *reinterpret_cast<double2*>(D + (r0 + i) * ld + c0 + 2) = make_double2(acc[i][2], acc[i][3]);
+    }
+}
+
+template <int n, int m>
+__global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kernel(const TvlqrArgs a) {
+    static_assert(n % 4 == 0 && m == 4 && n / 4 * (n + m) / 4 <= kRicPackLanes && n <= kRicPackLanes + 1,
+                  "4 x 4 tiles, one per lane");
+    constexpr int W = n + m;                              // row stride of [A | B]
+    constexpr int kOps = n * n + n * m + n + n;           // doubles of one step's operands: A, B, c, xd
+    constexpr int kPre = (kOps + kRicPackLanes - 1) / kRicPackLanes;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RicPackSmem<n, m>& sm = *reinterpret_cast<RicPackSmem<n, m>*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane / kRicPackLanes;                 // instance of this lane inside the warp (2: idle lanes)
+    const int j = lane % kRicPackLanes;                   // role lane
+    const int slot = warp * kRicPackPerWarp + (sub < kRicPackPerWarp ? sub : 0);
+    const long long inst_raw = (long long)blockIdx.x * kRicPackPerBlock + slot;
+    // idle lanes (24-31) and the lanes of a missing last instance shadow a valid one and write nothing
+    const bool live = sub < kRicPackPerWarp && inst_raw < a.I;
+    const long long inst = inst_raw < a.I ? inst_raw : (long long)a.I - 1;
+    RicPackInst<n, m>& s = sm.inst[slot];
+    for (int e = tid; e < n * n; e += kRicPackThreads) sm.Q[e] = a.Q[e];
+    for (int e = tid; e < m * m; e += kRicPackThreads) sm.Rh[e] = 0.5 * a.R[e];
+    const double* xd_i = a.xd + inst * a.xd_stride;
+    const double* At = a.At + inst * a.T * n * n;
+    const double* Bt = a.Bt + inst * a.T * n * m;
+    const double* ct = a.ct + inst * a.T * n;
+    // operand e of step t: A (n n) | B (n m) | c (n) | xd (n); lane j owns e = j, j + 12, ...
+    double pre[kPre];
+    auto prefetch = [&](int t) {
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int e = j + k * kRicPackLanes;
+            if (e < n * n) pre[k] = At[(long long)t * n * n + e];
+            else if (e < n * n + n * m) pre[k] = Bt[(long long)t * n * m + (e - n * n)];
+            else if (e < n * n + n * m + n) pre[k] = ct[(long long)t * n + (e - n * n - n * m)];
+            else if (e < kOps) pre[k] = xd_i[(long long)t * n + (e - n * n - n * m - n)];
+        }
+    };
+    auto publish = [&] {
+        if (!live) return;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int e = j + k * kRicPackLanes;
+            if (e < n * n) s.AB[(e / n) * W + e % n] = pre[k];
+            else if (e < n * n + n * m) s.AB[((e - n * n) / m) * W + n + (e - n * n) % m] = pre[k];
+            else if (e < n * n + n * m + n) s.c[e - n * n - n * m] = pre[k];
+            else if (e < kOps) s.xd[e - n * n - n * m - n] = pre[k];
+        }
+    };
+    prefetch(a.T - 1);
+    // terminal condition P_T = sym(Qd) (x' Qd x only sees the symmetric part), p_T = -Qd xd_T
+    if (live) {
+        for (int e = j; e < n * n; e += kRicPackLanes) {
+            const int r = e / n, c = e % n;
+            s.P[e] = 0.5 * (a.Qd[r * n + c] + a.Qd[c * n + r]);
+        }
+        if (j < n) {
+            double acc = 0.0;
+            for (int q = 0; q < n; ++q) acc -= a.Qd[j * n + q] * xd_i[(long long)a.T * n + q];
+            s.p[j] = acc;
+        }
+    }
+    publish();
+    __syncthreads();      // Q, Rh (block) and the first operands (warp) are in place
+    bool ok = true;
+    const int ab_r0 = 4 * (j / (W / 4)), ab_c0 = 4 * (j % (W / 4));      // tile of P [A | B]      (n/4 x W/4 tiles)
+    const int pn_r0 = 4 * (j / (n / 4)), pn_c0 = 4 * (j % (n / 4));      // tile of Pn             (n/4 x n/4 tiles)
+    for (int t = a.T - 1; t >= 0; --t) {
+        // ---- phase 1: [PA | PB] = P [A | B] (one 4 x 4 tile per lane), w = P c + p ----
+        {
+            double acc[4][4] = {};
+            tile4_atb<n>(s.P, n, ab_r0, s.AB, W, ab_c0, acc);
+            if (live) tile4_store(s.PAB, W, ab_r0, ab_c0, acc);
+            if (j < n) {
+                double wv = s.p[j];
+#pragma unroll
+                for (int q = 0; q < n; ++q) wv = fma(s.P[j * n + q], s.c[q], wv);
+                if (live) s.w[j] = wv;
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: [G | H0] = B^T [PA | PB] (lanes 0-3: W/4 tiles), g = B^T w (lanes 4-7) ----
+        if (j < W / 4) {
+            double acc[4][4] = {};
+            tile4_atb<n>(s.AB + n, W, 0, s.PAB, W, 4 * j, acc);
+            if (live) tile4_store(s.GH, W, 0, 4 * j, acc);
+        } else if (j < W / 4 + m) {
+            const int i = j - W / 4;
+            double gv = 0.0;
+#pragma unroll
+            for (int q = 0; q < n; ++q) gv = fma(s.AB[q * W + n + i], s.w[q], gv);
+            if (live) s.g[i] = gv;
+        }
+        __syncwarp();
+        // ---- phase 3: K = -H^-1 G, k = -H^-1 g; column `j` (j = n: the affine term needs a 13th lane ->
+        //      lane 0 does it after its own column); H = R/2 + sym(H0) inverted redundantly in registers ----
+        {
+            double Hs[m][m], Hi[m][m];
+#pragma unroll
+            for (int i = 0; i < m; ++i)
+#pragma unroll
+                for (int q = 0; q < m; ++q)
+                    Hs[i][q] = 0.5 * ((s.GH[i * W + n + q] + sm.Rh[i * m + q]) + (s.GH[q * W + n + i] + sm.Rh[q * m + i]));
+            ok = spd_inverse<m>(Hs, Hi) && ok;
+            double* Kg = a.K + (inst * a.T + t) * m * n;
+            if (j < n) {
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc = fma(-Hi[i][q], s.GH[q * W + j], acc);
+                    if (live) { s.Kt[i * n + j] = acc;  Kg[i * n + j] = acc; }
+                }
+            }
+            if (j == 0) {
+                double* kg = a.k + (inst * a.T + t) * m;
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < m; ++q) acc = fma(-Hi[i][q], s.g[q], acc);
+                    if (live) { s.kt[i] = acc;  kg[i] = acc; }
+                }
+            }
+        }
+        __syncwarp();
+        // next step's operands -> registers now (the 4 x 4 inverse of phase 3 is dead, the loads fly during
+        // phase 4 and the other warps' work; prefetching a whole step ahead spilled at 128 registers)
+        if (t > 0) prefetch(t - 1);
+        // ---- phase 4: Pn = Q + A^T PA + G^T K (lanes 0-8) -> stored over P (no phase reads P any more),
+        //               p <- -Q xd_t + A^T w + G^T k (every lane one row) ----
+        double pnew = 0.0;
+        {
+            double acc[4][4];
+            const bool tile = j < (n / 4) * (n / 4);
+            const int r0 = tile ? pn_r0 : 0, c0 = tile ? pn_c0 : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][q] = sm.Q[(r0 + i) * n + c0 + q];
+            if (tile) {
+                tile4_atb<n>(s.AB, W, r0, s.PAB, W, c0, acc);
+                tile4_atb<m>(s.GH, W, r0, s.Kt, n, c0, acc);
+            }
+            if (j < n) {
+                double av = 0.0, qv = 0.0, gv = 0.0;
+#pragma unroll
+                for (int q = 0; q < n; ++q) {
+                    av = fma(s.AB[q * W + j], s.w[q], av);
+                    qv = fma(sm.Q[j * n + q], s.xd[q], qv);
+                }
+#pragma unroll
+                for (int q = 0; q < m; ++q) gv = fma(s.GH[q * W + j], s.kt[q], gv);
+                pnew = (av - qv) + gv;
+            }
+            __syncwarp();      // (nothing below reads P before it is rewritten; the barrier orders the p / w reads)
+            if (tile && live) tile4_store(s.P, n, r0, c0, acc);
+        }
+        __syncwarp();
+        // ---- phase 5: P = sym(Pn) in place (each lane owns a set of (i, k) pairs), p, next operands ----
+        if (live) {
+            for (int e = j; e < n * (n - 1) / 2; e += kRicPackLanes) {
+                int i = 1, base = 0;                   // pair index e -> (i, k), k < i
+                while (base + i <= e) { base += i;  ++i; }
+                const int k = e - base;
+                const double v = 0.5 * (s.P[i * n + k] + s.P[k * n + i]);
+                s.P[i * n + k] = v;
+                s.P[k * n + i] = v;
+            }
+            if (j < n) s.p[j] = pnew;
+        }
+        if (t > 0) publish();
+        __syncwarp();
+    }
+    // NaN guard on the final value function; one status per instance
+    for (int e = j; e < n * n; e += kRicPackLanes)
+        if (!(s.P[e] == s.P[e])) ok = false;
+    const unsigned group = sub < kRicPackPerWarp ? (((1u << kRicPackLanes) - 1u) << (sub * kRicPackLanes)) : 0xff000000u;
+    ok = __all_sync(group, ok);
+    if (live && j == 0) a.status[inst] = ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Rollouts (warp per instance; x lives in lane 0's registers).
 //   closed loop: u_t = K_t x_t + k_t, x_{t+1} = f(x_t, u_t)      (irs_lqr.py:183-184)
 //   open loop  : x_{t+1} = f(x_t, u_t) for given u               (irs_lqr.py:105-119)

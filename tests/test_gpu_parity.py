@@ -344,6 +344,43 @@ def test_solve_tvlqr_matches_oracle(api, n, m):
     assert rel_err(xs, xs_o) < 1e-9 and rel_err(us, us_o) < 1e-9
 
 
+@pytest.mark.parametrize("I", [297, 1030])
+def test_packed_riccati_for_many_instances_matches_oracle_and_block_kernel(api, I, monkeypatch):
+    """Above 2 x 148 instances the quadrotor-sized backward pass runs two instances per warp with 4 x 4
+    register tiles (tvlqr_riccati_packed_kernel): gains against the float64 oracle (1e-9) and against the
+    one-block-per-instance kernel (IRS_TVLQR_VARIANT=block; different summation order: 1e-10), instance
+    counts that do not fill the last warp / block, per-instance desired trajectories, non-SPD steps flagged."""
+    import torch
+    from irs_mpc_b200 import _device
+    from irs_mpc_b200.tv_lqr import riccati_device
+    n, m, T = 12, 4, 9
+    rng = np.random.default_rng(I)
+    At = np.eye(n) + 0.1 * rng.standard_normal((I, T, n, n))
+    Bt = 0.3 * rng.standard_normal((I, T, n, m))
+    ct = 0.1 * rng.standard_normal((I, T, n))
+    Q = np.diag(rng.uniform(0.5, 2.0, n))
+    Qd = 10 * Q + 0.3 * rng.standard_normal((n, n))
+    Qd = Qd + Qd.T + 5 * np.eye(n)                             # dense, symmetric, positive definite
+    R = np.diag(rng.uniform(0.5, 2.0, m))
+    xd = rng.standard_normal((I, T + 1, n))
+    dev = lambda v: _device.to_device(np.ascontiguousarray(v))
+    args = (dev(At), dev(Bt), dev(ct), dev(Q), dev(Qd), dev(R), dev(xd), (T + 1) * n)
+    monkeypatch.delenv("IRS_TVLQR_VARIANT", raising=False)
+    K, k, status = riccati_device(*args)
+    assert int(status.sum().item()) == 0
+    K, k = _device.to_numpy(K), _device.to_numpy(k)
+    monkeypatch.setenv("IRS_TVLQR_VARIANT", "block")
+    Kb, kb, sb = riccati_device(*args)
+    monkeypatch.delenv("IRS_TVLQR_VARIANT", raising=False)
+    assert rel_err(K, _device.to_numpy(Kb)) < 1e-10 and rel_err(k, _device.to_numpy(kb)) < 1e-10
+    for b in (0, 1, 7, 8, I // 2, I - 2, I - 1):
+        Ko, ko = cr.tvlqr_riccati(At[b], Bt[b], ct[b], Q, 0.5 * (Qd + Qd.T), R, xd[b])
+        assert rel_err(K[b], Ko) < 1e-9 and rel_err(k[b], ko) < 1e-9, b
+    # an indefinite terminal weight (H = R/2 + B'PB not SPD) is flagged for every instance
+    K2, k2, st2 = riccati_device(args[0], args[1], args[2], args[3], dev(-np.eye(n)), dev(1e-6 * R), args[6], args[7])
+    assert int(st2.sum().item()) == I
+
+
 def test_solve_tvlqr_error_conventions(api):
     n, m, T = 2, 1, 3
     At = np.tile(np.eye(n), (T, 1, 1))
