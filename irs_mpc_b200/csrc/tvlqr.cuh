@@ -512,82 +512,115 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
 // Throughput variant for MANY instances and n, m multiples of four (quadrotor 12/4; BASELINE.json
 // configs[4]: 4096 instances).  The block kernel above is shared-memory bound there (73 % LSU, ~48 KB of
 // operand traffic per instance and step with 2 x 2 tiles, a third of its threads busy, five block barriers
-// per step).  Here TWO instances share a warp — 12 lanes each — and every matrix product is cut into 4 x 4
-// register tiles of ONE code shape, so the lanes of both instances run the same instruction stream:
-//     [PA | PB] = P [A | B]              12 x 16 -> 12 tiles, one per lane   (P symmetric: its rows are its columns)
-//     [G | H0]  = B^T [PA | PB]           4 x 16 ->  4 tiles
-//     Pn        = Q + A^T PA + G^T K     12 x 12 ->  9 tiles
-// A tile step is 4 LDS.128 for 16 DFMA (4 bytes of shared memory per DFMA against 8 with 2 x 2 tiles), a
-// DFMA warp instruction carries 24 useful lanes instead of 4-32, and the phases are separated by __syncwarp
-// only: an instance never leaves its warp.  Eight instances per block of 128 threads, 46 KB of shared
-// memory, four blocks per SM: all 4096 instances of configs[4] are resident at once.  Next step's operands
-// are prefetched into registers (18 doubles per lane) during the last product of the current step.
+// per step).  Here TWO instances share a warp — 12 lanes each, lanes 24-31 retire at once — and every matrix
+// product is cut into 4 x 4 register tiles of ONE code shape, so the lanes of both instances run the same
+// instruction stream:
+//     [PA | PB]          = P [A | B]                 12 x 16 -> 12 tiles, one per lane (P symmetric: rows = columns)
+//     [A | B]^T [PA | PB], upper block triangle      6 tiles of A^T P A + 4 tiles of B^T [PA | PB] = [G | H0]
+//     Pn (upper)        += G^T K                      6 tiles, 4 terms
+// The lower block triangle of P is the mirror of the upper one (a lane stores its tile and its transpose; the
+// diagonal tiles are symmetrised in registers), so the recursion keeps P exactly symmetric without a pass of
+// its own.  The kernel is bound by the shared-memory pipe (one wavefront per clock and SM, an LDS.128 of a warp
+// costs one per quarter warp with an active lane; ncu: profiles/r2_riccati_packed.txt), hence: the idle
+// quarter warp exits, the second instance of a warp sits 16 bytes (mod 32) beside the first so that their
+// quarter-warp-sharing lanes hit different banks, the rows of P [A | B] are shifted by 16 bytes per row group so
+// that tile stores of two row groups do too, and vector operands are read along contiguous rows (P is
+// symmetric, Q is kept transposed).  Eight instances per block of 128 threads, four blocks per SM: all 4096
+// instances of configs[4] are resident at once.  Next step's operands are prefetched into registers (18
+// doubles per lane) during the last product of the current step.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRicPackThreads = 128;
 constexpr int kRicPackLanes = 12;                       // lanes per instance
 constexpr int kRicPackPerWarp = 2;                      // instances per warp
 constexpr int kRicPackPerBlock = kRicPackPerWarp * kRicPackThreads / 32;
+constexpr unsigned kRicPackMask = (1u << (kRicPackPerWarp * kRicPackLanes)) - 1u;      // the working lanes
 
 template <int n, int m>
 struct RicPackInst {
+    static constexpr int W = n + m;
+    static constexpr int kPab = n * W + 2 * (n / 4 - 1);      // rows of group g start 2 g doubles late
     double P[n * n];              // value-function Hessian (exactly symmetric)
-    double AB[n * (n + m)];       // [A | B] of the current step, row stride n + m
-    double PAB[n * (n + m)];      // P [A | B]
-    double GH[m * (n + m)];       // B^T [PA | PB] = [G | H - R/2]
+    double AB[n * W];             // [A | B] of the current step, row stride n + m
+    double PAB[kPab + (kPab & 1)];  // P [A | B]
+    double GH[m * W];             // B^T [PA | PB] = [G | H - R/2]
     double Kt[m * n];
     double p[n], w[n], c[n], xd[n], g[m], kt[m];
+    double pad[2];                // size = 4 (mod 8) words: the warp's second instance lands on the other banks
+    __device__ __forceinline__ static constexpr int pab_row(int r) { return r * W + 2 * (r >> 2); }
 };
 template <int n, int m>
 struct RicPackSmem {
-    double Q[n * n], Rh[m * m];
+    double Qs[n * n], Qt[n * n], Rh[m * m];      // sym(Q) (value function), Q^T (gradient term), R / 2
     RicPackInst<n, m> inst[kRicPackPerBlock];
 };
 
-// acc[i][j] += sum_q X[q * ldx + x0 + i] * Y[q * ldy + y0 + j]   (4 x 4 tile of X^T Y; x0, y0 multiples of 4)
-template <int len>
+// acc[i][j] += sum_q X[q * ldx + x0 + i] * Y[row(q) + y0 + j]   (4 x 4 tile of X^T Y; x0, y0 multiples of 4);
+// row(q) = q * ldy, plus the row-group shift of RicPackInst::PAB when YSHIFT
+template <int len, bool YSHIFT>
 __device__ __forceinline__ void tile4_atb(const double* X, int ldx, int x0, const double* Y, int ldy, int y0,
                                           double (&acc)[4][4]) {
-#pragma unroll 4      // full unrolling hoists all 48 operand loads and spills at 128 registers
-    for (int q = 0; q < len; ++q) {
-        const double2 xa = *reinterpret_cast<const double2*>(X + q * ldx + x0);
-        const double2 xb = *reinterpret_cast<const double2*>(X + q * ldx + x0 + 2);
-        const double2 ya = *reinterpret_cast<const double2*>(Y + q * ldy + y0);
-        const double2 yb = *reinterpret_cast<const double2*>(Y + q * ldy + y0 + 2);
-        const double x[4] = {xa.x, xa.y, xb.x, xb.y}, y[4] = {ya.x, ya.y, yb.x, yb.y};
+    static_assert(len % 4 == 0, "row groups of four");
+#pragma unroll 1      // one row group per trip: full unrolling hoists all 48 operand loads and spills at 128 registers
+    for (int g = 0; g < len / 4; ++g) {
+        const double* Xg = X + 4 * g * ldx + x0;
+        const double* Yg = Y + 4 * g * ldy + y0 + (YSHIFT ? 2 * g : 0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int q = 0; q < 4; ++q) {
+            const double2 xa = *reinterpret_cast<const double2*>(Xg + q * ldx);
+            const double2 xb = *reinterpret_cast<const double2*>(Xg + q * ldx + 2);
+            const double2 ya = *reinterpret_cast<const double2*>(Yg + q * ldy);
+            const double2 yb = *reinterpret_cast<const double2*>(Yg + q * ldy + 2);
+            const double x[4] = {xa.x, xa.y, xb.x, xb.y}, y[4] = {ya.x, ya.y, yb.x, yb.y};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(x[i], y[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(x[i], y[j], acc[i][j]);
+        }
     }
 }
+// D[r0 + i][c0 + j] = acc[i][j] (TRANSPOSED: = acc[j][i]); `shift` doubles are added once (PAB row groups)
+template <bool TRANSPOSED>
 __device__ __forceinline__ void tile4_store(double* D, int ld, int r0, int c0, const double (&acc)[4][4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<double2*>(D + (r0 + i) * ld + c0) = make_double2(acc[i][0], acc[i][1]);
-        *reinterpret_cast<double2*>(D + (r0 + i) * ld + c0 + 2) = make_double2(acc[i][2], acc[i][3]);
+        double* d = D + (r0 + i) * ld + c0;
+        if constexpr (TRANSPOSED) {
+            *reinterpret_cast<double2*>(d) = make_double2(acc[0][i], acc[1][i]);
+            *reinterpret_cast<double2*>(d + 2) = make_double2(acc[2][i], acc[3][i]);
+        } else {
+            *reinterpret_cast<double2*>(d) = make_double2(acc[i][0], acc[i][1]);
+            *reinterpret_cast<double2*>(d + 2) = make_double2(acc[i][2], acc[i][3]);
+        }
     }
 }
 
 template <int n, int m>
 __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kernel(const TvlqrArgs a) {
-    static_assert(n % 4 == 0 && m == 4 && n / 4 * (n + m) / 4 <= kRicPackLanes && n <= kRicPackLanes + 1,
-                  "4 x 4 tiles, one per lane");
+    static_assert(n == 12 && m == 4, "tile roles below are laid out for three row groups and one input group");
+    using Inst = RicPackInst<n, m>;
+    static_assert(sizeof(Inst) % 16 == 0 && (sizeof(Inst) / 4) % 8 == 4, "second instance of a warp: other banks");
     constexpr int W = n + m;                              // row stride of [A | B]
     constexpr int kOps = n * n + n * m + n + n;           // doubles of one step's operands: A, B, c, xd
     constexpr int kPre = (kOps + kRicPackLanes - 1) / kRicPackLanes;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RicPackSmem<n, m>& sm = *reinterpret_cast<RicPackSmem<n, m>*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sub = lane / kRicPackLanes;                 // instance of this lane inside the warp (2: idle lanes)
-    const int j = lane % kRicPackLanes;                   // role lane
-    const int slot = warp * kRicPackPerWarp + (sub < kRicPackPerWarp ? sub : 0);
-    const long long inst_raw = (long long)blockIdx.x * kRicPackPerBlock + slot;
-    // idle lanes (24-31) and the lanes of a missing last instance shadow a valid one and write nothing
-    const bool live = sub < kRicPackPerWarp && inst_raw < a.I;
-    const long long inst = inst_raw < a.I ? inst_raw : (long long)a.I - 1;
-    RicPackInst<n, m>& s = sm.inst[slot];
-    for (int e = tid; e < n * n; e += kRicPackThreads) sm.Q[e] = a.Q[e];
+    for (int e = tid; e < n * n; e += kRicPackThreads) {
+        const int r = e / n, c = e % n;
+        sm.Qs[e] = 0.5 * (a.Q[e] + a.Q[c * n + r]);       // x' Q x only sees the symmetric part
+        sm.Qt[e] = a.Q[c * n + r];
+    }
     for (int e = tid; e < m * m; e += kRicPackThreads) sm.Rh[e] = 0.5 * a.R[e];
+    __syncthreads();
+    if (lane >= kRicPackPerWarp * kRicPackLanes) return;   // the idle quarter warp: its loads would cost wavefronts
+    const int sub = lane / kRicPackLanes;                 // instance of this lane inside the warp
+    const int j = lane % kRicPackLanes;                   // role lane
+    const int slot = warp * kRicPackPerWarp + sub;
+    const long long inst_raw = (long long)blockIdx.x * kRicPackPerBlock + slot;
+    // the lanes of a missing last instance shadow a valid one and write nothing outside their own slot
+    const bool live = inst_raw < a.I;
+    const long long inst = live ? inst_raw : (long long)a.I - 1;
+    Inst& s = sm.inst[slot];
     const double* xd_i = a.xd + inst * a.xd_stride;
     const double* At = a.At + inst * a.T * n * n;
     const double* Bt = a.Bt + inst * a.T * n * m;
@@ -605,7 +638,6 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
         }
     };
     auto publish = [&] {
-        if (!live) return;
 #pragma unroll
         for (int k = 0; k < kPre; ++k) {
             const int e = j + k * kRicPackLanes;
@@ -617,49 +649,56 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
     };
     prefetch(a.T - 1);
     // terminal condition P_T = sym(Qd) (x' Qd x only sees the symmetric part), p_T = -Qd xd_T
-    if (live) {
-        for (int e = j; e < n * n; e += kRicPackLanes) {
-            const int r = e / n, c = e % n;
-            s.P[e] = 0.5 * (a.Qd[r * n + c] + a.Qd[c * n + r]);
-        }
-        if (j < n) {
-            double acc = 0.0;
-            for (int q = 0; q < n; ++q) acc -= a.Qd[j * n + q] * xd_i[(long long)a.T * n + q];
-            s.p[j] = acc;
-        }
+    for (int e = j; e < n * n; e += kRicPackLanes) {
+        const int r = e / n, c = e % n;
+        s.P[e] = 0.5 * (a.Qd[r * n + c] + a.Qd[c * n + r]);
+    }
+    {
+        double acc = 0.0;
+        for (int q = 0; q < n; ++q) acc -= a.Qd[j * n + q] * xd_i[(long long)a.T * n + q];
+        s.p[j] = acc;
     }
     publish();
-    __syncthreads();      // Q, Rh (block) and the first operands (warp) are in place
+    __syncwarp(kRicPackMask);
     bool ok = true;
-    const int ab_r0 = 4 * (j / (W / 4)), ab_c0 = 4 * (j % (W / 4));      // tile of P [A | B]      (n/4 x W/4 tiles)
-    const int pn_r0 = 4 * (j / (n / 4)), pn_c0 = 4 * (j % (n / 4));      // tile of Pn             (n/4 x n/4 tiles)
+    const int ab_r0 = 4 * (j / (W / 4)), ab_c0 = 4 * (j % (W / 4));      // tile of P [A | B]  (n/4 x W/4 tiles)
+    // second product: lanes 0-5 the upper block triangle of A^T PA ((0,0) (0,4) (0,8) (4,4) (4,8) (8,8)),
+    // lanes 6-9 the four tiles of B^T [PA | PB]
+    const bool pn_tile = j < 6, gh_tile = j >= 6 && j < 6 + W / 4;
+    const int pn_r0 = j < 3 ? 0 : (j < 5 ? 4 : 8);
+    const int pn_c0 = j < 3 ? 4 * j : (j < 5 ? 4 * (j - 2) : 8);
+    const int x0_2 = pn_tile ? pn_r0 : n;                                // columns of [A | B] that form X
+    const int y0_2 = pn_tile ? pn_c0 : (gh_tile ? 4 * (j - 6) : 0);
     for (int t = a.T - 1; t >= 0; --t) {
         // ---- phase 1: [PA | PB] = P [A | B] (one 4 x 4 tile per lane), w = P c + p ----
         {
             double acc[4][4] = {};
-            tile4_atb<n>(s.P, n, ab_r0, s.AB, W, ab_c0, acc);
-            if (live) tile4_store(s.PAB, W, ab_r0, ab_c0, acc);
-            if (j < n) {
-                double wv = s.p[j];
+            tile4_atb<n, false>(s.P, n, ab_r0, s.AB, W, ab_c0, acc);
+            tile4_store<false>(s.PAB + 2 * (ab_r0 >> 2), W, ab_r0, ab_c0, acc);
+            double wv = s.p[j];
 #pragma unroll
-                for (int q = 0; q < n; ++q) wv = fma(s.P[j * n + q], s.c[q], wv);
-                if (live) s.w[j] = wv;
-            }
+            for (int q = 0; q < n; ++q) wv = fma(s.P[q * n + j], s.c[q], wv);      // P[j][q] = P[q][j]
+            s.w[j] = wv;
         }
-        __syncwarp();
-        // ---- phase 2: [G | H0] = B^T [PA | PB] (lanes 0-3: W/4 tiles), g = B^T w (lanes 4-7) ----
-        if (j < W / 4) {
-            double acc[4][4] = {};
-            tile4_atb<n>(s.AB + n, W, 0, s.PAB, W, 4 * j, acc);
-            if (live) tile4_store(s.GH, W, 0, 4 * j, acc);
-        } else if (j < W / 4 + m) {
-            const int i = j - W / 4;
+        __syncwarp(kRicPackMask);
+        // ---- phase 2: sym(Q) + A^T PA (upper block triangle, kept in registers) and [G | H0] = B^T [PA | PB];
+        //               g = B^T w ----
+        double pn[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pn[i][q] = pn_tile ? sm.Qs[(pn_r0 + i) * n + pn_c0 + q] : 0.0;
+        if (pn_tile || gh_tile) {
+            tile4_atb<n, true>(s.AB, W, x0_2, s.PAB, W, y0_2, pn);
+            if (gh_tile) tile4_store<false>(s.GH, W, 0, y0_2, pn);
+        }
+        if (j < m) {
             double gv = 0.0;
 #pragma unroll
-            for (int q = 0; q < n; ++q) gv = fma(s.AB[q * W + n + i], s.w[q], gv);
-            if (live) s.g[i] = gv;
+            for (int q = 0; q < n; ++q) gv = fma(s.AB[q * W + n + j], s.w[q], gv);
+            s.g[j] = gv;
         }
-        __syncwarp();
+        __syncwarp(kRicPackMask);
         // ---- phase 3: K = -H^-1 G, k = -H^-1 g; column `j` (j = n: the affine term needs a 13th lane ->
         //      lane 0 does it after its own column); H = R/2 + sym(H0) inverted redundantly in registers ----
         {
@@ -671,14 +710,13 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
                     Hs[i][q] = 0.5 * ((s.GH[i * W + n + q] + sm.Rh[i * m + q]) + (s.GH[q * W + n + i] + sm.Rh[q * m + i]));
             ok = spd_inverse<m>(Hs, Hi) && ok;
             double* Kg = a.K + (inst * a.T + t) * m * n;
-            if (j < n) {
 #pragma unroll
-                for (int i = 0; i < m; ++i) {
-                    double acc = 0.0;
+            for (int i = 0; i < m; ++i) {
+                double acc = 0.0;
 #pragma unroll
-                    for (int q = 0; q < m; ++q) acc = fma(-Hi[i][q], s.GH[q * W + j], acc);
-                    if (live) { s.Kt[i * n + j] = acc;  Kg[i * n + j] = acc; }
-                }
+                for (int q = 0; q < m; ++q) acc = fma(-Hi[i][q], s.GH[q * W + j], acc);
+                s.Kt[i * n + j] = acc;
+                if (live) Kg[i * n + j] = acc;
             }
             if (j == 0) {
                 double* kg = a.k + (inst * a.T + t) * m;
@@ -687,64 +725,50 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
                     double acc = 0.0;
 #pragma unroll
                     for (int q = 0; q < m; ++q) acc = fma(-Hi[i][q], s.g[q], acc);
-                    if (live) { s.kt[i] = acc;  kg[i] = acc; }
+                    s.kt[i] = acc;
+                    if (live) kg[i] = acc;
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(kRicPackMask);
         // next step's operands -> registers now (the 4 x 4 inverse of phase 3 is dead, the loads fly during
         // phase 4 and the other warps' work; prefetching a whole step ahead spilled at 128 registers)
         if (t > 0) prefetch(t - 1);
-        // ---- phase 4: Pn = Q + A^T PA + G^T K (lanes 0-8) -> stored over P (no phase reads P any more),
+        // ---- phase 4: Pn += G^T K (lanes 0-5) -> P and its mirror (no phase reads P any more),
         //               p <- -Q xd_t + A^T w + G^T k (every lane one row) ----
-        double pnew = 0.0;
+        if (pn_tile) {
+            tile4_atb<m, false>(s.GH, W, pn_r0, s.Kt, n, pn_c0, pn);
+            if (pn_r0 == pn_c0) {
+#pragma unroll
+                for (int i = 1; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q < i; ++q) pn[i][q] = pn[q][i] = 0.5 * (pn[i][q] + pn[q][i]);
+            } else {
+                tile4_store<true>(s.P, n, pn_c0, pn_r0, pn);
+            }
+            tile4_store<false>(s.P, n, pn_r0, pn_c0, pn);
+        }
+        double pnew;
         {
-            double acc[4][4];
-            const bool tile = j < (n / 4) * (n / 4);
-            const int r0 = tile ? pn_r0 : 0, c0 = tile ? pn_c0 : 0;
+            double av = 0.0, qv = 0.0, gv = 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[i][q] = sm.Q[(r0 + i) * n + c0 + q];
-            if (tile) {
-                tile4_atb<n>(s.AB, W, r0, s.PAB, W, c0, acc);
-                tile4_atb<m>(s.GH, W, r0, s.Kt, n, c0, acc);
+            for (int q = 0; q < n; ++q) {
+                av = fma(s.AB[q * W + j], s.w[q], av);
+                qv = fma(sm.Qt[q * n + j], s.xd[q], qv);
             }
-            if (j < n) {
-                double av = 0.0, qv = 0.0, gv = 0.0;
 #pragma unroll
-                for (int q = 0; q < n; ++q) {
-                    av = fma(s.AB[q * W + j], s.w[q], av);
-                    qv = fma(sm.Q[j * n + q], s.xd[q], qv);
-                }
-#pragma unroll
-                for (int q = 0; q < m; ++q) gv = fma(s.GH[q * W + j], s.kt[q], gv);
-                pnew = (av - qv) + gv;
-            }
-            __syncwarp();      // (nothing below reads P before it is rewritten; the barrier orders the p / w reads)
-            if (tile && live) tile4_store(s.P, n, r0, c0, acc);
+            for (int q = 0; q < m; ++q) gv = fma(s.GH[q * W + j], s.kt[q], gv);
+            pnew = (av - qv) + gv;
         }
-        __syncwarp();
-        // ---- phase 5: P = sym(Pn) in place (each lane owns a set of (i, k) pairs), p, next operands ----
-        if (live) {
-            for (int e = j; e < n * (n - 1) / 2; e += kRicPackLanes) {
-                int i = 1, base = 0;                   // pair index e -> (i, k), k < i
-                while (base + i <= e) { base += i;  ++i; }
-                const int k = e - base;
-                const double v = 0.5 * (s.P[i * n + k] + s.P[k * n + i]);
-                s.P[i * n + k] = v;
-                s.P[k * n + i] = v;
-            }
-            if (j < n) s.p[j] = pnew;
-        }
+        __syncwarp(kRicPackMask);      // every read of [A | B], c, xd, p and w of this step is done
+        s.p[j] = pnew;
         if (t > 0) publish();
-        __syncwarp();
+        __syncwarp(kRicPackMask);
     }
     // NaN guard on the final value function; one status per instance
     for (int e = j; e < n * n; e += kRicPackLanes)
         if (!(s.P[e] == s.P[e])) ok = false;
-    const unsigned group = sub < kRicPackPerWarp ? (((1u << kRicPackLanes) - 1u) << (sub * kRicPackLanes)) : 0xff000000u;
-    ok = __all_sync(group, ok);
+    ok = __all_sync(((1u << kRicPackLanes) - 1u) << (sub * kRicPackLanes), ok);
     if (live && j == 0) a.status[inst] = ok ? 0 : 1;
 }
 
