@@ -20,14 +20,26 @@
 extern "C" {
 #endif
 
-#define IRS_ABI_VERSION 2
+#define IRS_ABI_VERSION 3
 
 /* system ids — the reference's four analytic DynamicalSystem subclasses
  * (examples/pendulum/pendulum_dynamics.py:8, examples/bicycle/bicycle_dynamics.py:8,
  *  examples/quadrotor/quadrotor_dynamics.py:15, examples/three_cart/three_cart_dynamics.py:8).
  * `params` (host, doubles): pendulum [h]; bicycle [h];
- *   quadrotor [h, mass, L, g, Ixx, Iyy, Izz, kF, kM]; three_cart [h, d]. */
-enum { IRS_PENDULUM = 0, IRS_BICYCLE = 1, IRS_QUADROTOR = 2, IRS_THREE_CART = 3 };
+ *   quadrotor [h, mass, L, g, Ixx, Iyy, Izz, kF, kM]; three_cart [h, d].
+ * IRS_MLP_2_1: learned dynamics of a 2-state / 1-input system, x+ = net([x, u]) — the reference's
+ *   PendulumNN (examples/pendulum/pendulum_nn.py:19-33 network, :66-90 DynamicalSystem wrapper);
+ *   params [h, handle] with `handle` from irs_mlp_register. */
+enum { IRS_PENDULUM = 0, IRS_BICYCLE = 1, IRS_QUADROTOR = 2, IRS_THREE_CART = 3, IRS_MLP_2_1 = 4 };
+
+/* Registers a network Linear(dim_x + dim_u, h1) ReLU Linear(h1, h2) ReLU Linear(h2, dim_x) (the architecture of
+ * examples/pendulum/pendulum_nn.py:23-29; torch.nn.Linear layout: W [out, in] row-major, float32 HOST arrays)
+ * on the current device and returns its handle; h1, h2 <= 128.  The network is evaluated in float32, as the
+ * reference does (pendulum_nn.py:72-76: torch.Tensor inputs, float32 module).  irs_mlp_release frees it
+ * (after synchronising with the device). */
+int irs_mlp_register(int dim_x, int dim_u, int h1, int h2, const float* W1, const float* b1, const float* W2,
+                     const float* b2, const float* W3, const float* b3, int* handle);
+int irs_mlp_release(int handle);
 
 /* smoothing flags */
 enum {

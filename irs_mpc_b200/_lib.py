@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("IRS_MPC_B200_LIB") or os.path.join(_HERE, "libirs_mpc
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-ABI_VERSION = 2      # IRS_ABI_VERSION of include/irs_mpc_b200.h this binding was written against
+ABI_VERSION = 3      # IRS_ABI_VERSION of include/irs_mpc_b200.h this binding was written against
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -79,6 +79,8 @@ SIGNATURES = {
     "irs_tvlqr_riccati": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp],
     "irs_tvlqr_riccati_segment": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "irs_tvlqr_riccati_ex": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "irs_mlp_register": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "irs_mlp_release": [_i],
     "irs_cem_refit": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "irs_gram_block_f64": [_i, _i, _vp, _vp, _ll, _vp, _vp],
     "irs_tvlqr_plan_rows": [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],

@@ -6,6 +6,6 @@ from .irs_lqr import (IrsLqr, IrsLqrExact, IrsLqrFirstOrder, IrsLqrParameters,  
 from .batched import BatchedIrsLqrZeroOrder  # noqa: F401
 from .cem import CemParameters, CrossEntropyMethod  # noqa: F401
 from .sampling import GaussianSampling  # noqa: F401
-from .systems import (BicycleDynamics, PendulumDynamics, QuadrotorDynamics,  # noqa: F401
+from .systems import (BicycleDynamics, MlpDynamics, PendulumDynamics, QuadrotorDynamics,  # noqa: F401
                       ThreeCartDynamics)
 from .tv_lqr import get_solver, solve_tvlqr  # noqa: F401

@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "../../include/irs_mpc_b200.h"
 #include "smooth.cuh"
@@ -31,8 +33,16 @@ int check_launch(const char* what) {
     return 0;
 }
 
+// Registered networks of the learned-dynamics system (irs_mlp_register): device blobs, one per handle.
+struct MlpEntry {
+    float* blob;
+    int d, n, h1, h2, device;
+};
+static std::vector<MlpEntry> g_mlps;
+static std::mutex g_mlp_mutex;
+
 static int load_params(int system, const double* params_host, int nparams, SysParams* out) {
-    static const int expected[kNumSystems] = {1, 1, 9, 2};
+    static const int expected[kNumSystems] = {1, 1, 9, 2, 2};
     IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
     IRS_REQUIRE(params_host != nullptr && nparams == expected[system],
                 "system %d expects %d parameters, got %d", system, expected[system], nparams);
@@ -40,6 +50,22 @@ static int load_params(int system, const double* params_host, int nparams, SysPa
     for (int i = 0; i < nparams; ++i) {
         out->v[i] = params_host[i];
         out->f[i] = (float)params_host[i];
+    }
+    if (system == kMlp21) {          // [h, handle] -> the registered network
+        const int handle = (int)params_host[1];
+        std::lock_guard<std::mutex> lock(g_mlp_mutex);
+        IRS_REQUIRE(handle >= 0 && handle < (int)g_mlps.size() && g_mlps[handle].blob != nullptr,
+                    "unknown network handle %d (irs_mlp_register)", handle);
+        const MlpEntry& e = g_mlps[handle];
+        const SystemDims dm = system_dims(system);
+        IRS_REQUIRE(e.n == dm.n && e.d == dm.n + dm.m, "network %d maps %d -> %d, system %d needs %d -> %d", handle,
+                    e.d, e.n, system, dm.n + dm.m, dm.n);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        IRS_REQUIRE(dev == e.device, "network %d was registered on device %d, current device is %d", handle, e.device, dev);
+        out->mlp = e.blob;
+        out->h1 = e.h1;
+        out->h2 = e.h2;
     }
     if (system == kQuadrotor) {      // derived invariants of Quadrotor<float>::step, rounded once
         const double* v = out->v;    // [h, mass, L, g, Ixx, Iyy, Izz, kF, kM]
@@ -421,6 +447,7 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
         case kPendulum: return launch_zero_order<Pendulum<float>, 1>(a, st);
         case kBicycle: return launch_zero_order<Bicycle<float>, 1>(a, st);
         case kThreeCart: return launch_zero_order<ThreeCart<float>, 1>(a, st);
+        case kMlp21: return launch_zero_order<Mlp21<float>, 1>(a, st);
         case kQuadrotor:
             IRS_REQUIRE(S % 128 == 0, "quadrotor chunk size must be a multiple of 128");
             // 16 regressors: the Gram rows are split over the 4 warps of a block sharing one sample tile
@@ -457,6 +484,10 @@ int irs_smooth_first_order_accumulate(int system, const double* params_host, int
             g_last_smooth_func = (const void*)smooth_first_order_kernel<Quadrotor<float>>;
             smooth_first_order_kernel<Quadrotor<float>><<<grid, 128, 0, st>>>(a);
             break;
+        case kMlp21:
+            g_last_smooth_func = (const void*)smooth_first_order_kernel<Mlp21<float>>;
+            smooth_first_order_kernel<Mlp21<float>><<<grid, 128, 0, st>>>(a);
+            break;
         default: set_error("unknown system id %d", system); return 1;
     }
     return check_launch("smooth_first_order_kernel");
@@ -492,6 +523,7 @@ static int finalize_resident_blocks(int system, int order, int* out) {
             case kPendulum: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Pendulum<double>>, kFinalizeThreads, 0); break;
             case kBicycle: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Bicycle<double>>, kFinalizeThreads, 0); break;
             case kQuadrotor: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Quadrotor<double>>, kFinalizeThreads, 0); break;
+            case kMlp21: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finalize_first_order_kernel<Mlp21<double>>, kFinalizeThreads, 0); break;
             default: set_error("system %d has no first-order path", system); return 1;
         }
     }
@@ -559,6 +591,7 @@ static int smooth_finalize_impl(int system, const double* params_host, int npara
             case kPendulum: finalize_first_order_kernel<Pendulum<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
             case kBicycle: finalize_first_order_kernel<Bicycle<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
             case kQuadrotor: finalize_first_order_kernel<Quadrotor<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
+            case kMlp21: finalize_first_order_kernel<Mlp21<double>><<<grid, kFinalizeThreads, 0, st>>>(a); break;
             default: set_error("unknown system id %d", system); return 1;
         }
     }
@@ -640,9 +673,49 @@ int irs_exact_linearize(int system, const double* params_host, int nparams,
         case kPendulum: exact_linearize_kernel<Pendulum<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
         case kBicycle: exact_linearize_kernel<Bicycle<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
         case kQuadrotor: exact_linearize_kernel<Quadrotor<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
+        case kMlp21: exact_linearize_kernel<Mlp21<double>><<<(P + 63) / 64, 64, 0, st>>>(prm, x_nom, u_nom, P, At, Bt, ct); break;
         default: set_error("unknown system id %d", system); return 1;
     }
     return check_launch("exact_linearize_kernel");
+}
+
+int irs_mlp_register(int dim_x, int dim_u, int h1, int h2, const float* W1, const float* b1, const float* W2,
+                     const float* b2, const float* W3, const float* b3, int* handle) {
+    IRS_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && handle, "null pointer argument");
+    IRS_REQUIRE(dim_x >= 1 && dim_u >= 1, "need dim_x >= 1 and dim_u >= 1");
+    IRS_REQUIRE(h1 >= 1 && h1 <= kMlpMaxHidden && h2 >= 1 && h2 <= kMlpMaxHidden,
+                "hidden widths must lie in [1, %d], got %d and %d", kMlpMaxHidden, h1, h2);
+    const int d = dim_x + dim_u, n = dim_x;
+    const long long count = MlpView::floats(d, n, h1, h2);
+    std::vector<float> host((size_t)count);
+    MlpView v(host.data(), d, n, h1, h2);
+    memcpy(const_cast<float*>(v.w1), W1, sizeof(float) * h1 * d);
+    memcpy(const_cast<float*>(v.b1), b1, sizeof(float) * h1);
+    memcpy(const_cast<float*>(v.w2), W2, sizeof(float) * h2 * h1);
+    memcpy(const_cast<float*>(v.b2), b2, sizeof(float) * h2);
+    memcpy(const_cast<float*>(v.w3), W3, sizeof(float) * n * h2);
+    memcpy(const_cast<float*>(v.b3), b3, sizeof(float) * n);
+    for (float x : host) IRS_REQUIRE(x == x && x - x == 0.f, "network weights must be finite");
+    MlpEntry e{nullptr, d, n, h1, h2, 0};
+    cudaGetDevice(&e.device);
+    if (cudaMalloc(&e.blob, sizeof(float) * count) != cudaSuccess) return check_launch("cudaMalloc(network)");
+    if (cudaMemcpy(e.blob, host.data(), sizeof(float) * count, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(e.blob);
+        return check_launch("cudaMemcpy(network)");
+    }
+    std::lock_guard<std::mutex> lock(g_mlp_mutex);
+    g_mlps.push_back(e);
+    *handle = (int)g_mlps.size() - 1;
+    return 0;
+}
+
+int irs_mlp_release(int handle) {
+    std::lock_guard<std::mutex> lock(g_mlp_mutex);
+    IRS_REQUIRE(handle >= 0 && handle < (int)g_mlps.size() && g_mlps[handle].blob != nullptr,
+                "unknown network handle %d", handle);
+    cudaFree(g_mlps[handle].blob);      // synchronises with the device: no kernel still reads it
+    g_mlps[handle].blob = nullptr;
+    return 0;
 }
 
 int irs_philox_dump(int P, long long N, int d, const float* sigma_host, unsigned long long seed,
@@ -834,6 +907,7 @@ int irs_tvlqr_box_solve(int system, const double* params_host, int nparams, int 
         case kBicycle: return launch_box_mpc<Bicycle<double>>(a, st);
         case kQuadrotor: return launch_box_mpc<Quadrotor<double>>(a, st);
         case kThreeCart: return launch_box_mpc<ThreeCart<double>>(a, st);
+        case kMlp21: return launch_box_mpc<Mlp21<double>>(a, st);
     }
     set_error("unknown system id %d", system);
     return 1;

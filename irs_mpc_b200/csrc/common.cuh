@@ -27,6 +27,9 @@ int check_launch(const char* what);
 struct SysParams {
     double v[10];
     float f[20];
+    // learned dynamics (systems.cuh: Mlp): device blob of the registered network, hidden widths
+    const float* mlp;
+    int h1, h2;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// __device__ functors for the four analytic systems of the reference, templated on the scalar
+// __device__ functors for the four analytic systems of the reference and its learned (MLP) dynamics, templated on the scalar
 // type R (float for the T x N sample work, double for the sequential rollouts).
 //
 // Interface (all static-shape, everything stays in registers after unrolling):
@@ -17,7 +17,7 @@
 
 namespace irs {
 
-enum SystemId { kPendulum = 0, kBicycle = 1, kQuadrotor = 2, kThreeCart = 3, kNumSystems = 4 };
+enum SystemId { kPendulum = 0, kBicycle = 1, kQuadrotor = 2, kThreeCart = 3, kMlp21 = 4, kNumSystems = 5 };
 
 // ---------------------------------------------------------------------------------------------
 // parameter i in the functor's scalar type: fp32 reads the host-rounded mirror
@@ -338,6 +338,120 @@ __device__ __forceinline__ void centred_frame(const double* xb, const double* ub
     for (int q = 0; q < m; ++q) uf[q] = (float)(2.0 * ub[q]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Learned dynamics — examples/pendulum/pendulum_nn.py:19-33 (network), :66-90 (the DynamicalSystem
+// wrapper): x+ = net([x, u]) with net = Linear(d, H1) ReLU Linear(H1, H2) ReLU Linear(H2, n), float32
+// (the reference evaluates the torch module on float32 tensors and returns float32).  The Jacobian is
+// the exact derivative of the piecewise-linear network, W3 diag(a2 > 0) W2 diag(a1 > 0) W1, which is
+// what torch.autograd returns in pendulum_nn.py:78-85.
+// This per-thread functor serves every generic kernel (dynamics / Jacobian batches, rollouts, first-order
+// smoothing, the fp64 nominal point of the fit); the T x N zero-order sample work runs the hidden layer on
+// the tensor cores instead (smooth_mlp.cuh).
+// blob (float32): W1[H1][d] | b1[H1] | W2[H2][H1] | b2[H2] | W3[n][H2] | b3[n]; registered with irs_mlp_register.
+// params: [h, handle]
+// ---------------------------------------------------------------------------------------------
+constexpr int kMlpMaxHidden = 128;
+
+struct MlpView {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    int H1, H2;
+    __host__ __device__ MlpView(const float* blob, int d, int n, int h1, int h2) : H1(h1), H2(h2) {
+        w1 = blob;          b1 = w1 + h1 * d;
+        w2 = b1 + h1;       b2 = w2 + h2 * h1;
+        w3 = b2 + h2;       b3 = w3 + n * h2;
+    }
+    static __host__ __device__ long long floats(int d, int n, int h1, int h2) {
+        return (long long)h1 * d + h1 + (long long)h2 * h1 + h2 + (long long)n * h2 + n;
+    }
+};
+
+template <typename R, int N_, int M_>
+struct Mlp {
+    template <typename S> using Rebind = Mlp<S, N_, M_>;
+    static constexpr int N = N_, M = M_, D = N_ + M_, NJ = N_ * (N_ + M_);
+    static constexpr bool kHasJacobian = true;
+    static constexpr int kTrigAhead = 0;
+    static constexpr bool kHasProjection = false;
+    static constexpr bool kIsMlp = true;
+    MlpView net;
+    __device__ explicit Mlp(const SysParams& p) : net(p.mlp, D, N, p.h1, p.h2) {}
+
+    // hidden activations of ([x, u]); sums in four interleaved partial chains (the dependent FFMA chain of a
+    // 100-term dot product would otherwise be latency bound)
+    __device__ __forceinline__ void hidden(const float* in, float* a1, float* a2) const {
+        for (int j = 0; j < net.H1; ++j) {
+            float s = __ldg(net.b1 + j);
+#pragma unroll
+            for (int q = 0; q < D; ++q) s = fmaf(__ldg(net.w1 + j * D + q), in[q], s);
+            a1[j] = fmaxf(s, 0.f);
+        }
+        for (int j = 0; j < net.H2; ++j) a2[j] = fmaxf(dot_row(net.w2 + (long long)j * net.H1, a1, net.H1, __ldg(net.b2 + j)), 0.f);
+    }
+    static __device__ __forceinline__ float dot_row(const float* w, const float* a, int len, float init) {
+        float s0 = init, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int q = 0;
+        for (; q + 4 <= len; q += 4) {
+            s0 = fmaf(__ldg(w + q), a[q], s0);
+            s1 = fmaf(__ldg(w + q + 1), a[q + 1], s1);
+            s2 = fmaf(__ldg(w + q + 2), a[q + 2], s2);
+            s3 = fmaf(__ldg(w + q + 3), a[q + 3], s3);
+        }
+        for (; q < len; ++q) s0 = fmaf(__ldg(w + q), a[q], s0);
+        return (s0 + s1) + (s2 + s3);
+    }
+
+    template <bool BATCH>
+    __device__ __forceinline__ void step(const R* x, const R* u, R* o) const {
+        float in[D], a1[kMlpMaxHidden], a2[kMlpMaxHidden];
+#pragma unroll
+        for (int q = 0; q < N; ++q) in[q] = (float)x[q];
+#pragma unroll
+        for (int q = 0; q < M; ++q) in[N + q] = (float)u[q];
+        hidden(in, a1, a2);
+#pragma unroll
+        for (int k = 0; k < N; ++k) o[k] = R(dot_row(net.w3 + (long long)k * net.H2, a2, net.H2, __ldg(net.b3 + k)));
+    }
+    __device__ __forceinline__ void jac_var(const R* x, const R* u, R* v) const {
+        float in[D], a1[kMlpMaxHidden], a2[kMlpMaxHidden];
+#pragma unroll
+        for (int q = 0; q < N; ++q) in[q] = (float)x[q];
+#pragma unroll
+        for (int q = 0; q < M; ++q) in[N + q] = (float)u[q];
+        hidden(in, a1, a2);
+        // reverse mode, one output row at a time: r1 = (W3[k] o mask2) W2 o mask1, J[k] = r1 W1
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            float r1[kMlpMaxHidden];
+            for (int j = 0; j < net.H1; ++j) r1[j] = 0.f;
+            for (int q = 0; q < net.H2; ++q) {
+                if (a2[q] > 0.f) {
+                    const float g = __ldg(net.w3 + (long long)k * net.H2 + q);
+                    const float* row = net.w2 + (long long)q * net.H1;
+                    for (int j = 0; j < net.H1; ++j) r1[j] = fmaf(g, __ldg(row + j), r1[j]);
+                }
+            }
+            float acc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = 0.f;
+            for (int j = 0; j < net.H1; ++j) {
+                if (a1[j] > 0.f) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) acc[c] = fmaf(r1[j], __ldg(net.w1 + j * D + c), acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) v[k * D + c] = R(acc[c]);
+        }
+    }
+    __device__ __forceinline__ void jac_assemble(const R* v, R* J) const {
+#pragma unroll
+        for (int i = 0; i < N * D; ++i) J[i] = v[i];
+    }
+    __device__ __forceinline__ void project(R* x) const {}
+};
+template <typename R>
+using Mlp21 = Mlp<R, 2, 1>;
+
 // Host-side dimension table (kept in sync with the functors by static_asserts in api.cu).
 struct SystemDims {
     int n, m, nj;
@@ -348,6 +462,7 @@ inline SystemDims system_dims(int id) {
         case kBicycle: return {5, 2, 6};
         case kQuadrotor: return {12, 4, IRS_QUAD_NJ};
         case kThreeCart: return {6, 2, 0};
+        case kMlp21: return {2, 1, 6};
         default: return {0, 0, 0};
     }
 }
@@ -359,6 +474,7 @@ inline SystemDims system_dims(int id) {
         case irs::kBicycle: { using SYS = irs::Bicycle<R>; __VA_ARGS__; break; }     \
         case irs::kQuadrotor: { using SYS = irs::Quadrotor<R>; __VA_ARGS__; break; } \
         case irs::kThreeCart: { using SYS = irs::ThreeCart<R>; __VA_ARGS__; break; } \
+        case irs::kMlp21: { using SYS = irs::Mlp21<R>; __VA_ARGS__; break; }         \
         default: irs::set_error("unknown system id %d", id); return 1;         \
     }
 

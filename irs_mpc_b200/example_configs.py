@@ -62,6 +62,14 @@ def three_cart(T=100):
                 projection=True)
 
 
+def pendulum_nn(T=200):
+    # pendulum/pendulum_nn.py:92-110 (problem), :141-150 (sampling: sigma 1 / iter^0.5, 10000 samples); the
+    # system is the learned network of :19-62, no step size of its own
+    cfg = pendulum(T)
+    cfg.update(system="pendulum_nn", h=0.0, num_samples=10000)
+    return cfg
+
+
 def quadrotor_batch(lo, hi, T=100, total=4096):
     """BASELINE.json configs[4]: instances lo..hi-1 of `total` independent quadrotor MPC problems (the
     reference runs one IrsLqr object per problem, irs_lqr/irs_lqr.py:34-71).  Instance b tracks the helix
