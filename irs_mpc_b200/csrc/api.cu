@@ -12,6 +12,7 @@
 #include "tvlqr.cuh"
 #include "tvlqr_box.cuh"
 #include "cem.cuh"
+#include "smooth_mlp.cuh"
 
 namespace irs {
 
@@ -36,6 +37,7 @@ int check_launch(const char* what) {
 // Registered networks of the learned-dynamics system (irs_mlp_register): device blobs, one per handle.
 struct MlpEntry {
     float* blob;
+    unsigned short* w2_tc;      // [W2 | b2] as K-major bf16 operand pieces (smooth_mlp.cuh: MlpTcLayout)
     int d, n, h1, h2, device;
 };
 static std::vector<MlpEntry> g_mlps;
@@ -64,6 +66,7 @@ static int load_params(int system, const double* params_host, int nparams, SysPa
         cudaGetDevice(&dev);
         IRS_REQUIRE(dev == e.device, "network %d was registered on device %d, current device is %d", handle, e.device, dev);
         out->mlp = e.blob;
+        out->mlp_w2 = e.w2_tc;
         out->h1 = e.h1;
         out->h2 = e.h2;
     }
@@ -127,6 +130,39 @@ static int num_sms() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// Learned dynamics: hidden layer on the tensor cores (smooth_mlp.cuh).  Persistent grid of the blocks that are
+// resident together; IRS_MLP_ENGINE=0 selects the generic per-thread functor instead (parity tests).
+template <class Sys>
+static int launch_zero_order_mlp(const SmoothArgs& a, cudaStream_t st) {
+    const MlpTcLayout L(a.prm.h1, a.prm.h2);
+    const MlpTcSmem<Sys> sm(L);
+    auto kern = smooth_zero_order_mlp_kernel<Sys>;
+    static int max_smem = 0;
+    if (max_smem == 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(smooth_zero_order_mlp)");
+        max_smem = optin;
+    }
+    IRS_REQUIRE(sm.total <= max_smem, "hidden widths %d / %d need %d bytes of shared memory (limit %d)", L.H1, L.H2,
+                sm.total, max_smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, (size_t)sm.total) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    if (per_sm > 4) per_sm = 4;                   // 128 TMEM columns per block, 512 per SM
+    const long long items = (long long)a.P * a.C;
+    const long long resident = (long long)per_sm * num_sms();
+    g_last_smooth_func = (const void*)kern;
+    kern<<<(unsigned)(items < resident ? items : resident), 128, (size_t)sm.total, st>>>(a);
+    return check_launch("smooth_zero_order_mlp_kernel");
+}
+static bool use_mlp_tensor_cores() {
+    const char* e = getenv("IRS_MLP_ENGINE");      // read per call: the parity tests switch engines
+    return !(e != nullptr && atoi(e) == 0);
 }
 
 template <class Sys, int MODE, bool CENTERED>
@@ -414,6 +450,7 @@ int irs_smooth_plan(int system, int order, int P, long long N, long long chunk_s
     long long target = 4096;
     const char* e = getenv("IRS_CHUNK_SAMPLES");
     if (e && atoll(e) > 0) target = atoll(e);
+    if (system == kMlp21 && order == 0 && !(e && atoll(e) > 0)) target = 1024;   // 8 tiles of 128: several waves of items
     if (chunk_samples > 0) target = chunk_samples;
     long long c = (N + target - 1) / target;
     long long s = (N + c - 1) / c;
@@ -447,7 +484,9 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
         case kPendulum: return launch_zero_order<Pendulum<float>, 1>(a, st);
         case kBicycle: return launch_zero_order<Bicycle<float>, 1>(a, st);
         case kThreeCart: return launch_zero_order<ThreeCart<float>, 1>(a, st);
-        case kMlp21: return launch_zero_order<Mlp21<float>, 1>(a, st);
+        case kMlp21:
+            if (use_mlp_tensor_cores()) return launch_zero_order_mlp<Mlp21<float>>(a, st);
+            return launch_zero_order<Mlp21<float>, 1>(a, st);
         case kQuadrotor:
             IRS_REQUIRE(S % 128 == 0, "quadrotor chunk size must be a multiple of 128");
             // 16 regressors: the Gram rows are split over the 4 warps of a block sharing one sample tile
@@ -696,11 +735,41 @@ int irs_mlp_register(int dim_x, int dim_u, int h1, int h2, const float* W1, cons
     memcpy(const_cast<float*>(v.w3), W3, sizeof(float) * n * h2);
     memcpy(const_cast<float*>(v.b3), b3, sizeof(float) * n);
     for (float x : host) IRS_REQUIRE(x == x && x - x == 0.f, "network weights must be finite");
-    MlpEntry e{nullptr, d, n, h1, h2, 0};
+    // hidden layer as tensor-core operand: B[j][k] = W2[j][k] (k < h1), b2[j] (k = h1), zero padding; two bf16
+    // pieces, round to nearest even, hi + lo = the float32 weight to 2^-17 relative
+    const MlpTcLayout L(h1, h2);
+    std::vector<unsigned short> tc((size_t)L.b_piece_bytes(), 0);      // 2 pieces x (bytes / 2) elements
+    auto bf16_rn = [](float x) -> unsigned short {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7fffu + ((u >> 16) & 1u);
+        return (unsigned short)(u >> 16);
+    };
+    auto bf16_float = [](unsigned short h) -> float {
+        const uint32_t u = (uint32_t)h << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    for (int j = 0; j < h2; ++j)
+        for (int k = 0; k <= h1; ++k) {
+            const float wv = k < h1 ? W2[(size_t)j * h1 + k] : b2[j];
+            const unsigned short hi = bf16_rn(wv), lo = bf16_rn(wv - bf16_float(hi));
+            const size_t at = (size_t)L.b_offset(j, k) / 2;
+            tc[at] = hi;
+            tc[(size_t)L.b_piece_bytes() / 2 + at] = lo;
+        }
+    MlpEntry e{nullptr, nullptr, d, n, h1, h2, 0};
     cudaGetDevice(&e.device);
     if (cudaMalloc(&e.blob, sizeof(float) * count) != cudaSuccess) return check_launch("cudaMalloc(network)");
-    if (cudaMemcpy(e.blob, host.data(), sizeof(float) * count, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMalloc(&e.w2_tc, sizeof(unsigned short) * tc.size()) != cudaSuccess) {
         cudaFree(e.blob);
+        return check_launch("cudaMalloc(network operand)");
+    }
+    if (cudaMemcpy(e.blob, host.data(), sizeof(float) * count, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(e.w2_tc, tc.data(), sizeof(unsigned short) * tc.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(e.blob);
+        cudaFree(e.w2_tc);
         return check_launch("cudaMemcpy(network)");
     }
     std::lock_guard<std::mutex> lock(g_mlp_mutex);
@@ -714,7 +783,9 @@ int irs_mlp_release(int handle) {
     IRS_REQUIRE(handle >= 0 && handle < (int)g_mlps.size() && g_mlps[handle].blob != nullptr,
                 "unknown network handle %d", handle);
     cudaFree(g_mlps[handle].blob);      // synchronises with the device: no kernel still reads it
+    cudaFree(g_mlps[handle].w2_tc);
     g_mlps[handle].blob = nullptr;
+    g_mlps[handle].w2_tc = nullptr;
     return 0;
 }
 

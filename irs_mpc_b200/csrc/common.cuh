@@ -29,6 +29,7 @@ struct SysParams {
     float f[20];
     // learned dynamics (systems.cuh: Mlp): device blob of the registered network, hidden widths
     const float* mlp;
+    const unsigned short* mlp_w2;      // hidden layer as tensor-core operand: bf16 pieces [hi | lo] (smooth_mlp.cuh)
     int h1, h2;
 };
 

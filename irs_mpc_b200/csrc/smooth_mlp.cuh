@@ -1,0 +1,260 @@
+// Zero-order smoothing of LEARNED dynamics (systems.cuh: Mlp; the reference's examples/pendulum/pendulum_nn.py)
+// with the hidden layer on the 5th-generation tensor cores.
+//
+// Per sample the network costs d H1 + H1 H2 + H2 n multiply-adds (3 x 100 + 100 x 100 + 100 x 2 for the
+// reference's network): 95 % of them are the hidden layer, a dense GEMM over the samples of a tile:
+//
+//     D[128 x Np] (TMEM, fp32)  =  A[128 x Kp] (smem)  *  B[Kp x Np] (smem),      kind::f16 (bf16), both K-major
+//
+// A row  = one sample: relu(W1 [x; u] + b1), then a constant 1 (column H1) that carries the bias, zero padding
+// B      = [W2 | b2]^T, prepared once per registered network (api.cu: irs_mlp_register)
+// Kp = ceil16(H1 + 1), Np = ceil16(H2).  Both operands are split into two bf16 pieces (x ~ x_hi + x_lo,
+// |x - x_hi - x_lo| <= 2^-17 |x|) and three products are accumulated, a_hi w_hi + a_hi w_lo + a_lo w_hi: the
+// float32 product to ~2^-16 relative, inside the 1e-4 budget with margin (the reference evaluates the torch
+// module in float32, pendulum_nn.py:72-81).  The activation residual is staged NEGATED (split_bf16x2) and the
+// third product issued with the negate-A bit of the instruction descriptor.
+//
+// K-major canonical layout without swizzle (verified on hardware by tools/test_umma_mlp.cu):
+//     byte address of (row r, k) = (r/8)*128 + (k/8)*LBO + (r%8)*16 + (k%8)*2,   LBO = (rows/8)*128
+// A thread (= sample row) stores eight consecutive k with one 16-byte STS; a warp's store is 512 contiguous bytes.
+//
+// One block = 128 threads = one tile of 128 samples at a time: every thread draws its sample, evaluates the first
+// layer (CUDA cores), the tile is multiplied (one elected thread issues 3 Kp/16 UMMAs), every thread reads its own
+// accumulator row back (TMEM lane = sample), applies ReLU and the last layer (CUDA cores) and updates its Gram
+// registers (smooth.cuh: gram_update — the same packed block the generic kernel writes, so the fp64 fit is shared).
+// Two blocks per SM alternate between the tensor pipe and the CUDA cores.  Persistent: blocks walk the
+// (nominal point, sample chunk) items with stride gridDim.x and load the network once.
+#pragma once
+#include "smooth_tc.cuh"
+
+namespace irs {
+
+struct MlpTcLayout {
+    int H1, H2, Kp, Np;
+    __host__ __device__ MlpTcLayout(int h1, int h2)
+        : H1(h1), H2(h2), Kp((h1 + 1 + 15) / 16 * 16), Np((h2 + 15) / 16 * 16) {}
+    static constexpr int kRows = 128;                                        // samples per tile (UMMA M)
+    __host__ __device__ int lbo_a() const { return kRows / 8 * 128; }
+    __host__ __device__ int lbo_b() const { return Np / 8 * 128; }
+    __host__ __device__ int a_piece_bytes() const { return kRows * Kp * 2; }
+    __host__ __device__ int b_piece_bytes() const { return Np * Kp * 2; }
+    // byte offset of element (row j, k) inside a B piece
+    __host__ __device__ int b_offset(int j, int k) const { return (j / 8) * 128 + (k / 8) * lbo_b() + (j % 8) * 16 + (k % 8) * 2; }
+};
+
+template <class Sys>
+struct MlpTcSmem {
+    static constexpr int n = Sys::N, d = Sys::D;
+    static constexpr int WIDTH = gram_width_of<Sys>();
+    // byte offsets of the regions behind the operand tiles
+    MlpTcLayout L;
+    int a_hi, a_lo, b_hi, b_lo, w1b, w3, act1, act2, fbar, slabs, bar, total;
+    __host__ __device__ explicit MlpTcSmem(const MlpTcLayout& l) : L(l) {
+        int o = 0;
+        a_hi = o;  o += L.a_piece_bytes();
+        a_lo = o;  o += L.a_piece_bytes();
+        b_hi = o;  o += L.b_piece_bytes();
+        b_lo = o;  o += L.b_piece_bytes();
+        w1b = o;   o += L.Kp * (d + 1) * 4;          // [Kp][d + 1]: first-layer row and bias; row H1 = (0, .., 0, 1)
+        w3 = o;    o += (n * L.Np + n) * 4;          // [n][Np] last layer (zero padded) | b3[n]
+        act1 = o;  o += kMlpMaxHidden * 4;           // nominal point: hidden activations
+        act2 = o;  o += kMlpMaxHidden * 4;
+        fbar = o;  o += ((n + 3) / 4 * 4) * 4;
+        slabs = o; o += 4 * WIDTH * 4;
+        o = (o + 7) / 8 * 8;
+        bar = o;   o += 16;                          // mbarrier | TMEM base address
+        total = o;
+    }
+};
+
+template <class Sys>
+__global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const SmoothArgs a) {
+    static_assert(Sys::kIsMlp, "learned dynamics only");
+    using C = ZeroOrderCfg<Sys, 1>;
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
+    constexpr int NP = role_pairs(d, C::Wp, 1, 0);
+    constexpr int WIDTH = gram_width_of<Sys>();
+    static_assert(WIDTH == C::NACC, "no first moments for learned dynamics");
+    const Sys sys(a.prm);
+    const MlpView& net = sys.net;
+    const MlpTcLayout L(net.H1, net.H2);
+    const MlpTcSmem<Sys> sm(L);
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* w1b = reinterpret_cast<float*>(smem + sm.w1b);
+    float* w3s = reinterpret_cast<float*>(smem + sm.w3);
+    float* act1 = reinterpret_cast<float*>(smem + sm.act1);
+    float* act2 = reinterpret_cast<float*>(smem + sm.act2);
+    float* fbar_s = reinterpret_cast<float*>(smem + sm.fbar);
+    float* slabs = reinterpret_cast<float*>(smem + sm.slabs);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + sm.bar);
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + sm.bar + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- once per block: the network ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.prm.mlp_w2);
+        uint4* dst = reinterpret_cast<uint4*>(smem + sm.b_hi);
+        for (int e = tid; e < 2 * L.b_piece_bytes() / 16; e += 128) dst[e] = __ldg(src + e);
+        for (int e = tid; e < L.Kp * (d + 1); e += 128) {
+            const int j = e / (d + 1), q = e % (d + 1);
+            float v = 0.f;
+            if (j < L.H1) v = q < d ? __ldg(net.w1 + j * d + q) : __ldg(net.b1 + j);
+            else if (j == L.H1 && q == d) v = 1.f;                    // the constant column that carries b2
+            w1b[e] = v;
+        }
+        for (int e = tid; e < n * L.Np; e += 128) {
+            const int k = e / L.Np, j = e % L.Np;
+            w3s[e] = j < L.H2 ? __ldg(net.w3 + k * L.H2 + j) : 0.f;
+        }
+        if (tid < n) w3s[n * L.Np + tid] = __ldg(net.b3 + tid);
+    }
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * warp) << 16);      // this warp's lane quarter
+    // instruction descriptor: D fp32, A / B bf16, both K-major, N >> 3, M >> 4; bit 13 negates A
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_neg_a = idesc | (1u << 13);
+    const uint32_t sa_hi = smem_u32(smem + sm.a_hi), sa_lo = smem_u32(smem + sm.a_lo);
+    const uint32_t sb_hi = smem_u32(smem + sm.b_hi), sb_lo = smem_u32(smem + sm.b_lo);
+    uint32_t phase = 0;
+
+    const int items = a.P * a.C;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int p = item / a.C, c = item % a.C;
+        const long long s_begin = (long long)c * a.S;
+        const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
+        float nom[d];
+#pragma unroll
+        for (int q = 0; q < n; ++q) nom[q] = (float)a.x_nom[(long long)p * n + q];
+#pragma unroll
+        for (int q = 0; q < m; ++q) nom[n + q] = (float)a.u_nom[(long long)p * m + q];
+        // ---- f(xbar, ubar) in float32 with the exact weights, the block's threads over the units ----
+        if (tid < L.H1) {
+            float s = w1b[tid * (d + 1) + d];
+#pragma unroll
+            for (int q = 0; q < d; ++q) s = fmaf(w1b[tid * (d + 1) + q], nom[q], s);
+            act1[tid] = fmaxf(s, 0.f);
+        }
+        __syncthreads();
+        if (tid < L.H2) act2[tid] = fmaxf(Sys::dot_row(net.w2 + (long long)tid * L.H1, act1, L.H1, __ldg(net.b2 + tid)), 0.f);
+        __syncthreads();
+        if (tid < n) fbar_s[tid] = Sys::dot_row(net.w3 + (long long)tid * L.H2, act2, L.H2, __ldg(net.b3 + tid));
+        __syncthreads();
+        float fbar[n];
+#pragma unroll
+        for (int k = 0; k < n; ++k) fbar[k] = fbar_s[k];
+
+        float2 acc[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
+        for (long long s0 = s_begin; s0 < s_end; s0 += 128) {
+            const long long s = s0 + tid;
+            const bool valid = s < s_end;
+            float w[C::RS];
+#pragma unroll
+            for (int q = 0; q < C::RS; ++q) w[q] = 0.f;
+            if (valid) draw_deltas<Sys, C::RS>(a, p, s, w);
+            float in[d];
+#pragma unroll
+            for (int q = 0; q < d; ++q) in[q] = nom[q] + w[q];
+            // ---- first layer -> operand row (two bf16 pieces) ----
+            {
+                unsigned char* row_hi = smem + sm.a_hi + tid * 16;
+                unsigned char* row_lo = smem + sm.a_lo + tid * 16;
+                for (int k0 = 0; k0 < L.Kp; k0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float* wr = w1b + (k0 + q) * (d + 1);
+                        float sacc = wr[d];
+#pragma unroll
+                        for (int r = 0; r < d; ++r) sacc = fmaf(wr[r], in[r], sacc);
+                        v[q] = fmaxf(sacc, 0.f);
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+                    *reinterpret_cast<uint4*>(row_hi + (k0 >> 3) * L.lbo_a()) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(row_lo + (k0 >> 3) * L.lbo_a()) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // this thread's accumulator reads of the last tile
+            __syncthreads();
+            // ---- hidden layer: 3 Kp / 16 UMMAs, one issuing thread ----
+            if (warp == 0) {
+                if (elect_one()) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t la = (uint32_t)L.lbo_a(), lb = (uint32_t)L.lbo_b();
+                    for (int kb = 0; kb < L.Kp / 16; ++kb) {
+                        const uint64_t ah = umma_smem_desc(sa_hi + kb * 2 * la, la, 128);
+                        const uint64_t al = umma_smem_desc(sa_lo + kb * 2 * la, la, 128);
+                        const uint64_t bh = umma_smem_desc(sb_hi + kb * 2 * lb, lb, 128);
+                        const uint64_t bl = umma_smem_desc(sb_lo + kb * 2 * lb, lb, 128);
+                        const uint32_t first = kb > 0 ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(tmem_base), "l"(ah), "l"(bh), "r"(idesc), "r"(first));
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(tmem_base), "l"(ah), "l"(bl), "r"(idesc), "r"(1u));
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(tmem_base), "l"(al), "l"(bh), "r"(idesc_neg_a), "r"(1u));
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+                                 : "memory");
+                }
+                __syncwarp();
+            }
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- own accumulator row: ReLU, last layer ----
+            float o[n];
+#pragma unroll
+            for (int k = 0; k < n; ++k) o[k] = w3s[n * L.Np + k];
+            for (int c0 = 0; c0 < L.Np; c0 += 16) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(tmem_row + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float h = fmaxf(__uint_as_float(v[q]), 0.f);
+#pragma unroll
+                    for (int k = 0; k < n; ++k) o[k] = fmaf(w3s[k * L.Np + c0 + q], h, o[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < n; ++k) w[d + k] = valid ? o[k] - fbar[k] : 0.f;
+            gram_update<Sys, 1, 0, NP>(w, acc);
+        }
+        // ---- packed Gram block of the item (as zero_order_registers) ----
+        float* slab = slabs + warp * WIDTH;
+        gram_flush<Sys, 1, 0, NP>(acc, slab, lane);
+        __syncthreads();
+        float* out = a.partials + (long long)item * WIDTH;
+        for (int e = tid; e < WIDTH; e += 128) out[e] = (slabs[e] + slabs[WIDTH + e]) + (slabs[2 * WIDTH + e] + slabs[3 * WIDTH + e]);
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+}
+
+}  // namespace irs

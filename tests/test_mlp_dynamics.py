@@ -133,6 +133,25 @@ def test_zero_order_philox_matches_oracle_on_same_deltas(api, system, gold, N, a
     assert rel_err(ct, ct_o) < FP32_RTOL
 
 
+@pytest.mark.parametrize("N", [37, 128, 1000, 5000])
+def test_tensor_core_engine_matches_the_per_thread_functor(api, system, gold, N, monkeypatch):
+    """The hidden layer on the tensor cores (bf16 split, smooth_mlp.cuh) against the generic kernel that evaluates
+    the network per thread in float32 (IRS_MLP_ENGINE=0), same Philox noise; ragged tiles and chunks included."""
+    from irs_mpc_b200 import _graph
+    monkeypatch.setattr(_graph, "USE_GRAPHS", False)
+    T = 7
+    cfg = ec.pendulum_nn(T=T)
+    u_trj = cfg["u_trj_initial"] + np.random.default_rng(11).standard_normal((T, 1))
+    res = {}
+    for engine in ("1", "0"):
+        monkeypatch.setenv("IRS_MLP_ENGINE", engine)
+        sampler = api.GaussianSampling(cfg["sigma"][:2], cfg["sigma"][2:], N, power=cfg["power"], seed=31)
+        solver = api.IrsLqrZeroOrder(system, make_params(api, cfg, T, u_trj=u_trj), sampler)
+        res[engine] = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+    for got, want in zip(res["1"], res["0"]):
+        assert rel_err(got, want) < FP32_RTOL
+
+
 def test_first_order_and_exact_match_oracle(api, system, gold):
     T, N = 5, 1500
     cfg = ec.pendulum_nn(T=T)
