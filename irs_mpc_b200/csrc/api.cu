@@ -734,6 +734,8 @@ int irs_mlp_register(int dim_x, int dim_u, int h1, int h2, const float* W1, cons
     memcpy(const_cast<float*>(v.b2), b2, sizeof(float) * h2);
     memcpy(const_cast<float*>(v.w3), W3, sizeof(float) * n * h2);
     memcpy(const_cast<float*>(v.b3), b3, sizeof(float) * n);
+    for (int j = 0; j < h2; ++j)
+        for (int q = 0; q < h1; ++q) const_cast<float*>(v.w2t)[(size_t)q * h2 + j] = W2[(size_t)j * h1 + q];
     for (float x : host) IRS_REQUIRE(x == x && x - x == 0.f, "network weights must be finite");
     // hidden layer as tensor-core operand: B[j][k] = W2[j][k] (k < h1), b2[j] (k = h1), zero padding; two bf16
     // pieces, round to nearest even, hi + lo = the float32 weight to 2^-17 relative

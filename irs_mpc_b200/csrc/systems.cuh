@@ -347,21 +347,23 @@ __device__ __forceinline__ void centred_frame(const double* xb, const double* ub
 // This per-thread functor serves every generic kernel (dynamics / Jacobian batches, rollouts, first-order
 // smoothing, the fp64 nominal point of the fit); the T x N zero-order sample work runs the hidden layer on
 // the tensor cores instead (smooth_mlp.cuh).
-// blob (float32): W1[H1][d] | b1[H1] | W2[H2][H1] | b2[H2] | W3[n][H2] | b3[n]; registered with irs_mlp_register.
+// blob (float32): W1[H1][d] | b1[H1] | W2[H2][H1] | b2[H2] | W3[n][H2] | b3[n] | W2^T[H1][H2] (for the warp-cooperative
+// step of the rollouts: lanes over units read it coalesced); registered with irs_mlp_register.
 // params: [h, handle]
 // ---------------------------------------------------------------------------------------------
 constexpr int kMlpMaxHidden = 128;
 
 struct MlpView {
-    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    const float *w1, *b1, *w2, *b2, *w3, *b3, *w2t;
     int H1, H2;
     __host__ __device__ MlpView(const float* blob, int d, int n, int h1, int h2) : H1(h1), H2(h2) {
         w1 = blob;          b1 = w1 + h1 * d;
         w2 = b1 + h1;       b2 = w2 + h2 * h1;
         w3 = b2 + h2;       b3 = w3 + n * h2;
+        w2t = b3 + n;
     }
     static __host__ __device__ long long floats(int d, int n, int h1, int h2) {
-        return (long long)h1 * d + h1 + (long long)h2 * h1 + h2 + (long long)n * h2 + n;
+        return (long long)h1 * d + h1 + 2ll * h2 * h1 + h2 + (long long)n * h2 + n;
     }
 };
 
@@ -387,17 +389,71 @@ struct Mlp {
         }
         for (int j = 0; j < net.H2; ++j) a2[j] = fmaxf(dot_row(net.w2 + (long long)j * net.H1, a1, net.H1, __ldg(net.b2 + j)), 0.f);
     }
-    static __device__ __forceinline__ float dot_row(const float* w, const float* a, int len, float init) {
+    // sum_q w[q * stride] a[q] + init: the ONE summation order of every float32 evaluation of a unit
+    static __device__ __forceinline__ float dot_row(const float* w, const float* a, int len, float init, int stride = 1) {
         float s0 = init, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int q = 0;
         for (; q + 4 <= len; q += 4) {
-            s0 = fmaf(__ldg(w + q), a[q], s0);
-            s1 = fmaf(__ldg(w + q + 1), a[q + 1], s1);
-            s2 = fmaf(__ldg(w + q + 2), a[q + 2], s2);
-            s3 = fmaf(__ldg(w + q + 3), a[q + 3], s3);
+            s0 = fmaf(__ldg(w + q * stride), a[q], s0);
+            s1 = fmaf(__ldg(w + (q + 1) * stride), a[q + 1], s1);
+            s2 = fmaf(__ldg(w + (q + 2) * stride), a[q + 2], s2);
+            s3 = fmaf(__ldg(w + (q + 3) * stride), a[q + 3], s3);
         }
-        for (; q < len; ++q) s0 = fmaf(__ldg(w + q), a[q], s0);
+        for (; q < len; ++q) s0 = fmaf(__ldg(w + q * stride), a[q], s0);
         return (s0 + s1) + (s2 + s3);
+    }
+    // step() by one warp: every lane holds the same (x, u) and receives o; lanes over the hidden units, each unit
+    // summed exactly as in step() (bit-identical result).  a1s, a2s: kMlpMaxHidden floats of shared memory each.
+    __device__ __forceinline__ void step_warp(const R* x, const R* u, R* o, float* a1s, float* a2s, int lane) const {
+        float in[D];
+#pragma unroll
+        for (int q = 0; q < N; ++q) in[q] = (float)x[q];
+#pragma unroll
+        for (int q = 0; q < M; ++q) in[N + q] = (float)u[q];
+        for (int j = lane; j < net.H1; j += 32) {
+            float s = __ldg(net.b1 + j);
+#pragma unroll
+            for (int q = 0; q < D; ++q) s = fmaf(__ldg(net.w1 + j * D + q), in[q], s);
+            a1s[j] = fmaxf(s, 0.f);
+        }
+        __syncwarp();
+        {   // hidden layer: a lane carries its (up to four) units j = lane + 32 r TOGETHER — sixteen independent FFMA
+            // chains instead of four, one pass over the activations; per unit the order of dot_row
+            static_assert(kMlpMaxHidden <= 128, "four units per lane");
+            float sacc[4][4];
+            int col[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int j = lane + 32 * r;
+                col[r] = j < net.H2 ? j : net.H2 - 1;                      // surplus lanes shadow the last unit
+                sacc[r][0] = __ldg(net.b2 + col[r]);
+                sacc[r][1] = sacc[r][2] = sacc[r][3] = 0.f;
+            }
+            int q = 0;
+            for (; q + 4 <= net.H1; q += 4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float av = a1s[q + c];
+                    const float* wrow = net.w2t + (long long)(q + c) * net.H2;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sacc[r][c] = fmaf(__ldg(wrow + col[r]), av, sacc[r][c]);
+                }
+            }
+            for (; q < net.H1; ++q) {
+                const float av = a1s[q];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sacc[r][0] = fmaf(__ldg(net.w2t + (long long)q * net.H2 + col[r]), av, sacc[r][0]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (lane + 32 * r < net.H2) a2s[lane + 32 * r] = fmaxf((sacc[r][0] + sacc[r][1]) + (sacc[r][2] + sacc[r][3]), 0.f);
+        }
+        __syncwarp();
+        float mine = 0.f;
+        if (lane < N) mine = dot_row(net.w3 + (long long)lane * net.H2, a2s, net.H2, __ldg(net.b3 + lane));
+#pragma unroll
+        for (int k = 0; k < N; ++k) o[k] = R(__shfl_sync(0xffffffffu, mine, k));
+        __syncwarp();      // a1s / a2s may be rewritten by the next call
     }
 
     template <bool BATCH>
@@ -451,6 +507,11 @@ struct Mlp {
 };
 template <typename R>
 using Mlp21 = Mlp<R, 2, 1>;
+
+template <class Sys>
+struct is_mlp : std::false_type {};
+template <typename R, int N_, int M_>
+struct is_mlp<Mlp<R, N_, M_>> : std::true_type {};
 
 // Host-side dimension table (kept in sync with the functors by static_asserts in api.cu).
 struct SystemDims {

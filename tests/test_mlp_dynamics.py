@@ -66,6 +66,20 @@ def test_jacobian_matches_autograd(system, gold):
     np.testing.assert_array_equal(system.jacobian_xu(gold["pts"][9, :2], gold["pts"][9, 2:]), J[9])
 
 
+def test_rollout_by_the_warp_equals_stepping_the_per_thread_functor(api, system):
+    """IrsLqr.rollout (irs_lqr.py:105-119) runs the network with one warp per trajectory; `dynamics` with one thread
+    per point: every hidden unit is summed in the same order, so the trajectories are bit-identical."""
+    T = 40
+    cfg = ec.pendulum_nn(T=T)
+    u_trj = cfg["u_trj_initial"] + np.random.default_rng(2).standard_normal((T, 1))
+    solver = api.IrsLqrExact(system, make_params(api, cfg, T, u_trj=u_trj))
+    x = np.zeros((T + 1, 2))
+    x[0] = cfg["x0"]
+    for t in range(T):
+        x[t + 1] = system.dynamics(x[t], u_trj[t])
+    np.testing.assert_array_equal(solver.rollout(cfg["x0"], u_trj), x)
+
+
 def test_from_a_torch_module_and_refuses_other_architectures(api, gold):
     import torch
     import torch.nn as nn
