@@ -137,27 +137,39 @@ static int num_sms() {
 template <class Sys>
 static int launch_zero_order_mlp(const SmoothArgs& a, cudaStream_t st) {
     const MlpTcLayout L(a.prm.h1, a.prm.h2);
-    const MlpTcSmem<Sys> sm(L);
     auto kern = smooth_zero_order_mlp_kernel<Sys>;
-    static int max_smem = 0;
+    static int max_smem = 0, per_sm_smem = 0;
     if (max_smem == 0) {
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&per_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(smooth_zero_order_mlp)");
         max_smem = optin;
     }
-    IRS_REQUIRE(sm.total <= max_smem, "hidden widths %d / %d need %d bytes of shared memory (limit %d)", L.H1, L.H2,
-                sm.total, max_smem);
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, (size_t)sm.total) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    if (per_sm > 4) per_sm = 4;                   // 128 TMEM columns per block, 512 per SM
+    // Tile groups per block and blocks per SM (1 KB of shared memory reserved per block, 512 TMEM columns per SM).
+    // Two one-group blocks per SM were measured faster than one block of two or three groups (the reference's
+    // 100 / 100 network: 0.272 against 0.305 / 0.289 ms); wider networks, whose operand tiles leave room for one
+    // block only, take as many groups as fit.  IRS_MLP_GROUPS forces a count (tuning).
+    const int max_groups = MlpTcSmem<Sys>::groups_for(L, max_smem);
+    IRS_REQUIRE(max_groups >= 1, "hidden widths %d / %d need %d bytes of shared memory (limit %d)", L.H1, L.H2,
+                MlpTcSmem<Sys>(L, 1).total, max_smem);
+    int groups = per_sm_smem / (MlpTcSmem<Sys>(L, 1).total + 1024) >= 2 ? 1 : max_groups;
+    if (const char* e = getenv("IRS_MLP_GROUPS")) {
+        const int want = atoi(e);
+        if (want >= 1 && want <= max_groups) groups = want;
+    }
+    const MlpTcSmem<Sys> sm(L, groups);
+    int per_sm = per_sm_smem / (sm.total + 1024);
+    const int tmem_cols = groups == 1 ? 128 : (groups == 2 ? 256 : 512);
+    if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+    if (per_sm < 1) per_sm = 1;
     const long long items = (long long)a.P * a.C;
     const long long resident = (long long)per_sm * num_sms();
+    const long long want = (items + groups - 1) / groups;       // every group is a worker with its own items
     g_last_smooth_func = (const void*)kern;
-    kern<<<(unsigned)(items < resident ? items : resident), 128, (size_t)sm.total, st>>>(a);
+    kern<<<(unsigned)(want < resident ? want : resident), 128 * groups, (size_t)sm.total, st>>>(a);
     return check_launch("smooth_zero_order_mlp_kernel");
 }
 static bool use_mlp_tensor_cores() {
@@ -450,7 +462,7 @@ int irs_smooth_plan(int system, int order, int P, long long N, long long chunk_s
     long long target = 4096;
     const char* e = getenv("IRS_CHUNK_SAMPLES");
     if (e && atoll(e) > 0) target = atoll(e);
-    if (system == kMlp21 && order == 0 && !(e && atoll(e) > 0)) target = 1024;   // 8 tiles of 128: several waves of items
+    if (system == kMlp21 && order == 0 && !(e && atoll(e) > 0)) target = 1536;   // 12 tiles of 128 for up to 3 tile groups; several waves of items
     if (chunk_samples > 0) target = chunk_samples;
     long long c = (N + target - 1) / target;
     long long s = (N + c - 1) / c;

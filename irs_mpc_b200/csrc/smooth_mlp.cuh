@@ -18,12 +18,17 @@
 //     byte address of (row r, k) = (r/8)*128 + (k/8)*LBO + (r%8)*16 + (k%8)*2,   LBO = (rows/8)*128
 // A thread (= sample row) stores eight consecutive k with one 16-byte STS; a warp's store is 512 contiguous bytes.
 //
-// One block = 128 threads = one tile of 128 samples at a time: every thread draws its sample, evaluates the first
-// layer (CUDA cores), the tile is multiplied (one elected thread issues 3 Kp/16 UMMAs), every thread reads its own
-// accumulator row back (TMEM lane = sample), applies ReLU and the last layer (CUDA cores) and updates its Gram
+// A GROUP of 128 threads works on one tile of 128 samples at a time: every thread draws its sample, evaluates the
+// first layer (CUDA cores), the tile is multiplied (one elected thread issues 3 Kp/16 UMMAs), every thread reads its
+// own accumulator row back (TMEM lane = sample), applies ReLU and the last layer (CUDA cores) and updates its Gram
 // registers (smooth.cuh: gram_update — the same packed block the generic kernel writes, so the fp64 fit is shared).
-// Two blocks per SM alternate between the tensor pipe and the CUDA cores.  Persistent: blocks walk the
-// (nominal point, sample chunk) items with stride gridDim.x and load the network once.
+// A block holds up to three groups (as many as the shared memory takes: ONE copy of the network, one operand tile
+// and 128 TMEM columns per group).  The groups are independent workers — each walks its own items and synchronises
+// on its own named barrier — so their phases drift apart: while one group waits for its UMMAs or its TMEM loads the
+// others keep the CUDA cores busy (every phase of a tile is latency bound for a single warp per scheduler; the
+// tensor pipe needs 72 cycles per 128 x 112 x 16 UMMA, a quarter of a tile's time: tools/test_umma_mlp.cu, ncu:
+// profiles/r2_mlp_tc.txt).  Persistent: the groups walk the (nominal point, sample chunk) items with stride
+// gridDim.x * groups and the block loads the network once.
 #pragma once
 #include "smooth_tc.cuh"
 
@@ -47,73 +52,91 @@ struct MlpTcSmem {
     static constexpr int n = Sys::N, d = Sys::D;
     static constexpr int WIDTH = gram_width_of<Sys>();
     // byte offsets of the regions behind the operand tiles
+    static constexpr int kMaxGroups = 3;
     MlpTcLayout L;
-    int a_hi, a_lo, b_hi, b_lo, w1b, w3, act1, act2, fbar, slabs, bar, total;
-    __host__ __device__ explicit MlpTcSmem(const MlpTcLayout& l) : L(l) {
+    int G;
+    int a_hi, a_lo, a_stride, b_hi, b_lo, w1b, w3, act1, act2, fbar, slabs, bar, total;
+    __host__ __device__ MlpTcSmem(const MlpTcLayout& l, int groups) : L(l), G(groups) {
         int o = 0;
-        a_hi = o;  o += L.a_piece_bytes();
-        a_lo = o;  o += L.a_piece_bytes();
+        a_stride = 2 * L.a_piece_bytes();            // per group: [hi piece | lo piece]
+        a_hi = o;
+        a_lo = o + L.a_piece_bytes();
+        o += G * a_stride;
         b_hi = o;  o += L.b_piece_bytes();
         b_lo = o;  o += L.b_piece_bytes();
         w1b = o;   o += L.Kp * (d + 1) * 4;          // [Kp][d + 1]: first-layer row and bias; row H1 = (0, .., 0, 1)
         w3 = o;    o += (n * L.Np + n) * 4;          // [n][Np] last layer (zero padded) | b3[n]
-        act1 = o;  o += kMlpMaxHidden * 4;           // nominal point: hidden activations
-        act2 = o;  o += kMlpMaxHidden * 4;
-        fbar = o;  o += ((n + 3) / 4 * 4) * 4;
-        slabs = o; o += 4 * WIDTH * 4;
+        act1 = o;  o += G * kMlpMaxHidden * 4;       // per group — nominal point: hidden activations
+        act2 = o;  o += G * kMlpMaxHidden * 4;
+        fbar = o;  o += G * ((n + 3) / 4 * 4) * 4;
+        slabs = o; o += 4 * G * WIDTH * 4;
         o = (o + 7) / 8 * 8;
-        bar = o;   o += 16;                          // mbarrier | TMEM base address
+        bar = o;   o += 8 * kMaxGroups + 8;          // one mbarrier per group | TMEM base address
         total = o;
+    }
+    // groups per block that fit `limit` bytes of shared memory (0: not even one)
+    static __host__ int groups_for(const MlpTcLayout& l, int limit) {
+        for (int g = kMaxGroups; g >= 1; --g)
+            if (MlpTcSmem(l, g).total <= limit) return g;
+        return 0;
     }
 };
 
+// (Measured and dropped: the first / last layer weights as a kernel parameter — constant-bank loads — with the
+// layers unrolled for the reference's 100 / 100 network: LDC of the first layer is slower than the broadcast LDS,
+// uniform-register operands for the last layer gain 3 %.)
 template <class Sys>
-__global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const SmoothArgs a) {
+__global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_order_mlp_kernel(const SmoothArgs a) {
     static_assert(Sys::kIsMlp, "learned dynamics only");
     using C = ZeroOrderCfg<Sys, 1>;
     constexpr int n = Sys::N, m = Sys::M, d = Sys::D;
-    constexpr int NP = role_pairs(d, C::Wp, 1, 0);
+    constexpr int NPAIR = role_pairs(d, C::Wp, 1, 0);
     constexpr int WIDTH = gram_width_of<Sys>();
     static_assert(WIDTH == C::NACC, "no first moments for learned dynamics");
     const Sys sys(a.prm);
     const MlpView& net = sys.net;
     const MlpTcLayout L(net.H1, net.H2);
-    const MlpTcSmem<Sys> sm(L);
+    const int G = blockDim.x >> 7;                      // tile groups of this block
+    const MlpTcSmem<Sys> sm(L, G);
     extern __shared__ __align__(128) unsigned char smem[];
     float* w1b = reinterpret_cast<float*>(smem + sm.w1b);
     float* w3s = reinterpret_cast<float*>(smem + sm.w3);
-    float* act1 = reinterpret_cast<float*>(smem + sm.act1);
-    float* act2 = reinterpret_cast<float*>(smem + sm.act2);
-    float* fbar_s = reinterpret_cast<float*>(smem + sm.fbar);
-    float* slabs = reinterpret_cast<float*>(smem + sm.slabs);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + sm.bar);
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + sm.bar + 8);
+    const int group0 = (int)(threadIdx.x >> 7);
+    float* act1 = reinterpret_cast<float*>(smem + sm.act1) + group0 * kMlpMaxHidden;
+    float* act2 = reinterpret_cast<float*>(smem + sm.act2) + group0 * kMlpMaxHidden;
+    float* fbar_s = reinterpret_cast<float*>(smem + sm.fbar) + group0 * ((n + 3) / 4 * 4);
+    float* slabs = reinterpret_cast<float*>(smem + sm.slabs) + group0 * 4 * WIDTH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = tid >> 7, gtid = tid & 127, gwarp = warp & 3;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + sm.bar) + group;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + sm.bar + 8 * MlpTcSmem<Sys>::kMaxGroups);
+    const int nthreads = blockDim.x;
+    const uint32_t tmem_cols = G == 1 ? 128u : (G == 2 ? 256u : 512u);
 
     // ---- once per block: the network ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.prm.mlp_w2);
         uint4* dst = reinterpret_cast<uint4*>(smem + sm.b_hi);
-        for (int e = tid; e < 2 * L.b_piece_bytes() / 16; e += 128) dst[e] = __ldg(src + e);
-        for (int e = tid; e < L.Kp * (d + 1); e += 128) {
+        for (int e = tid; e < 2 * L.b_piece_bytes() / 16; e += nthreads) dst[e] = __ldg(src + e);
+        for (int e = tid; e < L.Kp * (d + 1); e += nthreads) {
             const int j = e / (d + 1), q = e % (d + 1);
             float v = 0.f;
             if (j < L.H1) v = q < d ? __ldg(net.w1 + j * d + q) : __ldg(net.b1 + j);
             else if (j == L.H1 && q == d) v = 1.f;                    // the constant column that carries b2
             w1b[e] = v;
         }
-        for (int e = tid; e < n * L.Np; e += 128) {
+        for (int e = tid; e < n * L.Np; e += nthreads) {
             const int k = e / L.Np, j = e % L.Np;
             w3s[e] = j < L.H2 ? __ldg(net.w3 + k * L.H2 + j) : 0.f;
         }
         if (tid < n) w3s[n * L.Np + tid] = __ldg(net.b3 + tid);
     }
-    if (tid == 0) {
+    if (gtid == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -121,16 +144,22 @@ __global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const Smooth
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_s;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * warp) << 16);      // this warp's lane quarter
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(128 * group);                 // this group's accumulator columns
+    const uint32_t tmem_row = tmem_acc + ((uint32_t)(32 * gwarp) << 16);           // this warp's lane quarter
     // instruction descriptor: D fp32, A / B bf16, both K-major, N >> 3, M >> 4; bit 13 negates A
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_neg_a = idesc | (1u << 13);
-    const uint32_t sa_hi = smem_u32(smem + sm.a_hi), sa_lo = smem_u32(smem + sm.a_lo);
+    unsigned char* a_tile = smem + group * sm.a_stride;
+    const uint32_t sa_hi = smem_u32(a_tile + sm.a_hi), sa_lo = smem_u32(a_tile + sm.a_lo);
     const uint32_t sb_hi = smem_u32(smem + sm.b_hi), sb_lo = smem_u32(smem + sm.b_lo);
     uint32_t phase = 0;
 
+    // the groups of a block are independent workers (they share the network in shared memory and nothing else):
+    // each walks its own items and synchronises on its own named barrier, so their phases drift apart and one
+    // group's UMMA / TMEM latency is covered by the others' CUDA-core work
+    auto group_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory"); };
     const int items = a.P * a.C;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int item = blockIdx.x * G + group; item < items; item += gridDim.x * G) {
         const int p = item / a.C, c = item % a.C;
         const long long s_begin = (long long)c * a.S;
         const long long s_end = s_begin + a.S < a.N ? s_begin + a.S : a.N;
@@ -140,26 +169,26 @@ __global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const Smooth
 #pragma unroll
         for (int q = 0; q < m; ++q) nom[n + q] = (float)a.u_nom[(long long)p * m + q];
         // ---- f(xbar, ubar) in float32 with the exact weights, the block's threads over the units ----
-        if (tid < L.H1) {
-            float s = w1b[tid * (d + 1) + d];
+        if (gtid < L.H1) {
+            float s = w1b[gtid * (d + 1) + d];
 #pragma unroll
-            for (int q = 0; q < d; ++q) s = fmaf(w1b[tid * (d + 1) + q], nom[q], s);
-            act1[tid] = fmaxf(s, 0.f);
+            for (int q = 0; q < d; ++q) s = fmaf(w1b[gtid * (d + 1) + q], nom[q], s);
+            act1[gtid] = fmaxf(s, 0.f);
         }
-        __syncthreads();
-        if (tid < L.H2) act2[tid] = fmaxf(Sys::dot_row(net.w2 + (long long)tid * L.H1, act1, L.H1, __ldg(net.b2 + tid)), 0.f);
-        __syncthreads();
-        if (tid < n) fbar_s[tid] = Sys::dot_row(net.w3 + (long long)tid * L.H2, act2, L.H2, __ldg(net.b3 + tid));
-        __syncthreads();
+        group_sync();
+        if (gtid < L.H2) act2[gtid] = fmaxf(Sys::dot_row(net.w2 + (long long)gtid * L.H1, act1, L.H1, __ldg(net.b2 + gtid)), 0.f);
+        group_sync();
+        if (gtid < n) fbar_s[gtid] = Sys::dot_row(net.w3 + (long long)gtid * L.H2, act2, L.H2, __ldg(net.b3 + gtid));
+        group_sync();
         float fbar[n];
 #pragma unroll
         for (int k = 0; k < n; ++k) fbar[k] = fbar_s[k];
 
-        float2 acc[NP];
+        float2 acc[NPAIR];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
+        for (int k = 0; k < NPAIR; ++k) acc[k] = make_float2(0.f, 0.f);
         for (long long s0 = s_begin; s0 < s_end; s0 += 128) {
-            const long long s = s0 + tid;
+            const long long s = s0 + gtid;
             const bool valid = s < s_end;
             float w[C::RS];
 #pragma unroll
@@ -170,8 +199,8 @@ __global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const Smooth
             for (int q = 0; q < d; ++q) in[q] = nom[q] + w[q];
             // ---- first layer -> operand row (two bf16 pieces) ----
             {
-                unsigned char* row_hi = smem + sm.a_hi + tid * 16;
-                unsigned char* row_lo = smem + sm.a_lo + tid * 16;
+                unsigned char* row_hi = a_tile + sm.a_hi + gtid * 16;
+                unsigned char* row_lo = a_tile + sm.a_lo + gtid * 16;
                 for (int k0 = 0; k0 < L.Kp; k0 += 8) {
                     float v[8];
 #pragma unroll
@@ -191,9 +220,9 @@ __global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const Smooth
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // this thread's accumulator reads of the last tile
-            __syncthreads();
-            // ---- hidden layer: 3 Kp / 16 UMMAs, one issuing thread ----
-            if (warp == 0) {
+            group_sync();                                                          // the group's operand tile is complete
+            // ---- hidden layer: 3 Kp / 16 UMMAs, one issuing thread per group ----
+            if (gwarp == 0) {
                 if (elect_one()) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t la = (uint32_t)L.lbo_a(), lb = (uint32_t)L.lbo_b();
@@ -205,13 +234,13 @@ __global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const Smooth
                         const uint32_t first = kb > 0 ? 1u : 0u;
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                     ::"r"(tmem_base), "l"(ah), "l"(bh), "r"(idesc), "r"(first));
+                                     ::"r"(tmem_acc), "l"(ah), "l"(bh), "r"(idesc), "r"(first));
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                     ::"r"(tmem_base), "l"(ah), "l"(bl), "r"(idesc), "r"(1u));
+                                     ::"r"(tmem_acc), "l"(ah), "l"(bl), "r"(idesc), "r"(1u));
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                     ::"r"(tmem_base), "l"(al), "l"(bh), "r"(idesc_neg_a), "r"(1u));
+                                     ::"r"(tmem_acc), "l"(al), "l"(bh), "r"(idesc_neg_a), "r"(1u));
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
                                  : "memory");
@@ -242,19 +271,20 @@ __global__ void __launch_bounds__(128) smooth_zero_order_mlp_kernel(const Smooth
             }
 #pragma unroll
             for (int k = 0; k < n; ++k) w[d + k] = valid ? o[k] - fbar[k] : 0.f;
-            gram_update<Sys, 1, 0, NP>(w, acc);
+            gram_update<Sys, 1, 0, NPAIR>(w, acc);
         }
         // ---- packed Gram block of the item (as zero_order_registers) ----
-        float* slab = slabs + warp * WIDTH;
-        gram_flush<Sys, 1, 0, NP>(acc, slab, lane);
-        __syncthreads();
+        float* slab = slabs + gwarp * WIDTH;
+        gram_flush<Sys, 1, 0, NPAIR>(acc, slab, lane);
+        group_sync();
         float* out = a.partials + (long long)item * WIDTH;
-        for (int e = tid; e < WIDTH; e += 128) out[e] = (slabs[e] + slabs[WIDTH + e]) + (slabs[2 * WIDTH + e] + slabs[3 * WIDTH + e]);
-        __syncthreads();
+        for (int e = gtid; e < WIDTH; e += 128)
+            out[e] = (slabs[e] + slabs[WIDTH + e]) + (slabs[2 * WIDTH + e] + slabs[3 * WIDTH + e]);
+        group_sync();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
 }  // namespace irs

@@ -36,7 +36,7 @@ def timed(fn, reps=20, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
-for engine in ("1", "0"):
+for engine in ("1", "0") if os.environ.get("MB_BOTH", "1") == "1" else ("1",):
     os.environ["IRS_MLP_ENGINE"] = engine
     ws = smoothing.Workspace(system, 0, T, N)
     seed = [0]

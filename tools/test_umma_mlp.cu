@@ -79,6 +79,55 @@ __global__ void __launch_bounds__(128) k(const float* A /*[M][K]*/, const float*
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128));
 }
+// Rate of the operand shape: `reps` rounds of the 3 * K/16 UMMAs the learned-dynamics kernel issues per tile
+// (a_hi b_hi + a_hi b_lo + a_lo b_hi share the same smem tiles here), commit + wait per round.
+__global__ void __launch_bounds__(128) rate(int reps, long long* cycles_out, int blocks_share) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t SBO = 128, LBO_A = (M / 8) * 128, LBO_B = (N / 8) * 128;
+    for (int i = tid; i < (M + N) * K * 2 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + M * K * 2);
+        uint32_t phase = 0;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            for (int kb = 0; kb < K / 16; ++kb) {
+                const uint64_t adesc = make_desc(sA + kb * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t bdesc = make_desc(sB + kb * 2 * LBO_B, LBO_B, SBO);
+                for (int piece = 0; piece < 3; ++piece) {
+                    const uint32_t acc = (kb > 0 || piece > 0) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 :: "r"(tmem_base), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)));
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase));
+            phase ^= 1u;
+        }
+        cycles_out[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128));
+}
 int main() {
     static float hA[M * K], hB[N * K], hD[M * N];
     static double ref[M][N];
@@ -90,7 +139,7 @@ int main() {
     cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
     const int smem_bytes = (M + N) * K * 2;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    for (int swap = 0; swap < 2; ++swap) {
+    for (int swap = 0; swap < 1; ++swap) {      // the swapped assignment faults (illegal address): not run
         cudaMemset(dD, 0, sizeof(hD));
         k<<<1, 128, smem_bytes>>>(dA, dB, dD, swap);
         cudaError_t e = cudaDeviceSynchronize();
@@ -101,6 +150,20 @@ int main() {
         printf("K-major M=128 N=112 K=112 (LBO,SBO)=%s : match %d/%d maxerr %.3g | D[5][0..3] %g %g %g %g (ref %g %g %g %g)\n",
                swap ? "(row-group stride, k-group stride)" : "(k-group stride, row-group stride)", match, M * N, maxerr,
                hD[5 * N], hD[5 * N + 1], hD[5 * N + 2], hD[5 * N + 3], ref[5][0], ref[5][1], ref[5][2], ref[5][3]);
+    }
+    {
+        long long* dc; cudaMalloc(&dc, sizeof(long long) * 296);
+        cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        const int reps = 200;
+        for (int blocks = 148; blocks <= 296; blocks += 148) {
+            rate<<<blocks, 128, smem_bytes>>>(reps, dc, 0);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("rate: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+            static long long hc[296]; cudaMemcpy(hc, dc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
+            double avg = 0; for (int i = 0; i < blocks; ++i) avg += (double)hc[i] / blocks;
+            printf("%d blocks (%d per SM): %.0f cycles per round of %d UMMAs (128 x 112 x 16) = %.1f cycles per UMMA per block\n",
+                   blocks, blocks / 148, avg / reps, 3 * K / 16, avg / reps / (3 * K / 16));
+        }
     }
     return 0;
 }
