@@ -380,6 +380,47 @@ def run_gpu(args, rank, local_rank, world):
             ms2 = timed(step2, max(5, min(args.steps, 20)), 3) / max(5, min(args.steps, 20))
             other[label] = {"ms_per_linearization": ms2, "samples_per_s": Tn * Nn / (ms2 * 1e-3)}
             del ws2
+        # learned dynamics (the reference's examples/pendulum/pendulum_nn.py: 3-100-100-2 ReLU network,
+        # T=200, N=1e4 samples per step): hidden layer of the network on tcgen05; committed weights of a network
+        # trained the way the script trains it (tests/golden/mlp_pendulum.npz, oracle/make_mlp_fixture.py)
+        try:
+            from irs_mpc_b200.all import MlpDynamics
+            gw = np.load(os.path.join(ROOT, "tests", "golden", "mlp_pendulum.npz"))
+            net = MlpDynamics([(gw["W1"], gw["b1"]), (gw["W2"], gw["b2"]), (gw["W3"], gw["b3"])])
+            c3 = gec.pendulum_nn(T=200)
+            xn3 = _device.to_device(np.cumsum(0.02 * np.ones((200, 2)), axis=0))
+            un3 = _device.to_device(c3["u_trj_initial"])
+            ws3 = smoothing.Workspace(net, smoothing.ZERO_ORDER, 200, 10000)
+
+            def acc3(k):
+                smoothing.accumulate(net, smoothing.ZERO_ORDER, xn3, un3, 10000, ws3, sigma=c3["sigma"], seed=SEED0 + k,
+                                     it=1, flags=sampler.flags())
+
+            def step3(k):
+                acc3(k)
+                smoothing.finalize(net, smoothing.ZERO_ORDER, xn3, un3, ws3, 10000)
+            reps3 = max(5, min(args.steps, 20))
+            ms3 = timed(step3, reps3, 3) / reps3
+            ms3k = timed(acc3, reps3, 3) / reps3
+            net_flops = 2 * (3 * 100 + 100 * 100 + 100 * 2)
+            tf = 200 * 10000 * net_flops / (ms3k * 1e-3) / 1e12
+            bf16_peak = None
+            try:
+                bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops")
+            except Exception:
+                pass
+            other["learned dynamics (pendulum_nn.py network 3-100-100-2) zero-order T=200 N=1e4"] = {
+                "ms_per_linearization": ms3, "samples_per_s": 200 * 10000 / (ms3 * 1e-3),
+                "kernel": "smooth_zero_order_mlp_kernel (hidden layer: tcgen05 UMMA 128x112x16, bf16-split x3)",
+                "kernel_ms": ms3k, "network_tflops_algorithmic": tf,
+                "tensor_peak_bf16_tflops": bf16_peak,
+                "frac_of_tensor_peak": (3.0 * (112 * 112) / (100.0 * 100.0) * tf / bf16_peak) if bf16_peak else None,
+                "frac_note": "executed tensor flops (3 split products on operands padded to 112 x 112) over the measured "
+                             "bf16 peak; the kernel is bound by the CUDA-core / shared-memory side of a tile, not by the "
+                             "tensor pipe (profiles/r2_mlp_tc_full.txt)"}
+            del ws3, net
+        except Exception as e:      # the headline line must not depend on the optional leg
+            other["learned dynamics"] = {"error": repr(e)}
 
     # 5d. STRONG scaling of the named configs: the TOTAL sample count of BASELINE.json configs[2] (N = 1e5 per
     #     step) and configs[3] (three_cart, N = 1e6 per step) split over the ranks — sample axis (fused peer
