@@ -927,8 +927,29 @@ __global__ void __launch_bounds__(BT, 1) finalize_zero_order_kernel(const Finali
         }
     }
     __syncthreads();
-    if (tid == 32) {
-        nominal_compute_to_smem<Sys>(a, p, nom);
+    // learned dynamics: warp 1 evaluates the network together (Mlp::step_warp, bit-identical to the functor)
+    constexpr bool kWarpNominal = is_mlp<Sys>::value;
+    __shared__ float mlp_act[kWarpNominal ? 2 * kMlpMaxHidden : 1];
+    if (kWarpNominal ? (tid >= 32 && tid < 64) : (tid == 32)) {
+        if constexpr (kWarpNominal) {
+            const Sys sys(a.prm);
+            double xb[n], ub[m], fb[n];
+#pragma unroll
+            for (int q = 0; q < n; ++q) xb[q] = a.x_nom[(long long)p * n + q];
+#pragma unroll
+            for (int q = 0; q < m; ++q) ub[q] = a.u_nom[(long long)p * m + q];
+            sys.step_warp(xb, ub, fb, mlp_act, mlp_act + kMlpMaxHidden, tid - 32);
+            if (tid == 32) {
+#pragma unroll
+                for (int q = 0; q < n; ++q) nom[q] = xb[q];
+#pragma unroll
+                for (int q = 0; q < m; ++q) nom[n + q] = ub[q];
+#pragma unroll
+                for (int q = 0; q < n; ++q) nom[n + m + q] = fb[q];
+            }
+        } else {
+            nominal_compute_to_smem<Sys>(a, p, nom);
+        }
     } else if (tid < 32) {
         // 2. Cholesky G = L L^T by warp 0, left-looking, lane = row with the row of the factor in
         //    REGISTERS: row k reaches the other lanes by shuffles, every lane recomputes the pivot (same
