@@ -162,7 +162,7 @@ static int launch_zero_order_mlp(const SmoothArgs& a, cudaStream_t st) {
     }
     const MlpTcSmem<Sys> sm(L, groups);
     int per_sm = per_sm_smem / (sm.total + 1024);
-    const int tmem_cols = groups == 1 ? 128 : (groups == 2 ? 256 : 512);
+    const int tmem_cols = MlpTcLayout::tmem_alloc_cols(groups * L.tmem_cols_per_group());
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     if (per_sm < 1) per_sm = 1;
     const long long items = (long long)a.P * a.C;
@@ -752,7 +752,7 @@ int irs_mlp_register(int dim_x, int dim_u, int h1, int h2, const float* W1, cons
     // hidden layer as tensor-core operand: B[j][k] = W2[j][k] (k < h1), b2[j] (k = h1), zero padding; two bf16
     // pieces, round to nearest even, hi + lo = the float32 weight to 2^-17 relative
     const MlpTcLayout L(h1, h2);
-    std::vector<unsigned short> tc((size_t)L.b_piece_bytes(), 0);      // 2 pieces x (bytes / 2) elements
+    std::vector<unsigned short> tc((size_t)L.blob_bytes() / 2, 0);     // [W2 hi | W2 lo | B1 hi | B1 lo] bf16 elements
     auto bf16_rn = [](float x) -> unsigned short {
         uint32_t u;
         memcpy(&u, &x, 4);
@@ -773,6 +773,19 @@ int irs_mlp_register(int dim_x, int dim_u, int h1, int h2, const float* W1, cons
             tc[at] = hi;
             tc[(size_t)L.b_piece_bytes() / 2 + at] = lo;
         }
+    // first layer as operand: row j = (W1[j][0..d), b1[j], 0..), row h1 = (0, .., 0, 1): the constant unit
+    IRS_REQUIRE(d + 1 <= 8, "the first layer takes at most 7 inputs");
+    {
+        const size_t base_hi = (size_t)L.b_piece_bytes(), base_lo = base_hi + (size_t)L.b1_piece_bytes() / 2;
+        for (int j = 0; j <= h1; ++j)
+            for (int k = 0; k <= d; ++k) {
+                const float wv = j < h1 ? (k < d ? W1[(size_t)j * d + k] : b1[j]) : (k == d ? 1.f : 0.f);
+                const unsigned short hi = bf16_rn(wv), lo = bf16_rn(wv - bf16_float(hi));
+                const size_t at = (size_t)L.b1_offset(j, k) / 2;
+                tc[base_hi + at] = hi;
+                tc[base_lo + at] = lo;
+            }
+    }
     MlpEntry e{nullptr, nullptr, d, n, h1, h2, 0};
     cudaGetDevice(&e.device);
     if (cudaMalloc(&e.blob, sizeof(float) * count) != cudaSuccess) return check_launch("cudaMalloc(network)");

@@ -1,34 +1,31 @@
 // Zero-order smoothing of LEARNED dynamics (systems.cuh: Mlp; the reference's examples/pendulum/pendulum_nn.py)
-// with the hidden layer on the 5th-generation tensor cores.
+// with the first and the hidden layer on the 5th-generation tensor cores.
 //
 // Per sample the network costs d H1 + H1 H2 + H2 n multiply-adds (3 x 100 + 100 x 100 + 100 x 2 for the
-// reference's network): 95 % of them are the hidden layer, a dense GEMM over the samples of a tile:
+// reference's network): 98 % of them are the first two layers, dense GEMMs over the samples of a tile:
 //
-//     D[128 x Np] (TMEM, fp32)  =  A[128 x Kp] (smem)  *  B[Kp x Np] (smem),      kind::f16 (bf16), both K-major
-//
-// A row  = one sample: relu(W1 [x; u] + b1), then a constant 1 (column H1) that carries the bias, zero padding
-// B      = [W2 | b2]^T, prepared once per registered network (api.cu: irs_mlp_register)
-// Kp = ceil16(H1 + 1), Np = ceil16(H2).  Both operands are split into two bf16 pieces (x ~ x_hi + x_lo,
+//     D1[128 x Kp] (TMEM, fp32) = A1[128 x 16] (smem) * B1[16 x Kp] (smem)         first layer, pre-activations
+//     D [128 x Np] (TMEM, fp32) = A [128 x Kp] (smem) * B [Kp x Np] (smem)         hidden layer
+//                                                                   kind::f16 (bf16), all operands K-major
+// A1 row = one sample [x; u; 1 | 0 ..];  B1 = [W1 | b1]^T plus one constant unit (column H1 = 1)
+// A  row = relu(D1 row): the sample's hidden activations, the constant 1 in column H1 carries b2
+// B      = [W2 | b2]^T;  B1, B prepared once per registered network (api.cu: irs_mlp_register)
+// Kp = ceil16(H1 + 1), Np = ceil16(H2).  Every operand is split into two bf16 pieces (x ~ x_hi + x_lo,
 // |x - x_hi - x_lo| <= 2^-17 |x|) and three products are accumulated, a_hi w_hi + a_hi w_lo + a_lo w_hi: the
 // float32 product to ~2^-16 relative, inside the 1e-4 budget with margin (the reference evaluates the torch
-// module in float32, pendulum_nn.py:72-81).  The activation residual is staged NEGATED (split_bf16x2) and the
-// third product issued with the negate-A bit of the instruction descriptor.
+// module in float32, pendulum_nn.py:72-81).  Residual pieces of A1 / A are staged NEGATED (split_bf16x2) and the
+// third product is issued with the negate-A bit of the instruction descriptor.
 //
 // K-major canonical layout without swizzle (verified on hardware by tools/test_umma_mlp.cu):
 //     byte address of (row r, k) = (r/8)*128 + (k/8)*LBO + (r%8)*16 + (k%8)*2,   LBO = (rows/8)*128
 // A thread (= sample row) stores eight consecutive k with one 16-byte STS; a warp's store is 512 contiguous bytes.
 //
-// A GROUP of 128 threads works on one tile of 128 samples at a time: every thread draws its sample, evaluates the
-// first layer (CUDA cores), the tile is multiplied (one elected thread issues 3 Kp/16 UMMAs), every thread reads its
-// own accumulator row back (TMEM lane = sample), applies ReLU and the last layer (CUDA cores) and updates its Gram
+// A GROUP of 128 threads works on one tile of 128 samples at a time: every thread draws its sample and stages its
+// A1 row (and the group B1) in the part of the operand tile that is still free, one elected thread issues the three
+// UMMAs of the first layer, every thread reads its own row of D1 back (TMEM lane = sample), applies ReLU, splits
+// and stores its A row; the elected thread issues the 3 Kp/16 UMMAs of the hidden layer into the same TMEM
+// columns; every thread reads its row of D, applies ReLU and the last layer (CUDA cores) and updates its Gram
 // registers (smooth.cuh: gram_update — the same packed block the generic kernel writes, so the fp64 fit is shared).
-// A block holds up to three groups (as many as the shared memory takes: ONE copy of the network, one operand tile
-// and 128 TMEM columns per group).  The groups are independent workers — each walks its own items and synchronises
-// on its own named barrier — so their phases drift apart: while one group waits for its UMMAs or its TMEM loads the
-// others keep the CUDA cores busy (every phase of a tile is latency bound for a single warp per scheduler; the
-// tensor pipe needs 72 cycles per 128 x 112 x 16 UMMA, a quarter of a tile's time: tools/test_umma_mlp.cu, ncu:
-// profiles/r2_mlp_tc.txt).  Persistent: the groups walk the (nominal point, sample chunk) items with stride
-// gridDim.x * groups and the block loads the network once.
 #pragma once
 #include "smooth_tc.cuh"
 
@@ -45,6 +42,18 @@ struct MlpTcLayout {
     __host__ __device__ int b_piece_bytes() const { return Np * Kp * 2; }
     // byte offset of element (row j, k) inside a B piece
     __host__ __device__ int b_offset(int j, int k) const { return (j / 8) * 128 + (k / 8) * lbo_b() + (j % 8) * 16 + (k % 8) * 2; }
+    // first layer as a UMMA too: D1[128 x Kp] = [x; u; 1 | 0..] (K = 16) * B1^T, B1 row j = (W1[j], b1[j], 0..) and row H1 =
+    // (0, .., 0, 1) — the constant unit that carries b2 through the hidden layer
+    static constexpr int kK1 = 16;
+    __host__ __device__ int lbo_b1() const { return Kp / 8 * 128; }
+    __host__ __device__ int b1_piece_bytes() const { return Kp * kK1 * 2; }
+    __host__ __device__ int a1_piece_bytes() const { return kRows * kK1 * 2; }
+    __host__ __device__ int b1_offset(int j, int k) const { return (j / 8) * 128 + (k / 8) * lbo_b1() + (j % 8) * 16 + (k % 8) * 2; }
+    // TMEM columns of a tile group: the accumulator holds the first layer's Kp, then the hidden layer's Np columns
+    __host__ __device__ int tmem_cols_per_group() const { return (Kp > 128 || Np > 128) ? 256 : 128; }
+    static __host__ __device__ int tmem_alloc_cols(int cols) { return cols <= 128 ? 128 : (cols <= 256 ? 256 : 512); }
+    // device blob of operand pieces: [W2 hi | W2 lo | B1 hi | B1 lo]
+    __host__ __device__ int blob_bytes() const { return 2 * b_piece_bytes() + 2 * b1_piece_bytes(); }
 };
 
 template <class Sys>
@@ -77,7 +86,7 @@ struct MlpTcSmem {
     // groups per block that fit `limit` bytes of shared memory (0: not even one)
     static __host__ int groups_for(const MlpTcLayout& l, int limit) {
         for (int g = kMaxGroups; g >= 1; --g)
-            if (MlpTcSmem(l, g).total <= limit) return g;
+            if (MlpTcSmem(l, g).total <= limit && g * l.tmem_cols_per_group() <= 512) return g;
         return 0;
     }
 };
@@ -99,19 +108,19 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
     const int G = blockDim.x >> 7;                      // tile groups of this block
     const MlpTcSmem<Sys> sm(L, G);
     extern __shared__ __align__(128) unsigned char smem[];
-    float* w1b = reinterpret_cast<float*>(smem + sm.w1b);
-    float* w3s = reinterpret_cast<float*>(smem + sm.w3);
-    const int group0 = (int)(threadIdx.x >> 7);
-    float* act1 = reinterpret_cast<float*>(smem + sm.act1) + group0 * kMlpMaxHidden;
-    float* act2 = reinterpret_cast<float*>(smem + sm.act2) + group0 * kMlpMaxHidden;
-    float* fbar_s = reinterpret_cast<float*>(smem + sm.fbar) + group0 * ((n + 3) / 4 * 4);
-    float* slabs = reinterpret_cast<float*>(smem + sm.slabs) + group0 * 4 * WIDTH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = tid >> 7, gtid = tid & 127, gwarp = warp & 3;
+    float* w1b = reinterpret_cast<float*>(smem + sm.w1b);
+    float* w3s = reinterpret_cast<float*>(smem + sm.w3);
+    // per group: scratch of the nominal point, warp slabs of the Gram flush, mbarrier
+    float* act1 = reinterpret_cast<float*>(smem + sm.act1) + group * kMlpMaxHidden;
+    float* act2 = reinterpret_cast<float*>(smem + sm.act2) + group * kMlpMaxHidden;
+    float* fbar_s = reinterpret_cast<float*>(smem + sm.fbar) + group * ((n + 3) / 4 * 4);
+    float* slabs = reinterpret_cast<float*>(smem + sm.slabs) + group * 4 * WIDTH;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + sm.bar) + group;
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + sm.bar + 8 * MlpTcSmem<Sys>::kMaxGroups);
     const int nthreads = blockDim.x;
-    const uint32_t tmem_cols = G == 1 ? 128u : (G == 2 ? 256u : 512u);
+    const uint32_t tmem_cols = (uint32_t)MlpTcLayout::tmem_alloc_cols(G * L.tmem_cols_per_group());
 
     // ---- once per block: the network ----
     {
@@ -144,11 +153,12 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_s;
-    const uint32_t tmem_acc = tmem_base + (uint32_t)(128 * group);                 // this group's accumulator columns
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(L.tmem_cols_per_group() * group);   // this group's accumulator columns
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(32 * gwarp) << 16);           // this warp's lane quarter
     // instruction descriptor: D fp32, A / B bf16, both K-major, N >> 3, M >> 4; bit 13 negates A
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_neg_a = idesc | (1u << 13);
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.Kp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     unsigned char* a_tile = smem + group * sm.a_stride;
     const uint32_t sa_hi = smem_u32(a_tile + sm.a_hi), sa_lo = smem_u32(a_tile + sm.a_lo);
     const uint32_t sb_hi = smem_u32(smem + sm.b_hi), sb_lo = smem_u32(smem + sm.b_lo);
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
         for (int q = 0; q < n; ++q) nom[q] = (float)a.x_nom[(long long)p * n + q];
 #pragma unroll
         for (int q = 0; q < m; ++q) nom[n + q] = (float)a.u_nom[(long long)p * m + q];
-        // ---- f(xbar, ubar) in float32 with the exact weights, the block's threads over the units ----
+        // ---- f(xbar, ubar) in float32 with the exact weights, the group's threads over the units ----
         if (gtid < L.H1) {
             float s = w1b[gtid * (d + 1) + d];
 #pragma unroll
@@ -176,7 +186,8 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
             act1[gtid] = fmaxf(s, 0.f);
         }
         group_sync();
-        if (gtid < L.H2) act2[gtid] = fmaxf(Sys::dot_row(net.w2 + (long long)gtid * L.H1, act1, L.H1, __ldg(net.b2 + gtid)), 0.f);
+        // W2^T: the threads of a warp read consecutive words (a row of W2 per thread is a cache line per load)
+        if (gtid < L.H2) act2[gtid] = fmaxf(Sys::dot_row(net.w2t + gtid, act1, L.H1, __ldg(net.b2 + gtid), L.H2), 0.f);
         group_sync();
         if (gtid < n) fbar_s[gtid] = Sys::dot_row(net.w3 + (long long)gtid * L.H2, act2, L.H2, __ldg(net.b3 + gtid));
         group_sync();
@@ -197,25 +208,75 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
             float in[d];
 #pragma unroll
             for (int q = 0; q < d; ++q) in[q] = nom[q] + w[q];
-            // ---- first layer -> operand row (two bf16 pieces) ----
+            // ---- first layer on the tensor cores: stage [x; u; 1] (two bf16 pieces, K = 16) and B1 in the part of the
+            //      operand tile that is free until the activations are written (the residual piece) ----
+            {
+                static_assert(d + 1 <= 8, "inputs and the constant fit the first k-group");
+                unsigned char* st = a_tile + sm.a_lo;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = q < d ? in[q] : (q == d ? 1.f : 0.f);
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(st + gtid * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(st + L.lbo_a() + gtid * 16) = zero;
+                *reinterpret_cast<uint4*>(st + L.a1_piece_bytes() + gtid * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(st + L.a1_piece_bytes() + L.lbo_a() + gtid * 16) = zero;
+                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.prm.mlp_w2) + 2 * L.b_piece_bytes());
+                uint4* dst = reinterpret_cast<uint4*>(st + 2 * L.a1_piece_bytes());
+                for (int e = gtid; e < 2 * L.b1_piece_bytes() / 16; e += 128) dst[e] = __ldg(src + e);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // this thread's accumulator reads of the last tile
+            group_sync();
+            if (gwarp == 0) {
+                if (elect_one()) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(a_tile + sm.a_lo);
+                    const uint32_t la = (uint32_t)L.lbo_a(), l1 = (uint32_t)L.lbo_b1();
+                    const uint64_t ah = umma_smem_desc(base, la, 128);
+                    const uint64_t al = umma_smem_desc(base + L.a1_piece_bytes(), la, 128);
+                    const uint64_t bh = umma_smem_desc(base + 2 * L.a1_piece_bytes(), l1, 128);
+                    const uint64_t bl = umma_smem_desc(base + 2 * L.a1_piece_bytes() + L.b1_piece_bytes(), l1, 128);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem_acc), "l"(ah), "l"(bh), "r"(idesc1), "r"(0u));
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem_acc), "l"(ah), "l"(bl), "r"(idesc1), "r"(1u));
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem_acc), "l"(al), "l"(bh), "r"(idesc1 | (1u << 13)), "r"(1u));
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+                                 : "memory");
+                }
+                __syncwarp();
+            }
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- own row of pre-activations: ReLU, two bf16 pieces -> operand row of the hidden layer ----
             {
                 unsigned char* row_hi = a_tile + sm.a_hi + gtid * 16;
                 unsigned char* row_lo = a_tile + sm.a_lo + gtid * 16;
-                for (int k0 = 0; k0 < L.Kp; k0 += 8) {
-                    float v[8];
+                for (int c0 = 0; c0 < L.Kp; c0 += 16) {
+                    uint32_t v[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(tmem_row + (uint32_t)c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float* wr = w1b + (k0 + q) * (d + 1);
-                        float sacc = wr[d];
-#pragma unroll
-                        for (int r = 0; r < d; ++r) sacc = fmaf(wr[r], in[r], sacc);
-                        v[q] = fmaxf(sacc, 0.f);
-                    }
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-                    *reinterpret_cast<uint4*>(row_hi + (k0 >> 3) * L.lbo_a()) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(row_lo + (k0 >> 3) * L.lbo_a()) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int q = 0; q < 8; ++q)
+                        split_bf16x2(fmaxf(__uint_as_float(v[2 * q]), 0.f), fmaxf(__uint_as_float(v[2 * q + 1]), 0.f), hi[q], lo[q]);
+                    *reinterpret_cast<uint4*>(row_hi + (c0 >> 3) * L.lbo_a()) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(row_hi + ((c0 >> 3) + 1) * L.lbo_a()) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(row_lo + (c0 >> 3) * L.lbo_a()) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(row_lo + ((c0 >> 3) + 1) * L.lbo_a()) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
