@@ -63,7 +63,11 @@ SIGNATURES = {
                                           _ull, _u, _u, _u, _ull, _i, _ll, _vp, _vp],
     "irs_smooth_reduce_chunks": [_i, _i, _vp, _i, _i, _vp, _vp],
     "irs_smooth_finalize_peer": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i,
-                                 _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp, _vp, _vp, _vp],
+                                 _i, _i, ctypes.c_double, ctypes.c_double, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "irs_smooth_push_supported": [_i, _i],
+    "irs_smooth_zero_order_accumulate_push": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _ll, _vp, _vp,
+                                              _ull, _u, _u, _u, _ull, _i, _ll, _vp,
+                                              _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
     "irs_smooth_finalize_peer_capacity": [_i, _i, ctypes.POINTER(_i)],
     "irs_smooth_finalize_gather": [_i, _c_double_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i,
                                    _i, _i, ctypes.c_double, ctypes.c_double, _i, _vp, _vp],

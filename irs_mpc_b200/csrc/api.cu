@@ -234,6 +234,7 @@ static int fill_smooth_args(SmoothArgs* a, int system, const double* params_host
                             unsigned iter, unsigned stream_id, unsigned p0, unsigned long long i0,
                             int C, long long S, float* partials) {
     if (load_params(system, params_host, nparams, &a->prm)) return 1;
+    memset(&a->push, 0, sizeof(a->push));
     IRS_REQUIRE(x_nom && u_nom && partials, "null pointer argument");
     IRS_REQUIRE(P >= 1 && N >= 1, "need at least one nominal point and one sample (P=%d, N=%lld)", P, N);
     IRS_REQUIRE(C >= 1 && S >= 1 && (long long)C * S >= N, "chunk plan (C=%d, S=%lld) does not cover N=%lld", C, S, N);
@@ -473,16 +474,20 @@ int irs_smooth_plan(int system, int order, int P, long long N, long long chunk_s
     return 0;
 }
 
-int irs_smooth_zero_order_accumulate(int system, const double* params_host, int nparams, int flags,
-                                     const double* x_nom, const double* u_nom, int P, long long N,
-                                     const float* sigma_host, const float* noise,
-                                     unsigned long long seed, unsigned iter, unsigned stream_id,
-                                     unsigned p0, unsigned long long i0,
-                                     int C, long long S, float* partials, void* stream) {
+static int zero_order_accumulate_impl(int system, const double* params_host, int nparams, int flags,
+                                      const double* x_nom, const double* u_nom, int P, long long N,
+                                      const float* sigma_host, const float* noise,
+                                      unsigned long long seed, unsigned iter, unsigned stream_id,
+                                      unsigned p0, unsigned long long i0,
+                                      int C, long long S, float* partials, const PeerPushArgs* push, void* stream) {
     SmoothArgs a;
     if (fill_smooth_args(&a, system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma_host, noise,
                          seed, iter, stream_id, p0, i0, C, S, partials))
         return 1;
+    if (push != nullptr) {
+        IRS_REQUIRE(use_tensor_cores(system), "system %d accumulates on the CUDA cores: no in-kernel push", system);
+        a.push = *push;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (use_tensor_cores(system)) {
         switch (system) {
@@ -506,6 +511,40 @@ int irs_smooth_zero_order_accumulate(int system, const double* params_host, int 
     }
     set_error("unknown system id %d", system);
     return 1;
+}
+
+int irs_smooth_zero_order_accumulate(int system, const double* params_host, int nparams, int flags,
+                                     const double* x_nom, const double* u_nom, int P, long long N,
+                                     const float* sigma_host, const float* noise,
+                                     unsigned long long seed, unsigned iter, unsigned stream_id,
+                                     unsigned p0, unsigned long long i0,
+                                     int C, long long S, float* partials, void* stream) {
+    return zero_order_accumulate_impl(system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma_host, noise, seed,
+                                      iter, stream_id, p0, i0, C, S, partials, nullptr, stream);
+}
+
+int irs_smooth_push_supported(int system, int order) {
+    return (system >= 0 && system < kNumSystems && order == 0 && system != kMlp21 && use_tensor_cores(system)) ? 1 : 0;
+}
+
+int irs_smooth_zero_order_accumulate_push(int system, const double* params_host, int nparams, int flags,
+                                          const double* x_nom, const double* u_nom, int P, long long N,
+                                          const float* sigma_host, const float* noise,
+                                          unsigned long long seed, unsigned iter, unsigned stream_id,
+                                          unsigned p0, unsigned long long i0,
+                                          int C, long long S, float* partials,
+                                          const void* peer_bufs_dev, const void* peer_flags_dev, const int* epoch_dev,
+                                          unsigned int* point_counters, long long slot_stride, int flag_stride,
+                                          int rank, int world, void* stream) {
+    IRS_REQUIRE(peer_bufs_dev && peer_flags_dev && epoch_dev && point_counters, "null pointer argument");
+    IRS_REQUIRE(world >= 1 && world <= kFinalizeThreads && rank >= 0 && rank < world, "bad rank / world");
+    IRS_REQUIRE(irs_smooth_push_supported(system, 0), "system %d has no in-kernel push (irs_smooth_push_supported)", system);
+    const int width = irs_partial_width(system, 0);
+    IRS_REQUIRE(slot_stride >= (long long)P * width && flag_stride >= P, "exchange buffers too small for P=%d", P);
+    const PeerPushArgs push{(double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, point_counters,
+                            slot_stride, flag_stride, rank, world};
+    return zero_order_accumulate_impl(system, params_host, nparams, flags, x_nom, u_nom, P, N, sigma_host, noise, seed,
+                                      iter, stream_id, p0, i0, C, S, partials, &push, stream);
 }
 
 int irs_smooth_first_order_accumulate(int system, const double* params_host, int nparams, int flags,
@@ -667,7 +706,7 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
                              const double* x_nom, const double* u_nom, int P, int C, const float* partials,
                              const void* peer_bufs_dev, const void* peer_flags_dev, int* epoch_dev,
                              unsigned int* done_counter, long long slot_stride, int flag_stride,
-                             int rank, int world, double timeout_s, double n_total, int centered,
+                             int rank, int world, double timeout_s, double n_total, int centered, int prepushed,
                              double* At, double* Bt, double* ct, int* status, void* stream) {
     IRS_REQUIRE(system >= 0 && system < kNumSystems, "unknown system id %d", system);
     IRS_REQUIRE(partials && peer_bufs_dev && peer_flags_dev && epoch_dev && done_counter, "null pointer argument");
@@ -680,7 +719,7 @@ int irs_smooth_finalize_peer(int system, const double* params_host, int nparams,
     IRS_REQUIRE(P <= resident, "the fused exchange needs its %d blocks co-resident (%d fit): use the all-gather path", P, resident);
     PeerFusedArgs px{(double* const*)peer_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, done_counter,
                      slot_stride, flag_stride, rank, world, (unsigned long long)(timeout_s * 1e9),
-                     kPeerExchange, 0, 0, 0};
+                     kPeerExchange, 0, 0, 0, prepushed ? 1 : 0};
     return smooth_finalize_impl(system, params_host, nparams, order, x_nom, u_nom, P, C, partials, nullptr, 1, 0,
                                 n_total, centered, At, Bt, ct, status, &px, stream);
 }
@@ -698,7 +737,7 @@ int irs_smooth_finalize_gather(int system, const double* params_host, int nparam
     const SystemDims dm = system_dims(system);
     IRS_REQUIRE(out_stride >= (long long)P_total * (dm.n * (dm.n + dm.m + 1) + 1), "output buffers too small");
     PeerFusedArgs px{(double* const*)peer_out_bufs_dev, (int* const*)peer_flags_dev, epoch_dev, done_counter,
-                     0, 0, rank, world, (unsigned long long)(timeout_s * 1e9), kPeerGather, p0, P_total, out_stride};
+                     0, 0, rank, world, (unsigned long long)(timeout_s * 1e9), kPeerGather, p0, P_total, out_stride, 0};
     if (P == 0) {      // this rank owns no timestep: it still takes part in the step
         peer_gather_wait_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(px);
         return check_launch("peer_gather_wait_kernel");
