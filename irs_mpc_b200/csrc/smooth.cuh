@@ -703,15 +703,18 @@ __device__ __forceinline__ int peer_exchange_point(const FinalizeArgs& a, int p,
         const int* local = x.peer_flags[x.rank] + (long long)tid * x.flag_stride + p;
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        // relaxed polls, ONE acquire fence once the flag is there (an acquire load per poll is a MEMBAR.SYS and an L1
+        // invalidate each time round)
         while (true) {
             int v;
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+            asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
             if (v >= epoch) break;
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             if (t - t0 > x.timeout_ns) { late = 1;  break; }
             __nanosleep(100);
         }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
     *timed_out = __syncthreads_or(late) != 0;
     src->partials = nullptr;
@@ -791,7 +794,7 @@ __device__ __forceinline__ void peer_gather_wait(const PeerFusedArgs& x, int epo
     for (int g = tid; g < x.P_total; g += BT) {
         while (true) {
             int v;
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local + g) : "memory");
+            asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local + g) : "memory");
             if (v >= epoch) break;
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -799,6 +802,7 @@ __device__ __forceinline__ void peer_gather_wait(const PeerFusedArgs& x, int epo
             __nanosleep(100);
         }
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");      // one acquire after the relaxed polls
     __syncthreads();
     if (tid == 0) {
         *x.done_counter = 0u;
