@@ -931,10 +931,19 @@ static int tvlqr_riccati_impl(int n, int m, const double* At, const double* Bt, 
     const bool extra = Hinv_out != nullptr || P_out != nullptr;     // only the generic kernel writes them
     static const bool no_tiles = getenv("IRS_TVLQR_NO_TILES") != nullptr;
     // many instances of a 4-divisible problem (quadrotor): two instances per warp, 4 x 4 register tiles
-    // (tvlqr.cuh: tvlqr_riccati_packed_kernel).  The switch point lies above every instance count the
-    // few-instance callers use and below a rank's share of a sharded batch, so a problem's result does not
-    // depend on how a large batch is sharded.  IRS_TVLQR_VARIANT=block|warp overrides.
-    if (n == 12 && m == 4 && !extra && t_hi == 0 && I > 2 * num_sms() && getenv("IRS_TVLQR_VARIANT") == nullptr) {
+    // (tvlqr.cuh: tvlqr_riccati_packed_kernel).  That kernel's time is flat up to one block of eight instances per
+    // SM (0.37 ms at T = 100 up to 1,184 instances, then 0.49 / 0.64 / 0.83 ms at 2048 / 3072 / 4096); the block
+    // kernel takes 0.19 / 0.23 / 0.30 / 0.47 / 0.71 / 1.28 ms at 300 / 512 / 768 / 1024 / 2048 / 4096 and crosses it
+    // between 768 and 1024 instances (IRS_PACKED_MIN_INSTANCES; measured with tools/batched_bench.py).  Results of
+    // the two kernels agree to 1e-10 (summation order), so a shard of 512 instances and the unsharded 4096 differ at
+    // that level.  IRS_TVLQR_VARIANT=block|warp|packed overrides.
+    static const long long packed_min = [] {
+        const char* e = getenv("IRS_PACKED_MIN_INSTANCES");
+        return e && atoll(e) > 0 ? atoll(e) : 1000ll;
+    }();
+    const char* variant = getenv("IRS_TVLQR_VARIANT");
+    const bool force_packed = variant != nullptr && !strcmp(variant, "packed");
+    if (n == 12 && m == 4 && !extra && t_hi == 0 && (force_packed || (variant == nullptr && I >= packed_min))) {
         auto kern = tvlqr_riccati_packed_kernel<12, 4>;
         const int smem = (int)sizeof(RicPackSmem<12, 4>);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)

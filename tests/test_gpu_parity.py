@@ -346,8 +346,8 @@ def test_solve_tvlqr_matches_oracle(api, n, m):
 
 @pytest.mark.parametrize("I", [297, 1030])
 def test_packed_riccati_for_many_instances_matches_oracle_and_block_kernel(api, I, monkeypatch):
-    """Above 2 x 148 instances the quadrotor-sized backward pass runs two instances per warp with 4 x 4
-    register tiles (tvlqr_riccati_packed_kernel): gains against the float64 oracle (1e-9) and against the
+    """For thousands of instances the quadrotor-sized backward pass runs two instances per warp with 4 x 4
+    register tiles (tvlqr_riccati_packed_kernel; forced here below its switch point): gains against the float64 oracle (1e-9) and against the
     one-block-per-instance kernel (IRS_TVLQR_VARIANT=block; different summation order: 1e-10), instance
     counts that do not fill the last warp / block, per-instance desired trajectories, non-SPD steps flagged."""
     import torch
@@ -365,7 +365,7 @@ def test_packed_riccati_for_many_instances_matches_oracle_and_block_kernel(api, 
     xd = rng.standard_normal((I, T + 1, n))
     dev = lambda v: _device.to_device(np.ascontiguousarray(v))
     args = (dev(At), dev(Bt), dev(ct), dev(Q), dev(Qd), dev(R), dev(xd), (T + 1) * n)
-    monkeypatch.delenv("IRS_TVLQR_VARIANT", raising=False)
+    monkeypatch.setenv("IRS_TVLQR_VARIANT", "packed")
     K, k, status = riccati_device(*args)
     assert int(status.sum().item()) == 0
     K, k = _device.to_numpy(K), _device.to_numpy(k)
@@ -377,7 +377,9 @@ def test_packed_riccati_for_many_instances_matches_oracle_and_block_kernel(api, 
         Ko, ko = cr.tvlqr_riccati(At[b], Bt[b], ct[b], Q, 0.5 * (Qd + Qd.T), R, xd[b])
         assert rel_err(K[b], Ko) < 1e-9 and rel_err(k[b], ko) < 1e-9, b
     # an indefinite terminal weight (H = R/2 + B'PB not SPD) is flagged for every instance
+    monkeypatch.setenv("IRS_TVLQR_VARIANT", "packed")
     K2, k2, st2 = riccati_device(args[0], args[1], args[2], args[3], dev(-np.eye(n)), dev(1e-6 * R), args[6], args[7])
+    monkeypatch.delenv("IRS_TVLQR_VARIANT", raising=False)
     assert int(st2.sum().item()) == I
 
 

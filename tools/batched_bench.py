@@ -13,7 +13,7 @@ from irs_mpc_b200 import _device, example_configs as ec                         
 from irs_mpc_b200.all import BatchedIrsLqrZeroOrder, GaussianSampling, QuadrotorDynamics   # noqa: E402
 from irs_mpc_b200.tv_lqr import riccati_device                                             # noqa: E402
 
-I, T = 4096, 100
+I, T = int(os.environ.get("BB_I", "4096")), 100
 cfg = ec.quadrotor(T=T)
 system = QuadrotorDynamics(cfg["h"])
 x0, xd = ec.quadrotor_batch(0, I, T=T, total=I)
