@@ -573,21 +573,40 @@ __device__ __forceinline__ PartialSource partial_source(const FinalizeArgs& a) {
 // unrolled by eight so that the loads are in flight together while the adds keep their order).
 __device__ __forceinline__ double sum_partials(const PartialSource& a, int p, int e, int width) {
     double s = 0.0;
-    for (int r = 0; r < a.R; ++r) {
-        if (a.reduced != nullptr) {
-            s += __ldcg(a.reduced + r * a.rank_stride + (long long)p * width + e);      // L2: may be peer-written
-        } else {
-            const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * width + e;
-            int c = 0;
-            for (; c + 8 <= a.C; c += 8) {       // eight loads in flight, adds in chunk order
-                float v[8];
+    if (a.reduced != nullptr) {
+        // rank blocks (L2: may be peer-written): eight loads in flight, adds in rank order — one load latency per
+        // eight ranks instead of one per rank (8 GPUs: 32 serial L2 round trips per thread of the fused exchange)
+        const double* src = a.reduced + (long long)p * width + e;
+        int r = 0;
+        for (; r + 8 <= a.R; r += 8) {
+            double v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = src[(long long)(c + k) * width];
+            for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + (long long)(r + k) * a.rank_stride);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) s += (double)v[k];
-            }
-            for (; c < a.C; ++c) s += (double)src[(long long)c * width];
+            for (int k = 0; k < 8; ++k) s += v[k];
         }
+        if (r + 4 <= a.R) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldcg(src + (long long)(r + k) * a.rank_stride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += v[k];
+            r += 4;
+        }
+        for (; r < a.R; ++r) s += __ldcg(src + (long long)r * a.rank_stride);
+        return s;
+    }
+    for (int r = 0; r < a.R; ++r) {
+        const float* src = a.partials + r * a.rank_stride + ((long long)p * a.C) * width + e;
+        int c = 0;
+        for (; c + 8 <= a.C; c += 8) {       // eight loads in flight, adds in chunk order
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = src[(long long)(c + k) * width];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += (double)v[k];
+        }
+        for (; c < a.C; ++c) s += (double)src[(long long)c * width];
     }
     return s;
 }
