@@ -232,11 +232,18 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    tick = torch.zeros((1,), dtype=torch.float32, device="cuda")
+
     def timed(fn, steps, warmup):
         for k in range(warmup):
             fn(k)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            # the host threads leave the barrier up to ~0.2 ms apart, which the first exchange of the timed steps
+            # would pay as a one-time wait (7 us per step at 30 steps): align the ranks ON THE DEVICE with a
+            # stream-ordered collective right before the start event — no host sync, the timed launches queue behind it
+            dist.all_reduce(tick)
         e0.record()
         for k in range(steps):
             fn(warmup + k)
