@@ -52,6 +52,10 @@ struct MlpTcLayout {
     // TMEM columns of a tile group: the accumulator holds the first layer's Kp, then the hidden layer's Np columns
     __host__ __device__ int tmem_cols_per_group() const { return (Kp > 128 || Np > 128) ? 256 : 128; }
     static __host__ __device__ int tmem_alloc_cols(int cols) { return cols <= 128 ? 128 : (cols <= 256 ? 256 : 512); }
+    // bytes the first-layer operands of a tile need: A1 hi | A1 lo | B1 hi | B1 lo.  They live in the residual piece of
+    // the operand tile (free until the activations are written) when it is large enough, else in a region of their own
+    __host__ __device__ int stage_bytes() const { return 2 * a1_piece_bytes() + 2 * b1_piece_bytes(); }
+    __host__ __device__ bool stage_in_tile() const { return a_piece_bytes() >= stage_bytes(); }
     // device blob of operand pieces: [W2 hi | W2 lo | B1 hi | B1 lo]
     __host__ __device__ int blob_bytes() const { return 2 * b_piece_bytes() + 2 * b1_piece_bytes(); }
 };
@@ -64,12 +68,14 @@ struct MlpTcSmem {
     static constexpr int kMaxGroups = 3;
     MlpTcLayout L;
     int G;
-    int a_hi, a_lo, a_stride, b_hi, b_lo, w1b, w3, act1, act2, fbar, slabs, bar, total;
+    int a_hi, a_lo, a_stage, a_stride, b_hi, b_lo, w1b, w3, act1, act2, fbar, slabs, bar, total;
     __host__ __device__ MlpTcSmem(const MlpTcLayout& l, int groups) : L(l), G(groups) {
         int o = 0;
-        a_stride = 2 * L.a_piece_bytes();            // per group: [hi piece | lo piece]
+        // per group: [hi piece | lo piece (| first-layer staging, when the lo piece is too small for it)]
+        a_stride = 2 * L.a_piece_bytes() + (L.stage_in_tile() ? 0 : L.stage_bytes());
         a_hi = o;
         a_lo = o + L.a_piece_bytes();
+        a_stage = L.stage_in_tile() ? a_lo : o + 2 * L.a_piece_bytes();
         o += G * a_stride;
         b_hi = o;  o += L.b_piece_bytes();
         b_lo = o;  o += L.b_piece_bytes();
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
             //      operand tile that is free until the activations are written (the residual piece) ----
             {
                 static_assert(d + 1 <= 8, "inputs and the constant fit the first k-group");
-                unsigned char* st = a_tile + sm.a_lo;
+                unsigned char* st = a_tile + sm.a_stage;
                 float v[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = q < d ? in[q] : (q == d ? 1.f : 0.f);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
             if (gwarp == 0) {
                 if (elect_one()) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t base = smem_u32(a_tile + sm.a_lo);
+                    const uint32_t base = smem_u32(a_tile + sm.a_stage);
                     const uint32_t la = (uint32_t)L.lbo_a(), l1 = (uint32_t)L.lbo_b1();
                     const uint64_t ah = umma_smem_desc(base, la, 128);
                     const uint64_t al = umma_smem_desc(base + L.a1_piece_bytes(), la, 128);

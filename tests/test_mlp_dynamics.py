@@ -166,6 +166,42 @@ def test_tensor_core_engine_matches_the_per_thread_functor(api, system, gold, N,
         assert rel_err(got, want) < FP32_RTOL
 
 
+@pytest.mark.parametrize("H1,H2", [(16, 16), (64, 32), (100, 37), (111, 112), (128, 128), (5, 1)])
+def test_other_hidden_widths(api, H1, H2, monkeypatch):
+    """Random networks of other widths (operand padding, TMEM columns beyond 128 for H1 = 128, several tile groups
+    per block): tensor-core engine against the oracle on the same Philox deltas and against the per-thread engine."""
+    from irs_mpc_b200 import _graph
+    monkeypatch.setattr(_graph, "USE_GRAPHS", False)
+    rng = np.random.default_rng(100 * H1 + H2)
+    layers = [((rng.standard_normal((H1, 3)) / np.sqrt(3)).astype(np.float32), (0.3 * rng.standard_normal(H1)).astype(np.float32)),
+              ((rng.standard_normal((H2, H1)) / np.sqrt(H1)).astype(np.float32), (0.3 * rng.standard_normal(H2)).astype(np.float32)),
+              ((rng.standard_normal((2, H2)) / np.sqrt(H2)).astype(np.float32), (0.3 * rng.standard_normal(2)).astype(np.float32))]
+    s = api.MlpDynamics(layers)
+    orc = MlpOracle([a for pair in layers for a in pair])
+    pts = rng.standard_normal((33, 3))
+    assert rel_err(s.dynamics_batch(pts[:, :2], pts[:, 2:]), orc.dynamics_batch(pts[:, :2], pts[:, 2:])) < 1e-5
+    assert rel_err(s.jacobian_xu_batch(pts[:, :2], pts[:, 2:]), orc.jacobian_xu_batch(pts[:, :2], pts[:, 2:])) < 1e-5
+    T, N = 4, 3000
+    cfg = ec.pendulum_nn(T=T)
+    u_trj = cfg["u_trj_initial"] + rng.standard_normal((T, 1))
+    res = {}
+    for engine in ("1", "0"):
+        monkeypatch.setenv("IRS_MLP_ENGINE", engine)
+        sampler = api.GaussianSampling(cfg["sigma"][:2], cfg["sigma"][2:], N, power=cfg["power"], seed=41)
+        solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T, u_trj=u_trj), sampler)
+        res[engine] = solver.get_TV_matrices(solver.x_trj, solver.u_trj)
+        deltas = sampler.deltas(T, solver.iter).astype(np.float64)
+        x_trj = solver.x_trj
+    want = cr.zero_order_tv_matrices(orc, x_trj, u_trj, deltas)
+    for got, w, other in zip(res["1"], want, res["0"]):
+        assert rel_err(got, w) < FP32_RTOL
+        assert rel_err(got, other) < FP32_RTOL
+    with pytest.raises(Exception, match="hidden widths"):
+        api.MlpDynamics([(np.zeros((129, 3), np.float32), np.zeros(129, np.float32)),
+                         (np.zeros((8, 129), np.float32), np.zeros(8, np.float32)),
+                         (np.zeros((2, 8), np.float32), np.zeros(2, np.float32))])
+
+
 def test_first_order_and_exact_match_oracle(api, system, gold):
     T, N = 5, 1500
     cfg = ec.pendulum_nn(T=T)
