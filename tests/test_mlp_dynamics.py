@@ -238,3 +238,35 @@ def test_descent_matches_oracle_and_iterations_lower_the_cost(api, system, gold)
     first = solver.cost
     solver.iterate(6)
     assert len(solver.cost_lst) == 8 and solver.cost < 0.6 * first
+
+
+def test_batched_instances_and_cem_run_on_the_learned_system(api, system, gold):
+    """The instance-batched path (one warp per instance in the Riccati and rollout kernels) and the CEM baseline
+    (one warp per candidate) on the learned system: every instance equals its own single-instance solver bit for bit."""
+    T, N, I = 30, 2000, 5
+    cfg = ec.pendulum_nn(T=T)
+    rng = np.random.default_rng(8)
+    x0 = 0.3 * rng.standard_normal((I, 2))
+    smp = api.GaussianSampling(cfg["sigma"][:2], cfg["sigma"][2:], N, power=cfg["power"], seed=77)
+    bat = api.BatchedIrsLqrZeroOrder(system, cfg["Q"], cfg["Qd"], cfg["R"], x0, cfg["xd_trj"], cfg["u_trj_initial"], smp)
+    xb, ub, cb = bat.iterate(1)
+    for b in (0, 3):
+        smp1 = api.GaussianSampling(cfg["sigma"][:2], cfg["sigma"][2:], N, power=cfg["power"], seed=77, stream_id=0)
+        one = api.BatchedIrsLqrZeroOrder(system, cfg["Q"], cfg["Qd"], cfg["R"], x0[b:b + 1], cfg["xd_trj"],
+                                         cfg["u_trj_initial"], smp1, instance_offset=b)
+        x1, u1, c1 = one.iterate(1)
+        np.testing.assert_array_equal(x1[0], xb[b])
+        np.testing.assert_array_equal(u1[0], ub[b])
+    assert np.all(np.isfinite(cb))
+    prm = api.CemParameters()
+    prm.Q, prm.Qd, prm.R, prm.x0, prm.xd_trj = cfg["Q"], cfg["Qd"], cfg["R"], cfg["x0"], cfg["xd_trj"]
+    prm.u_trj_initial = cfg["u_trj_initial"]
+    prm.n_elite, prm.batch_size, prm.initial_std = 10, 64, np.array([1.0])
+    np.random.seed(3)
+    cem = api.CrossEntropyMethod(system, prm)
+    first = cem.cost
+    cem.iterate(4, verbose=False)
+    assert len(cem.cost_lst) == 6 and min(cem.cost_lst[1:]) < first
+    orc = MlpOracle([gold[k] for k in KEYS])
+    x_o = cr.rollout(orc, cfg["x0"], cem.u_trj)
+    assert rel_err(cem.x_trj, x_o) < 1e-4
