@@ -397,6 +397,14 @@ static void launch_rollout(const RolloutArgs& a, cudaStream_t st) {
             return;
         }
     }
+    if constexpr (is_mlp<Sys>::value) {
+        // learned dynamics: one block per instance with the network in registers (IRS_ROLLOUT_MLP=0: the warp kernel)
+        const char* e = getenv("IRS_ROLLOUT_MLP");
+        if (e == nullptr || atoi(e) != 0) {
+            rollout_mlp_kernel<Sys, CLOSED><<<(unsigned)a.I, kMlpMaxHidden, 0, st>>>(a);
+            return;
+        }
+    }
     rollout_kernel<Sys, CLOSED><<<(a.I + kRolloutWarps - 1) / kRolloutWarps, 32 * kRolloutWarps, 0, st>>>(a);
 }
 

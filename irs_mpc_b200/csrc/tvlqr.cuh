@@ -926,6 +926,151 @@ __global__ void __launch_bounds__(32 * kRolloutWarps) rollout_kernel(const Rollo
     if (lane == 0) a.cost[inst] = c;
 }
 
+// Rollout of LEARNED dynamics (systems.cuh: Mlp): one block of 128 threads per instance, thread j = hidden unit j
+// with ITS rows of the first two layers in registers for the whole trajectory (the network does not change from
+// step to step), the activations handed over through shared memory, two block barriers per layer.  The last layer
+// runs on 4 n lanes: lane (k, c) carries partial chain c of output k.  Every unit is summed in exactly the order of
+// Mlp::dot_row (four interleaved chains), so the trajectory is bit-identical to stepping the per-thread functor
+// (test); a step costs ~0.3 us instead of the ~7 us of one warp reading the weights through L1 every step.
+template <class Sys, bool CLOSED>
+__global__ void __launch_bounds__(kMlpMaxHidden) rollout_mlp_kernel(const RolloutArgs a) {
+    constexpr int n = Sys::N, m = Sys::M, d = Sys::D, H = kMlpMaxHidden;
+    static_assert(4 * n <= 32, "last layer: four chain lanes per output inside warp 0");
+    __shared__ float in_s[d], a1_s[H], a2_s[H], out_s[n];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int inst = blockIdx.x;
+    const Sys sys(a.prm);
+    const MlpView& net = sys.net;
+    const int H1 = net.H1, H2 = net.H2;
+    const double* xd_i = a.xd + inst * a.xd_stride;
+    // this thread's unit: first-layer row, hidden-layer row (zero weights beyond the widths: the products vanish
+    // and the sums of the live units are unchanged)
+    float w1r[d], b1r = 0.f, b2r = 0.f;
+    float w2r[H];
+#pragma unroll
+    for (int q = 0; q < d; ++q) w1r[q] = tid < H1 ? __ldg(net.w1 + tid * d + q) : 0.f;
+    if (tid < H1) b1r = __ldg(net.b1 + tid);
+    if (tid < H2) b2r = __ldg(net.b2 + tid);
+#pragma unroll
+    for (int q = 0; q < H; ++q) w2r[q] = (tid < H2 && q < H1) ? __ldg(net.w2t + (long long)q * H2 + tid) : 0.f;
+    // last layer: lane (k, c) of warp 0 holds w3[k][q] for q = c, c + 4, ... below the multiple of four, lane (k, 0)
+    // also the tail q >= 4 (H2 / 4) — the order of dot_row
+    const int ok = lane >> 2, oc = lane & 3;
+    const int main4 = H2 & ~3;
+    float w3r[H / 4], w3t[3];
+#pragma unroll
+    for (int i = 0; i < H / 4; ++i) w3r[i] = (tid < 4 * n && 4 * i + oc < main4) ? __ldg(net.w3 + (long long)ok * H2 + 4 * i + oc) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w3t[i] = (tid < 4 * n && oc == 0 && main4 + i < H2) ? __ldg(net.w3 + (long long)ok * H2 + main4 + i) : 0.f;
+    const float b3r = (tid < 4 * n && oc == 0) ? __ldg(net.b3 + ok) : 0.f;
+
+    double x[n], u[m];
+#pragma unroll
+    for (int q = 0; q < n; ++q) x[q] = a.x0[(long long)inst * n + q];
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < n; ++q) a.x_trj[((long long)inst * (a.T + 1)) * n + q] = x[q];
+    }
+    // gains / inputs of the NEXT step are loaded while the current one is evaluated (no global round trip on the
+    // sequential path)
+    constexpr int kGain = CLOSED ? m * n + m : m;
+    double gain[kGain], gain_next[kGain];
+    auto fetch = [&](int t, double (&g)[kGain]) {
+        const long long it = (long long)inst * a.T + t;
+#pragma unroll
+        for (int e = 0; e < kGain; ++e) {
+            if (CLOSED) g[e] = e < m * n ? a.K[it * m * n + e] : a.k[it * m + (e - m * n)];
+            else g[e] = a.u_in[it * m + e];
+        }
+    };
+    fetch(0, gain_next);
+    for (int t = 0; t < a.T; ++t) {
+        const long long it = (long long)inst * a.T + t;
+#pragma unroll
+        for (int e = 0; e < kGain; ++e) gain[e] = gain_next[e];
+        if (t + 1 < a.T) fetch(t + 1, gain_next);
+        // every thread carries the state and forms the input (same operations on the same values)
+        if (CLOSED) {
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                double acc = gain[m * n + i];
+#pragma unroll
+                for (int q = 0; q < n; ++q) acc += gain[i * n + q] * x[q];
+                u[i] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < m; ++i) u[i] = gain[i];
+        }
+        float in[d];
+#pragma unroll
+        for (int q = 0; q < n; ++q) in[q] = (float)x[q];
+#pragma unroll
+        for (int q = 0; q < m; ++q) in[n + q] = (float)u[q];
+        // layer 1 (as Mlp::hidden: sequential fmaf from the bias)
+        {
+            float sacc = b1r;
+#pragma unroll
+            for (int q = 0; q < d; ++q) sacc = fmaf(w1r[q], in[q], sacc);
+            a1_s[tid] = tid < H1 ? fmaxf(sacc, 0.f) : 0.f;
+        }
+        __syncthreads();
+        // layer 2 (as Mlp::dot_row with the transposed weights: chains q % 4 below the multiple of four, tail on chain 0)
+        {
+            float s0 = b2r, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const int m4 = H1 & ~3;
+#pragma unroll
+            for (int q = 0; q < H; q += 4) {
+                if (q < m4) {
+                    const float4 av = *reinterpret_cast<const float4*>(a1_s + q);
+                    s0 = fmaf(w2r[q], av.x, s0);
+                    s1 = fmaf(w2r[q + 1], av.y, s1);
+                    s2 = fmaf(w2r[q + 2], av.z, s2);
+                    s3 = fmaf(w2r[q + 3], av.w, s3);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < H; ++q)
+                if (q >= m4 && q < H1) s0 = fmaf(w2r[q], a1_s[q], s0);
+            a2_s[tid] = tid < H2 ? fmaxf((s0 + s1) + (s2 + s3), 0.f) : 0.f;
+        }
+        __syncthreads();
+        // layer 3 on 4 n lanes of warp 0
+        if (tid < 32) {
+            float sc = b3r;
+#pragma unroll
+            for (int i = 0; i < H / 4; ++i)
+                if (4 * i < main4) sc = fmaf(w3r[i], a2_s[4 * i + oc], sc);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (main4 + i < H2) sc = fmaf(w3t[i], a2_s[main4 + i], sc);      // (zero weights off lane (k, 0))
+            const float p1 = __shfl_down_sync(0xffffffffu, sc, 1);
+            const float s01 = sc + p1;                        // lanes c = 0: s0 + s1; c = 2: s2 + s3
+            const float p2 = __shfl_down_sync(0xffffffffu, s01, 2);
+            if (tid < 4 * n && oc == 0) out_s[ok] = s01 + p2;  // (s0 + s1) + (s2 + s3)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < n; ++q) x[q] = (double)out_s[q];
+        if (tid == 0) {
+            if (CLOSED) {
+#pragma unroll
+                for (int i = 0; i < m; ++i) a.u_trj[it * m + i] = u[i];
+            }
+#pragma unroll
+            for (int q = 0; q < n; ++q) a.x_trj[((long long)inst * (a.T + 1) + t + 1) * n + q] = x[q];
+        }
+    }
+    // cost of the finished trajectory by warp 0 (thread 0's stores: block-visible after the fence + barrier)
+    __threadfence_block();
+    __syncthreads();
+    if (tid < 32) {
+        const double* u_used = CLOSED ? a.u_trj + (long long)inst * a.T * m : a.u_in + (long long)inst * a.T * m;
+        const double c = warp_trajectory_cost<n, m>(a.x_trj + (long long)inst * (a.T + 1) * n, u_used, xd_i, a.Q, a.R, a.T, lane);
+        if (lane == 0) a.cost[inst] = c;
+    }
+}
+
 // Rollout for systems whose next Euler angles do not depend on the input (Sys::kTrigAhead, the
 // quadrotor): the three fp64 sincos evaluations are two thirds of a step on the sequential path, and
 // the angles of step t+1 are known at the START of step t.  One block of two warps per instance:
