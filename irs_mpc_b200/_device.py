@@ -28,6 +28,8 @@ def to_device(a, dtype=torch.float64):
     arr = np.ascontiguousarray(np.asarray(a), dtype={torch.float64: np.float64,
                                                      torch.float32: np.float32,
                                                      torch.int32: np.int32}[dtype])
+    if not arr.flags.writeable:      # e.g. a contiguous slice of np.broadcast_to: torch refuses read-only memory
+        arr = arr.copy()
     return torch.from_numpy(arr).to(dev, non_blocking=False)
 
 
