@@ -31,6 +31,21 @@
 
 namespace irs {
 
+// 16 accumulator columns of this thread's TMEM lane -> registers (asynchronous), and the wait that makes them
+// readable.  The wait names the registers as in / out operands, so the compiler cannot move a use above it; loads
+// are issued one chunk ahead of the chunk being processed (the TMEM load latency hides behind the arithmetic).
+#define IRS_TMEM_LD16(v, taddr)                                                                                             \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"    \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),           \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])      \
+                 : "r"(taddr))
+#define IRS_TMEM_WAIT16(v)                                                                                                  \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                           \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),           \
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])      \
+                 :                                                                                                          \
+                 : "memory")
+
 struct MlpTcLayout {
     int H1, H2, Kp, Np;
     __host__ __device__ MlpTcLayout(int h1, int h2)
@@ -267,14 +282,7 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
             {
                 unsigned char* row_hi = a_tile + sm.a_hi + gtid * 16;
                 unsigned char* row_lo = a_tile + sm.a_lo + gtid * 16;
-                for (int c0 = 0; c0 < L.Kp; c0 += 16) {
-                    uint32_t v[16];
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                        : "r"(tmem_row + (uint32_t)c0));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                auto to_operand = [&](const uint32_t (&v)[16], int c0) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -283,6 +291,18 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
                     *reinterpret_cast<uint4*>(row_hi + ((c0 >> 3) + 1) * L.lbo_a()) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(row_lo + (c0 >> 3) * L.lbo_a()) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(row_lo + ((c0 >> 3) + 1) * L.lbo_a()) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                };
+                uint32_t va[16], vb[16];
+                IRS_TMEM_LD16(va, tmem_row);
+                for (int c0 = 0; c0 < L.Kp; c0 += 32) {
+                    IRS_TMEM_WAIT16(va);
+                    if (c0 + 16 < L.Kp) IRS_TMEM_LD16(vb, tmem_row + (uint32_t)(c0 + 16));
+                    to_operand(va, c0);
+                    if (c0 + 16 < L.Kp) {
+                        IRS_TMEM_WAIT16(vb);
+                        if (c0 + 32 < L.Kp) IRS_TMEM_LD16(va, tmem_row + (uint32_t)(c0 + 32));
+                        to_operand(vb, c0 + 16);
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -321,19 +341,26 @@ __global__ void __launch_bounds__(128 * MlpTcSmem<Sys>::kMaxGroups) smooth_zero_
             float o[n];
 #pragma unroll
             for (int k = 0; k < n; ++k) o[k] = w3s[n * L.Np + k];
-            for (int c0 = 0; c0 < L.Np; c0 += 16) {
-                uint32_t v[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(tmem_row + (uint32_t)c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            {
+                auto last_layer = [&](const uint32_t (&v)[16], int c0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float h = fmaxf(__uint_as_float(v[q]), 0.f);
+                    for (int q = 0; q < 16; ++q) {
+                        const float h = fmaxf(__uint_as_float(v[q]), 0.f);
 #pragma unroll
-                    for (int k = 0; k < n; ++k) o[k] = fmaf(w3s[k * L.Np + c0 + q], h, o[k]);
+                        for (int k = 0; k < n; ++k) o[k] = fmaf(w3s[k * L.Np + c0 + q], h, o[k]);
+                    }
+                };
+                uint32_t va[16], vb[16];
+                IRS_TMEM_LD16(va, tmem_row);
+                for (int c0 = 0; c0 < L.Np; c0 += 32) {
+                    IRS_TMEM_WAIT16(va);
+                    if (c0 + 16 < L.Np) IRS_TMEM_LD16(vb, tmem_row + (uint32_t)(c0 + 16));
+                    last_layer(va, c0);
+                    if (c0 + 16 < L.Np) {
+                        IRS_TMEM_WAIT16(vb);
+                        if (c0 + 32 < L.Np) IRS_TMEM_LD16(va, tmem_row + (uint32_t)(c0 + 32));
+                        last_layer(vb, c0 + 16);
+                    }
                 }
             }
 #pragma unroll
