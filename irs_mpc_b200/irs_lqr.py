@@ -319,6 +319,75 @@ class IrsLqr:
         self._last_descent = (x_out, u_out, x_out.copy(), u_out.copy())
         return x_out, u_out
 
+    def profile_descent(self, x_trj=None, u_trj=None, repeats=5):
+        """Per-phase device times of one descent from (x_trj, u_trj) (default: the current trajectory), in ms:
+        the phases run one after the other on the current stream with CUDA events between them — linearization
+        (one un-pipelined pass), backward Riccati pass, closed-loop rollout, plan check — next to the wall time of
+        `local_descent` itself (pipelined, graph-replayed, staging copies and the synchronising read-back
+        included).  Stored in `self.timings` and returned; the solver's trajectory, cost and iteration count are not
+        changed (a user `sampling` closure is called for the extra linearizations, which advances ITS random stream;
+        `GaussianSampling` is stateless)."""
+        T, n, m = self.T, self.dim_x, self.dim_u
+        x_trj = self.x_trj if x_trj is None else x_trj
+        u_trj = self.u_trj if u_trj is None else u_trj
+        x_all = _device.to_device(np.asarray(x_trj, dtype=np.float64)[:T + 1])
+        u_nom = _device.to_device(np.asarray(u_trj, dtype=np.float64)[:T])
+        x_nom = x_all[:T]
+        db = self._descent_buffers()
+        prm, nprm = self.system._params()
+        state = {}
+
+        def linearize():
+            state["lin"] = self._tv_matrices_device(x_nom, u_nom)
+
+        def riccati():
+            At, Bt, ct, _ = state["lin"]
+            _lib.call("irs_tvlqr_riccati", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct),
+                      _device.ptr(self._dQ), _device.ptr(self._dQd), _device.ptr(self._dR), _device.ptr(self._dxd), 0, 1, T,
+                      _device.ptr(db["K"]), _device.ptr(db["k"]), _device.ptr(db["rstatus"]), _device.stream_ptr())
+
+        def rollout():
+            _lib.call("irs_rollout_closed_loop", self.system.system_id, prm, nprm, _device.ptr(db["K"]), _device.ptr(db["k"]),
+                      _device.ptr(x_all), _device.ptr(self._dxd), 0, _device.ptr(self._dQ), _device.ptr(self._dR), 1, T,
+                      _device.ptr(db["x_new"]), _device.ptr(db["u_new"]), _device.ptr(db["cost"]), _device.stream_ptr())
+
+        def plan_check():
+            At, Bt, ct, _ = state["lin"]
+            xlo, xhi, ulo, uhi = db["box"]
+            _lib.call("irs_tvlqr_plan_check", n, m, _device.ptr(At), _device.ptr(Bt), _device.ptr(ct), _device.ptr(db["K"]),
+                      _device.ptr(db["k"]), _device.ptr(db["x_new"]), _device.ptr(xlo), _device.ptr(xhi), _device.ptr(ulo),
+                      _device.ptr(uhi), BOUND_TOL, 1, T, 0, _device.ptr(db["violated"]), _device.ptr(db["plan_scratch"]),
+                      _device.stream_ptr())
+
+        phases = [("linearize_ms", linearize), ("riccati_ms", riccati), ("rollout_ms", rollout)]
+        if db["box"] is not None:
+            phases.append(("plan_check_ms", plan_check))
+        for _, fn in phases:      # warm: workspaces, first launches
+            fn()
+        torch.cuda.synchronize()
+        out = {key: 0.0 for key, _ in phases}
+        for _ in range(repeats):
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)]
+            marks[0].record()
+            for i, (_, fn) in enumerate(phases):
+                fn()
+                marks[i + 1].record()
+            torch.cuda.synchronize()
+            for i, (key, _) in enumerate(phases):
+                out[key] += marks[i].elapsed_time(marks[i + 1]) / repeats
+        out["phases_sum_ms"] = float(sum(out[key] for key, _ in phases))
+        saved = (getattr(self, "_last_descent_cost", None), getattr(self, "_last_descent", None))
+        self.local_descent(x_trj, u_trj)      # warm (graph capture on the third call of a shape)
+        self.local_descent(x_trj, u_trj)
+        self.local_descent(x_trj, u_trj)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            self.local_descent(x_trj, u_trj)
+        out["local_descent_wall_ms"] = (time.perf_counter() - t0) / repeats * 1e3
+        self._last_descent_cost, self._last_descent = saved
+        self.timings = out
+        return out
+
     def _bounded_descent(self, db):
         """irs_lqr.py:169-184 with active bounds: a box QP over the remaining horizon at every timestep
         (ADMM, csrc/tvlqr_box.cuh), first input applied to the true dynamics."""

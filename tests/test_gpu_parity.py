@@ -1118,3 +1118,20 @@ def test_bicycle_exact_loop_lands_on_the_stored_curve(api, golden_dir):
     assert len(solver.cost_lst) == len(goldc)
     assert abs(solver.cost_lst[-1] - goldc[-1]) <= 0.03 * goldc[-1]
     assert np.max(np.abs(solver.x_trj[:, 4])) <= np.pi / 4 + 1e-6
+
+
+def test_profile_descent_reports_phase_times(api):
+    """`solver.profile_descent()`: per-phase device times of a descent (the reference has no timing hooks beyond the
+    elapsed-time print of iterate, irs_lqr.py:205-208); the solver's state and noise stream position are untouched."""
+    cfg = ec.CONFIGS["quadrotor"](T=30)
+    s = make_system(api, "quadrotor")
+    smp = api.GaussianSampling(cfg["sigma"][:12], cfg["sigma"][12:], 4096, power=cfg["power"], seed=3)
+    solver = api.IrsLqrZeroOrder(s, make_params(api, cfg, T=30), smp)
+    x0, u0, c0, it0 = solver.x_trj.copy(), solver.u_trj.copy(), solver.cost, solver.iter
+    t = solver.profile_descent(repeats=2)
+    for key in ("linearize_ms", "riccati_ms", "rollout_ms", "plan_check_ms", "phases_sum_ms", "local_descent_wall_ms"):
+        assert key in t and t[key] > 0.0, key
+    assert abs(t["phases_sum_ms"] - (t["linearize_ms"] + t["riccati_ms"] + t["rollout_ms"] + t["plan_check_ms"])) < 1e-9
+    assert solver.timings is t and solver.iter == it0 and solver.cost == c0
+    np.testing.assert_array_equal(solver.x_trj, x0)
+    np.testing.assert_array_equal(solver.u_trj, u0)
