@@ -387,6 +387,26 @@ def run_gpu(args, rank, local_rank, world):
             ms2 = timed(step2, max(5, min(args.steps, 20)), 3) / max(5, min(args.steps, 20))
             other[label] = {"ms_per_linearization": ms2, "samples_per_s": Tn * Nn / (ms2 * 1e-3)}
             del ws2
+            # the same linearization end to end through the public API (numpy in -> get_TV_matrices -> numpy out)
+            try:
+                from irs_mpc_b200.all import IrsLqrFirstOrder
+                p2 = IrsLqrParameters()
+                for key in ("Q", "Qd", "R", "x0", "xd_trj", "u_trj_initial", "xbound", "ubound"):
+                    setattr(p2, key, c2[key])
+                smp2 = GaussianSampling(c2["sigma"][:sys2.dim_x], c2["sigma"][sys2.dim_x:], Nn, power=c2["power"],
+                                        seed=SEED0 + 31, projection="absolute" if proj else None)
+                cls2 = IrsLqrZeroOrder if order == smoothing.ZERO_ORDER else IrsLqrFirstOrder
+                sol2 = cls2(sys2, p2, smp2)
+                xh2, uh2 = sol2.x_trj, sol2.u_trj
+
+                def e2e2(k, sol2=sol2, smp2=smp2, xh2=xh2, uh2=uh2):
+                    smp2.seed = SEED0 + 31 + k
+                    return sol2.get_TV_matrices(xh2, uh2)
+                reps2 = max(5, min(args.steps, 20))
+                other[label]["e2e_ms_per_linearization"] = timed(e2e2, reps2, 4) / reps2
+                del sol2
+            except Exception as e:
+                other[label]["e2e_error"] = repr(e)
         # learned dynamics (the reference's examples/pendulum/pendulum_nn.py: 3-100-100-2 ReLU network,
         # T=200, N=1e4 samples per step): hidden layer of the network on tcgen05; committed weights of a network
         # trained the way the script trains it (tests/golden/mlp_pendulum.npz, oracle/make_mlp_fixture.py)
