@@ -176,6 +176,30 @@ def main():
     flags = torch.tensor([1.0 if same else 0.0], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     report("instance sharding bit-identical", bool(flags.item() == 1.0), "(%d instances over %d ranks)" % (I, world))
+    # 5. learned dynamics (tcgen05 network kernel) under both shardings: timestep axis bit-identical to one GPU,
+    #    sample axis equal to one GPU drawing all the samples (1e-5) and identical on every rank
+    from irs_mpc_b200.all import MlpDynamics
+    gm = np.load(os.path.join(ROOT, "tests", "golden", "mlp_pendulum.npz"))
+    net = MlpDynamics([(gm["W1"], gm["b1"]), (gm["W2"], gm["b2"]), (gm["W3"], gm["b3"])])
+    Tm, Nm = 23, 6000
+    xm = _device.to_device(np.cumsum(0.05 * np.ones((Tm, 2)), axis=0))
+    um = _device.to_device(0.3 * rng.standard_normal((Tm, 1)))
+    kwm = dict(sigma=np.array([1.0, 1.0, 1.0]), seed=17, it=1, flags=8)
+    shm = ShardedLinearizer(net, smoothing.ZERO_ORDER)
+    A1m, B1m, c1m, _, _ = smoothing.linearize(net, smoothing.ZERO_ORDER, xm, um, Nm, **kwm)
+    A1m, B1m, c1m = A1m.clone(), B1m.clone(), c1m.clone()
+    Atm, Btm, ctm, sttm = shm.linearize_t(xm, um, Nm, **kwm)
+    same_t = torch.equal(Atm, A1m) and torch.equal(Btm, B1m) and torch.equal(ctm, c1m) and int(sttm.sum()) == 0
+    Anm, Bnm, cnm, stnm = shm.linearize_n(xm, um, Nm, **kwm)
+    Anm, Bnm = Anm.clone(), Bnm.clone()
+    Awm, Bwm, _, _, _ = smoothing.linearize(net, smoothing.ZERO_ORDER, xm, um, Nm * world, **kwm)
+    errm = max(rel(Anm, Awm), rel(Bnm, Bwm))
+    gathered = [torch.empty_like(Anm) for _ in range(world)]
+    dist.all_gather(gathered, Anm)
+    same_n = all(torch.equal(g, gathered[0]) for g in gathered) and int(stnm.sum()) == 0
+    flags = torch.tensor([1.0 if (same_t and same_n and errm < 1e-5) else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    report("learned dynamics sharded", bool(flags.item() == 1.0), "(timestep axis bit-identical: %s, sample axis rel err %.2e)" % (same_t, errm))
     if rank == 0:
         print("ALL PASS" if ok else "FAILURES", flush=True)
     dist.destroy_process_group()
