@@ -33,7 +33,7 @@ N_SAMPLES = 100000
 FLOPS_PER_SAMPLE = 838        # quadrotor zero-order, algorithmic, FMA = 2
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 SEED0 = 0x1255 + 3
-DRAM_BYTES_PER_LAUNCH = 50688   # ncu capture of the dominant kernel, see roofline.traffic_source
+DRAM_BYTES_PER_LAUNCH = 64512   # ncu capture of the dominant kernel, see roofline.traffic_source
 
 
 def log(*a):
