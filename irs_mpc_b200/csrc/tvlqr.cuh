@@ -523,8 +523,8 @@ __global__ void __launch_bounds__(kTvlqrTiledThreads) tvlqr_riccati_tiled_kernel
 // its own.  The kernel is bound by the shared-memory pipe (one wavefront per clock and SM, an LDS.128 of a warp
 // costs one per quarter warp with an active lane; ncu: profiles/r2_riccati_packed.txt), hence: the idle
 // quarter warp exits, the second instance of a warp sits 16 bytes (mod 32) beside the first so that their
-// quarter-warp-sharing lanes hit different banks, the rows of P [A | B] are shifted by 16 bytes per row group so
-// that tile stores of two row groups do too, and vector operands are read along contiguous rows (P is
+// quarter-warp-sharing lanes hit different banks, the rows of P [A | B], of P and of sym(Q) are shifted by 16 bytes
+// per row group so that tile accesses of different row groups do too, and vector operands are read along contiguous rows (P is
 // symmetric, Q is kept transposed).  Eight instances per block of 128 threads, four blocks per SM: all 4096
 // instances of configs[4] are resident at once.  Next step's operands are prefetched into registers (18
 // doubles per lane) during the last product of the current step.
@@ -539,7 +539,9 @@ template <int n, int m>
 struct RicPackInst {
     static constexpr int W = n + m;
     static constexpr int kPab = n * W + 2 * (n / 4 - 1);      // rows of group g start 2 g doubles late
-    double P[n * n];              // value-function Hessian (exactly symmetric)
+    static constexpr int kP = n * n + 2 * (n / 4 - 1);        // the same row-group shift for P (tile stores of the
+                                                              // second product: three row groups in one quarter warp)
+    double P[kP + (kP & 1)];      // value-function Hessian (exactly symmetric), row r at r n + 2 (r >> 2)
     double AB[n * W];             // [A | B] of the current step, row stride n + m
     double PAB[kPab + (kPab & 1)];  // P [A | B]
     double GH[m * W];             // B^T [PA | PB] = [G | H - R/2]
@@ -547,22 +549,24 @@ struct RicPackInst {
     double p[n], w[n], c[n], xd[n], g[m], kt[m];
     double pad[2];                // size = 4 (mod 8) words: the warp's second instance lands on the other banks
     __device__ __forceinline__ static constexpr int pab_row(int r) { return r * W + 2 * (r >> 2); }
+    __device__ __forceinline__ static constexpr int p_row(int r) { return r * n + 2 * (r >> 2); }
 };
 template <int n, int m>
 struct RicPackSmem {
-    double Qs[n * n], Qt[n * n], Rh[m * m];      // sym(Q) (value function), Q^T (gradient term), R / 2
+    double Qs[RicPackInst<n, m>::kP + (RicPackInst<n, m>::kP & 1)];      // sym(Q), rows shifted like P (tile loads)
+    double Qt[n * n], Rh[m * m];                                         // Q^T (gradient term), R / 2
     RicPackInst<n, m> inst[kRicPackPerBlock];
 };
 
 // acc[i][j] += sum_q X[q * ldx + x0 + i] * Y[row(q) + y0 + j]   (4 x 4 tile of X^T Y; x0, y0 multiples of 4);
-// row(q) = q * ldy, plus the row-group shift of RicPackInst::PAB when YSHIFT
-template <int len, bool YSHIFT>
+// row(q) = q * ldy, plus the row-group shift of RicPackInst::PAB when YSHIFT (XSHIFT: the same for X = P)
+template <int len, bool YSHIFT, bool XSHIFT = false>
 __device__ __forceinline__ void tile4_atb(const double* X, int ldx, int x0, const double* Y, int ldy, int y0,
                                           double (&acc)[4][4]) {
     static_assert(len % 4 == 0, "row groups of four");
 #pragma unroll 1      // one row group per trip: full unrolling hoists all 48 operand loads and spills at 128 registers
     for (int g = 0; g < len / 4; ++g) {
-        const double* Xg = X + 4 * g * ldx + x0;
+        const double* Xg = X + 4 * g * ldx + x0 + (XSHIFT ? 2 * g : 0);
         const double* Yg = Y + 4 * g * ldy + y0 + (YSHIFT ? 2 * g : 0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int e = tid; e < n * n; e += kRicPackThreads) {
         const int r = e / n, c = e % n;
-        sm.Qs[e] = 0.5 * (a.Q[e] + a.Q[c * n + r]);       // x' Q x only sees the symmetric part
+        sm.Qs[Inst::p_row(r) + c] = 0.5 * (a.Q[e] + a.Q[c * n + r]);       // x' Q x only sees the symmetric part
         sm.Qt[e] = a.Q[c * n + r];
     }
     for (int e = tid; e < m * m; e += kRicPackThreads) sm.Rh[e] = 0.5 * a.R[e];
@@ -651,7 +655,7 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
     // terminal condition P_T = sym(Qd) (x' Qd x only sees the symmetric part), p_T = -Qd xd_T
     for (int e = j; e < n * n; e += kRicPackLanes) {
         const int r = e / n, c = e % n;
-        s.P[e] = 0.5 * (a.Qd[r * n + c] + a.Qd[c * n + r]);
+        s.P[Inst::p_row(r) + c] = 0.5 * (a.Qd[r * n + c] + a.Qd[c * n + r]);
     }
     {
         double acc = 0.0;
@@ -673,11 +677,11 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
         // ---- phase 1: [PA | PB] = P [A | B] (one 4 x 4 tile per lane), w = P c + p ----
         {
             double acc[4][4] = {};
-            tile4_atb<n, false>(s.P, n, ab_r0, s.AB, W, ab_c0, acc);
+            tile4_atb<n, false, true>(s.P, n, ab_r0, s.AB, W, ab_c0, acc);
             tile4_store<false>(s.PAB + 2 * (ab_r0 >> 2), W, ab_r0, ab_c0, acc);
             double wv = s.p[j];
 #pragma unroll
-            for (int q = 0; q < n; ++q) wv = fma(s.P[q * n + j], s.c[q], wv);      // P[j][q] = P[q][j]
+            for (int q = 0; q < n; ++q) wv = fma(s.P[Inst::p_row(q) + j], s.c[q], wv);      // P[j][q] = P[q][j]
             s.w[j] = wv;
         }
         __syncwarp(kRicPackMask);
@@ -687,7 +691,7 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pn[i][q] = pn_tile ? sm.Qs[(pn_r0 + i) * n + pn_c0 + q] : 0.0;
+            for (int q = 0; q < 4; ++q) pn[i][q] = pn_tile ? sm.Qs[Inst::p_row(pn_r0 + i) + pn_c0 + q] : 0.0;
         if (pn_tile || gh_tile) {
             tile4_atb<n, true>(s.AB, W, x0_2, s.PAB, W, y0_2, pn);
             if (gh_tile) tile4_store<false>(s.GH, W, 0, y0_2, pn);
@@ -744,9 +748,9 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
 #pragma unroll
                     for (int q = 0; q < i; ++q) pn[i][q] = pn[q][i] = 0.5 * (pn[i][q] + pn[q][i]);
             } else {
-                tile4_store<true>(s.P, n, pn_c0, pn_r0, pn);
+                tile4_store<true>(s.P + 2 * (pn_c0 >> 2), n, pn_c0, pn_r0, pn);
             }
-            tile4_store<false>(s.P, n, pn_r0, pn_c0, pn);
+            tile4_store<false>(s.P + 2 * (pn_r0 >> 2), n, pn_r0, pn_c0, pn);
         }
         double pnew;
         {
@@ -766,8 +770,10 @@ __global__ void __launch_bounds__(kRicPackThreads, 4) tvlqr_riccati_packed_kerne
         __syncwarp(kRicPackMask);
     }
     // NaN guard on the final value function; one status per instance
-    for (int e = j; e < n * n; e += kRicPackLanes)
-        if (!(s.P[e] == s.P[e])) ok = false;
+    for (int e = j; e < n * n; e += kRicPackLanes) {
+        const double v = s.P[Inst::p_row(e / n) + e % n];
+        if (!(v == v)) ok = false;
+    }
     ok = __all_sync(((1u << kRicPackLanes) - 1u) << (sub * kRicPackLanes), ok);
     if (live && j == 0) a.status[inst] = ok ? 0 : 1;
 }
